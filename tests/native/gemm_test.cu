@@ -1,0 +1,229 @@
+// Standalone check of the tcgen05 GEMM against a plain SIMT reference (fp32 accumulate from the same
+// bf16 inputs).  Prints max abs / rel error per shape and a timing for the large shapes.
+// Build: see clip_embedder_rs_b200/csrc/Makefile (target gemm_test).  Run on a B200 only.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "../../clip_embedder_rs_b200/csrc/gemm_sm100.cuh"
+
+using namespace clipb200;
+
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) {                                                           \
+      printf("CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      exit(2);                                                                         \
+    }                                                                                  \
+  } while (0)
+
+__global__ void fill_bf16(__nv_bfloat16* p, size_t n, uint32_t seed, float scale) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t z = (i + 1) * 0x9E3779B97F4A7C15ull + seed;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  float u = (float)(z & 0xFFFFFF) / 16777216.0f - 0.5f;
+  p[i] = __float2bfloat16(u * scale);
+}
+__global__ void fill_f32(float* p, size_t n, uint32_t seed, float scale) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t z = (i + 1) * 0x9E3779B97F4A7C15ull + seed;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  p[i] = ((float)(z & 0xFFFFFF) / 16777216.0f - 0.5f) * scale;
+}
+
+// reference for selected rows: ref[i, n] = sum_k A[rows[i], k] * W[n, k]
+__global__ void ref_rows(const __nv_bfloat16* A, const __nv_bfloat16* W, const int* rows, int nrows, int N, int K,
+                         float* ref) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y;
+  if (n >= N || i >= nrows) return;
+  const __nv_bfloat16* a = A + (size_t)rows[i] * K;
+  const __nv_bfloat16* w = W + (size_t)n * K;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc += __bfloat162float(a[k]) * __bfloat162float(w[k]);
+  ref[(size_t)i * N + n] = acc;
+}
+
+static float host_act(float x, int act) {
+  switch (act) {
+    case ACT_QUICKGELU: return x / (1.0f + expf(-1.702f * x));
+    case ACT_GELU_TANH: return 0.5f * x * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+    case ACT_GELU_ERF: return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));
+    default: return x;
+  }
+}
+static float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+static int run_case(int M, int N, int K, int epi, int act, int force_bn, bool time_it, int num_sms) {
+  __nv_bfloat16 *A, *W, *Cb;
+  float *bias, *Cf, *Cf0, *gamma, *pos;
+  const int rows_in = (epi == EPI_F32) ? 7 : 0, rows_out = 8, row_off = 1;  // CLS-style remap test
+  const long long out_rows = (epi == EPI_F32) ? (long long)((M + rows_in - 1) / rows_in) * rows_out : M;
+  CK(cudaMalloc(&A, (size_t)M * K * 2));
+  CK(cudaMalloc(&W, (size_t)N * K * 2));
+  CK(cudaMalloc(&Cb, (size_t)M * N * 2));
+  CK(cudaMalloc(&Cf, (size_t)out_rows * N * 4));
+  CK(cudaMalloc(&Cf0, (size_t)out_rows * N * 4));
+  CK(cudaMalloc(&bias, (size_t)N * 4));
+  CK(cudaMalloc(&gamma, (size_t)N * 4));
+  CK(cudaMalloc(&pos, (size_t)rows_out * N * 4));
+  auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
+  fill_bf16<<<blocks((size_t)M * K), 256>>>(A, (size_t)M * K, 1, 2.0f);
+  fill_bf16<<<blocks((size_t)N * K), 256>>>(W, (size_t)N * K, 2, 0.25f);
+  fill_f32<<<blocks(N), 256>>>(bias, N, 3, 1.0f);
+  fill_f32<<<blocks(N), 256>>>(gamma, N, 4, 2.0f);
+  fill_f32<<<blocks((size_t)rows_out * N), 256>>>(pos, (size_t)rows_out * N, 5, 1.0f);
+  fill_f32<<<blocks((size_t)out_rows * N), 256>>>(Cf0, (size_t)out_rows * N, 6, 1.0f);
+  CK(cudaMemcpy(Cf, Cf0, (size_t)out_rows * N * 4, cudaMemcpyDeviceToDevice));
+  CK(cudaMemset(Cb, 0, (size_t)M * N * 2));
+  CK(cudaDeviceSynchronize());
+
+  GemmEpilogue ep;
+  ep.bias = bias;
+  ep.act = act;
+  ep.ldc = N;
+  ep.out_bf16 = Cb;
+  ep.out_f32 = Cf;
+  if (epi == EPI_RESID) ep.gamma = gamma;
+  if (epi == EPI_F32) { ep.pos = pos; ep.rows_in = rows_in; ep.rows_out = rows_out; ep.row_off = row_off; }
+  CK(gemm_bf16(A, K, W, K, M, N, K, epi, ep, num_sms, 0, force_bn));
+  CK(cudaDeviceSynchronize());
+
+  // rows to verify
+  std::vector<int> rows;
+  if (M <= 512) { for (int r = 0; r < M; ++r) rows.push_back(r); }
+  else {
+    for (int r = 0; r < 160; ++r) rows.push_back(r);
+    for (int r = M - 160; r < M; ++r) rows.push_back(r);
+    for (int i = 0; i < 192; ++i) rows.push_back((int)(((long long)i * 2654435761ll) % M));
+  }
+  int nrows = (int)rows.size();
+  int* drows; float* dref;
+  CK(cudaMalloc(&drows, nrows * 4));
+  CK(cudaMalloc(&dref, (size_t)nrows * N * 4));
+  CK(cudaMemcpy(drows, rows.data(), nrows * 4, cudaMemcpyHostToDevice));
+  ref_rows<<<dim3((N + 127) / 128, nrows), 128>>>(A, W, drows, nrows, N, K, dref);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> ref((size_t)nrows * N), hb(N), hg(N), hpos((size_t)rows_out * N);
+  CK(cudaMemcpy(ref.data(), dref, ref.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hb.data(), bias, N * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hg.data(), gamma, N * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hpos.data(), pos, hpos.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<__nv_bfloat16> hcb;
+  std::vector<float> hcf, hcf0;
+  if (epi == EPI_BF16) { hcb.resize((size_t)M * N); CK(cudaMemcpy(hcb.data(), Cb, hcb.size() * 2, cudaMemcpyDeviceToHost)); }
+  else {
+    hcf.resize((size_t)out_rows * N); hcf0.resize((size_t)out_rows * N);
+    CK(cudaMemcpy(hcf.data(), Cf, hcf.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hcf0.data(), Cf0, hcf0.size() * 4, cudaMemcpyDeviceToHost));
+  }
+  double max_abs = 0, max_rel = 0;
+  long long bad = 0;
+  for (int i = 0; i < nrows; ++i) {
+    const int r = rows[i];
+    for (int n = 0; n < N; ++n) {
+      float want = ref[(size_t)i * N + n] + hb[n];
+      float got;
+      float tol;
+      if (epi == EPI_BF16) {
+        want = host_act(want, act);
+        got = __bfloat162float(hcb[(size_t)r * N + n]);
+        tol = 0.02f + fabsf(want) * (1.0f / 128.0f);
+      } else if (epi == EPI_RESID) {
+        want = hcf0[(size_t)r * N + n] + hg[n] * want;
+        got = hcf[(size_t)r * N + n];
+        tol = 0.02f + fabsf(want) * 1e-3f;
+      } else {
+        const int b = r / rows_in, t = r % rows_in;
+        const long long orow = (long long)b * rows_out + t + row_off;
+        want = want + hpos[(size_t)(t + row_off) * N + n];
+        got = hcf[(size_t)orow * N + n];
+        tol = 0.02f + fabsf(want) * 1e-3f;
+      }
+      const double d = fabs((double)got - (double)want);
+      if (d > max_abs) max_abs = d;
+      const double rel = d / (fabs((double)want) + 1e-3);
+      if (rel > max_rel) max_rel = rel;
+      if (!(d <= tol)) {
+        if (bad < 5) printf("   mismatch r=%d n=%d got=%f want=%f\n", r, n, got, want);
+        ++bad;
+      }
+    }
+  }
+  // EPI_F32 remap: untouched rows (row 0 of every group of rows_out) must keep their original contents
+  if (epi == EPI_F32) {
+    for (long long g = 0; g < out_rows / rows_out; ++g)
+      for (int n = 0; n < N; ++n)
+        if (hcf[(size_t)(g * rows_out) * N + n] != hcf0[(size_t)(g * rows_out) * N + n]) { ++bad; }
+  }
+  double ms = 0;
+  if (time_it) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) CK(gemm_bf16(A, K, W, K, M, N, K, epi, ep, num_sms, 0, force_bn));
+    CK(cudaEventRecord(e0));
+    const int iters = 10;
+    for (int i = 0; i < iters; ++i) CK(gemm_bf16(A, K, W, K, M, N, K, epi, ep, num_sms, 0, force_bn));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float t; CK(cudaEventElapsedTime(&t, e0, e1));
+    ms = t / iters;
+  }
+  const char* en = epi == EPI_BF16 ? "bf16" : (epi == EPI_RESID ? "resid" : "f32");
+  printf("%s M=%d N=%d K=%d epi=%s act=%d bn=%d max_abs=%.4g max_rel=%.4g bad=%lld", bad ? "FAIL" : "ok  ", M, N, K,
+         en, act, force_bn ? force_bn : gemm_pick_bn(N), max_abs, max_rel, bad);
+  if (time_it) printf("  %.3f ms  %.1f TFLOP/s", ms, 2.0 * M * N * K / ms * 1e-9);
+  printf("\n");
+  fflush(stdout);
+  cudaFree(A); cudaFree(W); cudaFree(Cb); cudaFree(Cf); cudaFree(Cf0); cudaFree(bias); cudaFree(gamma); cudaFree(pos);
+  cudaFree(drows); cudaFree(dref);
+  return bad ? 1 : 0;
+}
+
+int main(int argc, char** argv) {
+  int dev = 0;
+  CK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  printf("device %s sm_%d%d SMs=%d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+  const int num_sms = prop.multiProcessorCount;
+  CK(gemm_configure_device());
+  int fails = 0;
+  const bool quick = argc > 1 && atoi(argv[1]) == 1;
+  // smallest cases first: one tile, one k-block
+  fails += run_case(128, 256, 64, EPI_BF16, ACT_NONE, 256, false, num_sms);
+  fails += run_case(128, 128, 64, EPI_BF16, ACT_NONE, 128, false, num_sms);
+  fails += run_case(128, 192, 64, EPI_BF16, ACT_NONE, 192, false, num_sms);
+  fails += run_case(128, 256, 256, EPI_BF16, ACT_NONE, 256, false, num_sms);
+  fails += run_case(128, 256, 1152, EPI_BF16, ACT_NONE, 256, false, num_sms);
+  // tails in M, N, K
+  fails += run_case(50, 512, 768, EPI_BF16, ACT_QUICKGELU, 0, false, num_sms);
+  fails += run_case(300, 1152, 1152, EPI_BF16, ACT_GELU_TANH, 0, false, num_sms);
+  fails += run_case(389, 4304, 1152, EPI_BF16, ACT_GELU_ERF, 0, false, num_sms);
+  fails += run_case(389, 1152, 4304, EPI_RESID, ACT_NONE, 0, false, num_sms);
+  fails += run_case(343, 768, 592, EPI_F32, ACT_NONE, 0, false, num_sms);
+  fails += run_case(77 * 5, 1024, 1024, EPI_RESID, ACT_NONE, 0, false, num_sms);
+  if (!quick) {
+    // multi-tile persistent scheduling + perf (SO400M layer shapes at a 128-image micro-batch, M = 73728)
+    const int M = 128 * 576;
+    fails += run_case(M, 3456, 1152, EPI_BF16, ACT_NONE, 0, true, num_sms);
+    fails += run_case(M, 3456, 1152, EPI_BF16, ACT_NONE, 256, true, num_sms);
+    fails += run_case(M, 1152, 1152, EPI_RESID, ACT_NONE, 0, true, num_sms);
+    fails += run_case(M, 4304, 1152, EPI_BF16, ACT_GELU_TANH, 0, true, num_sms);
+    fails += run_case(M, 4304, 1152, EPI_BF16, ACT_GELU_TANH, 256, true, num_sms);
+    fails += run_case(M, 1152, 4304, EPI_RESID, ACT_NONE, 0, true, num_sms);
+    fails += run_case(M, 1152, 4304, EPI_RESID, ACT_NONE, 128, true, num_sms);
+    fails += run_case(8192, 8192, 8192, EPI_BF16, ACT_NONE, 256, true, num_sms);
+  }
+  printf("%s (%d failing cases)\n", fails ? "GEMM TEST FAILED" : "GEMM TEST PASSED", fails);
+  return fails ? 1 : 0;
+}
