@@ -1,0 +1,232 @@
+// extern "C" boundary (include/clipb200.h).  Nothing throws across it; errors become status codes plus a
+// thread-local message, the way `ort::Error` becomes `ClipError::Ort(String)` in the reference (src/error.rs:62-66).
+#include <cuda_runtime.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/clipb200.h"
+#include "engine.h"
+#include "kernels.cuh"
+
+using clipb200::Engine;
+using clipb200::Status;
+
+struct clipb200_engine {
+  Engine* impl;
+};
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+static int done(const Status& s) {
+  if (s.ok()) return CLIPB200_OK;
+  g_last_error = s.msg;
+  return s.code;
+}
+
+#define API_GUARD_BEGIN try {
+#define API_GUARD_END                                                        \
+  }                                                                          \
+  catch (const std::bad_alloc&) {                                            \
+    return fail(CLIPB200_ERR_CUDA, "host allocation failed");                \
+  }                                                                          \
+  catch (const std::exception& ex) {                                         \
+    return fail(CLIPB200_ERR_INVALID_ARG, std::string("exception: ") + ex.what()); \
+  }                                                                          \
+  catch (...) {                                                              \
+    return fail(CLIPB200_ERR_INVALID_ARG, "unknown exception");              \
+  }
+
+extern "C" {
+
+const char* clipb200_last_error(void) { return g_last_error.c_str(); }
+const char* clipb200_version(void) { return "clipb200 0.1.0 (sm_100a)"; }
+
+int clipb200_engine_create(const char* onnx_path, int cuda_device, const clipb200_opts* opts, clipb200_engine** out) {
+  API_GUARD_BEGIN
+  if (onnx_path == nullptr || out == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  Engine* e = nullptr;
+  Status s = Engine::Create(onnx_path, cuda_device, opts, &e);
+  if (!s.ok()) return done(s);
+  clipb200_engine* h = new clipb200_engine();
+  h->impl = e;
+  *out = h;
+  return CLIPB200_OK;
+  API_GUARD_END
+}
+
+void clipb200_engine_destroy(clipb200_engine* e) {
+  if (e == nullptr) return;
+  try {
+    delete e->impl;
+    delete e;
+  } catch (...) {
+  }
+}
+
+int clipb200_engine_num_inputs(const clipb200_engine* e) {
+  return e == nullptr ? 0 : static_cast<int>(e->impl->input_names.size());
+}
+const char* clipb200_engine_input_name(const clipb200_engine* e, int i) {
+  if (e == nullptr || i < 0 || i >= static_cast<int>(e->impl->input_names.size())) return nullptr;
+  return e->impl->input_names[i].c_str();
+}
+int clipb200_engine_kind(const clipb200_engine* e) { return e == nullptr ? -1 : e->impl->kind; }
+int64_t clipb200_engine_embed_dim(const clipb200_engine* e) { return e == nullptr ? 0 : e->impl->embed_dim; }
+int64_t clipb200_engine_image_size(const clipb200_engine* e) { return e == nullptr ? 0 : e->impl->image_size; }
+int64_t clipb200_engine_context_length(const clipb200_engine* e) { return e == nullptr ? 0 : e->impl->context_length; }
+int64_t clipb200_engine_weight_bytes(const clipb200_engine* e) { return e == nullptr ? 0 : e->impl->weight_bytes; }
+int64_t clipb200_engine_launch_count(const clipb200_engine* e) { return e == nullptr ? 0 : e->impl->launch_count; }
+
+int clipb200_vision_embed_f32(clipb200_engine* e, const float* nchw, int64_t batch, float* out) {
+  API_GUARD_BEGIN
+  if (e == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null engine");
+  return done(e->impl->VisionEmbedF32(nchw, batch, out));
+  API_GUARD_END
+}
+
+int clipb200_vision_embed_rgb8(clipb200_engine* e, const uint8_t* hwc, int64_t batch, int32_t width, int32_t height,
+                               const clipb200_preproc* pp, float* out) {
+  API_GUARD_BEGIN
+  if (e == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null engine");
+  return done(e->impl->VisionEmbedRgb8(hwc, batch, width, height, pp, out, false));
+  API_GUARD_END
+}
+
+int clipb200_preprocess_rgb8(clipb200_engine* e, const uint8_t* hwc, int64_t batch, int32_t width, int32_t height,
+                             const clipb200_preproc* pp, float* out_nchw) {
+  API_GUARD_BEGIN
+  if (e == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null engine");
+  return done(e->impl->PreprocessRgb8(hwc, batch, width, height, pp, out_nchw));
+  API_GUARD_END
+}
+
+int clipb200_vision_embed_rgb8_device(clipb200_engine* e, const uint8_t* d_hwc, int64_t batch,
+                                      const clipb200_preproc* pp, float* d_out) {
+  API_GUARD_BEGIN
+  if (e == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null engine");
+  const int s = static_cast<int>(e->impl->image_size);
+  return done(e->impl->VisionEmbedRgb8(d_hwc, batch, s, s, pp, d_out, true));
+  API_GUARD_END
+}
+
+int clipb200_text_embed(clipb200_engine* e, const int64_t* input_ids, const int64_t* /*attention_mask_or_null*/,
+                        int64_t batch, int64_t ctx, float* out) {
+  API_GUARD_BEGIN
+  if (e == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null engine");
+  return done(e->impl->TextEmbed(input_ids, batch, ctx, out, false));
+  API_GUARD_END
+}
+
+int clipb200_text_embed_device(clipb200_engine* e, const int64_t* d_input_ids, int64_t batch, int64_t ctx,
+                               float* d_out) {
+  API_GUARD_BEGIN
+  if (e == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null engine");
+  return done(e->impl->TextEmbed(d_input_ids, batch, ctx, d_out, true));
+  API_GUARD_END
+}
+
+int clipb200_similarity(int cuda_device, const float* A, const float* b, int64_t n, int64_t d, float scale,
+                        float bias, int activation, float* probs) {
+  API_GUARD_BEGIN
+  if (A == nullptr || b == nullptr || probs == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null buffer");
+  if (n <= 0 || d <= 0 || n > 0x7fffffff || d > 0x7fffffff) return fail(CLIPB200_ERR_INVALID_ARG, "bad shape");
+  cudaError_t ce = cudaSetDevice(cuda_device);
+  if (ce != cudaSuccess) return fail(CLIPB200_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+  float *dA = nullptr, *db = nullptr, *dp = nullptr;
+  const size_t abytes = static_cast<size_t>(n) * d * 4;
+  int rc = CLIPB200_OK;
+  do {
+    if ((ce = cudaMalloc(&dA, abytes)) != cudaSuccess) break;
+    if ((ce = cudaMalloc(&db, d * 4)) != cudaSuccess) break;
+    if ((ce = cudaMalloc(&dp, n * 4 + 16)) != cudaSuccess) break;
+    if ((ce = cudaMemcpy(dA, A, abytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+    if ((ce = cudaMemcpy(db, b, d * 4, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+    if ((ce = clipb200::launch_similarity(dA, db, static_cast<int>(n), static_cast<int>(d), scale, bias, activation, dp,
+                                          nullptr, 0)) != cudaSuccess)
+      break;
+    if ((ce = cudaMemcpy(probs, dp, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+  } while (0);
+  if (ce != cudaSuccess) rc = fail(CLIPB200_ERR_CUDA, std::string("similarity: ") + cudaGetErrorString(ce));
+  cudaFree(dA);
+  cudaFree(db);
+  cudaFree(dp);
+  return rc;
+  API_GUARD_END
+}
+
+void* clipb200_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void clipb200_host_free(void* p) {
+  if (p != nullptr) cudaFreeHost(p);
+}
+void* clipb200_device_alloc(int cuda_device, size_t bytes) {
+  void* p = nullptr;
+  if (cudaSetDevice(cuda_device) != cudaSuccess) return nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void clipb200_device_free(int cuda_device, void* p) {
+  if (p == nullptr) return;
+  cudaSetDevice(cuda_device);
+  cudaFree(p);
+}
+int clipb200_memcpy_h2d(int cuda_device, void* dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaSetDevice(cuda_device);
+  if (e == cudaSuccess) e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+  return e == cudaSuccess ? CLIPB200_OK : fail(CLIPB200_ERR_CUDA, cudaGetErrorString(e));
+}
+int clipb200_memcpy_d2h(int cuda_device, void* dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaSetDevice(cuda_device);
+  if (e == cudaSuccess) e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? CLIPB200_OK : fail(CLIPB200_ERR_CUDA, cudaGetErrorString(e));
+}
+int clipb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int clipb200_engine_record_event(clipb200_engine* e, int slot) {
+  API_GUARD_BEGIN
+  if (e == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null engine");
+  return done(e->impl->RecordEvent(slot));
+  API_GUARD_END
+}
+int clipb200_engine_elapsed_ms(clipb200_engine* e, int slot_start, int slot_end, double* ms) {
+  API_GUARD_BEGIN
+  if (e == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null engine");
+  return done(e->impl->ElapsedMs(slot_start, slot_end, ms));
+  API_GUARD_END
+}
+int clipb200_engine_synchronize(clipb200_engine* e) {
+  API_GUARD_BEGIN
+  if (e == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null engine");
+  return done(e->impl->Synchronize());
+  API_GUARD_END
+}
+int clipb200_engine_profile(clipb200_engine* e, clipb200_profile* out, int reset) {
+  API_GUARD_BEGIN
+  if (e == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null engine");
+  return done(e->impl->ReadProfile(out, reset != 0));
+  API_GUARD_END
+}
+int clipb200_engine_flush_l2(clipb200_engine* e) {
+  API_GUARD_BEGIN
+  if (e == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null engine");
+  return done(e->impl->FlushL2());
+  API_GUARD_END
+}
+
+}  // extern "C"

@@ -1,0 +1,858 @@
+#include "engine.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "gemm_sm100.cuh"
+#include "kernels.cuh"
+
+namespace clipb200 {
+
+#define RET_IF_ERR(expr)      \
+  do {                        \
+    Status s_ = (expr);       \
+    if (!s_.ok()) return s_;  \
+  } while (0)
+#define CUDA_RET(expr, what)                      \
+  do {                                            \
+    Status s_ = Check((expr), what);              \
+    if (!s_.ok()) return s_;                      \
+  } while (0)
+
+Status Engine::Check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return Status::OK();
+  return Status::Err(CLIPB200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+static float half_to_float(uint16_t h) {
+  const uint32_t sign = (h & 0x8000u) << 16;
+  uint32_t exp = (h >> 10) & 0x1F, man = h & 0x3FF, bits;
+  if (exp == 0) {
+    if (man == 0) bits = sign;
+    else {
+      exp = 127 - 15 + 1;
+      while (!(man & 0x400)) { man <<= 1; --exp; }
+      bits = sign | (exp << 23) | ((man & 0x3FF) << 13);
+    }
+  } else if (exp == 31) bits = sign | 0x7F800000u | (man << 13);
+  else bits = sign | ((exp + 127 - 15) << 23) | (man << 13);
+  float f;
+  memcpy(&f, &bits, 4);
+  return f;
+}
+
+// ------------------------------------------------------------------------------------------------ create
+Status Engine::Create(const std::string& onnx_path, int device, const clipb200_opts* opts, Engine** out) {
+  Engine* e = new Engine();
+  Status s = e->Init(onnx_path, device, opts);
+  if (!s.ok()) {
+    delete e;
+    return s;
+  }
+  *out = e;
+  return Status::OK();
+}
+
+Status Engine::DevAlloc(void** p, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess)
+    return Status::Err(CLIPB200_ERR_CUDA, "cudaMalloc(" + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+  dev_allocs_.push_back(*p);
+  return Status::OK();
+}
+
+Status Engine::HostF32(const OnnxModel& m, const std::string& name, int64_t expect_numel, std::vector<float>* out) {
+  const OnnxTensor* t = m.find(name);
+  if (t == nullptr) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "initializer '" + name + "' not found in graph");
+  if (expect_numel >= 0 && t->numel() != expect_numel)
+    return Status::Err(CLIPB200_ERR_UNSUPPORTED, "initializer '" + name + "' has " + std::to_string(t->numel()) +
+                                                     " elements, expected " + std::to_string(expect_numel));
+  const int64_t n = t->numel();
+  out->resize(static_cast<size_t>(n));
+  if (t->data_type == 1) {
+    memcpy(out->data(), t->data, static_cast<size_t>(n) * 4);
+  } else if (t->data_type == 10) {
+    const uint16_t* p = reinterpret_cast<const uint16_t*>(t->data);
+    for (int64_t i = 0; i < n; ++i) (*out)[i] = half_to_float(p[i]);
+  } else if (t->data_type == 16) {
+    const uint16_t* p = reinterpret_cast<const uint16_t*>(t->data);
+    for (int64_t i = 0; i < n; ++i) {
+      const uint32_t bits = static_cast<uint32_t>(p[i]) << 16;
+      memcpy(&(*out)[i], &bits, 4);
+    }
+  } else {
+    return Status::Err(CLIPB200_ERR_UNSUPPORTED,
+                       "initializer '" + name + "' has data_type " + std::to_string(t->data_type) + " (need f32/f16/bf16)");
+  }
+  return Status::OK();
+}
+
+Status Engine::UploadF32(const OnnxModel& m, const std::string& name, int64_t expect_numel, float** out) {
+  const OnnxTensor* t = m.find(name);
+  if (t == nullptr) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "initializer '" + name + "' not found in graph");
+  const float* src = nullptr;
+  std::vector<float> tmp;
+  if (t->data_type == 1 && (expect_numel < 0 || t->numel() == expect_numel)) {
+    src = reinterpret_cast<const float*>(t->data);
+  } else {
+    RET_IF_ERR(HostF32(m, name, expect_numel, &tmp));
+    src = tmp.data();
+  }
+  const size_t bytes = static_cast<size_t>(t->numel()) * 4;
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(out), bytes));
+  CUDA_RET(cudaMemcpy(*out, src, bytes, cudaMemcpyHostToDevice), "upload fp32 initializer");
+  weight_bytes += static_cast<int64_t>(bytes);
+  return Status::OK();
+}
+
+// Linear weight -> bf16 [N, ldk] (K contiguous, zero padded to a multiple of 8).  `transpose`: the initializer is
+// stored [K, N] (open_clip `proj` / `text_projection` parameters that are applied as x @ P).
+Status Engine::UploadLinear(const OnnxModel& m, const std::string& wname, const std::string& bname, int N, int K,
+                            bool transpose, LinearW* out) {
+  const OnnxTensor* t = m.find(wname);
+  if (t == nullptr) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "initializer '" + wname + "' not found in graph");
+  if (t->numel() != static_cast<int64_t>(N) * K)
+    return Status::Err(CLIPB200_ERR_UNSUPPORTED, "initializer '" + wname + "' has " + std::to_string(t->numel()) +
+                                                     " elements, expected " + std::to_string(N) + "x" + std::to_string(K));
+  const float* src = nullptr;
+  std::vector<float> tmp;
+  if (t->data_type == 1) src = reinterpret_cast<const float*>(t->data);
+  else {
+    RET_IF_ERR(HostF32(m, wname, -1, &tmp));
+    src = tmp.data();
+  }
+  const int ldk = (K + 7) & ~7;
+  float* staging = nullptr;
+  const size_t fbytes = static_cast<size_t>(N) * K * 4;
+  CUDA_RET(cudaMalloc(&staging, fbytes), "staging alloc");
+  cudaError_t ce = cudaMemcpy(staging, src, fbytes, cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) {
+    cudaFree(staging);
+    return Check(ce, "upload weight");
+  }
+  Status s = DevAlloc(reinterpret_cast<void**>(&out->w), static_cast<size_t>(N) * ldk * 2);
+  if (s.ok()) s = Check(launch_convert_f32_bf16(staging, N, K, ldk, transpose, out->w, 0), "convert weight");
+  if (s.ok()) s = Check(cudaDeviceSynchronize(), "convert weight sync");
+  cudaFree(staging);
+  RET_IF_ERR(s);
+  weight_bytes += static_cast<int64_t>(N) * ldk * 2;
+  out->N = N;
+  out->K = K;
+  out->ldk = ldk;
+  out->b = nullptr;
+  if (!bname.empty()) RET_IF_ERR(UploadF32(m, bname, N, &out->b));
+  return Status::OK();
+}
+
+Status Engine::LoadBlock(const OnnxModel& m, const std::string& p, bool timm, BlockW* b) {
+  const std::string n1 = timm ? ".norm1" : ".ln_1", n2 = timm ? ".norm2" : ".ln_2";
+  RET_IF_ERR(UploadF32(m, p + n1 + ".weight", D_, &b->ln1.g));
+  RET_IF_ERR(UploadF32(m, p + n1 + ".bias", D_, &b->ln1.b));
+  RET_IF_ERR(UploadF32(m, p + n2 + ".weight", D_, &b->ln2.g));
+  RET_IF_ERR(UploadF32(m, p + n2 + ".bias", D_, &b->ln2.b));
+  if (timm) {
+    RET_IF_ERR(UploadLinear(m, p + ".attn.qkv.weight", p + ".attn.qkv.bias", 3 * D_, D_, false, &b->qkv));
+    RET_IF_ERR(UploadLinear(m, p + ".attn.proj.weight", p + ".attn.proj.bias", D_, D_, false, &b->proj));
+    RET_IF_ERR(UploadLinear(m, p + ".mlp.fc1.weight", p + ".mlp.fc1.bias", mlp_, D_, false, &b->fc1));
+    RET_IF_ERR(UploadLinear(m, p + ".mlp.fc2.weight", p + ".mlp.fc2.bias", D_, mlp_, false, &b->fc2));
+  } else {
+    RET_IF_ERR(UploadLinear(m, p + ".attn.in_proj_weight", p + ".attn.in_proj_bias", 3 * D_, D_, false, &b->qkv));
+    RET_IF_ERR(UploadLinear(m, p + ".attn.out_proj.weight", p + ".attn.out_proj.bias", D_, D_, false, &b->proj));
+    RET_IF_ERR(UploadLinear(m, p + ".mlp.c_fc.weight", p + ".mlp.c_fc.bias", mlp_, D_, false, &b->fc1));
+    RET_IF_ERR(UploadLinear(m, p + ".mlp.c_proj.weight", p + ".mlp.c_proj.bias", D_, mlp_, false, &b->fc2));
+  }
+  return Status::OK();
+}
+
+static int meta_int(const OnnxModel& m, const char* key, int dflt) {
+  const std::string v = m.meta(std::string("clipb200.") + key);
+  return v.empty() ? dflt : atoi(v.c_str());
+}
+
+Status Engine::LoadVision(const OnnxModel& m) {
+  kind = CLIPB200_KIND_VISION;
+  const bool timm = m.has("model.visual.trunk.patch_embed.proj.weight");
+  const bool clip = m.has("model.visual.conv1.weight");
+  if (!timm && !clip)
+    return Status::Err(CLIPB200_ERR_UNSUPPORTED,
+                       "vision graph has neither model.visual.conv1.weight (open_clip ViT) nor "
+                       "model.visual.trunk.patch_embed.proj.weight (timm ViT); FastViT / renamed initializers are "
+                       "not supported yet");
+  family_ = timm ? "timm" : "clip";
+  const std::string pre = timm ? "model.visual.trunk" : "model.visual";
+  const OnnxTensor* pw = m.find(timm ? pre + ".patch_embed.proj.weight" : pre + ".conv1.weight");
+  if (pw->dims.size() != 4 || pw->dims[1] != 3 || pw->dims[2] != pw->dims[3])
+    return Status::Err(CLIPB200_ERR_UNSUPPORTED, "patch embedding weight must be [D,3,P,P]");
+  D_ = static_cast<int>(pw->dims[0]);
+  P_ = static_cast<int>(pw->dims[2]);
+  const OnnxTensor* pos = m.find(timm ? pre + ".pos_embed" : pre + ".positional_embedding");
+  if (pos == nullptr) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "positional embedding not found");
+  T_ = static_cast<int>(pos->numel() / D_);
+  has_cls_ = !timm;
+  Tp_ = has_cls_ ? T_ - 1 : T_;
+  G_ = static_cast<int>(lround(sqrt(static_cast<double>(Tp_))));
+  if (G_ * G_ != Tp_) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "non-square patch grid");
+  S_ = G_ * P_;
+  image_size = S_;
+  K_ = 3 * P_ * P_;
+  Kp_ = (K_ + 7) & ~7;
+  // depth: count blocks by probing names
+  L_ = 0;
+  while (m.has(pre + (timm ? ".blocks." : ".transformer.resblocks.") + std::to_string(L_) +
+               (timm ? ".norm1.weight" : ".ln_1.weight")))
+    ++L_;
+  if (L_ == 0) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "no transformer blocks found");
+  const OnnxTensor* fc1 = m.find(pre + (timm ? ".blocks.0.mlp.fc1.weight" : ".transformer.resblocks.0.mlp.c_fc.weight"));
+  if (fc1 == nullptr) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "MLP weight not found");
+  mlp_ = static_cast<int>(fc1->dims[0]);
+  // heads are not derivable from shapes: metadata first, then the family defaults (head width 64; the
+  // SigLIP so400m / giant-opt trunks use 16 heads, ViT-H/14 uses head width 80)
+  H_ = meta_int(m, "heads", 0);
+  if (H_ == 0) {
+    if (D_ == 1152 || D_ == 1536 || D_ == 1280) H_ = 16;
+    else H_ = D_ / 64;
+  }
+  if (H_ <= 0 || D_ % H_ != 0) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "bad head count");
+  hd_ = D_ / H_;
+  act_ = meta_int(m, "act", timm ? ACT_GELU_TANH : ACT_QUICKGELU);
+  const std::string eps = m.meta("clipb200.eps");
+  eps_ = eps.empty() ? (timm ? 1e-6f : 1e-5f) : static_cast<float>(atof(eps.c_str()));
+  pool_map_ = timm;
+
+  const OnnxTensor* out_w = timm ? nullptr : m.find(pre + ".proj");
+  E_ = timm ? D_ : static_cast<int>(out_w ? out_w->dims.back() : 0);
+  if (E_ <= 0) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "model.visual.proj not found");
+  embed_dim = E_;
+
+  RET_IF_ERR(UploadLinear(m, timm ? pre + ".patch_embed.proj.weight" : pre + ".conv1.weight",
+                          timm ? pre + ".patch_embed.proj.bias" : "", D_, K_, false, &patch_));
+  RET_IF_ERR(UploadF32(m, timm ? pre + ".pos_embed" : pre + ".positional_embedding", static_cast<int64_t>(T_) * D_, &pos_));
+  if (has_cls_) {
+    std::vector<float> cls, pos0;
+    RET_IF_ERR(HostF32(m, pre + ".class_embedding", D_, &cls));
+    RET_IF_ERR(HostF32(m, pre + ".positional_embedding", static_cast<int64_t>(T_) * D_, &pos0));
+    for (int i = 0; i < D_; ++i) cls[i] += pos0[i];
+    RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&cls_row_), D_ * 4));
+    CUDA_RET(cudaMemcpy(cls_row_, cls.data(), D_ * 4, cudaMemcpyHostToDevice), "upload cls row");
+    RET_IF_ERR(UploadF32(m, pre + ".ln_pre.weight", D_, &ln_pre_.g));
+    RET_IF_ERR(UploadF32(m, pre + ".ln_pre.bias", D_, &ln_pre_.b));
+  }
+  blocks_.resize(L_);
+  for (int i = 0; i < L_; ++i)
+    RET_IF_ERR(LoadBlock(m, pre + (timm ? ".blocks." : ".transformer.resblocks.") + std::to_string(i), timm, &blocks_[i]));
+  if (timm) {
+    RET_IF_ERR(UploadF32(m, pre + ".norm.weight", D_, &ln_post_.g));
+    RET_IF_ERR(UploadF32(m, pre + ".norm.bias", D_, &ln_post_.b));
+    const std::string ap = pre + ".attn_pool";
+    // the pooling query is weight-only: q = (latent @ Wq^T + bq) * hd^-0.5, folded at load time
+    std::vector<float> latent, wq, bq;
+    RET_IF_ERR(HostF32(m, ap + ".latent", D_, &latent));
+    RET_IF_ERR(HostF32(m, ap + ".q.weight", static_cast<int64_t>(D_) * D_, &wq));
+    RET_IF_ERR(HostF32(m, ap + ".q.bias", D_, &bq));
+    std::vector<float> q(D_);
+    const double sc = 1.0 / sqrt(static_cast<double>(hd_));
+    for (int o = 0; o < D_; ++o) {
+      double acc = bq[o];
+      for (int i = 0; i < D_; ++i) acc += static_cast<double>(wq[static_cast<size_t>(o) * D_ + i]) * latent[i];
+      q[o] = static_cast<float>(acc * sc);
+    }
+    RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&map_q_), D_ * 4));
+    CUDA_RET(cudaMemcpy(map_q_, q.data(), D_ * 4, cudaMemcpyHostToDevice), "upload pool query");
+    RET_IF_ERR(UploadLinear(m, ap + ".kv.weight", ap + ".kv.bias", 2 * D_, D_, false, &map_kv_));
+    RET_IF_ERR(UploadLinear(m, ap + ".proj.weight", ap + ".proj.bias", D_, D_, false, &map_proj_));
+    RET_IF_ERR(UploadF32(m, ap + ".norm.weight", D_, &map_norm_.g));
+    RET_IF_ERR(UploadF32(m, ap + ".norm.bias", D_, &map_norm_.b));
+    RET_IF_ERR(UploadLinear(m, ap + ".mlp.fc1.weight", ap + ".mlp.fc1.bias", mlp_, D_, false, &map_fc1_));
+    RET_IF_ERR(UploadLinear(m, ap + ".mlp.fc2.weight", ap + ".mlp.fc2.bias", D_, mlp_, false, &map_fc2_));
+  } else {
+    RET_IF_ERR(UploadF32(m, pre + ".ln_post.weight", D_, &ln_post_.g));
+    RET_IF_ERR(UploadF32(m, pre + ".ln_post.bias", D_, &ln_post_.b));
+    RET_IF_ERR(UploadLinear(m, pre + ".proj", "", E_, D_, true, &head_));
+  }
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&lut_), 3 * 256 * 4));
+  return Status::OK();
+}
+
+Status Engine::LoadText(const OnnxModel& m) {
+  kind = CLIPB200_KIND_TEXT;
+  std::string pre;
+  if (m.has("model.token_embedding.weight")) pre = "model";
+  else if (m.has("model.text.token_embedding.weight")) pre = "model.text";
+  else
+    return Status::Err(CLIPB200_ERR_UNSUPPORTED,
+                       "text graph has no model.token_embedding.weight / model.text.token_embedding.weight");
+  family_ = pre == "model" ? "clip" : "custom";
+  const OnnxTensor* te = m.find(pre + ".token_embedding.weight");
+  if (te->dims.size() != 2) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "token embedding must be 2-D");
+  vocab_ = static_cast<int>(te->dims[0]);
+  D_ = static_cast<int>(te->dims[1]);
+  const OnnxTensor* pos = m.find(pre + ".positional_embedding");
+  if (pos == nullptr) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "text positional embedding not found");
+  T_ = static_cast<int>(pos->numel() / D_);
+  context_length = T_;
+  L_ = 0;
+  while (m.has(pre + ".transformer.resblocks." + std::to_string(L_) + ".ln_1.weight")) ++L_;
+  if (L_ == 0) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "no text transformer blocks found");
+  const OnnxTensor* fc1 = m.find(pre + ".transformer.resblocks.0.mlp.c_fc.weight");
+  if (fc1 == nullptr) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "text MLP weight not found");
+  mlp_ = static_cast<int>(fc1->dims[0]);
+  H_ = meta_int(m, "heads", 0);
+  if (H_ == 0) H_ = (D_ == 1152) ? 16 : D_ / 64;
+  if (H_ <= 0 || D_ % H_ != 0) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "bad text head count");
+  hd_ = D_ / H_;
+  const bool linear_head = m.has(pre + ".text_projection.weight");
+  act_ = meta_int(m, "act", linear_head ? ACT_GELU_TANH : ACT_QUICKGELU);
+  const std::string eps = m.meta("clipb200.eps");
+  eps_ = eps.empty() ? (linear_head ? 1e-6f : 1e-5f) : static_cast<float>(atof(eps.c_str()));
+  causal_ = meta_int(m, "causal", linear_head ? 0 : 1) != 0;
+  const std::string pool = m.meta("clipb200.pool", linear_head ? "last" : "argmax");
+  pool_argmax_ = pool == "argmax";
+  if (linear_head) E_ = static_cast<int>(m.find(pre + ".text_projection.weight")->dims[0]);
+  else {
+    const OnnxTensor* tp = m.find(pre + ".text_projection");
+    if (tp == nullptr) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "text_projection not found");
+    E_ = static_cast<int>(tp->dims.back());
+  }
+  embed_dim = E_;
+  RET_IF_ERR(UploadF32(m, pre + ".token_embedding.weight", static_cast<int64_t>(vocab_) * D_, &tok_emb_));
+  RET_IF_ERR(UploadF32(m, pre + ".positional_embedding", static_cast<int64_t>(T_) * D_, &pos_));
+  blocks_.resize(L_);
+  for (int i = 0; i < L_; ++i)
+    RET_IF_ERR(LoadBlock(m, pre + ".transformer.resblocks." + std::to_string(i), false, &blocks_[i]));
+  RET_IF_ERR(UploadF32(m, pre + ".ln_final.weight", D_, &ln_post_.g));
+  RET_IF_ERR(UploadF32(m, pre + ".ln_final.bias", D_, &ln_post_.b));
+  if (linear_head)
+    RET_IF_ERR(UploadLinear(m, pre + ".text_projection.weight", pre + ".text_projection.bias", E_, D_, false, &head_));
+  else
+    RET_IF_ERR(UploadLinear(m, pre + ".text_projection", "", E_, D_, true, &head_));
+  return Status::OK();
+}
+
+Status Engine::AllocWorkspace() {
+  const size_t rows = static_cast<size_t>(mb_) * T_;
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&x_), rows * D_ * 4));
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&h_), rows * D_ * 2));
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&qkv_), rows * 3 * D_ * 2));
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&mlpbuf_), rows * mlp_ * 2));
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&pooled_), static_cast<size_t>(mb_) * D_ * 2));
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&proj_out_), static_cast<size_t>(mb_) * std::max(E_, D_) * 4));
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&row_map_), static_cast<size_t>(mb_) * 4));
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&err_flag_), 4));
+  CUDA_RET(cudaMemset(err_flag_, 0, 4), "memset");
+  if (kind == CLIPB200_KIND_VISION) {
+    RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&patches_), static_cast<size_t>(mb_) * Tp_ * Kp_ * 2));
+    if (pool_map_) {
+      RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&y_), static_cast<size_t>(mb_) * D_ * 4));
+      RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&yh_), static_cast<size_t>(mb_) * D_ * 2));
+      RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&ymlp_), static_cast<size_t>(mb_) * mlp_ * 2));
+    }
+    in_slot_bytes_ = static_cast<size_t>(mb_) * S_ * S_ * 3;
+  } else {
+    in_slot_bytes_ = static_cast<size_t>(mb_) * T_ * 8;
+  }
+  for (int i = 0; i < 2; ++i) {
+    RET_IF_ERR(DevAlloc(&d_in_[i], in_slot_bytes_));
+    RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&d_out_[i]), static_cast<size_t>(mb_) * E_ * 4));
+    CUDA_RET(cudaHostAlloc(&h_in_[i], in_slot_bytes_, cudaHostAllocDefault), "pinned input staging");
+    CUDA_RET(cudaHostAlloc(reinterpret_cast<void**>(&h_out_[i]), static_cast<size_t>(mb_) * E_ * 4, cudaHostAllocDefault),
+             "pinned output staging");
+    CUDA_RET(cudaEventCreateWithFlags(&in_ready_[i], cudaEventDisableTiming), "event");
+    CUDA_RET(cudaEventCreateWithFlags(&in_consumed_[i], cudaEventDisableTiming), "event");
+    CUDA_RET(cudaEventCreateWithFlags(&out_ready_[i], cudaEventDisableTiming), "event");
+    CUDA_RET(cudaEventCreateWithFlags(&out_copied_[i], cudaEventDisableTiming), "event");
+  }
+  for (int i = 0; i < 16; ++i) CUDA_RET(cudaEventCreate(&user_events_[i]), "event");
+  return Status::OK();
+}
+
+Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* opts) {
+  device = dev;
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0)
+    return Status::Err(CLIPB200_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                              cudaGetErrorString(ce));
+  if (dev < 0 || dev >= count)
+    return Status::Err(CLIPB200_ERR_INVALID_ARG, "cuda_device " + std::to_string(dev) + " out of range");
+  CUDA_RET(cudaSetDevice(dev), "cudaSetDevice");
+  cudaDeviceProp prop;
+  CUDA_RET(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return Status::Err(CLIPB200_ERR_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                              std::to_string(prop.minor) + "; this engine is built for sm_100a only");
+  num_sms_ = prop.multiProcessorCount;
+
+  OnnxModel m;
+  std::string err;
+  if (!load_onnx(onnx_path, &m, &err)) {
+    const bool io = err.find("cannot open") != std::string::npos || err.find("cannot stat") != std::string::npos ||
+                    err.find("cannot mmap") != std::string::npos || err.find("is empty") != std::string::npos;
+    return Status::Err(io ? CLIPB200_ERR_IO : CLIPB200_ERR_PARSE, err);
+  }
+  input_names = m.inputs;
+  CUDA_RET(gemm_configure_device(), "configure GEMM kernels");
+  CUDA_RET(flash_attention_configure_device(), "configure attention kernels");
+  CUDA_RET(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking), "stream");
+  CUDA_RET(cudaStreamCreateWithFlags(&copy_in_, cudaStreamNonBlocking), "stream");
+  CUDA_RET(cudaStreamCreateWithFlags(&copy_out_, cudaStreamNonBlocking), "stream");
+
+  bool is_text = false;
+  for (const std::string& n : m.inputs) if (n == "input_ids") is_text = true;
+  const std::string tower = m.meta("clipb200.tower");
+  if (tower == "text") is_text = true;
+  if (is_text) RET_IF_ERR(LoadText(m));
+  else RET_IF_ERR(LoadVision(m));
+  if (hd_ != 32 && hd_ != 64 && hd_ != 72 && hd_ != 80 && hd_ != 96 && hd_ != 128)
+    return Status::Err(CLIPB200_ERR_UNSUPPORTED, "head_dim " + std::to_string(hd_) + " not supported");
+  if ((D_ & 7) || (mlp_ & 7) || (E_ & 7) || D_ > 2048)
+    return Status::Err(CLIPB200_ERR_UNSUPPORTED, "width / mlp / embed_dim must be multiples of 8 and width <= 2048");
+
+  profile_ = opts != nullptr && opts->profile != 0;
+  mb_ = opts != nullptr ? opts->micro_batch : 0;
+  if (const char* env = getenv("CLIPB200_MICRO_BATCH")) if (mb_ <= 0) mb_ = atoi(env);
+  if (mb_ <= 0) {
+    mb_ = 73728 / T_;  // ~72k token rows per step keeps every GEMM at >= 20 waves of 128-row tiles
+    if (mb_ > 1024) mb_ = 1024;
+    if (mb_ < 1) mb_ = 1;
+  }
+  RET_IF_ERR(AllocWorkspace());
+  CUDA_RET(cudaDeviceSynchronize(), "init sync");
+  return Status::OK();
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device);
+  cudaDeviceSynchronize();
+  for (void* p : dev_allocs_) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    if (h_in_[i]) cudaFreeHost(h_in_[i]);
+    if (h_in_f32_[i]) cudaFreeHost(h_in_f32_[i]);
+    if (h_out_[i]) cudaFreeHost(h_out_[i]);
+    if (d_in_f32_[i]) cudaFree(d_in_f32_[i]);
+    if (in_ready_[i]) cudaEventDestroy(in_ready_[i]);
+    if (in_consumed_[i]) cudaEventDestroy(in_consumed_[i]);
+    if (out_ready_[i]) cudaEventDestroy(out_ready_[i]);
+    if (out_copied_[i]) cudaEventDestroy(out_copied_[i]);
+  }
+  for (int i = 0; i < 16; ++i) if (user_events_[i]) cudaEventDestroy(user_events_[i]);
+  for (auto& p : prof_pending_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto& e : prof_free_) cudaEventDestroy(e);
+  if (l2_flush_) cudaFree(l2_flush_);
+  if (compute_) cudaStreamDestroy(compute_);
+  if (copy_in_) cudaStreamDestroy(copy_in_);
+  if (copy_out_) cudaStreamDestroy(copy_out_);
+}
+
+// ------------------------------------------------------------------------------------------------ profiling
+void Engine::ProfBegin(int cls, cudaStream_t st) {
+  if (cls < PC_H2D) ++launch_count;  // kernels only; the two copy classes are DMA transfers
+  if (!profile_) return;
+  ProfPair p;
+  p.cls = cls;
+  auto get = [&]() {
+    cudaEvent_t e;
+    if (!prof_free_.empty()) { e = prof_free_.back(); prof_free_.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+  };
+  p.a = get();
+  p.b = get();
+  cudaEventRecord(p.a, st);
+  prof_pending_.push_back(p);
+}
+void Engine::ProfEnd(int cls, cudaStream_t st) {
+  if (!profile_) return;
+  (void)cls;
+  cudaEventRecord(prof_pending_.back().b, st);
+}
+
+Status Engine::ReadProfile(clipb200_profile* out, bool reset) {
+  CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
+  CUDA_RET(cudaDeviceSynchronize(), "profile sync");
+  for (auto& p : prof_pending_) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      prof_acc_.ms[p.cls] += ms;
+      prof_acc_.launches[p.cls] += 1;
+    }
+    prof_free_.push_back(p.a);
+    prof_free_.push_back(p.b);
+  }
+  prof_pending_.clear();
+  if (out != nullptr) *out = prof_acc_;
+  if (reset) memset(&prof_acc_, 0, sizeof(prof_acc_));
+  return Status::OK();
+}
+
+Status Engine::RecordEvent(int slot) {
+  if (slot < 0 || slot >= 16) return Status::Err(CLIPB200_ERR_INVALID_ARG, "event slot out of range");
+  CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
+  CUDA_RET(cudaEventRecord(user_events_[slot], compute_), "cudaEventRecord");
+  return Status::OK();
+}
+Status Engine::ElapsedMs(int a, int b, double* ms) {
+  if (a < 0 || a >= 16 || b < 0 || b >= 16 || ms == nullptr)
+    return Status::Err(CLIPB200_ERR_INVALID_ARG, "event slot out of range");
+  CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
+  CUDA_RET(cudaEventSynchronize(user_events_[b]), "cudaEventSynchronize");
+  float f = 0.f;
+  CUDA_RET(cudaEventElapsedTime(&f, user_events_[a], user_events_[b]), "cudaEventElapsedTime");
+  *ms = f;
+  return Status::OK();
+}
+Status Engine::Synchronize() {
+  CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
+  CUDA_RET(cudaStreamSynchronize(copy_in_), "sync");
+  CUDA_RET(cudaStreamSynchronize(compute_), "sync");
+  CUDA_RET(cudaStreamSynchronize(copy_out_), "sync");
+  return Status::OK();
+}
+Status Engine::FlushL2() {
+  CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
+  const size_t bytes = 256u << 20;  // 2x the 126 MB L2
+  if (l2_flush_ == nullptr) CUDA_RET(cudaMalloc(&l2_flush_, bytes), "l2 flush buffer");
+  CUDA_RET(cudaMemsetAsync(l2_flush_, 0x5a, bytes, compute_), "l2 flush");
+  return Status::OK();
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+Status Engine::Gemm(const __nv_bfloat16* A, long long lda, const LinearW& w, int M, int epi, GemmEpilogue* ep) {
+  if (ep->bias == nullptr) ep->bias = w.b;
+  ProfBegin(PC_GEMM, compute_);
+  cudaError_t e = gemm_bf16(A, lda, w.w, w.ldk, M, w.N, w.ldk, epi, *ep, num_sms_, compute_);
+  ProfEnd(PC_GEMM, compute_);
+  if (profile_) prof_acc_.gemm_flops += 2.0 * M * static_cast<double>(w.N) * w.K;
+  return Check(e, "gemm launch");
+}
+
+Status Engine::Blocks(int rows, int n_seq, int T, bool causal) {
+  for (int l = 0; l < L_; ++l) {
+    const BlockW& b = blocks_[l];
+    ProfBegin(PC_LN, compute_);
+    cudaError_t e = launch_layernorm(x_, nullptr, rows, D_, b.ln1.g, b.ln1.b, eps_, h_, nullptr, compute_);
+    ProfEnd(PC_LN, compute_);
+    CUDA_RET(e, "layernorm");
+    GemmEpilogue ep;
+    ep.out_bf16 = qkv_;
+    ep.ldc = 3 * D_;
+    RET_IF_ERR(Gemm(h_, D_, b.qkv, rows, EPI_BF16, &ep));
+    ProfBegin(PC_ATTN, compute_);
+    e = launch_flash_attention(qkv_, h_, n_seq, T, H_, hd_, causal, compute_);
+    ProfEnd(PC_ATTN, compute_);
+    CUDA_RET(e, "attention");
+    GemmEpilogue ep2;
+    ep2.out_f32 = x_;
+    ep2.ldc = D_;
+    RET_IF_ERR(Gemm(h_, D_, b.proj, rows, EPI_RESID, &ep2));
+    ProfBegin(PC_LN, compute_);
+    e = launch_layernorm(x_, nullptr, rows, D_, b.ln2.g, b.ln2.b, eps_, h_, nullptr, compute_);
+    ProfEnd(PC_LN, compute_);
+    CUDA_RET(e, "layernorm");
+    GemmEpilogue ep3;
+    ep3.out_bf16 = mlpbuf_;
+    ep3.ldc = mlp_;
+    ep3.act = act_;
+    RET_IF_ERR(Gemm(h_, D_, b.fc1, rows, EPI_BF16, &ep3));
+    GemmEpilogue ep4;
+    ep4.out_f32 = x_;
+    ep4.ldc = D_;
+    RET_IF_ERR(Gemm(mlpbuf_, mlp_, b.fc2, rows, EPI_RESID, &ep4));
+  }
+  return Status::OK();
+}
+
+Status Engine::SetPreproc(const clipb200_preproc* pp) {
+  if (pp == nullptr) return Status::Err(CLIPB200_ERR_INVALID_ARG, "preproc config is null");
+  if (lut_valid_ && memcmp(lut_mean_, pp->mean, 12) == 0 && memcmp(lut_std_, pp->std, 12) == 0) return Status::OK();
+  // vision.rs:253-254, evaluated in fp32 exactly as written there, for each of the 256 byte values
+  float lut[3 * 256];
+  for (int c = 0; c < 3; ++c)
+    for (int v = 0; v < 256; ++v) {
+      volatile float val = static_cast<float>(v) / 255.0f;
+      volatile float d = val - pp->mean[c];
+      lut[c * 256 + v] = d / pp->std[c];
+    }
+  CUDA_RET(cudaMemcpyAsync(lut_, lut, sizeof(lut), cudaMemcpyHostToDevice, compute_), "upload LUT");
+  CUDA_RET(cudaStreamSynchronize(compute_), "upload LUT sync");
+  memcpy(lut_mean_, pp->mean, 12);
+  memcpy(lut_std_, pp->std, 12);
+  lut_valid_ = true;
+  return Status::OK();
+}
+
+Status Engine::ForwardVision(int n, const uint8_t* d_u8, const float* d_f32, float* d_out) {
+  const int rows = n * T_;
+  ProfBegin(PC_PRE, compute_);
+  cudaError_t e = d_u8 != nullptr ? launch_preprocess_patches_u8(d_u8, n, S_, P_, Kp_, lut_, patches_, compute_)
+                                  : launch_im2col_f32(d_f32, n, S_, P_, Kp_, patches_, compute_);
+  ProfEnd(PC_PRE, compute_);
+  CUDA_RET(e, "preprocess");
+  {
+    GemmEpilogue ep;
+    ep.out_f32 = x_;
+    ep.ldc = D_;
+    ep.pos = pos_;
+    ep.rows_in = Tp_;
+    ep.rows_out = T_;
+    ep.row_off = has_cls_ ? 1 : 0;
+    RET_IF_ERR(Gemm(patches_, Kp_, patch_, n * Tp_, EPI_F32, &ep));
+  }
+  if (has_cls_) {
+    ProfBegin(PC_MISC, compute_);
+    e = launch_write_cls_rows(x_, n, T_, D_, cls_row_, compute_);
+    ProfEnd(PC_MISC, compute_);
+    CUDA_RET(e, "cls rows");
+    ProfBegin(PC_LN, compute_);
+    e = launch_layernorm(x_, nullptr, rows, D_, ln_pre_.g, ln_pre_.b, eps_, nullptr, x_, compute_);
+    ProfEnd(PC_LN, compute_);
+    CUDA_RET(e, "ln_pre");
+  }
+  RET_IF_ERR(Blocks(rows, n, T_, false));
+  if (!pool_map_) {
+    // open_clip ViT: ln_post on the class token, then x @ proj
+    ProfBegin(PC_MISC, compute_);
+    e = launch_affine_rows(n, T_, 0, row_map_, compute_);
+    ProfEnd(PC_MISC, compute_);
+    CUDA_RET(e, "row map");
+    ProfBegin(PC_LN, compute_);
+    e = launch_layernorm(x_, row_map_, n, D_, ln_post_.g, ln_post_.b, eps_, pooled_, nullptr, compute_);
+    ProfEnd(PC_LN, compute_);
+    CUDA_RET(e, "ln_post");
+    GemmEpilogue ep;
+    ep.out_f32 = proj_out_;
+    ep.ldc = E_;
+    RET_IF_ERR(Gemm(pooled_, D_, head_, n, EPI_F32, &ep));
+    ProfBegin(PC_MISC, compute_);
+    e = launch_l2_normalize(proj_out_, n, E_, d_out, compute_);
+    ProfEnd(PC_MISC, compute_);
+    CUDA_RET(e, "l2 normalize");
+  } else {
+    // timm: final norm, then AttentionPoolLatent (one latent query), then x + mlp(norm(x))
+    ProfBegin(PC_LN, compute_);
+    e = launch_layernorm(x_, nullptr, rows, D_, ln_post_.g, ln_post_.b, eps_, h_, nullptr, compute_);
+    ProfEnd(PC_LN, compute_);
+    CUDA_RET(e, "final norm");
+    GemmEpilogue ep;
+    ep.out_bf16 = qkv_;
+    ep.ldc = 2 * D_;
+    RET_IF_ERR(Gemm(h_, D_, map_kv_, rows, EPI_BF16, &ep));
+    ProfBegin(PC_ATTN, compute_);
+    e = launch_map_pool_attention(qkv_, map_q_, pooled_, n, T_, H_, hd_, compute_);
+    ProfEnd(PC_ATTN, compute_);
+    CUDA_RET(e, "attention pool");
+    GemmEpilogue ep2;
+    ep2.out_f32 = y_;
+    ep2.ldc = D_;
+    RET_IF_ERR(Gemm(pooled_, D_, map_proj_, n, EPI_F32, &ep2));
+    ProfBegin(PC_LN, compute_);
+    e = launch_layernorm(y_, nullptr, n, D_, map_norm_.g, map_norm_.b, eps_, yh_, nullptr, compute_);
+    ProfEnd(PC_LN, compute_);
+    CUDA_RET(e, "pool norm");
+    GemmEpilogue ep3;
+    ep3.out_bf16 = ymlp_;
+    ep3.ldc = mlp_;
+    ep3.act = act_;
+    RET_IF_ERR(Gemm(yh_, D_, map_fc1_, n, EPI_BF16, &ep3));
+    GemmEpilogue ep4;
+    ep4.out_f32 = y_;
+    ep4.ldc = D_;
+    RET_IF_ERR(Gemm(ymlp_, mlp_, map_fc2_, n, EPI_RESID, &ep4));
+    ProfBegin(PC_MISC, compute_);
+    e = launch_l2_normalize(y_, n, D_, d_out, compute_);
+    ProfEnd(PC_MISC, compute_);
+    CUDA_RET(e, "l2 normalize");
+  }
+  return Status::OK();
+}
+
+Status Engine::ForwardText(int n, const int64_t* d_ids, float* d_out) {
+  const int rows = n * T_;
+  ProfBegin(PC_MISC, compute_);
+  cudaError_t e = launch_embed_tokens(d_ids, rows, T_, D_, vocab_, tok_emb_, pos_, x_, err_flag_, compute_);
+  ProfEnd(PC_MISC, compute_);
+  CUDA_RET(e, "token embedding");
+  RET_IF_ERR(Blocks(rows, n, T_, causal_));
+  ProfBegin(PC_MISC, compute_);
+  e = launch_text_pool_rows(d_ids, n, T_, pool_argmax_, row_map_, compute_);
+  ProfEnd(PC_MISC, compute_);
+  CUDA_RET(e, "text pool rows");
+  ProfBegin(PC_LN, compute_);
+  e = launch_layernorm(x_, row_map_, n, D_, ln_post_.g, ln_post_.b, eps_, pooled_, nullptr, compute_);
+  ProfEnd(PC_LN, compute_);
+  CUDA_RET(e, "ln_final");
+  GemmEpilogue ep;
+  ep.out_f32 = proj_out_;
+  ep.ldc = E_;
+  RET_IF_ERR(Gemm(pooled_, D_, head_, n, EPI_F32, &ep));
+  ProfBegin(PC_MISC, compute_);
+  e = launch_l2_normalize(proj_out_, n, E_, d_out, compute_);
+  ProfEnd(PC_MISC, compute_);
+  CUDA_RET(e, "l2 normalize");
+  return Status::OK();
+}
+
+// ------------------------------------------------------------------------------------------------ pipeline
+// mode 0: vision u8, 1: vision f32 NCHW, 2: text ids
+template <typename InT>
+Status Engine::RunPipelined(const InT* in, int64_t batch, size_t in_elems_per_item, float* out, bool device_buffers,
+                            int mode) {
+  CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
+  const size_t item_bytes = in_elems_per_item * sizeof(InT);
+  const int64_t steps = (batch + mb_ - 1) / mb_;
+  if (device_buffers) {
+    for (int64_t s = 0; s < steps; ++s) {
+      const int n = static_cast<int>(std::min<int64_t>(mb_, batch - s * mb_));
+      const InT* src = in + static_cast<size_t>(s) * mb_ * in_elems_per_item;
+      float* dst = out + static_cast<size_t>(s) * mb_ * E_;
+      if (mode == 0) RET_IF_ERR(ForwardVision(n, reinterpret_cast<const uint8_t*>(src), nullptr, dst));
+      else if (mode == 1) RET_IF_ERR(ForwardVision(n, nullptr, reinterpret_cast<const float*>(src), dst));
+      else RET_IF_ERR(ForwardText(n, reinterpret_cast<const int64_t*>(src), dst));
+    }
+    return Status::OK();  // asynchronous on the compute stream; caller synchronises / records events
+  }
+  // host buffers: pinned staging unless the caller's memory is already pinned
+  cudaPointerAttributes attr;
+  bool in_pinned = cudaPointerGetAttributes(&attr, in) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  bool out_pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  void* const* d_in = mode == 1 ? reinterpret_cast<void* const*>(d_in_f32_) : d_in_;
+  void* const* h_in = mode == 1 ? reinterpret_cast<void* const*>(h_in_f32_) : h_in_;
+  Status st = Status::OK();
+  for (int64_t s = 0; s < steps && st.ok(); ++s) {
+    const int slot = static_cast<int>(s & 1);
+    const int n = static_cast<int>(std::min<int64_t>(mb_, batch - s * mb_));
+    const InT* src = in + static_cast<size_t>(s) * mb_ * in_elems_per_item;
+    const size_t bytes = static_cast<size_t>(n) * item_bytes;
+    if (s >= 2) {
+      // slot reuse: the H2D of step s-2 must have left the pinned buffer, its kernels must have consumed d_in
+      CUDA_RET(cudaEventSynchronize(in_ready_[slot]), "wait staging");
+      CUDA_RET(cudaStreamWaitEvent(copy_in_, in_consumed_[slot], 0), "wait consumed");
+    }
+    const void* hsrc = src;
+    if (!in_pinned) {
+      memcpy(h_in[slot], src, bytes);
+      hsrc = h_in[slot];
+    }
+    ProfBegin(PC_H2D, copy_in_);
+    cudaError_t e = cudaMemcpyAsync(d_in[slot], hsrc, bytes, cudaMemcpyHostToDevice, copy_in_);
+    ProfEnd(PC_H2D, copy_in_);
+    CUDA_RET(e, "H2D copy");
+    CUDA_RET(cudaEventRecord(in_ready_[slot], copy_in_), "record");
+    CUDA_RET(cudaStreamWaitEvent(compute_, in_ready_[slot], 0), "wait input");
+    if (s >= 2) CUDA_RET(cudaStreamWaitEvent(compute_, out_copied_[slot], 0), "wait output slot");
+    if (mode == 0) st = ForwardVision(n, static_cast<const uint8_t*>(d_in[slot]), nullptr, d_out_[slot]);
+    else if (mode == 1) st = ForwardVision(n, nullptr, static_cast<const float*>(d_in[slot]), d_out_[slot]);
+    else st = ForwardText(n, static_cast<const int64_t*>(d_in[slot]), d_out_[slot]);
+    if (!st.ok()) break;
+    CUDA_RET(cudaEventRecord(in_consumed_[slot], compute_), "record");
+    CUDA_RET(cudaEventRecord(out_ready_[slot], compute_), "record");
+    CUDA_RET(cudaStreamWaitEvent(copy_out_, out_ready_[slot], 0), "wait output");
+    float* user_dst = out + static_cast<size_t>(s) * mb_ * E_;
+    ProfBegin(PC_D2H, copy_out_);
+    e = cudaMemcpyAsync(out_pinned ? user_dst : h_out_[slot], d_out_[slot], static_cast<size_t>(n) * E_ * 4,
+                        cudaMemcpyDeviceToHost, copy_out_);
+    ProfEnd(PC_D2H, copy_out_);
+    CUDA_RET(e, "D2H copy");
+    CUDA_RET(cudaEventRecord(out_copied_[slot], copy_out_), "record");
+    // drain the previous step's output while this step runs
+    if (!out_pinned && s >= 1) {
+      const int ps = static_cast<int>((s - 1) & 1);
+      const int pn = static_cast<int>(std::min<int64_t>(mb_, batch - (s - 1) * mb_));
+      CUDA_RET(cudaEventSynchronize(out_copied_[ps]), "wait D2H");
+      memcpy(out + static_cast<size_t>(s - 1) * mb_ * E_, h_out_[ps], static_cast<size_t>(pn) * E_ * 4);
+    }
+  }
+  Status sync = Synchronize();
+  if (!st.ok()) return st;
+  RET_IF_ERR(sync);
+  if (!out_pinned) {
+    const int64_t s = steps - 1;
+    const int n = static_cast<int>(std::min<int64_t>(mb_, batch - s * mb_));
+    memcpy(out + static_cast<size_t>(s) * mb_ * E_, h_out_[s & 1], static_cast<size_t>(n) * E_ * 4);
+  }
+  if (mode == 2) {
+    int flag = 0;
+    CUDA_RET(cudaMemcpy(&flag, err_flag_, 4, cudaMemcpyDeviceToHost), "read error flag");
+    if (flag != 0) {
+      cudaMemset(err_flag_, 0, 4);
+      return Status::Err(CLIPB200_ERR_INVALID_ARG, "input_ids contains an id outside [0, vocab_size)");
+    }
+  }
+  return Status::OK();
+}
+
+Status Engine::VisionEmbedRgb8(const uint8_t* hwc, int64_t batch, int width, int height, const clipb200_preproc* pp,
+                               float* out, bool device_buffers) {
+  if (kind != CLIPB200_KIND_VISION) return Status::Err(CLIPB200_ERR_INVALID_ARG, "not a vision engine");
+  if (batch <= 0) return Status::Err(CLIPB200_ERR_INVALID_ARG, "Empty batch");
+  if (hwc == nullptr || out == nullptr) return Status::Err(CLIPB200_ERR_INVALID_ARG, "null buffer");
+  if (width != S_ || height != S_)
+    return Status::Err(CLIPB200_ERR_UNSUPPORTED, "images must already be " + std::to_string(S_) + "x" + std::to_string(S_) +
+                                                     " (GPU resize is not implemented yet)");
+  CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
+  RET_IF_ERR(SetPreproc(pp));
+  return RunPipelined<uint8_t>(hwc, batch, static_cast<size_t>(S_) * S_ * 3, out, device_buffers, 0);
+}
+
+// The reference's public `preprocess_batch` (vision.rs:120-135): u8 HWC -> normalised f32 NCHW, on the GPU.
+Status Engine::PreprocessRgb8(const uint8_t* hwc, int64_t batch, int width, int height, const clipb200_preproc* pp,
+                              float* out_nchw) {
+  if (kind != CLIPB200_KIND_VISION) return Status::Err(CLIPB200_ERR_INVALID_ARG, "not a vision engine");
+  if (batch <= 0) return Status::Err(CLIPB200_ERR_INVALID_ARG, "Empty batch");
+  if (hwc == nullptr || out_nchw == nullptr) return Status::Err(CLIPB200_ERR_INVALID_ARG, "null buffer");
+  if (width != S_ || height != S_)
+    return Status::Err(CLIPB200_ERR_UNSUPPORTED, "images must already be " + std::to_string(S_) + "x" + std::to_string(S_) +
+                                                     " (GPU resize is not implemented yet)");
+  CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
+  RET_IF_ERR(SetPreproc(pp));
+  const size_t px = static_cast<size_t>(S_) * S_ * 3;
+  const int64_t chunk = 256;
+  uint8_t* d_u8 = nullptr;
+  float* d_f = nullptr;
+  CUDA_RET(cudaMalloc(reinterpret_cast<void**>(&d_u8), chunk * px), "preprocess alloc");
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_f), chunk * px * 4);
+  for (int64_t i = 0; i < batch && e == cudaSuccess; i += chunk) {
+    const int n = static_cast<int>(std::min<int64_t>(chunk, batch - i));
+    e = cudaMemcpyAsync(d_u8, hwc + i * px, n * px, cudaMemcpyHostToDevice, compute_);
+    if (e == cudaSuccess) {
+      ProfBegin(PC_PRE, compute_);
+      e = launch_normalize_nchw_f32(d_u8, n, S_, lut_, d_f, compute_);
+      ProfEnd(PC_PRE, compute_);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_nchw + i * px, d_f, n * px * 4, cudaMemcpyDeviceToHost, compute_);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(compute_);
+  }
+  cudaFree(d_u8);
+  cudaFree(d_f);
+  return Check(e, "preprocess");
+}
+
+Status Engine::VisionEmbedF32(const float* nchw, int64_t batch, float* out) {
+  if (kind != CLIPB200_KIND_VISION) return Status::Err(CLIPB200_ERR_INVALID_ARG, "not a vision engine");
+  if (batch <= 0) return Status::Err(CLIPB200_ERR_INVALID_ARG, "Empty batch");
+  if (nchw == nullptr || out == nullptr) return Status::Err(CLIPB200_ERR_INVALID_ARG, "null buffer");
+  CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
+  const size_t slot = static_cast<size_t>(mb_) * 3 * S_ * S_ * 4;
+  for (int i = 0; i < 2; ++i) {
+    if (d_in_f32_[i] == nullptr) CUDA_RET(cudaMalloc(reinterpret_cast<void**>(&d_in_f32_[i]), slot), "f32 input slot");
+    if (h_in_f32_[i] == nullptr)
+      CUDA_RET(cudaHostAlloc(reinterpret_cast<void**>(&h_in_f32_[i]), slot, cudaHostAllocDefault), "f32 pinned slot");
+  }
+  return RunPipelined<float>(nchw, batch, static_cast<size_t>(3) * S_ * S_, out, false, 1);
+}
+
+Status Engine::TextEmbed(const int64_t* ids, int64_t batch, int64_t ctx, float* out, bool device_buffers) {
+  if (kind != CLIPB200_KIND_TEXT) return Status::Err(CLIPB200_ERR_INVALID_ARG, "not a text engine");
+  if (batch <= 0) return Status::Err(CLIPB200_ERR_INVALID_ARG, "Empty batch");
+  if (ids == nullptr || out == nullptr) return Status::Err(CLIPB200_ERR_INVALID_ARG, "null buffer");
+  if (ctx != T_)
+    return Status::Err(CLIPB200_ERR_INVALID_ARG, "input_ids has context length " + std::to_string(ctx) +
+                                                     ", the graph expects " + std::to_string(T_));
+  return RunPipelined<int64_t>(ids, batch, static_cast<size_t>(T_), out, device_buffers, 2);
+}
+
+}  // namespace clipb200

@@ -1,0 +1,156 @@
+// Engine: one (model file, GPU) pair.  Owns HBM-resident weights (bf16 GEMM operands, fp32 norms / biases /
+// embeddings), an activation workspace sized for one micro-batch, two input and two output staging slots (device +
+// pinned host) and three streams (H2D, compute, D2H) so that the copies of micro-batch i+1 overlap the kernels of
+// micro-batch i.  It plays the role of `ort::Session` behind `OnnxSession` (reference src/onnx.rs:8-29).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/clipb200.h"
+#include "onnx_loader.h"
+
+namespace clipb200 {
+
+struct Status {
+  int code = CLIPB200_OK;
+  std::string msg;
+  bool ok() const { return code == CLIPB200_OK; }
+  static Status OK() { return Status(); }
+  static Status Err(int c, const std::string& m) {
+    Status s;
+    s.code = c;
+    s.msg = m;
+    return s;
+  }
+};
+
+struct LinearW {
+  __nv_bfloat16* w = nullptr;  // [N, ldk] bf16, K contiguous
+  float* b = nullptr;          // [N] or null
+  int N = 0, K = 0, ldk = 0;
+};
+struct NormW {
+  float* g = nullptr;
+  float* b = nullptr;
+};
+struct BlockW {
+  NormW ln1, ln2;
+  LinearW qkv, proj, fc1, fc2;
+};
+
+enum ProfClass { PC_GEMM = 0, PC_ATTN = 1, PC_LN = 2, PC_PRE = 3, PC_MISC = 4, PC_H2D = 5, PC_D2H = 6 };
+
+class Engine {
+ public:
+  static Status Create(const std::string& onnx_path, int device, const clipb200_opts* opts, Engine** out);
+  ~Engine();
+
+  Status VisionEmbedRgb8(const uint8_t* hwc, int64_t batch, int width, int height, const clipb200_preproc* pp,
+                         float* out, bool device_buffers);
+  Status VisionEmbedF32(const float* nchw, int64_t batch, float* out);
+  Status PreprocessRgb8(const uint8_t* hwc, int64_t batch, int width, int height, const clipb200_preproc* pp,
+                        float* out_nchw);
+  Status TextEmbed(const int64_t* ids, int64_t batch, int64_t ctx, float* out, bool device_buffers);
+
+  Status RecordEvent(int slot);
+  Status ElapsedMs(int a, int b, double* ms);
+  Status Synchronize();
+  Status ReadProfile(clipb200_profile* out, bool reset);
+  Status FlushL2();
+
+  int kind = CLIPB200_KIND_VISION;
+  int device = 0;
+  std::vector<std::string> input_names;
+  int embed_dim = 0, image_size = 0, context_length = 0;
+  int64_t weight_bytes = 0;
+  int64_t launch_count = 0;
+
+ private:
+  Engine() = default;
+  Status Init(const std::string& onnx_path, int device, const clipb200_opts* opts);
+  Status LoadVision(const OnnxModel& m);
+  Status LoadText(const OnnxModel& m);
+  Status LoadBlock(const OnnxModel& m, const std::string& prefix, bool timm, BlockW* b);
+  Status AllocWorkspace();
+  Status UploadF32(const OnnxModel& m, const std::string& name, int64_t expect_numel, float** out);
+  Status UploadLinear(const OnnxModel& m, const std::string& wname, const std::string& bname, int N, int K,
+                      bool transpose, LinearW* out);
+  Status HostF32(const OnnxModel& m, const std::string& name, int64_t expect_numel, std::vector<float>* out);
+  Status DevAlloc(void** p, size_t bytes);
+  Status SetPreproc(const clipb200_preproc* pp);
+
+  // forward passes on the compute stream, inputs already on the device
+  Status ForwardVision(int n, const uint8_t* d_u8, const float* d_f32, float* d_out);
+  Status ForwardText(int n, const int64_t* d_ids, float* d_out);
+  Status Blocks(int rows, int n_seq, int T, bool causal);
+  Status Gemm(const __nv_bfloat16* A, long long lda, const LinearW& w, int M, int epi, struct GemmEpilogue* ep);
+  Status Check(cudaError_t e, const char* what);
+
+  void ProfBegin(int cls, cudaStream_t st);
+  void ProfEnd(int cls, cudaStream_t st);
+
+  // architecture
+  std::string family_;
+  int S_ = 0, P_ = 0, G_ = 0, Tp_ = 0, T_ = 0, D_ = 0, L_ = 0, H_ = 0, hd_ = 0, mlp_ = 0, act_ = 0, E_ = 0;
+  int K_ = 0, Kp_ = 0, vocab_ = 0;
+  float eps_ = 1e-5f;
+  bool has_cls_ = false, causal_ = false, pool_map_ = false, pool_argmax_ = false;
+  int num_sms_ = 148;
+  int mb_ = 0;  // micro-batch (sequences)
+  bool profile_ = false;
+
+  // weights
+  LinearW patch_;  // [D, Kp]
+  float* pos_ = nullptr;      // vision [T, D] / text [ctx, D]
+  float* cls_row_ = nullptr;  // [D] = class_embedding + pos[0]
+  NormW ln_pre_, ln_post_;    // ln_post_: vision ln_post / trunk.norm, text ln_final
+  std::vector<BlockW> blocks_;
+  LinearW head_;              // visual.proj^T / text_projection
+  // MAP pool
+  float* map_q_ = nullptr;    // [D] scaled query
+  LinearW map_kv_, map_proj_, map_fc1_, map_fc2_;
+  NormW map_norm_;
+  float* tok_emb_ = nullptr;  // [vocab, D] fp32
+  float* lut_ = nullptr;      // [3][256] normalisation LUT
+  float lut_mean_[3] = {0, 0, 0}, lut_std_[3] = {0, 0, 0};
+  bool lut_valid_ = false;
+
+  // workspace (device)
+  __nv_bfloat16 *patches_ = nullptr, *h_ = nullptr, *qkv_ = nullptr, *mlpbuf_ = nullptr, *pooled_ = nullptr,
+                *yh_ = nullptr, *ymlp_ = nullptr;
+  float *x_ = nullptr, *y_ = nullptr, *proj_out_ = nullptr;
+  int* row_map_ = nullptr;
+  int* err_flag_ = nullptr;
+  void* d_in_[2] = {nullptr, nullptr};
+  float* d_in_f32_[2] = {nullptr, nullptr};
+  float* d_out_[2] = {nullptr, nullptr};
+  void* h_in_[2] = {nullptr, nullptr};
+  float* h_in_f32_[2] = {nullptr, nullptr};
+  float* h_out_[2] = {nullptr, nullptr};
+  void* l2_flush_ = nullptr;
+  size_t in_slot_bytes_ = 0;
+  std::vector<void*> dev_allocs_;
+
+  cudaStream_t compute_ = nullptr, copy_in_ = nullptr, copy_out_ = nullptr;
+  cudaEvent_t in_ready_[2] = {nullptr, nullptr}, in_consumed_[2] = {nullptr, nullptr},
+              out_ready_[2] = {nullptr, nullptr}, out_copied_[2] = {nullptr, nullptr};
+  cudaEvent_t user_events_[16] = {};
+
+  struct ProfPair {
+    int cls;
+    cudaEvent_t a, b;
+  };
+  std::vector<ProfPair> prof_pending_;
+  std::vector<cudaEvent_t> prof_free_;
+  clipb200_profile prof_acc_ = {};
+
+  template <typename InT>
+  Status RunPipelined(const InT* in, int64_t batch, size_t in_elems_per_item, float* out, bool device_buffers,
+                      int mode);
+};
+
+}  // namespace clipb200

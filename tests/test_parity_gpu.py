@@ -1,0 +1,148 @@
+"""GPU parity: the CUDA engine (through the C ABI and the host mirror) against the CPU oracle on the same seeded
+inputs and the same model files.  Bars (BASELINE.json north_star): per-embedding cosine >= 0.999 with the max-abs
+error printed, identical classify label order, bit-exact preprocessing and token ids."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import cosine_rows, random_images, random_texts
+
+pytestmark = pytest.mark.gpu
+
+COS_BAR = 0.999
+SMALL = ["tiny_clip", "tiny_clip_p14", "tiny_siglip"]
+
+
+@pytest.fixture(scope="module")
+def clips(make_model):
+    import clip_embedder_rs_b200 as cb
+
+    cache = {}
+
+    def get(config):
+        if config not in cache:
+            cache[config] = (cb.Clip.from_local_dir(make_model(config)).build(), make_model(config))
+        return cache[config]
+
+    return get
+
+
+def _oracle(model_dir):
+    from oracle import reference_forward as R
+
+    return R.OracleClip(model_dir)
+
+
+@pytest.mark.parametrize("config", SMALL)
+def test_preprocess_bit_exact(clips, config):
+    clip, model_dir = clips(config)
+    from oracle import reference_forward as R
+
+    size = clip.vision.config.model_cfg.vision_cfg.image_size
+    imgs = random_images(5, size, seed=11)
+    imgs[0, 0, :256 if size >= 256 else size, 0] = np.arange(min(256, size), dtype=np.uint8)  # every byte value
+    imgs[1, :, :, :] = 0
+    imgs[2, :, :, :] = 255
+    pc = clip.vision.config.preprocess_cfg
+    want = R.preprocess_batch(list(imgs), size, pc.mean, pc.std)
+    got = clip.vision.preprocess_batch(imgs)
+    assert got.dtype == np.float32 and got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "preprocessing must be bit-exact"
+
+
+@pytest.mark.parametrize("config", SMALL)
+def test_vision_embeddings(clips, config):
+    clip, model_dir = clips(config)
+    o = _oracle(model_dir)
+    size = clip.vision.config.model_cfg.vision_cfg.image_size
+    imgs = random_images(7, size, seed=21)
+    want = o.embed_images(list(imgs))
+    got = clip.vision.embed_images(imgs)
+    cos = cosine_rows(got, want)
+    print(f"\n[{config}] vision cos min {cos.min():.6f} max_abs {np.abs(got - want).max():.3e}")
+    assert got.shape == want.shape
+    assert np.all(np.abs(np.linalg.norm(got, axis=1) - 1.0) < 1e-3)
+    assert cos.min() >= COS_BAR
+    # single-image wrapper (vision.rs:94-98) and the ORT-style f32 entry point (vision.rs:105)
+    one = clip.vision.embed_image(imgs[3])
+    assert one.shape == (want.shape[1],)
+    assert cosine_rows(one[None], want[3:4])[0] >= COS_BAR
+    pc = clip.vision.config.preprocess_cfg
+    from oracle import reference_forward as R
+
+    pv = R.preprocess_batch(list(imgs), size, pc.mean, pc.std)
+    got2 = clip.vision.embed_pixel_values(pv)
+    assert cosine_rows(got2, want).min() >= COS_BAR
+
+
+@pytest.mark.parametrize("config", SMALL)
+def test_text_embeddings(clips, config):
+    clip, model_dir = clips(config)
+    o = _oracle(model_dir)
+    texts = random_texts(9, seed=31) + ["", "a", "A Photo Of A CAT " * 40]
+    from oracle import reference_forward as R
+
+    ids_want, mask_want = R.tokenize(model_dir, texts)
+    ids, mask = clip.text.tokenize(texts)
+    assert np.array_equal(ids, ids_want) and np.array_equal(mask, mask_want), "token ids must be bit-exact"
+    want = o.embed_texts(texts)
+    got = clip.text.embed_texts(texts)
+    cos = cosine_rows(got, want)
+    print(f"\n[{config}] text cos min {cos.min():.6f} max_abs {np.abs(got - want).max():.3e}")
+    assert cos.min() >= COS_BAR
+
+
+@pytest.mark.parametrize("config", SMALL)
+def test_classify_rank_compare(clips, config):
+    clip, model_dir = clips(config)
+    o = _oracle(model_dir)
+    size = clip.vision.config.model_cfg.vision_cfg.image_size
+    imgs = random_images(4, size, seed=41)
+    labels = random_texts(3, seed=2)
+    want = o.classify(imgs[0], labels)
+    got = clip.classify(imgs[0], labels)
+    print(f"\n[{config}] classify oracle {want}\n[{config}] classify engine {got}")
+    assert [l for l, _ in got] == [l for l, _ in want], "top-1 / full label order must match"
+    assert np.allclose([p for _, p in got], [p for _, p in want], atol=2e-2)
+    want_r = o.rank_images(list(imgs), labels[0])
+    got_r = clip.rank_images(imgs, labels[0])
+    assert np.allclose(sorted(p for _, p in got_r), sorted(p for _, p in want_r), atol=2e-2)
+    lw, lg = o.compare(imgs[1], labels[1]), clip.compare(imgs[1], labels[1])
+    scale = abs(clip.get_model_config().logit_scale or 1.0)
+    assert abs(lw - lg) <= 2e-3 * scale + 1e-3
+
+
+def test_errors(clips, make_model, tmp_path):
+    import clip_embedder_rs_b200 as cb
+    from clip_embedder_rs_b200 import error
+
+    clip, model_dir = clips("tiny_clip")
+    with pytest.raises(error.Inference, match="Empty batch"):
+        clip.vision.embed_images([])
+    with pytest.raises(error.ModelFolderNotFound):
+        cb.Clip.from_local_dir(tmp_path / "nope").build()
+    bad = tmp_path / "bad"
+    bad.mkdir()
+    for f in cb.model_manager.MODEL_FILES:
+        (bad / f).write_bytes(b"\x00garbage")
+    (bad / "open_clip_config.json").write_text(open(os.path.join(model_dir, "open_clip_config.json")).read())
+    (bad / "model_config.json").write_text("{}")
+    with pytest.raises(error.Ort):
+        cb.VisionEmbedder.from_local_dir(bad).build()
+    ids = np.full((2, 77), 10 ** 9, dtype=np.int64)
+    with pytest.raises(error.Ort, match="vocab"):
+        clip.text.embed_ids(ids)
+    with pytest.raises(error.Ort, match="context length"):
+        clip.text.embed_ids(np.zeros((2, 5), dtype=np.int64))
+
+
+def test_softmax_sigmoid_tail():
+    import clip_embedder_rs_b200 as cb
+    from oracle import reference_forward as R
+
+    logits = np.asarray([3.0, -1.5, 0.25, 12.0, 11.5], dtype=np.float32)
+    assert np.allclose(cb.Clip.softmax(logits), R.softmax(logits), rtol=1e-5, atol=1e-7)
+    for x in (-20.0, -1.0, 0.0, 2.5, 30.0):
+        assert abs(cb.Clip.sigmoid(x) - float(R.sigmoid(x))) < 1e-6
