@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: `VisionEmbedder::embed_images` (reference src/vision.rs:102-117) on
+ViT-SO400M-16-SigLIP2-384, batch 1024 per GPU, preprocessing included (BASELINE.json configs[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+One process per GPU (torchrun for N > 1, ranks read from the environment), an independent engine replica per
+rank, no collective on the data path (weak scaling: every rank embeds its own 1024 synthetic images per step).
+
+A step = one call of the C-ABI embed entry point over the whole per-rank batch.
+  value ...... images/s with the uint8 batch already resident in HBM (clipb200_vision_embed_rgb8_device), timed
+               with CUDA events on the engine's compute stream, max over ranks.
+  e2e ........ the same metric through the host-buffer entry point (clipb200_vision_embed_rgb8): pinned host
+               uint8 in, host fp32 embeddings out, H2D/D2H inside the timed region.
+  roofline ... the tcgen05 GEMM kernel class: algorithmic 2*M*N*K of all GEMM launches / their summed CUDA-event
+               durations, against the measured bf16 peak in MEASURED_PEAKS.json.
+  cpu_baseline the CPU oracle port (oracle/reference_forward.py, torch fp32, all host threads) on a bounded sample.
+`--impl reference` times that CPU port as the reference arm (the reference's ort CPU EP cannot be built here:
+no Rust toolchain and no onnxruntime in the image).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+WORKLOADS = {
+    # name: (export config, tower, per-GPU batch, GFLOP per unit, unit, description)
+    "so400m_vision": ("so400m_siglip2_384", "vision", 1024, 518.94, "images/s",
+                      "ViT-SO400M-16-SigLIP2-384 vision embedding, batch 1024 per GPU, uint8 384x384 inputs, "
+                      "GPU preprocessing included"),
+    "gopt_vision": ("gopt_siglip2_384", "vision", 512, 1392.98, "images/s",
+                    "ViT-gopt-16-SigLIP2-384 vision embedding, batch 512 per GPU"),
+    "dfn5b_text": ("dfn5b_h14_378", "text", 8192, 47.09, "texts/s",
+                   "DFN5B-CLIP-ViT-H-14-378 text encoder, batch 8192 per GPU, context 77"),
+    "vit_b32_vision": ("vit_b32", "vision", 1024, 8.82, "images/s", "ViT-B/32 vision embedding, batch 1024 per GPU"),
+    "small_vision": ("small_siglip", "vision", 256, 0.0, "images/s", "small SigLIP-shaped test tower"),
+}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def model_dir_for(config: str, towers, rank: int, world: int, barrier) -> str:
+    """Rank 0 writes the synthetic model directory once (seeded), everyone else waits for the marker."""
+    import export_synthetic as ex
+
+    base = os.environ.get("CLIPB200_MODEL_CACHE", os.path.join(tempfile.gettempdir(), "clipb200_models"))
+    path = os.path.join(base, f"{config}_{'_'.join(towers)}_s0")
+    marker = os.path.join(path, ".complete")
+    if rank == 0 and not os.path.exists(marker):
+        ex.write_model_dir(ex.CONFIGS[config], path, seed=0, towers=towers)
+        open(marker, "w").close()
+    barrier()
+    while not os.path.exists(marker):
+        time.sleep(0.2)
+    return path
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"burst": float(d["bf16_tflops"]), "sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "hbm": float(d["hbm_gbs"]), "source": "measured"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.path = os.path.join(tempfile.gettempdir(), f"clipb200_clocks_{os.getpid()}.csv")
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(gpu_index)], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            load = [s for s in sm if s >= 0.5 * max(sm)] or sm
+            out["sm_mhz"] = statistics.median(load)
+            out["sm_max_mhz"] = max(mx) if mx else None
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_reference_rate(model_dir: str, tower: str, seconds: float, sample_items: int, seed: int):
+    """Times the CPU oracle port on a bounded sample with all host threads.  Returns (units/s, cores, sample)."""
+    import numpy as np
+    import torch
+
+    from oracle import reference_forward as R
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    with open(os.path.join(model_dir, "open_clip_config.json")) as f:
+        cfg = json.load(f)
+    rng = np.random.default_rng(seed)
+    if tower == "vision":
+        t = R.Tower(os.path.join(model_dir, "visual.onnx"))
+        size = int(cfg["model_cfg"]["vision_cfg"]["image_size"])
+        pc = cfg["preprocess_cfg"]
+        imgs = rng.integers(0, 256, size=(sample_items, size, size, 3), dtype=np.uint8)
+
+        def run():
+            return R.vision_forward(t, R.preprocess_batch(list(imgs), size, pc["mean"], pc["std"]))
+    else:
+        t = R.Tower(os.path.join(model_dir, "text.onnx"))
+        ctx = int(cfg["model_cfg"]["text_cfg"]["context_length"])
+        ids = rng.integers(1, 40000, size=(sample_items, ctx), dtype=np.int64)
+        ids[:, -1] = 49407
+
+        def run():
+            return R.text_forward(t, ids)
+    run()  # warm-up (thread pool, allocator)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        run()
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= seconds or n >= 8:
+            break
+    return n * sample_items / el, cores, f"{sample_items} items x {n} passes in {el:.1f} s after 1 warm-up pass"
+
+
+def run_reference_arm(args, wl, rank, world):
+    config, tower, batch, gflop, unit, desc = wl
+    if rank != 0:
+        return
+    mdir = model_dir_for(config, (tower,), 0, 1, lambda: None)
+    sample = 4 if tower == "vision" else 32
+    rates = []
+    cores = os.cpu_count() or 1
+    note = ""
+    for i in range(args.warmup + args.steps):
+        r, cores, note = cpu_reference_rate(mdir, tower, seconds=6.0, sample_items=sample, seed=100 + i)
+        if i >= args.warmup:
+            rates.append(r)
+    value = statistics.mean(rates)
+    line = {
+        "impl": "reference", "metric": f"SigLIP2-SO400M-384 {unit}" if "so400m" in args.workload else f"{args.workload} {unit}",
+        "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sample / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "sample_per_step": sample,
+                   "note": "reference's ort CPU EP is not buildable here (no cargo / onnxruntime); this is the CPU "
+                           "oracle port (torch fp32) on all host threads"},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": note},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="so400m_vision", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--micro-batch", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-text", action="store_true", help="skip the secondary text-encoder measurement")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    wl = WORKLOADS[args.workload]
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank, world)
+        return
+
+    import numpy as np
+    import torch
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    import clip_embedder_rs_b200 as cb
+    from clip_embedder_rs_b200 import _native
+
+    lib = _native.lib
+    pk = peaks()
+
+    def measure(workload_name: str, steps: int, warmup: int, with_e2e: bool):
+        config, tower, batch, gflop, unit, desc = WORKLOADS[workload_name]
+        if args.batch > 0 and workload_name == args.workload:
+            batch = args.batch
+        mdir = model_dir_for(config, (tower,), rank, world, barrier)
+        dev = local_rank
+        if tower == "vision":
+            emb = cb.VisionEmbedder.from_local_dir(mdir).device(dev).micro_batch(args.micro_batch).profile(True).build()
+            size = emb.session.image_size
+            item_bytes = size * size * 3
+        else:
+            emb = cb.TextEmbedder.from_local_dir(mdir).device(dev).micro_batch(args.micro_batch).profile(True).build()
+            ctx = emb.session.context_length
+            item_bytes = ctx * 8
+        sess = emb.session
+        h = sess.handle
+        E = sess.embed_dim
+        in_bytes, out_bytes = batch * item_bytes, batch * E * 4
+        # pinned host input / output (the caller's buffers for the e2e arm)
+        h_in = lib.clipb200_host_alloc(in_bytes)
+        h_out = lib.clipb200_host_alloc(out_bytes)
+        if not h_in or not h_out:
+            raise RuntimeError("pinned allocation failed")
+        rng = np.random.default_rng(4 + rank)
+        if tower == "vision":
+            host = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_uint8)), shape=(in_bytes,))
+            chunk = 1 << 26
+            for o in range(0, in_bytes, chunk):
+                host[o:o + chunk] = rng.integers(0, 256, size=min(chunk, in_bytes - o), dtype=np.uint8)
+        else:
+            host = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_int64)), shape=(batch, ctx))
+            host[:] = 0
+            lens = rng.integers(4, ctx - 1, size=batch)
+            for i in range(batch):
+                host[i, 0] = 49406
+                host[i, 1:lens[i]] = rng.integers(1, 49000, size=lens[i] - 1)
+                host[i, lens[i]] = 49407
+        d_in = lib.clipb200_device_alloc(dev, in_bytes)
+        d_out = lib.clipb200_device_alloc(dev, out_bytes)
+        if not d_in or not d_out:
+            raise RuntimeError("device allocation failed")
+        sess.check(lib.clipb200_memcpy_h2d(dev, d_in, h_in, in_bytes))
+
+        def step_device():
+            if tower == "vision":
+                sess.check(lib.clipb200_vision_embed_rgb8_device(h, d_in, batch, emb._pp, d_out))
+            else:
+                sess.check(lib.clipb200_text_embed_device(h, d_in, batch, ctx, d_out))
+
+        def step_host():
+            if tower == "vision":
+                sess.check(lib.clipb200_vision_embed_rgb8(h, h_in, batch, size, size, emb._pp, h_out))
+            else:
+                sess.check(lib.clipb200_text_embed(h, h_in, None, batch, ctx, h_out))
+
+        # ---------------- device-resident timing (value) ----------------
+        for _ in range(warmup):
+            step_device()
+        sess.synchronize()
+        sess.profile(reset=True)
+        launches0 = sess.launch_count
+        barrier()
+        sampler = ClockSampler(dev) if rank == 0 else None
+        sess.check(lib.clipb200_engine_record_event(h, 0))
+        for _ in range(steps):
+            step_device()
+        sess.check(lib.clipb200_engine_record_event(h, 1))
+        ms = C.c_double()
+        sess.check(lib.clipb200_engine_elapsed_ms(h, 0, 1, C.byref(ms)))
+        sess.synchronize()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        prof = sess.profile(reset=True)
+        launches = sess.launch_count - launches0
+        dev_ms = max_over_ranks(ms.value)
+        res = {"unit": unit, "desc": desc, "batch": batch, "ms_per_step": dev_ms / steps,
+               "value": world * batch * steps / (dev_ms * 1e-3), "launches": launches, "prof": prof,
+               "clocks": clocks, "gflop": gflop, "h2d": in_bytes, "d2h": out_bytes,
+               "weight_bytes": sess.weight_bytes}
+        # ---------------- end-to-end timing (host buffers) ----------------
+        if with_e2e:
+            for _ in range(max(1, min(warmup, 2))):
+                step_host()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                step_host()
+            el = time.perf_counter() - t0
+            el = max_over_ranks(el)
+            res["e2e_value"] = world * batch * steps / el
+            out = np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_float)), shape=(batch, E))
+            res["out_norm_err"] = float(np.abs(np.linalg.norm(out[:64], axis=1) - 1.0).max())
+        lib.clipb200_device_free(dev, d_in)
+        lib.clipb200_device_free(dev, d_out)
+        lib.clipb200_host_free(h_in)
+        lib.clipb200_host_free(h_out)
+        sess.close()
+        return res, mdir
+
+    res, mdir = measure(args.workload, args.steps, args.warmup, with_e2e=True)
+    config, tower, _, gflop, unit, desc = wl
+
+    gemm_ms = res["prof"]["ms"]["gemm"]
+    gemm_tflops = res["prof"]["gemm_flops"] / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    total_kernel_ms = sum(v for k, v in res["prof"]["ms"].items() if k not in ("h2d", "d2h"))
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of the timed steps)",
+        "achieved": gemm_tflops, "peak": pk["sustained"], "unit": "TFLOP/s",
+        "frac": gemm_tflops / pk["sustained"] if pk["sustained"] else None,
+        "frac_of_burst_peak": gemm_tflops / pk["burst"] if pk["burst"] else None,
+        "peak_source": f"{pk['source']} (MEASURED_PEAKS.json bf16_tflops_sustained; burst {pk['burst']})",
+        "traffic": None,
+        "gemm_share_of_kernel_time": gemm_ms / total_kernel_ms if total_kernel_ms > 0 else None,
+        "kernel_ms_per_step": {k: v / args.steps for k, v in res["prof"]["ms"].items()},
+        "launches_per_step": {k: v / args.steps for k, v in res["prof"]["launches"].items()},
+    }
+    whole = None
+    if gflop > 0:
+        tf = res["value"] / world * gflop * 1e9 / 1e12  # per GPU
+        whole = {"tflops_per_gpu": tf, "frac_of_sustained_peak": tf / pk["sustained"],
+                 "frac_of_burst_peak": tf / pk["burst"], "gflop_per_unit": gflop}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r, cores, note = cpu_reference_rate(mdir, tower, seconds=15.0,
+                                                sample_items=4 if tower == "vision" else 32, seed=7)
+            cpu_baseline = {"value": r, "unit": unit, "cores": cores, "kind": "port", "sample": note}
+        except Exception as e:  # pragma: no cover
+            cpu_baseline = {"value": None, "unit": unit, "cores": os.cpu_count(), "kind": "port",
+                            "sample": f"failed: {e}"}
+
+    text_extra = None
+    if args.workload == "so400m_vision" and world == 1 and not args.no_text:
+        try:
+            tres, _ = measure("dfn5b_text", max(2, args.steps // 2), 2, with_e2e=True)
+            tf = tres["value"] * tres["gflop"] * 1e9 / 1e12
+            text_extra = {"workload": tres["desc"], "value": tres["value"], "unit": tres["unit"],
+                          "e2e": tres.get("e2e_value"), "ms_per_step": tres["ms_per_step"],
+                          "tflops_per_gpu": tf, "frac_of_sustained_peak": tf / pk["sustained"]}
+        except Exception as e:  # pragma: no cover
+            text_extra = {"error": str(e)}
+
+    if rank == 0:
+        line = {
+            "metric": "SigLIP2-SO400M-384 images/sec" if args.workload == "so400m_vision" else f"{args.workload} {unit}",
+            "value": res["value"], "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": desc, "per_gpu_batch": res["batch"], "global_batch": res["batch"] * world,
+                       "parallelism": f"replicas x{world}, batch row-sharded, no collective",
+                       "weights": "random-init, reference ONNX layout (tools/export_synthetic.py), bf16 in HBM",
+                       "cache": "inputs_larger_than_l2 (453 MB uint8 batch + >1 GB activations per micro-batch)",
+                       "weight_bytes": res["weight_bytes"]},
+            "e2e": {"value": res.get("e2e_value"), "unit": unit, "h2d_bytes_per_step": res["h2d"],
+                    "d2h_bytes_per_step": res["d2h"]},
+            "gpu_launches": res["launches"],
+            "clocks": res["clocks"],
+            "roofline": roofline,
+            "whole_step": whole,
+            "cpu_baseline": cpu_baseline,
+            "text": text_extra,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
