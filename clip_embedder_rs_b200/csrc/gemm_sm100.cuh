@@ -55,24 +55,58 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+// tanh-form GELU on the MUFU.TANH path: 0.5 x (1 + tanh(u)); one special-function op per element.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float apply_act_fast(float x, int act) {
+  switch (act) {
+    case ACT_QUICKGELU:
+      return __fdividef(x, 1.0f + __expf(-1.702f * x));
+    case ACT_GELU_TANH: {
+      const float u = 0.7978845608028654f * x * fmaf(0.044715f * x, x, 1.0f);
+      const float hx = 0.5f * x;
+      return fmaf(hx, tanh_approx(u), hx);
+    }
+    case ACT_GELU_ERF:
+      return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));
+    default:
+      return x;
+  }
+}
+__device__ __forceinline__ uint32_t pack2_act(float a, float b, int act) {
+  if (act != ACT_NONE) {
+    a = apply_act_fast(a, act);
+    b = apply_act_fast(b, act);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;                             // 2 per TMEM lane quarter
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;         // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+constexpr int GEMM_EPI_STAGE_BYTES = 32 * 128;                 // per epilogue warp: 32 rows x 128 B, 128B-swizzled
 
 template <int BN>
 struct GemmCfg {
   static constexpr int B_STAGE_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = GEMM_A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
+  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES;  // 32 KB
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+  static constexpr int BUDGET = 227 * 1024 - 1024 - BAR_BYTES - EPI_BYTES;
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                         int M, int N, int K, GemmEpilogue ep) {
+                         const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, GemmEpilogue ep) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -80,7 +114,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * GEMM_A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (stage sizes are multiples of 1024)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;           // [STAGES]  MMA -> TMA
   uint64_t* tmem_full_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
@@ -97,13 +132,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_w);
+    if (EPI != EPI_F32) ptx::prefetch_tmap(&tmap_c);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 128);
+      ptx::mbar_init(&tmem_empty_bar[a], 32 * GEMM_EPI_WARPS);
     }
     ptx::fence_mbar_init();
   }
@@ -163,98 +199,150 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps 2..5
+    // ------------------------------------------------------------ epilogue warps 2..9
+    // Two warps per TMEM lane quarter, interleaved over column chunks.  Per chunk: tcgen05.ld (one accumulator row
+    // per thread) -> bias / activation / layer-scale in registers -> 128B-swizzled smem staging tile (32 rows x 128 B)
+    // -> one elected lane issues a TMA bulk tensor store (bf16 out) or a TMA reduce-add (fp32 residual stream), so
+    // the global side is full-line, asynchronous and off the LSU.  The strided/remapped fp32 mode (patch embedding)
+    // reads the staging tile back transposed and stores 4 rows x 128 B per warp instruction.
+    const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = ew >> 2;
+    uint8_t* stg = smem_epi + ew * GEMM_EPI_STAGE_BYTES;
+    const int sw = lane & 7;  // 128B-swizzle phase of this thread's staging row
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const int row = m_blk * GEMM_BM + quarter * 32 + lane;
-      const bool row_ok = row < M;
-      long long out_row = row;
-      int pos_row = 0;
-      if (EPI == EPI_F32 && ep.rows_in > 0) {
-        const int b = row / ep.rows_in, t = row - b * ep.rows_in;
-        out_row = static_cast<long long>(b) * ep.rows_out + t + ep.row_off;
-        pos_row = t + ep.row_off;
-      }
+      const int row_base = m_blk * GEMM_BM + quarter * 32;
       const uint32_t taddr_row = tmem_base + static_cast<uint32_t>(acc * 256) +
                                  (static_cast<uint32_t>(quarter * 32) << 16);
+      if (EPI == EPI_BF16) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 >= N) break;  // warp-uniform
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(taddr_row + static_cast<uint32_t>(c * 32), r);
-        ptx::tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (ep.bias != nullptr) {
+        for (int c = half; c < BN / 64; c += 2) {
+          const int n0 = n_blk * BN + c * 64;
+          if (n0 >= N) break;  // warp-uniform
+          uint32_t r0[32], r1[32];
+          ptx::tmem_ld_32x32(taddr_row + static_cast<uint32_t>(c * 64), r0);
+          ptx::tmem_ld_32x32(taddr_row + static_cast<uint32_t>(c * 64 + 32), r1);
+          float4 b0[8], b1[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            if (n0 + 4 * j < N) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
-              v[4 * j + 0] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            b0[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            b1[j] = b0[j];
+            if (ep.bias != nullptr) {
+              if (n0 + 4 * j < N) b0[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
+              if (n0 + 32 + 4 * j < N) b1[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + 32) + j);
             }
+          }
+          ptx::tmem_ld_wait();
+          uint32_t pk[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            pk[2 * j] = pack2_act(__uint_as_float(r0[4 * j]) + b0[j].x, __uint_as_float(r0[4 * j + 1]) + b0[j].y, ep.act);
+            pk[2 * j + 1] = pack2_act(__uint_as_float(r0[4 * j + 2]) + b0[j].z, __uint_as_float(r0[4 * j + 3]) + b0[j].w, ep.act);
+            pk[16 + 2 * j] = pack2_act(__uint_as_float(r1[4 * j]) + b1[j].x, __uint_as_float(r1[4 * j + 1]) + b1[j].y, ep.act);
+            pk[16 + 2 * j + 1] = pack2_act(__uint_as_float(r1[4 * j + 2]) + b1[j].z, __uint_as_float(r1[4 * j + 3]) + b1[j].w, ep.act);
+          }
+          if (lane == 0) ptx::tma_store_wait_read<0>();  // the previous store of this warp has left the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ sw) << 4)) =
+                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmap_c, stg, n0, row_base);
+            ptx::tma_store_commit();
           }
         }
-        if (EPI == EPI_BF16) {
-          if (ep.act != ACT_NONE) {
+      } else if (EPI == EPI_RESID) {
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 >= N) break;  // warp-uniform
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr_row + static_cast<uint32_t>(c * 32), r);
+          float4 b4[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+          for (int j = 0; j < 8; ++j) {
+            b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.bias != nullptr && n0 + 4 * j < N) b4[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
           }
-          if (row_ok) {
-            __nv_bfloat16* dst = ep.out_bf16 + static_cast<long long>(row) * ep.ldc + n0;
+          ptx::tmem_ld_wait();
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (n0 + 8 * j < N) {
-                uint4 pk;
-                __nv_bfloat162 h;
-                h = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]); pk.x = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]); pk.y = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]); pk.z = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]); pk.w = *reinterpret_cast<uint32_t*>(&h);
-                *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
-              }
-            }
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4[j].x;
+            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4[j].y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4[j].z;
+            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4[j].w;
           }
-        } else if (EPI == EPI_RESID) {
-          if (row_ok) {
-            float* dst = ep.out_f32 + static_cast<long long>(row) * ep.ldc + n0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (n0 + 4 * j < N) {
-                float4 x = *reinterpret_cast<float4*>(dst + 4 * j);
-                if (ep.gamma != nullptr) {
-                  const float4 g = __ldg(reinterpret_cast<const float4*>(ep.gamma + n0) + j);
-                  x.x += g.x * v[4 * j + 0]; x.y += g.y * v[4 * j + 1];
-                  x.z += g.z * v[4 * j + 2]; x.w += g.w * v[4 * j + 3];
-                } else {
-                  x.x += v[4 * j + 0]; x.y += v[4 * j + 1]; x.z += v[4 * j + 2]; x.w += v[4 * j + 3];
-                }
-                *reinterpret_cast<float4*>(dst + 4 * j) = x;
-              }
-            }
-          }
-        } else {  // EPI_F32
-          if (row_ok) {
-            float* dst = ep.out_f32 + out_row * ep.ldc + n0;
-            const float* pp = ep.pos != nullptr ? ep.pos + static_cast<long long>(pos_row) * N + n0 : nullptr;
+          if (ep.gamma != nullptr) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (n0 + 4 * j < N) {
-                float4 x = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                if (pp != nullptr) {
-                  const float4 p4 = __ldg(reinterpret_cast<const float4*>(pp) + j);
-                  x.x += p4.x; x.y += p4.y; x.z += p4.z; x.w += p4.w;
-                }
-                *reinterpret_cast<float4*>(dst + 4 * j) = x;
+                const float4 g = __ldg(reinterpret_cast<const float4*>(ep.gamma + n0) + j);
+                v[4 * j + 0] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
               }
             }
           }
+          if (lane == 0) ptx::tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ sw) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_reduce_add_2d(&tmap_c, stg, n0, row_base);  // x[rows, cols] += tile, done in L2
+            ptx::tma_store_commit();
+          }
+        }
+      } else {
+        const int colq = lane & 7, rsub = lane >> 3;
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 >= N) break;  // warp-uniform
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr_row + static_cast<uint32_t>(c * 32), r);
+          const int col = n0 + colq * 4;
+          const bool col_ok = col < N;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col_ok && ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ sw) << 4)) =
+                make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + rsub;
+            const int grow = row_base + rl;
+            float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((colq ^ (rl & 7)) << 4));
+            a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+            if (grow < M && col_ok) {
+              long long out_row = grow;
+              int pos_row = 0;
+              if (ep.rows_in > 0) {
+                const int b = grow / ep.rows_in, t = grow - b * ep.rows_in;
+                out_row = static_cast<long long>(b) * ep.rows_out + t + ep.row_off;
+                pos_row = t + ep.row_off;
+              }
+              if (ep.pos != nullptr) {
+                const float4 p4 = __ldg(reinterpret_cast<const float4*>(ep.pos + static_cast<long long>(pos_row) * N + col));
+                a.x += p4.x; a.y += p4.y; a.z += p4.z; a.w += p4.w;
+              }
+              *reinterpret_cast<float4*>(ep.out_f32 + out_row * ep.ldc + col) = a;
+            }
+          }
+          __syncwarp();
         }
       }
       ptx::tc_fence_before();
@@ -262,6 +350,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (EPI != EPI_F32 && lane == 0) ptx::tma_store_wait<0>();  // all bulk stores of this warp are complete
   }
 
   ptx::tc_fence_before();
@@ -292,28 +381,29 @@ inline PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-// bf16 row-major [rows, cols] (cols contiguous, leading dimension ld elements), box = [box_rows, 64 cols], SW128.
-inline bool make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                              uint32_t box_rows) {
+// Row-major [rows, cols] tensor (cols contiguous, leading dimension ld elements), box = [box_rows, 128 bytes of
+// columns], 128-byte swizzle.  elem_bytes 2 = bf16 (64-column box), 4 = fp32 (32-column box).
+inline bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                         uint32_t box_rows, int elem_bytes) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (enc == nullptr) return false;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {GEMM_BK, box_rows};
+  cuuint64_t strides[1] = {ld * static_cast<uint64_t>(elem_bytes)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
 template <int BN, int EPI>
-inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, int M, int N, int K,
-                                 const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
+inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, int M, int N,
+                                 int K, const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tw, M, N, K, ep);
+  gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tw, tc, M, N, K, ep);
   return cudaGetLastError();
 }
 
@@ -338,14 +428,16 @@ inline cudaError_t gemm_configure_device() {
 }
 
 inline int gemm_pick_bn(int N) {
-  // minimise padded columns; prefer the wider tile on ties (fewer A re-reads, lower smem bandwidth per MMA)
+  // minimise (padded columns) x (relative cost per column of that tile width, measured on B200: the wider tile
+  // re-reads A less often and needs less smem bandwidth per MMA: 256 -> 1.00, 192 -> 1.055, 128 -> 1.14)
   const int cands[3] = {256, 192, 128};
+  const double factor[3] = {1.0, 1.055, 1.14};
   int best = 256;
-  long long best_cost = -1;
+  double best_cost = -1.0;
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
-    const long long padded = static_cast<long long>((N + bn - 1) / bn) * bn;
-    if (best_cost < 0 || padded < best_cost) { best_cost = padded; best = bn; }
+    const double cost = static_cast<double>((N + bn - 1) / bn) * bn * factor[i];
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
 }
@@ -355,16 +447,23 @@ inline cudaError_t gemm_bf16(const __nv_bfloat16* A, long long lda, const __nv_b
                              int N, int K, int epi_mode, const GemmEpilogue& ep, int num_sms, cudaStream_t stream,
                              int force_bn = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return cudaErrorInvalidValue;
-  if ((K & 7) || (N & 7) || (lda & 7) || (ldw & 7) || (ep.ldc & 3)) return cudaErrorInvalidValue;
+  if ((K & 7) || (N & 7) || (lda & 7) || (ldw & 7) || (ep.ldc & 7)) return cudaErrorInvalidValue;
   const int bn = force_bn ? force_bn : gemm_pick_bn(N);
-  CUtensorMap ta, tw;
-  if (!make_tmap_bf16_2d(&ta, A, M, K, lda, GEMM_BM)) return cudaErrorUnknown;
-  if (!make_tmap_bf16_2d(&tw, W, N, K, ldw, bn)) return cudaErrorUnknown;
+  CUtensorMap ta, tw, tc;
+  if (!make_tmap_2d(&ta, A, M, K, lda, GEMM_BM, 2)) return cudaErrorUnknown;
+  if (!make_tmap_2d(&tw, W, N, K, ldw, bn, 2)) return cudaErrorUnknown;
+  if (epi_mode == EPI_BF16) {
+    if (!make_tmap_2d(&tc, ep.out_bf16, M, N, ep.ldc, 32, 2)) return cudaErrorUnknown;
+  } else if (epi_mode == EPI_RESID) {
+    if (!make_tmap_2d(&tc, ep.out_f32, M, N, ep.ldc, 32, 4)) return cudaErrorUnknown;
+  } else {
+    tc = ta;  // unused by the kernel in this mode
+  }
 #define CLIPB200_GEMM_CASE(BN_)                                                                     \
   if (bn == BN_) {                                                                                  \
-    if (epi_mode == EPI_BF16) return gemm_launch_t<BN_, EPI_BF16>(ta, tw, M, N, K, ep, num_sms, stream);   \
-    if (epi_mode == EPI_RESID) return gemm_launch_t<BN_, EPI_RESID>(ta, tw, M, N, K, ep, num_sms, stream); \
-    return gemm_launch_t<BN_, EPI_F32>(ta, tw, M, N, K, ep, num_sms, stream);                       \
+    if (epi_mode == EPI_BF16) return gemm_launch_t<BN_, EPI_BF16>(ta, tw, tc, M, N, K, ep, num_sms, stream);   \
+    if (epi_mode == EPI_RESID) return gemm_launch_t<BN_, EPI_RESID>(ta, tw, tc, M, N, K, ep, num_sms, stream); \
+    return gemm_launch_t<BN_, EPI_F32>(ta, tw, tc, M, N, K, ep, num_sms, stream);                       \
   }
   CLIPB200_GEMM_CASE(256)
   CLIPB200_GEMM_CASE(192)
