@@ -2,6 +2,8 @@
 // thread-local message, the way `ort::Error` becomes `ClipError::Ort(String)` in the reference (src/error.rs:62-66).
 #include <cuda_runtime.h>
 
+#include <string.h>
+
 #include <new>
 #include <string>
 
@@ -67,6 +69,47 @@ void clipb200_engine_destroy(clipb200_engine* e) {
     delete e;
   } catch (...) {
   }
+}
+
+// Parses the file exactly as clipb200_engine_create does, without touching a GPU, and describes what it found.
+int clipb200_onnx_inspect(const char* onnx_path, char* json_out, size_t capacity) {
+  API_GUARD_BEGIN
+  if (onnx_path == nullptr || json_out == nullptr || capacity == 0) return fail(CLIPB200_ERR_INVALID_ARG, "null argument");
+  clipb200::OnnxModel m;
+  std::string err;
+  if (!clipb200::load_onnx(onnx_path, &m, &err)) {
+    const bool io = err.find("cannot open") != std::string::npos || err.find("cannot stat") != std::string::npos ||
+                    err.find("cannot mmap") != std::string::npos || err.find("is empty") != std::string::npos;
+    return fail(io ? CLIPB200_ERR_IO : CLIPB200_ERR_PARSE, err);
+  }
+  auto esc = [](const std::string& in) {
+    std::string o;
+    for (char c : in) {
+      if (c == '"' || c == '\\') { o.push_back('\\'); o.push_back(c); }
+      else if (static_cast<unsigned char>(c) < 0x20) o.push_back(' ');
+      else o.push_back(c);
+    }
+    return o;
+  };
+  size_t bytes = 0;
+  for (const auto& kv : m.initializers) bytes += kv.second.nbytes;
+  std::string j = "{\"inputs\": [";
+  for (size_t i = 0; i < m.inputs.size(); ++i) j += std::string(i ? ", " : "") + "\"" + esc(m.inputs[i]) + "\"";
+  j += "], \"outputs\": [";
+  for (size_t i = 0; i < m.outputs.size(); ++i) j += std::string(i ? ", " : "") + "\"" + esc(m.outputs[i]) + "\"";
+  j += "], \"opset\": " + std::to_string(m.opset) + ", \"num_initializers\": " + std::to_string(m.initializers.size()) +
+       ", \"initializer_bytes\": " + std::to_string(bytes) + ", \"num_nodes\": " + std::to_string(m.nodes.size()) +
+       ", \"metadata\": {";
+  bool first = true;
+  for (const auto& kv : m.metadata) {
+    j += std::string(first ? "" : ", ") + "\"" + esc(kv.first) + "\": \"" + esc(kv.second) + "\"";
+    first = false;
+  }
+  j += "}}";
+  if (j.size() + 1 > capacity) return fail(CLIPB200_ERR_INVALID_ARG, "output buffer too small");
+  memcpy(json_out, j.c_str(), j.size() + 1);
+  return CLIPB200_OK;
+  API_GUARD_END
 }
 
 int clipb200_engine_num_inputs(const clipb200_engine* e) {

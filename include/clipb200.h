@@ -80,6 +80,10 @@ void clipb200_engine_destroy(clipb200_engine* e);
 const char* clipb200_last_error(void); /* thread-local, valid until the next failing call on this thread */
 const char* clipb200_version(void);
 
+/* Parse-only probe (no GPU needed): writes a JSON description (inputs, outputs, opset, initializer count/bytes,
+ * metadata) of what clipb200_engine_create would load.  Same IO / PARSE status codes as create. */
+int clipb200_onnx_inspect(const char* onnx_path, char* json_out, size_t capacity);
+
 /* ---- introspection (src/onnx.rs:32-46) ---------------------------------------------------------------- */
 int clipb200_engine_num_inputs(const clipb200_engine* e);
 const char* clipb200_engine_input_name(const clipb200_engine* e, int i);
