@@ -1,0 +1,516 @@
+// tcgen05 / TMEM flash attention (forward) for sm_100a.
+//
+//   out[b, q, h, :] = softmax(Q K^T / sqrt(hd)) V      qkv: [B*T, 3*H*hd] bf16 (q | k | v), out: [B*T, H*hd] bf16
+//
+// Replaces the MatMul -> Mul -> (+mask) -> Softmax -> MatMul chain ONNX Runtime executes inside `session.run`
+// (reference src/vision.rs:108, src/text.rs:157-160).
+//
+// Persistent CTAs (2 per SM, 192 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..5 = softmax
+// (one query row per thread).  Work item = (batch, head, 128-query tile); K/V stream through a 2-stage smem ring in
+// blocks of BKV keys.
+//   S = Q K^T   : tcgen05.mma SS, M=128, N=BKV, accumulator S in TMEM (fp32)
+//   softmax     : tcgen05.ld S -> registers, online max / exp2 / sum in fp32, P written back to TMEM as packed bf16
+//   O += P V    : tcgen05.mma with the A operand (P) read from TMEM, V from smem as an MN-major operand
+//   epilogue    : O / l -> bf16 -> smem -> TMA store
+// Head dims that are not a multiple of 64 (72, 80, 96) are split into a 64-wide part (128-byte-swizzled tiles) and a
+// remainder of 8-element chunk planes (no-swizzle "interleaved" tiles, zero plane appended when the remainder is not
+// a multiple of 16), so neither the GEMMs nor HBM ever see padding.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_sm100.cuh"  // get_encode_tiled
+#include "ptx_sm100.cuh"
+
+namespace clipb200 {
+
+namespace attn {
+
+constexpr int BQ = 128;
+constexpr int THREADS = 192;
+
+template <int HD, int BKV>
+struct Cfg {
+  static_assert(HD >= 64 && HD % 8 == 0 && HD <= 128, "head dim");
+  static_assert(BKV % 16 == 0 && BKV >= 32 && BKV <= 128, "kv block");
+  static constexpr int REM = HD - 64;                    // elements beyond the 64-wide main part
+  static constexpr int REMP = (REM + 15) / 16 * 16;      // padded to the MMA K granularity
+  static constexpr int REM_PLANES = REM / 8;             // chunk planes TMA fills
+  static constexpr int REMP_PLANES = REMP / 8;           // chunk planes the MMA reads
+  static constexpr int HDP = 64 + REMP;
+  static constexpr int Q_MAIN = BQ * 128;                // bytes
+  static constexpr int Q_REM = REMP_PLANES * BQ * 16;
+  static constexpr int KV_MAIN = BKV * 128;
+  static constexpr int KV_REM = REMP_PLANES * BKV * 16;
+  static constexpr int KV_TILE = KV_MAIN + KV_REM;       // one of K or V
+  static constexpr int KV_STAGE = 2 * KV_TILE;
+  static constexpr int KV_TX = 2 * (KV_MAIN + REM_PLANES * BKV * 16);  // bytes TMA delivers per stage
+  static constexpr int Q_TX = Q_MAIN + REM_PLANES * BQ * 16;
+  static constexpr int STAGES = 2;
+  static constexpr int OUT_ROW = HD * 2;                 // bytes
+  static constexpr int OUT_WARP = 32 * OUT_ROW;
+  // smem carve (offsets from a 1024-aligned base)
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_KV = (Q_MAIN + Q_REM + 1023) / 1024 * 1024;
+  static constexpr int KV_STAGE_AL = (KV_STAGE + 1023) / 1024 * 1024;
+  static constexpr int OFF_OUT = OFF_KV + STAGES * KV_STAGE_AL;
+  static constexpr int OFF_BAR = OFF_OUT + (4 * OUT_WARP + 127) / 128 * 128;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  // TMEM columns
+  static constexpr int COL_S = 0;
+  static constexpr int COL_P = BKV;               // packed bf16: BKV/2 columns
+  static constexpr int COL_O = BKV + BKV / 2;
+  static constexpr int TMEM_COLS = 256;
+  static_assert(COL_O + HDP <= TMEM_COLS, "TMEM budget (2 CTAs per SM -> 256 columns each)");
+  static_assert(KV_MAIN % 1024 == 0, "swizzle atom alignment");
+};
+
+struct Params {
+  int T, H, B;
+  int q_tiles, n_items;
+  float scale_log2e;
+};
+
+// ---- descriptors ------------------------------------------------------------------------------------------------
+// no-swizzle ("interleaved") operand tile made of chunk planes [plane][row][8 elements]:
+//   K-major  (Q, K):  LBO = plane stride (next 8 elements along K), SBO = 128 B (next 8 rows)
+//   MN-major (V)   :  LBO = 128 B (next 8 keys along K),           SBO = plane stride (next 8 elements along N)
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // version
+  return d;                             // layout type 0 = no swizzle
+}
+// MN-major, 128-byte swizzle: rows (keys) are 128 B = 64 elements along N, 8-row groups 1024 B apart (SBO);
+// LBO (next 64-element block along N) is unused for N = 64.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1,
+                                            int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(ptx::smem_u32(bar)), "r"(c0),
+        "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1,
+                                             int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(ptx::smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int HD, int BKV, bool CAUSAL>
+__global__ void __launch_bounds__(THREADS, 2)
+attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_constant__ CUtensorMap tm_q_rem,
+                        const __grid_constant__ CUtensorMap tm_kv_main, const __grid_constant__ CUtensorMap tm_kv_rem,
+                        const __grid_constant__ CUtensorMap tm_out, Params p) {
+  using C = Cfg<HD, BKV>;
+  extern __shared__ uint8_t attn_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem + C::OFF_Q;
+  uint8_t* s_kv = smem + C::OFF_KV;
+  uint8_t* s_out = smem + C::OFF_OUT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;   // [2]
+  uint64_t* kv_empty = bars + 4;  // [2]
+  uint64_t* s_full = bars + 6;
+  uint64_t* s_empty = bars + 7;
+  uint64_t* p_full = bars + 8;
+  uint64_t* pv_done = bars + 9;
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv_blocks_total = (p.T + BKV - 1) / BKV;
+
+  // zero the padding chunk planes (TMA never writes them) of Q and of both K/V stages
+  if (C::REMP_PLANES > C::REM_PLANES) {
+    for (int i = threadIdx.x; i < (C::REMP_PLANES - C::REM_PLANES) * BQ; i += THREADS)
+      reinterpret_cast<uint4*>(s_q + C::Q_MAIN + C::REM_PLANES * BQ * 16)[i] = make_uint4(0, 0, 0, 0);
+    for (int st = 0; st < C::STAGES; ++st)
+      for (int kv = 0; kv < 2; ++kv) {
+        uint8_t* tile = s_kv + st * C::KV_STAGE_AL + kv * C::KV_TILE;
+        for (int i = threadIdx.x; i < (C::REMP_PLANES - C::REM_PLANES) * BKV; i += THREADS)
+          reinterpret_cast<uint4*>(tile + C::KV_MAIN + C::REM_PLANES * BKV * 16)[i] = make_uint4(0, 0, 0, 0);
+      }
+    ptx::fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_q_main);
+    ptx::prefetch_tmap(&tm_kv_main);
+    ptx::prefetch_tmap(&tm_out);
+    if (C::REM > 0) { ptx::prefetch_tmap(&tm_q_rem); ptx::prefetch_tmap(&tm_kv_rem); }
+    ptx::mbar_init(q_full, 1);
+    ptx::mbar_init(q_empty, 1);
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&kv_full[s], 1); ptx::mbar_init(&kv_empty[s], 1); }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(s_empty, 128);
+    ptx::mbar_init(p_full, 128);
+    ptx::mbar_init(pv_done, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<C::TMEM_COLS>(tmem_base_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  auto item_blocks = [&](int qt) {
+    if (!CAUSAL) return kv_blocks_total;
+    const int last_q = qt * BQ + BQ - 1;
+    const int nb = last_q / BKV + 1;
+    return nb < kv_blocks_total ? nb : kv_blocks_total;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t g = 0;   // running K/V block counter
+      uint32_t it = 0;  // running item counter
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int qt = item % p.q_tiles;
+        const int bh = item / p.q_tiles;
+        const int h = bh % p.H, b = bh / p.H;
+        const int col_q = h * HD, col_k = p.H * HD + h * HD, col_v = 2 * p.H * HD + h * HD;
+        ptx::mbar_wait(q_empty, (it & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(q_full, C::Q_TX);
+        tma_load_3d(&tm_q_main, q_full, s_q, col_q, qt * BQ, b);
+        for (int pl = 0; pl < C::REM_PLANES; ++pl)
+          tma_load_3d(&tm_q_rem, q_full, s_q + C::Q_MAIN + pl * BQ * 16, col_q + 64 + 8 * pl, qt * BQ, b);
+        const int nb = item_blocks(qt);
+        for (int j = 0; j < nb; ++j, ++g) {
+          const int st = g & 1;
+          ptx::mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&kv_full[st], C::KV_TX);
+          uint8_t* kt = s_kv + st * C::KV_STAGE_AL;
+          uint8_t* vt = kt + C::KV_TILE;
+          tma_load_3d(&tm_kv_main, &kv_full[st], kt, col_k, j * BKV, b);
+          tma_load_3d(&tm_kv_main, &kv_full[st], vt, col_v, j * BKV, b);
+          for (int pl = 0; pl < C::REM_PLANES; ++pl) {
+            tma_load_3d(&tm_kv_rem, &kv_full[st], kt + C::KV_MAIN + pl * BKV * 16, col_k + 64 + 8 * pl, j * BKV, b);
+            tma_load_3d(&tm_kv_rem, &kv_full[st], vt + C::KV_MAIN + pl * BKV * 16, col_v + 64 + 8 * pl, j * BKV, b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, 0);
+      constexpr uint32_t idesc_pv_main = make_idesc(BQ, 64, 1);
+      constexpr uint32_t idesc_pv_rem = make_idesc(BQ, C::REMP > 0 ? C::REMP : 16, 1);
+      const uint32_t t_s = tmem_base + C::COL_S, t_p = tmem_base + C::COL_P, t_o = tmem_base + C::COL_O;
+      const uint32_t q_addr = ptx::smem_u32(s_q);
+      uint32_t g = 0, it = 0;
+      auto issue_qk = [&](uint32_t gg) {
+        const int st = gg & 1;
+        const uint32_t k_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL);
+        ptx::mbar_wait(&kv_full[st], (gg >> 1) & 1);
+        ptx::mbar_wait(s_empty, (gg & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint64_t dq = ptx::make_kmajor_sw128_desc(q_addr);
+        const uint64_t dk = ptx::make_kmajor_sw128_desc(k_addr);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          ptx::umma_bf16_ss(t_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_qk,
+                            k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < C::REMP / 16; ++k) {
+          const uint64_t dqr = make_nosw_desc(q_addr + C::Q_MAIN + k * 2 * BQ * 16, BQ * 16, 128);
+          const uint64_t dkr = make_nosw_desc(k_addr + C::KV_MAIN + k * 2 * BKV * 16, BKV * 16, 128);
+          ptx::umma_bf16_ss(t_s, dqr, dkr, idesc_qk, 1u);
+        }
+        ptx::umma_commit(s_full);
+      };
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int qt = item % p.q_tiles;
+        const int nb = item_blocks(qt);
+        ptx::mbar_wait(q_full, it & 1);
+        ptx::tc_fence_after();
+        issue_qk(g);
+        for (int j = 0; j < nb; ++j, ++g) {
+          if (j + 1 < nb) issue_qk(g + 1);             // S(j+1) overlaps softmax(j)
+          else ptx::umma_commit(q_empty);              // all QK^T of this item are issued: Q tile is free when they retire
+          const int st = g & 1;
+          const uint32_t v_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL + C::KV_TILE);
+          ptx::mbar_wait(p_full, g & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {
+            const uint32_t acc = (j | k) != 0 ? 1u : 0u;
+            const uint64_t dv = make_mnmajor_sw128_desc(v_addr + k * 16 * 128);
+            umma_bf16_ts(t_o, t_p + static_cast<uint32_t>(k * 8), dv, idesc_pv_main, acc);
+            if (C::REMP > 0) {
+              const uint64_t dvr = make_nosw_desc(v_addr + C::KV_MAIN + k * 16 * 16, 128, BKV * 16);
+              umma_bf16_ts(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
+            }
+          }
+          ptx::umma_commit(&kv_empty[st]);
+          ptx::umma_commit(pv_done);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue (warps 2..5)
+    const int quarter = warp & 3;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + C::COL_S;
+    const uint32_t t_p = tmem_base + lane_base + C::COL_P;
+    const uint32_t t_o = tmem_base + lane_base + C::COL_O;
+    uint8_t* stg = s_out + (warp - 2) * C::OUT_WARP;
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int qt = item % p.q_tiles;
+      const int bh = item / p.q_tiles;
+      const int h = bh % p.H, b = bh / p.H;
+      const int nb = item_blocks(qt);
+      const int qrow = qt * BQ + quarter * 32 + lane;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < nb; ++j, ++g) {
+        ptx::mbar_wait(s_full, g & 1);
+        ptx::tc_fence_after();
+        float sv[BKV];
+#pragma unroll
+        for (int c = 0; c < BKV / 32; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_s + static_cast<uint32_t>(c * 32), r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) sv[c * 32 + e] = __uint_as_float(r[e]);
+        }
+        if (BKV % 32 != 0) {
+          uint32_t r[16];
+          tmem_ld_32x32_x16(t_s + static_cast<uint32_t>(BKV / 32 * 32), r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) sv[BKV / 32 * 32 + e] = __uint_as_float(r[e]);
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(s_empty);  // S is in registers: the next QK^T may overwrite it
+        const int key0 = j * BKV;
+        const bool need_mask = (key0 + BKV > p.T) || (CAUSAL && key0 + BKV - 1 > qt * BQ + quarter * 32);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < BKV; ++e) {
+          float v = sv[e] * p.scale_log2e;
+          if (need_mask) {
+            const int key = key0 + e;
+            if (key >= p.T || (CAUSAL && key > qrow)) v = -INFINITY;
+          }
+          sv[e] = v;
+          mx = fmaxf(mx, v);
+        }
+        const float m_new = fmaxf(m_run, mx);
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = ex2(m_run - m_use);
+        float rs = 0.f;
+        uint32_t pk[BKV / 2];
+#pragma unroll
+        for (int e = 0; e < BKV / 2; ++e) {
+          const float p0 = ex2(sv[2 * e] - m_use), p1 = ex2(sv[2 * e + 1] - m_use);
+          rs += p0 + p1;
+          pk[e] = pack_bf16(p0, p1);
+        }
+        l_run = l_run * alpha + rs;
+        m_run = m_new;
+        // P(j) and the O rescale must wait until PV(j-1) has finished reading P and writing O
+        ptx::mbar_wait(pv_done, (g & 1) ^ 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < BKV / 32; ++c) {
+          uint32_t r[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r[e] = pk[c * 16 + e];
+          tmem_st_32x32_x16(t_p + static_cast<uint32_t>(c * 16), r);
+        }
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+          for (int c = 0; c < C::HDP / 16; ++c) {
+            uint32_t r[16];
+            tmem_ld_32x32_x16(t_o + static_cast<uint32_t>(c * 16), r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+            tmem_st_32x32_x16(t_o + static_cast<uint32_t>(c * 16), r);
+          }
+        }
+        tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(p_full);
+      }
+      // epilogue: wait for the last PV, normalise, store
+      ptx::mbar_wait(pv_done, (g & 1) ^ 1);
+      ptx::tc_fence_after();
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+      if (lane == 0) ptx::tma_store_wait_read<0>();
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < (HD + 15) / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32_x16(t_o + static_cast<uint32_t>(c * 16), r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (c * 16 + e * 8 < HD) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(r[e * 8 + 0]) * inv, __uint_as_float(r[e * 8 + 1]) * inv);
+            o.y = pack_bf16(__uint_as_float(r[e * 8 + 2]) * inv, __uint_as_float(r[e * 8 + 3]) * inv);
+            o.z = pack_bf16(__uint_as_float(r[e * 8 + 4]) * inv, __uint_as_float(r[e * 8 + 5]) * inv);
+            o.w = pack_bf16(__uint_as_float(r[e * 8 + 6]) * inv, __uint_as_float(r[e * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(stg + lane * C::OUT_ROW + (c * 16 + e * 8) * 2) = o;
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tm_out, stg, h * HD, qt * BQ + quarter * 32, b);
+        ptx::tma_store_commit();
+      }
+    }
+    if (lane == 0) ptx::tma_store_wait<0>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// 3-D tensor map over a [B, T, cols] bf16 tensor (cols contiguous), box = {box_cols, box_rows, 1}
+inline bool make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t T, uint64_t B, uint32_t box_cols,
+                         uint32_t box_rows, bool swizzle128) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[3] = {cols, T, B};
+  cuuint64_t strides[2] = {cols * 2, cols * 2 * T};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int HD, int BKV, bool CAUSAL>
+inline cudaError_t launch_t(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int num_sms,
+                            cudaStream_t st) {
+  using C = Cfg<HD, BKV>;
+  CUtensorMap q_main, q_rem, kv_main, kv_rem, o_map;
+  const uint64_t cols = 3ull * H * HD;
+  if (!make_tmap_3d(&q_main, qkv, cols, T, B, 64, BQ, true)) return cudaErrorUnknown;
+  if (!make_tmap_3d(&kv_main, qkv, cols, T, B, 64, BKV, true)) return cudaErrorUnknown;
+  if (!make_tmap_3d(&q_rem, qkv, cols, T, B, 8, BQ, false)) return cudaErrorUnknown;
+  if (!make_tmap_3d(&kv_rem, qkv, cols, T, B, 8, BKV, false)) return cudaErrorUnknown;
+  if (!make_tmap_3d(&o_map, out, static_cast<uint64_t>(H) * HD, T, B, HD, 32, false)) return cudaErrorUnknown;
+  Params p;
+  p.T = T; p.H = H; p.B = B;
+  p.q_tiles = (T + BQ - 1) / BQ;
+  p.n_items = p.q_tiles * H * B;
+  p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  const int grid = p.n_items < 2 * num_sms ? p.n_items : 2 * num_sms;
+  attn_fwd_tcgen05_kernel<HD, BKV, CAUSAL><<<grid, THREADS, C::SMEM_BYTES, st>>>(q_main, q_rem, kv_main, kv_rem, o_map, p);
+  return cudaGetLastError();
+}
+template <int HD, int BKV>
+inline cudaError_t configure_t() {
+  cudaError_t e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<HD, BKV, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HD, BKV>::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<HD, BKV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              Cfg<HD, BKV>::SMEM_BYTES);
+}
+
+}  // namespace attn
+
+inline cudaError_t attn_tcgen05_configure_device() {
+  cudaError_t e;
+  if ((e = attn::configure_t<64, 96>()) != cudaSuccess) return e;
+  if ((e = attn::configure_t<72, 96>()) != cudaSuccess) return e;
+  if ((e = attn::configure_t<80, 96>()) != cudaSuccess) return e;
+  if ((e = attn::configure_t<96, 96>()) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+inline bool attn_tcgen05_supported(int hd) { return hd == 64 || hd == 72 || hd == 80 || hd == 96; }
+
+// qkv: [B*T, 3*H*hd] bf16, out: [B*T, H*hd] bf16
+inline cudaError_t attn_tcgen05(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, bool causal,
+                                int num_sms, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+#define CLIPB200_ATTN_CASE(HD_)                                                                   \
+  if (hd == HD_)                                                                                  \
+    return causal ? attn::launch_t<HD_, 96, true>(qkv, out, B, T, H, num_sms, st)                 \
+                  : attn::launch_t<HD_, 96, false>(qkv, out, B, T, H, num_sms, st);
+  CLIPB200_ATTN_CASE(64)
+  CLIPB200_ATTN_CASE(72)
+  CLIPB200_ATTN_CASE(80)
+  CLIPB200_ATTN_CASE(96)
+#undef CLIPB200_ATTN_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace clipb200

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 
+#include "attn_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "kernels.cuh"
 
@@ -396,6 +397,7 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
   input_names = m.inputs;
   CUDA_RET(gemm_configure_device(), "configure GEMM kernels");
   CUDA_RET(flash_attention_configure_device(), "configure attention kernels");
+  CUDA_RET(attn_tcgen05_configure_device(), "configure tcgen05 attention kernels");
   CUDA_RET(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking), "stream");
   CUDA_RET(cudaStreamCreateWithFlags(&copy_in_, cudaStreamNonBlocking), "stream");
   CUDA_RET(cudaStreamCreateWithFlags(&copy_out_, cudaStreamNonBlocking), "stream");
@@ -541,7 +543,9 @@ Status Engine::Blocks(int rows, int n_seq, int T, bool causal) {
     ep.ldc = 3 * D_;
     RET_IF_ERR(Gemm(h_, D_, b.qkv, rows, EPI_BF16, &ep));
     ProfBegin(PC_ATTN, compute_);
-    e = launch_flash_attention(qkv_, h_, n_seq, T, H_, hd_, causal, compute_);
+    // tcgen05/TMEM kernel for head dims >= 64; the mma.sync kernel remains for head dim 32 (FastViT-style heads)
+    e = attn_tcgen05_supported(hd_) ? attn_tcgen05(qkv_, h_, n_seq, T, H_, hd_, causal, num_sms_, compute_)
+                                    : launch_flash_attention(qkv_, h_, n_seq, T, H_, hd_, causal, compute_);
     ProfEnd(PC_ATTN, compute_);
     CUDA_RET(e, "attention");
     GemmEpilogue ep2;

@@ -175,6 +175,9 @@ cudaError_t launch_im2col_f32(const float* nchw, int n, int S, int P, int Kp, __
 // =================================================================================================
 constexpr int LN_MAX_VEC = 16;  // float4 per lane -> D <= 2048
 
+// LN_MAX_VEC is a template parameter so that a 1152-wide row keeps 9 float4 per lane in registers, not 16:
+// fewer registers -> more resident warps -> more loads in flight (this kernel is purely HBM-bound).
+template <int LN_MAX_VEC>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const int* __restrict__ row_map, int rows, int D,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -233,8 +236,23 @@ cudaError_t launch_layernorm(const float* x, const int* row_map, int rows, int D
                              const float* beta, float eps, __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   if ((D & 3) || D > LN_MAX_VEC * 128) return cudaErrorInvalidValue;
-  layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, row_map, rows, D, gamma, beta, eps, out_bf16, out_f32);
-  return cudaGetLastError();
+  const int nv = (D / 4 + 31) / 32;
+  const dim3 grid((rows + 7) / 8);
+#define CLIPB200_LN_CASE(NV_)                                                                                     \
+  if (nv <= NV_) {                                                                                                \
+    layernorm_kernel<NV_><<<grid, 256, 0, st>>>(x, row_map, rows, D, gamma, beta, eps, out_bf16, out_f32);        \
+    return cudaGetLastError();                                                                                    \
+  }
+  CLIPB200_LN_CASE(2)
+  CLIPB200_LN_CASE(4)
+  CLIPB200_LN_CASE(6)
+  CLIPB200_LN_CASE(8)
+  CLIPB200_LN_CASE(9)
+  CLIPB200_LN_CASE(10)
+  CLIPB200_LN_CASE(12)
+  CLIPB200_LN_CASE(16)
+#undef CLIPB200_LN_CASE
+  return cudaErrorInvalidValue;
 }
 
 // =================================================================================================
