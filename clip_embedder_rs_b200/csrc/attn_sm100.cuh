@@ -28,6 +28,10 @@ namespace clipb200 {
 
 namespace attn {
 
+#ifndef CLIPB200_ATTN_DBG
+#define CLIPB200_ATTN_DBG 0  // profiling aid (tests/native/attn_test.cu): 1 no exp, 2 no S load, 4 no P store
+#endif
+
 constexpr int BQ = 128;
 constexpr int THREADS = 192;
 
@@ -174,13 +178,17 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* kv_full = bars + 2;   // [2]
-  uint64_t* kv_empty = bars + 4;  // [2]
-  uint64_t* s_full = bars + 6;
-  uint64_t* s_empty = bars + 7;
-  uint64_t* p_full = bars + 8;
-  uint64_t* pv_done = bars + 9;
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+  // K and V have separate full/empty barriers: a K slot is released as soon as its QK^T retires (long before the
+  // matching PV), so the next K tile is prefetched about two iterations ahead even with a 2-deep ring.
+  uint64_t* k_full = bars + 2;    // [2]
+  uint64_t* k_empty = bars + 4;   // [2]
+  uint64_t* v_full = bars + 6;    // [2]
+  uint64_t* v_empty = bars + 8;   // [2]
+  uint64_t* s_full = bars + 10;
+  uint64_t* s_empty = bars + 11;
+  uint64_t* p_full = bars + 12;
+  uint64_t* pv_done = bars + 13;
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv_blocks_total = (p.T + BKV - 1) / BKV;
@@ -204,7 +212,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
     if (C::REM > 0) { ptx::prefetch_tmap(&tm_q_rem); ptx::prefetch_tmap(&tm_kv_rem); }
     ptx::mbar_init(q_full, 1);
     ptx::mbar_init(q_empty, 1);
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&kv_full[s], 1); ptx::mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&k_full[s], 1); ptx::mbar_init(&k_empty[s], 1);
+      ptx::mbar_init(&v_full[s], 1); ptx::mbar_init(&v_empty[s], 1);
+    }
     ptx::mbar_init(s_full, 1);
     ptx::mbar_init(s_empty, 128);
     ptx::mbar_init(p_full, 128);
@@ -242,16 +253,19 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
         const int nb = item_blocks(qt);
         for (int j = 0; j < nb; ++j, ++g) {
           const int st = g & 1;
-          ptx::mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&kv_full[st], C::KV_TX);
+          const uint32_t par = ((g >> 1) & 1) ^ 1;
           uint8_t* kt = s_kv + st * C::KV_STAGE_AL;
           uint8_t* vt = kt + C::KV_TILE;
-          tma_load_3d(&tm_kv_main, &kv_full[st], kt, col_k, j * BKV, b);
-          tma_load_3d(&tm_kv_main, &kv_full[st], vt, col_v, j * BKV, b);
-          for (int pl = 0; pl < C::REM_PLANES; ++pl) {
-            tma_load_3d(&tm_kv_rem, &kv_full[st], kt + C::KV_MAIN + pl * BKV * 16, col_k + 64 + 8 * pl, j * BKV, b);
-            tma_load_3d(&tm_kv_rem, &kv_full[st], vt + C::KV_MAIN + pl * BKV * 16, col_v + 64 + 8 * pl, j * BKV, b);
-          }
+          ptx::mbar_wait(&k_empty[st], par);
+          ptx::mbar_arrive_expect_tx(&k_full[st], C::KV_TX / 2);
+          tma_load_3d(&tm_kv_main, &k_full[st], kt, col_k, j * BKV, b);
+          for (int pl = 0; pl < C::REM_PLANES; ++pl)
+            tma_load_3d(&tm_kv_rem, &k_full[st], kt + C::KV_MAIN + pl * BKV * 16, col_k + 64 + 8 * pl, j * BKV, b);
+          ptx::mbar_wait(&v_empty[st], par);
+          ptx::mbar_arrive_expect_tx(&v_full[st], C::KV_TX / 2);
+          tma_load_3d(&tm_kv_main, &v_full[st], vt, col_v, j * BKV, b);
+          for (int pl = 0; pl < C::REM_PLANES; ++pl)
+            tma_load_3d(&tm_kv_rem, &v_full[st], vt + C::KV_MAIN + pl * BKV * 16, col_v + 64 + 8 * pl, j * BKV, b);
         }
       }
     }
@@ -267,7 +281,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
       auto issue_qk = [&](uint32_t gg) {
         const int st = gg & 1;
         const uint32_t k_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL);
-        ptx::mbar_wait(&kv_full[st], (gg >> 1) & 1);
+        ptx::mbar_wait(&k_full[st], (gg >> 1) & 1);
         ptx::mbar_wait(s_empty, (gg & 1) ^ 1);
         ptx::tc_fence_after();
         const uint64_t dq = ptx::make_kmajor_sw128_desc(q_addr);
@@ -282,6 +296,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
           const uint64_t dkr = make_nosw_desc(k_addr + C::KV_MAIN + k * 2 * BKV * 16, BKV * 16, 128);
           ptx::umma_bf16_ss(t_s, dqr, dkr, idesc_qk, 1u);
         }
+        ptx::umma_commit(&k_empty[st]);
         ptx::umma_commit(s_full);
       };
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
@@ -295,6 +310,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
           else ptx::umma_commit(q_empty);              // all QK^T of this item are issued: Q tile is free when they retire
           const int st = g & 1;
           const uint32_t v_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL + C::KV_TILE);
+          ptx::mbar_wait(&v_full[st], (g >> 1) & 1);
           ptx::mbar_wait(p_full, g & 1);
           ptx::tc_fence_after();
 #pragma unroll
@@ -307,7 +323,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
               umma_bf16_ts(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
             }
           }
-          ptx::umma_commit(&kv_empty[st]);
+          ptx::umma_commit(&v_empty[st]);
           ptx::umma_commit(pv_done);
         }
       }
@@ -332,47 +348,65 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
         ptx::mbar_wait(s_full, g & 1);
         ptx::tc_fence_after();
         float sv[BKV];
+        {
+          // issue every TMEM load of this row before the single wait
+          uint32_t r[(BKV + 31) / 32][32];
 #pragma unroll
-        for (int c = 0; c < BKV / 32; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(t_s + static_cast<uint32_t>(c * 32), r);
+          for (int c = 0; c < BKV / 32; ++c) {
+            if (CLIPB200_ATTN_DBG & 2) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) r[c][e] = 0;
+            } else {
+              ptx::tmem_ld_32x32(t_s + static_cast<uint32_t>(c * 32), r[c]);
+            }
+          }
+          if (BKV % 32 != 0) {
+            uint32_t r16[16];
+            tmem_ld_32x32_x16(t_s + static_cast<uint32_t>(BKV / 32 * 32), r16);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[BKV / 32][e] = r16[e];
+          }
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) sv[c * 32 + e] = __uint_as_float(r[e]);
-        }
-        if (BKV % 32 != 0) {
-          uint32_t r[16];
-          tmem_ld_32x32_x16(t_s + static_cast<uint32_t>(BKV / 32 * 32), r);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 16; ++e) sv[BKV / 32 * 32 + e] = __uint_as_float(r[e]);
+          for (int e = 0; e < BKV; ++e) sv[e] = __uint_as_float(r[e / 32][e % 32]);
         }
         ptx::tc_fence_before();
         ptx::mbar_arrive(s_empty);  // S is in registers: the next QK^T may overwrite it
         const int key0 = j * BKV;
         const bool need_mask = (key0 + BKV > p.T) || (CAUSAL && key0 + BKV - 1 > qt * BQ + quarter * 32);
+        if (need_mask) {  // warp-uniform, only the last kv block (and the diagonal blocks of causal towers)
+#pragma unroll
+          for (int e = 0; e < BKV; ++e) {
+            const int key = key0 + e;
+            if (key >= p.T || (CAUSAL && key > qrow)) sv[e] = -INFINITY;
+          }
+        }
+        // row maximum on the raw scores (the scale is positive, so max(s * scale) == scale * max(s))
         float mx = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < BKV; ++e) {
-          float v = sv[e] * p.scale_log2e;
-          if (need_mask) {
-            const int key = key0 + e;
-            if (key >= p.T || (CAUSAL && key > qrow)) v = -INFINITY;
-          }
-          sv[e] = v;
-          mx = fmaxf(mx, v);
-        }
-        const float m_new = fmaxf(m_run, mx);
+        for (int e = 0; e < BKV; ++e) mx = fmaxf(mx, sv[e]);
+        mx *= p.scale_log2e;
+        // Lazy rescaling: keep the running reference maximum unless the new block maximum exceeds it by more than
+        // 2^8; P then stays <= 256 (exact in the fp32 sums, fine in bf16) and O / l are rescaled only rarely.
+        // The result is mathematically identical because O and l always share the same reference maximum.
+        const bool bump = (mx > m_run + 8.0f) || (m_run == -INFINITY);
+        const float m_new = bump ? mx : m_run;
         const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-        const float alpha = ex2(m_run - m_use);
-        float rs = 0.f;
+        const float alpha = bump ? ex2(m_run - m_use) : 1.0f;
+        const float neg_m = -m_use;
+        float rs0 = 0.f, rs1 = 0.f;
         uint32_t pk[BKV / 2];
 #pragma unroll
         for (int e = 0; e < BKV / 2; ++e) {
-          const float p0 = ex2(sv[2 * e] - m_use), p1 = ex2(sv[2 * e + 1] - m_use);
-          rs += p0 + p1;
+          // exp2(s * scale - m): one FFMA + one MUFU per element
+          const float a0 = fmaf(sv[2 * e], p.scale_log2e, neg_m), a1 = fmaf(sv[2 * e + 1], p.scale_log2e, neg_m);
+          const float p0 = (CLIPB200_ATTN_DBG & 1) ? a0 * 0.001f : ex2(a0);
+          const float p1 = (CLIPB200_ATTN_DBG & 1) ? a1 * 0.001f : ex2(a1);
+          rs0 += p0;
+          rs1 += p1;
           pk[e] = pack_bf16(p0, p1);
         }
+        const float rs = rs0 + rs1;
         l_run = l_run * alpha + rs;
         m_run = m_new;
         // P(j) and the O rescale must wait until PV(j-1) has finished reading P and writing O
@@ -383,9 +417,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
           uint32_t r[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) r[e] = pk[c * 16 + e];
-          tmem_st_32x32_x16(t_p + static_cast<uint32_t>(c * 16), r);
+          if (!(CLIPB200_ATTN_DBG & 4)) tmem_st_32x32_x16(t_p + static_cast<uint32_t>(c * 16), r);
         }
-        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        if (j > 0 && __any_sync(0xffffffffu, bump)) {
 #pragma unroll
           for (int c = 0; c < C::HDP / 16; ++c) {
             uint32_t r[16];
@@ -492,7 +526,7 @@ inline cudaError_t attn_tcgen05_configure_device() {
   if ((e = attn::configure_t<64, 96>()) != cudaSuccess) return e;
   if ((e = attn::configure_t<72, 96>()) != cudaSuccess) return e;
   if ((e = attn::configure_t<80, 96>()) != cudaSuccess) return e;
-  if ((e = attn::configure_t<96, 96>()) != cudaSuccess) return e;
+  if ((e = attn::configure_t<96, 64>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 inline bool attn_tcgen05_supported(int hd) { return hd == 64 || hd == 72 || hd == 80 || hd == 96; }
@@ -501,14 +535,15 @@ inline bool attn_tcgen05_supported(int hd) { return hd == 64 || hd == 72 || hd =
 inline cudaError_t attn_tcgen05(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, bool causal,
                                 int num_sms, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-#define CLIPB200_ATTN_CASE(HD_)                                                                   \
+#define CLIPB200_ATTN_CASE(HD_, BKV_)                                                             \
   if (hd == HD_)                                                                                  \
-    return causal ? attn::launch_t<HD_, 96, true>(qkv, out, B, T, H, num_sms, st)                 \
-                  : attn::launch_t<HD_, 96, false>(qkv, out, B, T, H, num_sms, st);
-  CLIPB200_ATTN_CASE(64)
-  CLIPB200_ATTN_CASE(72)
-  CLIPB200_ATTN_CASE(80)
-  CLIPB200_ATTN_CASE(96)
+    return causal ? attn::launch_t<HD_, BKV_, true>(qkv, out, B, T, H, num_sms, st)               \
+                  : attn::launch_t<HD_, BKV_, false>(qkv, out, B, T, H, num_sms, st);
+  // kv block: 96 keys (576 = 6 x 96 exactly); 64 for head dim 96 so that two CTAs still fit in one SM's shared memory
+  CLIPB200_ATTN_CASE(64, 96)
+  CLIPB200_ATTN_CASE(72, 96)
+  CLIPB200_ATTN_CASE(80, 96)
+  CLIPB200_ATTN_CASE(96, 64)
 #undef CLIPB200_ATTN_CASE
   return cudaErrorInvalidValue;
 }

@@ -53,13 +53,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline barrier that does not flip within ~2 s means a protocol bug;
-// trap instead of hanging the device.
+// try_wait with a suspend-time hint: the thread sleeps in hardware (no issue slots burnt) until the phase completes
+// or the hint (ns) expires.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline barrier that does not flip within a few seconds means a protocol bug; trap instead of
+// hanging the device.  The slow path sleeps inside try_wait, so waiting warps do not compete for issue slots.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+  uint32_t tries = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (++tries > 400000u) {
       printf("clipb200: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
              smem_u32(bar), parity);
       __trap();

@@ -166,6 +166,8 @@ int main(int argc, char** argv) {
   run(2, 576, 16, 96, false, false);   // 10: giant-opt
   run(128, 576, 16, 72, false, true);  // 11: perf, SO400M micro-batch
   run(64, 576, 16, 96, false, true);   // 12
+  run(128, 576, 18, 64, false, true);  // 13: no remainder planes (same total width as 16 x 72)
+  run(128, 576, 14, 80, false, true);  // 14: two real remainder planes
   printf("%s (%d failing cases)\n", fails ? "ATTN TEST FAILED" : "ATTN TEST PASSED", fails);
   return fails ? 1 : 0;
 }
