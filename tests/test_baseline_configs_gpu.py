@@ -1,0 +1,132 @@
+"""Full-size parity for the BASELINE.json configs the engine supports (random-init weights in the reference's ONNX
+layout, synthetic inputs with the seeds SURVEY.md 8(d) names), engine vs CPU oracle:
+
+  C1  timm/vit_base_patch32_clip_224.openai  Clip::classify, 1 image + 3 labels: identical label order, probs, margin
+  C3  ViT-SO400M-16-SigLIP2-384 vision       first images of the seed-4 batch: cosine >= 0.999, max-abs printed
+  C4  DFN5B-CLIP-ViT-H-14-378 text           ctx-77 token strings (seed 5): cosine >= 0.999
+  C5  ViT-gopt-16-SigLIP2-384 vision         counter-based corpus images: cosine >= 0.999
+plus size-independent properties at full batch size: unit norms, batch-composition invariance (the same image gives
+the same embedding whatever its position / micro-batch), device-path == host-path.
+C2 (MobileCLIP2-S2, FastViT) is not supported by the engine yet.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import cosine_rows, random_images, random_texts
+
+pytestmark = pytest.mark.gpu
+COS_BAR = 0.999
+
+
+def _towers(make_model_towers, config, towers):
+    return make_model_towers(config, towers)
+
+
+@pytest.fixture(scope="module")
+def make_big(model_root):
+    import export_synthetic as ex
+
+    cache = {}
+
+    def _make(config, towers):
+        key = (config, towers)
+        if key not in cache:
+            cache[key] = ex.write_model_dir(ex.CONFIGS[config], os.path.join(model_root, f"{config}_{'_'.join(towers)}"),
+                                            seed=0, towers=towers)
+        return cache[key]
+
+    return _make
+
+
+def test_c1_vit_b32_classify(make_big):
+    import clip_embedder_rs_b200 as cb
+    from oracle import reference_forward as R
+
+    mdir = make_big("vit_b32", ("vision", "text"))
+    clip = cb.Clip.from_local_dir(mdir).build()
+    o = R.OracleClip(mdir)
+    img = np.random.default_rng(1).integers(0, 256, size=(224, 224, 3), dtype=np.uint8)
+    labels = random_texts(3, seed=2)
+    want, got = o.classify(img, labels), clip.classify(img, labels)
+    v_w, v_g = o.embed_images([img]), clip.vision.embed_images([img])
+    t_w, t_g = o.embed_texts(labels), clip.text.embed_texts(labels)
+    logits_w = 100.0 * (t_w @ v_w[0])
+    margin = float(np.sort(logits_w)[-1] - np.sort(logits_w)[-2])
+    print(f"\n[C1] oracle {want}\n[C1] engine {got}\n[C1] vision cos {cosine_rows(v_g, v_w).min():.6f} "
+          f"max_abs {np.abs(v_g - v_w).max():.2e}; text cos {cosine_rows(t_g, t_w).min():.6f} "
+          f"max_abs {np.abs(t_g - t_w).max():.2e}; top-1 logit margin {margin:.3f}")
+    assert [l for l, _ in got] == [l for l, _ in want]
+    assert cosine_rows(v_g, v_w).min() >= COS_BAR and cosine_rows(t_g, t_w).min() >= COS_BAR
+    assert np.allclose([p for _, p in got], [p for _, p in want], atol=3e-2)
+
+
+def test_c3_so400m_vision(make_big):
+    import clip_embedder_rs_b200 as cb
+    from oracle import reference_forward as R
+
+    mdir = make_big("so400m_siglip2_384", ("vision",))
+    emb = cb.VisionEmbedder.from_local_dir(mdir).micro_batch(8).build()
+    imgs = random_images(20, 384, seed=4)
+    got = emb.embed_images(imgs)  # 3 micro-batches of 8/8/4: exercises the copy/compute pipeline and the tail
+    o = R.OracleClip(mdir, towers=("vision",))
+    want = o.embed_images(list(imgs[:4]))
+    cos = cosine_rows(got[:4], want)
+    print(f"\n[C3] SO400M vision cos min {cos.min():.6f} max_abs {np.abs(got[:4] - want).max():.2e}")
+    assert cos.min() >= COS_BAR
+    assert np.all(np.abs(np.linalg.norm(got, axis=1) - 1.0) < 1e-3)
+    # batch-composition invariance: same images, different positions and micro-batch boundaries
+    perm = np.random.default_rng(0).permutation(20)
+    got_p = emb.embed_images(imgs[perm])
+    assert np.abs(got_p - got[perm]).max() < 2e-3, "embedding must not depend on batch position"
+    emb2 = cb.VisionEmbedder.from_local_dir(mdir).build()  # default micro-batch (128)
+    assert np.abs(emb2.embed_images(imgs) - got).max() < 2e-3
+
+
+def test_c4_dfn5b_text(make_big):
+    import clip_embedder_rs_b200 as cb
+    from oracle import reference_forward as R
+
+    mdir = make_big("dfn5b_h14_378", ("text",))
+    emb = cb.TextEmbedder.from_local_dir(mdir).build()
+    texts = random_texts(24, seed=5)
+    got = emb.embed_texts(texts)
+    o = R.OracleClip(mdir, towers=("text",))
+    want = o.embed_texts(texts[:8])
+    cos = cosine_rows(got[:8], want)
+    print(f"\n[C4] DFN5B text cos min {cos.min():.6f} max_abs {np.abs(got[:8] - want).max():.2e}")
+    assert cos.min() >= COS_BAR
+    assert np.all(np.abs(np.linalg.norm(got, axis=1) - 1.0) < 1e-3)
+    # causal property: tokens after EOT are padding and must not change the embedding
+    ids, _ = emb.tokenize(texts[:4])
+    ids2 = ids.copy()
+    for r in range(4):
+        eot = int(ids[r].argmax())
+        ids2[r, eot + 1:] = 7  # any id below EOT
+    assert np.abs(emb.embed_ids(ids2) - emb.embed_ids(ids)).max() < 1e-6
+
+
+def test_c5_gopt_vision_sharded_corpus(make_big):
+    import clip_embedder_rs_b200 as cb
+    from clip_embedder_rs_b200 import sharding
+    from oracle import reference_forward as R
+
+    mdir = make_big("gopt_siglip2_384", ("vision",))
+    emb = cb.VisionEmbedder.from_local_dir(mdir).micro_batch(16).build()
+    n = 40  # a slice of the 100k counter-based corpus; every index is reproducible anywhere
+    parts = []
+    for rank in range(2):  # two "ranks" processed back to back on the one GPU: same code path as N GPUs
+        start, rows = sharding.embed_sharded(
+            lambda s, e: emb.embed_images(sharding.counter_images(s, e, 384, seed=9)), n, rank, 2)
+        parts.append((start, rows))
+    full = np.concatenate([p[1] for p in parts])
+    assert parts[1][0] == 20 and full.shape == (n, 1536)
+    whole = emb.embed_images(sharding.counter_images(0, n, 384, seed=9))
+    assert np.abs(whole - full).max() < 2e-3, "sharded == unsharded"
+    o = R.OracleClip(mdir, towers=("vision",))
+    sample = [3, 27]
+    want = o.embed_images(list(sharding.counter_images(0, n, 384, seed=9)[sample]))
+    cos = cosine_rows(full[sample], want)
+    print(f"\n[C5] gopt vision cos min {cos.min():.6f} max_abs {np.abs(full[sample] - want).max():.2e}")
+    assert cos.min() >= COS_BAR
