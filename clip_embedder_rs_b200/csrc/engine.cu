@@ -149,6 +149,31 @@ Status Engine::UploadLinear(const OnnxModel& m, const std::string& wname, const 
   return Status::OK();
 }
 
+Status Engine::UploadHostF32(const float* src, size_t n, float** out) {
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(out), n * 4));
+  CUDA_RET(cudaMemcpy(*out, src, n * 4, cudaMemcpyHostToDevice), "upload fp32 tensor");
+  weight_bytes += static_cast<int64_t>(n) * 4;
+  return Status::OK();
+}
+
+Status Engine::UploadLinearFromHost(const float* w, int N, int K, const float* bias_or_null, LinearW* out) {
+  const int ldk = (K + 7) & ~7;
+  float* staging = nullptr;
+  const size_t fbytes = static_cast<size_t>(N) * K * 4;
+  CUDA_RET(cudaMalloc(&staging, fbytes), "staging alloc");
+  cudaError_t ce = cudaMemcpy(staging, w, fbytes, cudaMemcpyHostToDevice);
+  Status s = Check(ce, "upload weight");
+  if (s.ok()) s = DevAlloc(reinterpret_cast<void**>(&out->w), static_cast<size_t>(N) * ldk * 2);
+  if (s.ok()) s = Check(launch_convert_f32_bf16(staging, N, K, ldk, false, out->w, 0), "convert weight");
+  if (s.ok()) s = Check(cudaDeviceSynchronize(), "convert weight sync");
+  cudaFree(staging);
+  RET_IF_ERR(s);
+  weight_bytes += static_cast<int64_t>(N) * ldk * 2;
+  out->N = N; out->K = K; out->ldk = ldk; out->b = nullptr;
+  if (bias_or_null != nullptr) RET_IF_ERR(UploadHostF32(bias_or_null, N, &out->b));
+  return Status::OK();
+}
+
 Status Engine::LoadBlock(const OnnxModel& m, const std::string& p, bool timm, BlockW* b) {
   const std::string n1 = timm ? ".norm1" : ".ln_1", n2 = timm ? ".norm2" : ".ln_2";
   RET_IF_ERR(UploadF32(m, p + n1 + ".weight", D_, &b->ln1.g));
@@ -176,6 +201,7 @@ static int meta_int(const OnnxModel& m, const char* key, int dflt) {
 
 Status Engine::LoadVision(const OnnxModel& m) {
   kind = CLIPB200_KIND_VISION;
+  if (m.has("model.visual.trunk.stem.0.reparam_conv.weight")) return LoadFastVit(m);
   const bool timm = m.has("model.visual.trunk.patch_embed.proj.weight");
   const bool clip = m.has("model.visual.conv1.weight");
   if (!timm && !clip)
@@ -334,7 +360,7 @@ Status Engine::LoadText(const OnnxModel& m) {
 }
 
 Status Engine::AllocWorkspace() {
-  const size_t rows = static_cast<size_t>(mb_) * T_;
+  const size_t rows = fastvit_ ? 1 : static_cast<size_t>(mb_) * T_;  // FastViT sizes its own buffers below
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&x_), rows * D_ * 4));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&h_), rows * D_ * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&qkv_), rows * 3 * D_ * 2));
@@ -344,7 +370,9 @@ Status Engine::AllocWorkspace() {
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&row_map_), static_cast<size_t>(mb_) * 4));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&err_flag_), 4));
   CUDA_RET(cudaMemset(err_flag_, 0, 4), "memset");
-  if (kind == CLIPB200_KIND_VISION) {
+  if (kind == CLIPB200_KIND_VISION && fastvit_) {
+    in_slot_bytes_ = static_cast<size_t>(mb_) * S_ * S_ * 3;
+  } else if (kind == CLIPB200_KIND_VISION) {
     RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&patches_), static_cast<size_t>(mb_) * Tp_ * Kp_ * 2));
     if (pool_map_) {
       RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&y_), static_cast<size_t>(mb_) * D_ * 4));
@@ -367,6 +395,7 @@ Status Engine::AllocWorkspace() {
     CUDA_RET(cudaEventCreateWithFlags(&out_copied_[i], cudaEventDisableTiming), "event");
   }
   for (int i = 0; i < 16; ++i) CUDA_RET(cudaEventCreate(&user_events_[i]), "event");
+  if (fastvit_) RET_IF_ERR(AllocFastVitWorkspace());
   return Status::OK();
 }
 
@@ -408,14 +437,15 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
   if (tower == "text") is_text = true;
   if (is_text) RET_IF_ERR(LoadText(m));
   else RET_IF_ERR(LoadVision(m));
-  if (hd_ != 32 && hd_ != 64 && hd_ != 72 && hd_ != 80 && hd_ != 96 && hd_ != 128)
+  if (!fastvit_ && hd_ != 32 && hd_ != 64 && hd_ != 72 && hd_ != 80 && hd_ != 96 && hd_ != 128)
     return Status::Err(CLIPB200_ERR_UNSUPPORTED, "head_dim " + std::to_string(hd_) + " not supported");
-  if ((D_ & 7) || (mlp_ & 7) || (E_ & 7) || D_ > 2048)
+  if (!fastvit_ && ((D_ & 7) || (mlp_ & 7) || (E_ & 7) || D_ > 2048))
     return Status::Err(CLIPB200_ERR_UNSUPPORTED, "width / mlp / embed_dim must be multiples of 8 and width <= 2048");
 
   profile_ = opts != nullptr && opts->profile != 0;
   mb_ = opts != nullptr ? opts->micro_batch : 0;
   if (const char* env = getenv("CLIPB200_MICRO_BATCH")) if (mb_ <= 0) mb_ = atoi(env);
+  if (mb_ <= 0 && fastvit_) mb_ = 64;
   if (mb_ <= 0) {
     mb_ = 73728 / T_;  // ~72k token rows per step keeps every GEMM at >= 20 waves of 128-row tiles
     if (mb_ > 1024) mb_ = 1024;
@@ -589,6 +619,7 @@ Status Engine::SetPreproc(const clipb200_preproc* pp) {
 }
 
 Status Engine::ForwardVision(int n, const uint8_t* d_u8, const float* d_f32, float* d_out) {
+  if (fastvit_) return ForwardFastVit(n, d_u8, d_f32, d_out);
   const int rows = n * T_;
   ProfBegin(PC_PRE, compute_);
   cudaError_t e = d_u8 != nullptr ? launch_preprocess_patches_u8(d_u8, n, S_, P_, Kp_, lut_, patches_, compute_)

@@ -80,6 +80,46 @@ class Engine {
   Status UploadLinear(const OnnxModel& m, const std::string& wname, const std::string& bname, int N, int K,
                       bool transpose, LinearW* out);
   Status HostF32(const OnnxModel& m, const std::string& name, int64_t expect_numel, std::vector<float>* out);
+  Status UploadLinearFromHost(const float* w, int N, int K, const float* bias_or_null, LinearW* out);
+  Status UploadHostF32(const float* src, size_t n, float** out);
+
+  // ---- FastViT / MobileCLIP2 hybrid trunk (engine_fastvit.cu) ----
+  struct ConvW {  // depthwise / stem conv, weight rearranged to [taps][Cout]
+    float* w = nullptr;
+    float* b = nullptr;
+    int cout = 0, k = 0;
+  };
+  struct SeW {
+    float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+    int C = 0, R = 0;
+  };
+  struct FvBlock {
+    bool attn = false;
+    ConvW mixer, mlp_dw;
+    LinearW fc1, fc2, qkv, proj;
+    float *gamma = nullptr, *gamma1 = nullptr, *gamma2 = nullptr;
+  };
+  struct FvStage {
+    int C = 0;
+    bool down = false, down_se = false, cpe = false;
+    ConvW down_dw, cpe_dw;
+    SeW se;
+    LinearW down_pw;
+    std::vector<FvBlock> blocks;
+  };
+  Status LoadFastVit(const OnnxModel& m);
+  Status AllocFastVitWorkspace();
+  Status ForwardFastVit(int n, const uint8_t* d_u8, const float* d_f32, float* d_out);
+  Status UploadConv(const OnnxModel& m, const std::string& name, int cout, int cin_g, int k, ConvW* out);
+  Status UploadSe(const OnnxModel& m, const std::string& name, int C, SeW* out);
+  Status FvMlp(const FvBlock& b, float* cur, int n, int Hh, int C, const float* gamma);
+  bool fastvit_ = false;
+  ConvW fv_stem0_, fv_stem1_, fv_final_;
+  LinearW fv_stem2_;
+  SeW fv_final_se_;
+  std::vector<FvStage> fv_stages_;
+  float *fv_xa_ = nullptr, *fv_xb_ = nullptr, *fv_tmp_ = nullptr, *fv_s_ = nullptr, *fv_gate_ = nullptr;
+  __nv_bfloat16* fv_stem_out_ = nullptr;
   Status DevAlloc(void** p, size_t bytes);
   Status SetPreproc(const clipb200_preproc* pp);
 

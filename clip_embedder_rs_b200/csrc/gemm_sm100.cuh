@@ -327,6 +327,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const int grow = row_base + rl;
             float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((colq ^ (rl & 7)) << 4));
             a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+            if (ep.act != ACT_NONE) {  // 1x1 convolutions of the FastViT trunk that write the fp32 stream directly
+              a.x = apply_act_fast(a.x, ep.act); a.y = apply_act_fast(a.y, ep.act);
+              a.z = apply_act_fast(a.z, ep.act); a.w = apply_act_fast(a.w, ep.act);
+            }
             if (grow < M && col_ok) {
               long long out_row = grow;
               int pos_row = 0;

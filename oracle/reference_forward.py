@@ -200,11 +200,78 @@ def vision_forward(t: Tower, pixel_values: np.ndarray, normalize: bool = True) -
         h = _act(F.linear(h, w[f"{ap}.mlp.fc1.weight"], w[f"{ap}.mlp.fc1.bias"]), act)
         o = o + F.linear(h, w[f"{ap}.mlp.fc2.weight"], w[f"{ap}.mlp.fc2.bias"])
         out = o[:, 0]
+    elif fam == "fastvit":
+        out = _fastvit_forward(t, x)
     else:
         raise ValueError(fam)
     if normalize:
         out = F.normalize(out, dim=-1)
     return out.to(torch.float32).numpy()
+
+
+def _fastvit_forward(t: Tower, x: torch.Tensor) -> torch.Tensor:
+    """timm FastViT (fastvit_mci2 for MobileCLIP2-S2) after `reparameterize_model` (pull_onnx.py:110-116) with eval
+    BatchNorm folded: stem (3x3 s2, dw3x3 s2, 1x1) -> 4 stages (RepMixer blocks; last stage: conditional positional
+    encoding + attention blocks) with 7x7 s2 depthwise + 1x1 downsampling -> dw3x3 expansion + SE -> GAP -> Linear.
+    SURVEY.md Appendix A ("C2 MobileCLIP2-S2"); architecture is upstream recall, see DESIGN.md."""
+    w = t.w
+    pre = "model.visual.trunk"
+    dims = [int(v) for v in t.meta["dims"].split(",")]
+    depths = [int(v) for v in t.meta["depths"].split(",")]
+    se_down = [bool(int(v)) for v in t.meta["se_down"].split(",")]
+
+    def conv(name, x, stride=1, groups=1):
+        wt = w[f"{name}.weight"]
+        return F.conv2d(x, wt, w[f"{name}.bias"], stride=stride, padding=wt.shape[-1] // 2, groups=groups)
+
+    def se(name, x):
+        s = x.mean((2, 3), keepdim=True)
+        s = F.relu(conv(f"{name}.fc1", s))
+        return x * torch.sigmoid(conv(f"{name}.fc2", s))
+
+    def mlp(name, x):
+        c = x.shape[1]
+        h = conv(f"{name}.conv.conv", x, groups=c)
+        h = F.gelu(conv(f"{name}.fc1", h))
+        return conv(f"{name}.fc2", h)
+
+    d0 = dims[0]
+    x = F.gelu(conv(f"{pre}.stem.0.reparam_conv", x, stride=2))
+    x = F.gelu(conv(f"{pre}.stem.1.reparam_conv", x, stride=2, groups=d0))
+    x = F.gelu(conv(f"{pre}.stem.2.reparam_conv", x))
+    prev = d0
+    for i, (c, depth) in enumerate(zip(dims, depths)):
+        st = f"{pre}.stages.{i}"
+        if i > 0:
+            x = conv(f"{st}.downsample.proj.0.reparam_conv", x, stride=2, groups=prev)
+            if se_down[i]:
+                x = se(f"{st}.downsample.proj.0.se", x)
+            x = F.gelu(x)
+            x = F.gelu(conv(f"{st}.downsample.proj.1.reparam_conv", x))
+        last = i == len(dims) - 1
+        if last:
+            x = conv(f"{st}.pos_emb.reparam_conv", x, groups=c)  # RepCPE, identity branch folded in
+        for j in range(depth):
+            b = f"{st}.blocks.{j}"
+            if not last:
+                x = conv(f"{b}.token_mixer.reparam_conv", x, groups=c)  # RepMixer, re-parameterised
+                x = x + w[f"{b}.layer_scale.gamma"] * mlp(f"{b}.mlp", x)
+            else:
+                B, C, H, W = x.shape
+                h = F.batch_norm(x, w[f"{b}.norm.running_mean"], w[f"{b}.norm.running_var"], w[f"{b}.norm.weight"],
+                                 w[f"{b}.norm.bias"], False, 0.0, 1e-5)
+                tok = h.flatten(2).transpose(1, 2)  # [B, N, C]
+                heads = C // 32
+                a = _mha(tok, w[f"{b}.token_mixer.qkv.weight"], None, w[f"{b}.token_mixer.proj.weight"],
+                         w[f"{b}.token_mixer.proj.bias"], heads, None)
+                a = a.transpose(1, 2).reshape(B, C, H, W)
+                x = x + w[f"{b}.layer_scale_1.gamma"] * a
+                x = x + w[f"{b}.layer_scale_2.gamma"] * mlp(f"{b}.mlp", x)
+        prev = c
+    x = conv(f"{pre}.final_conv.reparam_conv", x, groups=prev)
+    x = F.gelu(se(f"{pre}.final_conv.se", x))
+    x = x.mean((2, 3))
+    return F.linear(x, w[f"{pre}.head.fc.weight"], w[f"{pre}.head.fc.bias"])
 
 
 @torch.no_grad()

