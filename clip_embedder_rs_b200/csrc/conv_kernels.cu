@@ -123,18 +123,28 @@ dwconv_kernel(const Tin* __restrict__ in, int H, int W, int Cin, const float* __
   const float bv = __ldg(bias + oc);
   const int oy = ty0 + row;
   if (oy >= Ho) return;
+  // sliding window in registers: one staged input row (IT values) serves all TILE outputs of this thread's output
+  // row, so shared-memory loads per output drop from K*K to K*IT/TILE
+  float acc[TILE];
+#pragma unroll
+  for (int x = 0; x < TILE; ++x) acc[x] = bv;
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    float rv[IT];
+#pragma unroll
+    for (int i = 0; i < IT; ++i) rv[i] = dw_smem[((row * STRIDE + ky) * IT + i) * CI + cl];
+#pragma unroll
+    for (int x = 0; x < TILE; ++x)
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) acc[x] = fmaf(rv[x * STRIDE + kx], wk[ky * K + kx], acc[x]);
+  }
 #pragma unroll
   for (int x = 0; x < TILE; ++x) {
     const int ox = tx0 + x;
-    if (ox >= Wo) break;
-    float acc = bv;
-#pragma unroll
-    for (int ky = 0; ky < K; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < K; ++kx)
-        acc = fmaf(dw_smem[((row * STRIDE + ky) * IT + x * STRIDE + kx) * CI + cl], wk[ky * K + kx], acc);
-    if (GELU) acc = gelu_erf(acc);
-    st_from_float(out + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * Cout + oc, acc);
+    if (ox < Wo) {
+      const float v = GELU ? gelu_erf(acc[x]) : acc[x];
+      st_from_float(out + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * Cout + oc, v);
+    }
   }
 }
 
