@@ -192,7 +192,7 @@ def run_reference_arm(args, wl, rank, world):
             rates.append(r)
     value = statistics.mean(rates)
     line = {
-        "impl": "reference", "metric": f"SigLIP2-SO400M-384 {unit}" if "so400m" in args.workload else f"{args.workload} {unit}",
+        "impl": "reference", "metric": "SigLIP2-SO400M-384 images/sec" if args.workload == "so400m_vision" else f"{args.workload} {unit}",
         "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sample / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",

@@ -50,6 +50,9 @@ SIGNATURES = {
     "clipb200_vision_embed_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "clipb200_vision_embed_rgb8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                              C.POINTER(Preproc), C.c_void_p]),
+    "clipb200_vision_embed_rgb8_var": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                                 C.POINTER(Preproc), C.c_void_p]),
+    "clipb200_resize_rgb8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Preproc), C.c_void_p]),
     "clipb200_preprocess_rgb8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                            C.POINTER(Preproc), C.c_void_p]),
     "clipb200_text_embed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),

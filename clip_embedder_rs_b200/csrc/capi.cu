@@ -149,6 +149,22 @@ int clipb200_preprocess_rgb8(clipb200_engine* e, const uint8_t* hwc, int64_t bat
   API_GUARD_END
 }
 
+int clipb200_vision_embed_rgb8_var(clipb200_engine* e, const uint8_t* const* images, const int32_t* widths,
+                                   const int32_t* heights, int64_t batch, const clipb200_preproc* pp, float* out) {
+  API_GUARD_BEGIN
+  if (e == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null engine");
+  return done(e->impl->VisionEmbedRgb8Var(images, widths, heights, batch, pp, out));
+  API_GUARD_END
+}
+
+int clipb200_resize_rgb8(clipb200_engine* e, const uint8_t* image, int32_t width, int32_t height,
+                         const clipb200_preproc* pp, uint8_t* out) {
+  API_GUARD_BEGIN
+  if (e == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null engine");
+  return done(e->impl->ResizeRgb8(image, width, height, pp, out));
+  API_GUARD_END
+}
+
 int clipb200_vision_embed_rgb8_device(clipb200_engine* e, const uint8_t* d_hwc, int64_t batch,
                                       const clipb200_preproc* pp, float* d_out) {
   API_GUARD_BEGIN

@@ -474,6 +474,8 @@ Engine::~Engine() {
   for (auto& p : prof_pending_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto& e : prof_free_) cudaEventDestroy(e);
   if (l2_flush_) cudaFree(l2_flush_);
+  if (rs_src_) cudaFree(rs_src_);
+  if (rs_tmp_) cudaFree(rs_tmp_);
   if (compute_) cudaStreamDestroy(compute_);
   if (copy_in_) cudaStreamDestroy(copy_in_);
   if (copy_out_) cudaStreamDestroy(copy_out_);
@@ -864,6 +866,114 @@ Status Engine::PreprocessRgb8(const uint8_t* hwc, int64_t batch, int width, int 
   cudaFree(d_u8);
   cudaFree(d_f);
   return Check(e, "preprocess");
+}
+
+Status Engine::GetResizePlan(int width, int height, int interpolation, bool squash, const ResizePlanDev** plan) {
+  const auto key = std::make_tuple(width, height, interpolation, squash ? 1 : 0);
+  auto it = resize_plans_.find(key);
+  if (it != resize_plans_.end()) {
+    *plan = &it->second;
+    return Status::OK();
+  }
+  double left, top, cw, ch;
+  resize_crop_box(width, height, S_, squash, &left, &top, &cw, &ch);
+  ResizePlanDev p;
+  p.left = left; p.top = top; p.sx = cw / S_; p.sy = ch / S_;
+  if (interpolation > 1) {
+    p.nearest = true;  // ResizeAlg::Nearest (vision.rs:179)
+  } else {
+    ResizeAxis ax = make_resize_axis(width, left, left + cw, S_, interpolation);
+    ResizeAxis ay = make_resize_axis(height, top, top + ch, S_, interpolation);
+    int y_first = height, y_last = 0;
+    for (int o = 0; o < S_; ++o) {
+      y_first = std::min(y_first, ay.start[o]);
+      y_last = std::max(y_last, ay.start[o] + ay.size[o]);
+    }
+    p.y_first = y_first;
+    p.rows = y_last - y_first;
+    p.xwindow = ax.window; p.ywindow = ay.window; p.xprecision = ax.precision; p.yprecision = ay.precision;
+    auto up_i = [&](const std::vector<int32_t>& v, int** d) -> Status {
+      RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(d), v.size() * 4));
+      return Check(cudaMemcpy(*d, v.data(), v.size() * 4, cudaMemcpyHostToDevice), "upload resize plan");
+    };
+    auto up_w = [&](const std::vector<int16_t>& v, int16_t** d) -> Status {
+      RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(d), v.size() * 2));
+      return Check(cudaMemcpy(*d, v.data(), v.size() * 2, cudaMemcpyHostToDevice), "upload resize plan");
+    };
+    RET_IF_ERR(up_i(ax.start, &p.xstart)); RET_IF_ERR(up_i(ax.size, &p.xsize)); RET_IF_ERR(up_w(ax.w, &p.xw));
+    RET_IF_ERR(up_i(ay.start, &p.ystart)); RET_IF_ERR(up_i(ay.size, &p.ysize)); RET_IF_ERR(up_w(ay.w, &p.yw));
+  }
+  auto ins = resize_plans_.emplace(key, p);
+  *plan = &ins.first->second;
+  return Status::OK();
+}
+
+// host image -> (upload) -> resized S x S RGB8 at d_dst, on the compute stream
+Status Engine::ResizeToDevice(const uint8_t* h_img, int width, int height, const clipb200_preproc* pp, uint8_t* d_dst) {
+  if (width <= 0 || height <= 0 || width > 32768 || height > 32768)
+    return Status::Err(CLIPB200_ERR_INVALID_ARG, "bad image size");
+  const size_t src_bytes = static_cast<size_t>(width) * height * 3;
+  if (width == S_ && height == S_) {  // the convolution is the identity at the model resolution
+    return Check(cudaMemcpyAsync(d_dst, h_img, src_bytes, cudaMemcpyHostToDevice, compute_), "H2D copy");
+  }
+  const ResizePlanDev* plan = nullptr;
+  RET_IF_ERR(GetResizePlan(width, height, pp->interpolation, pp->resize_mode == 1, &plan));
+  if (src_bytes > rs_src_bytes_) {
+    CUDA_RET(cudaStreamSynchronize(compute_), "sync");
+    if (rs_src_) cudaFree(rs_src_);
+    rs_src_ = nullptr;
+    CUDA_RET(cudaMalloc(reinterpret_cast<void**>(&rs_src_), src_bytes), "resize source buffer");
+    rs_src_bytes_ = src_bytes;
+  }
+  const size_t tmp_bytes = static_cast<size_t>(std::max(plan->rows, 1)) * S_ * 3;
+  if (tmp_bytes > rs_tmp_bytes_) {
+    CUDA_RET(cudaStreamSynchronize(compute_), "sync");
+    if (rs_tmp_) cudaFree(rs_tmp_);
+    rs_tmp_ = nullptr;
+    CUDA_RET(cudaMalloc(reinterpret_cast<void**>(&rs_tmp_), tmp_bytes), "resize temp buffer");
+    rs_tmp_bytes_ = tmp_bytes;
+  }
+  CUDA_RET(cudaMemcpyAsync(rs_src_, h_img, src_bytes, cudaMemcpyHostToDevice, compute_), "H2D copy");
+  ProfBegin(PC_PRE, compute_);
+  cudaError_t e = launch_resize(rs_src_, width, height, S_, *plan, rs_tmp_, d_dst, compute_);
+  ProfEnd(PC_PRE, compute_);
+  return Check(e, "resize");
+}
+
+Status Engine::ResizeRgb8(const uint8_t* img, int width, int height, const clipb200_preproc* pp, uint8_t* out) {
+  if (kind != CLIPB200_KIND_VISION) return Status::Err(CLIPB200_ERR_INVALID_ARG, "not a vision engine");
+  if (img == nullptr || out == nullptr || pp == nullptr) return Status::Err(CLIPB200_ERR_INVALID_ARG, "null buffer");
+  CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
+  uint8_t* dst = static_cast<uint8_t*>(d_in_[0]);
+  RET_IF_ERR(ResizeToDevice(img, width, height, pp, dst));
+  CUDA_RET(cudaMemcpyAsync(out, dst, static_cast<size_t>(S_) * S_ * 3, cudaMemcpyDeviceToHost, compute_), "D2H copy");
+  CUDA_RET(cudaStreamSynchronize(compute_), "sync");
+  return Status::OK();
+}
+
+Status Engine::VisionEmbedRgb8Var(const uint8_t* const* imgs, const int32_t* widths, const int32_t* heights, int64_t batch,
+                                  const clipb200_preproc* pp, float* out) {
+  if (kind != CLIPB200_KIND_VISION) return Status::Err(CLIPB200_ERR_INVALID_ARG, "not a vision engine");
+  if (batch <= 0) return Status::Err(CLIPB200_ERR_INVALID_ARG, "Empty batch");
+  if (imgs == nullptr || widths == nullptr || heights == nullptr || out == nullptr)
+    return Status::Err(CLIPB200_ERR_INVALID_ARG, "null buffer");
+  CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
+  RET_IF_ERR(SetPreproc(pp));
+  const size_t px = static_cast<size_t>(S_) * S_ * 3;
+  for (int64_t s = 0; s * mb_ < batch; ++s) {
+    const int n = static_cast<int>(std::min<int64_t>(mb_, batch - s * mb_));
+    uint8_t* slot = static_cast<uint8_t*>(d_in_[0]);
+    for (int i = 0; i < n; ++i) {
+      const int64_t g = s * mb_ + i;
+      if (imgs[g] == nullptr) return Status::Err(CLIPB200_ERR_INVALID_ARG, "null image pointer");
+      RET_IF_ERR(ResizeToDevice(imgs[g], widths[g], heights[g], pp, slot + static_cast<size_t>(i) * px));
+    }
+    RET_IF_ERR(ForwardVision(n, slot, nullptr, d_out_[0]));
+    CUDA_RET(cudaMemcpyAsync(out + static_cast<size_t>(s) * mb_ * E_, d_out_[0], static_cast<size_t>(n) * E_ * 4,
+                             cudaMemcpyDeviceToHost, compute_), "D2H copy");
+    CUDA_RET(cudaStreamSynchronize(compute_), "sync");
+  }
+  return Status::OK();
 }
 
 Status Engine::VisionEmbedF32(const float* nchw, int64_t batch, float* out) {

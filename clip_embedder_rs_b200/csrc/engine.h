@@ -11,7 +11,11 @@
 #include <vector>
 
 #include "../../include/clipb200.h"
+#include <map>
+#include <tuple>
+
 #include "onnx_loader.h"
+#include "resize.cuh"
 
 namespace clipb200 {
 
@@ -55,6 +59,10 @@ class Engine {
   Status PreprocessRgb8(const uint8_t* hwc, int64_t batch, int width, int height, const clipb200_preproc* pp,
                         float* out_nchw);
   Status TextEmbed(const int64_t* ids, int64_t batch, int64_t ctx, float* out, bool device_buffers);
+  // arbitrary-size RGB8 images: GPU resize (vision.rs:164-198) -> normalise -> tower
+  Status VisionEmbedRgb8Var(const uint8_t* const* imgs, const int32_t* widths, const int32_t* heights, int64_t batch,
+                            const clipb200_preproc* pp, float* out);
+  Status ResizeRgb8(const uint8_t* img, int width, int height, const clipb200_preproc* pp, uint8_t* out);
 
   Status RecordEvent(int slot);
   Status ElapsedMs(int a, int b, double* ms);
@@ -113,6 +121,12 @@ class Engine {
   Status UploadConv(const OnnxModel& m, const std::string& name, int cout, int cin_g, int k, ConvW* out);
   Status UploadSe(const OnnxModel& m, const std::string& name, int C, SeW* out);
   Status FvMlp(const FvBlock& b, float* cur, int n, int Hh, int C, const float* gamma);
+  // resize plans (coefficient tables) cached per (width, height, interpolation, squash)
+  Status GetResizePlan(int width, int height, int interpolation, bool squash, const ResizePlanDev** plan);
+  Status ResizeToDevice(const uint8_t* h_img, int width, int height, const clipb200_preproc* pp, uint8_t* d_dst);
+  std::map<std::tuple<int, int, int, int>, ResizePlanDev> resize_plans_;
+  uint8_t *rs_src_ = nullptr, *rs_tmp_ = nullptr;
+  size_t rs_src_bytes_ = 0, rs_tmp_bytes_ = 0;
   bool fastvit_ = false;
   ConvW fv_stem0_, fv_stem1_, fv_final_;
   LinearW fv_stem2_;

@@ -5,6 +5,7 @@ for `image::DynamicImage`.  `embed_images` hands the packed RGB8 batch to the en
 (vision.rs:235-259) and runs the tower; nothing is computed on the CPU."""
 from __future__ import annotations
 
+import ctypes as C
 import os
 from pathlib import Path
 from typing import Optional, Sequence
@@ -128,32 +129,57 @@ class VisionEmbedder:
         return type(self)._load(self.model_dir, self.session.execution_providers, **self._kw)
 
     # ---------------------------------------------------------------------------------------------- hot path
-    def _pack(self, images: Sequence) -> np.ndarray:
+    def _rgb_list(self, images: Sequence):
         if len(images) == 0:
             raise error.Inference("Empty batch")  # vision.rs:121-123
-        size = self.config.model_cfg.vision_cfg.image_size
         if isinstance(images, np.ndarray) and images.ndim == 4:
-            arrs = images
-            if arrs.dtype != np.uint8 or arrs.shape[3] != 3:
-                raise error.Image(f"Image error: expected uint8 [B,H,W,3], got {arrs.dtype} {arrs.shape}")
-        else:
-            arrs = [_to_rgb8(im) for im in images]
-        for a in arrs:
-            if a.shape[0] != size or a.shape[1] != size:
-                raise error.Resize(f"Resize error: image is {a.shape[1]}x{a.shape[0]}, engine needs {size}x{size} "
-                                   f"(GPU resize, SURVEY 8f.1, is not implemented yet)")
-        return np.ascontiguousarray(arrs if isinstance(arrs, np.ndarray) else np.stack(arrs, axis=0))
+            if images.dtype != np.uint8 or images.shape[3] != 3:
+                raise error.Image(f"Image error: expected uint8 [B,H,W,3], got {images.dtype} {images.shape}")
+            return images
+        return [np.ascontiguousarray(_to_rgb8(im)) for im in images]
+
+    def _pack(self, images: Sequence):
+        """Returns a packed [B,S,S,3] array when every image is already at the model resolution, else None."""
+        size = self.config.model_cfg.vision_cfg.image_size
+        arrs = self._rgb_list(images)
+        if all(a.shape[0] == size and a.shape[1] == size for a in arrs):
+            return np.ascontiguousarray(arrs if isinstance(arrs, np.ndarray) else np.stack(arrs, axis=0)), arrs
+        return None, arrs
+
+    @staticmethod
+    def _pointer_arrays(arrs):
+        n = len(arrs)
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        ws = np.asarray([a.shape[1] for a in arrs], dtype=np.int32)
+        hs = np.asarray([a.shape[0] for a in arrs], dtype=np.int32)
+        return ptrs, ws, hs
 
     def embed_image(self, image) -> np.ndarray:  # vision.rs:94-98
         return self.embed_images([image]).reshape(-1)
 
     def embed_images(self, images: Sequence) -> np.ndarray:  # vision.rs:102-117
-        batch = self._pack(images)
-        n, size = batch.shape[0], batch.shape[1]
+        batch, arrs = self._pack(images)
+        n = len(arrs)
         out = np.empty((n, self.session.embed_dim), dtype=np.float32)
         with self.session._lock:
-            self.session.check(_native.lib.clipb200_vision_embed_rgb8(
-                self.session.handle, batch.ctypes.data, n, size, size, self._pp, out.ctypes.data))
+            if batch is not None:
+                size = batch.shape[1]
+                self.session.check(_native.lib.clipb200_vision_embed_rgb8(
+                    self.session.handle, batch.ctypes.data, n, size, size, self._pp, out.ctypes.data))
+            else:  # arbitrary sizes: resize (vision.rs:164-198) on the GPU
+                ptrs, ws, hs = self._pointer_arrays(arrs)
+                self.session.check(_native.lib.clipb200_vision_embed_rgb8_var(
+                    self.session.handle, ptrs, ws.ctypes.data, hs.ctypes.data, n, self._pp, out.ctypes.data))
+        return out
+
+    def resize(self, image) -> np.ndarray:
+        """`resize_with_fast_image_resize` (vision.rs:164-198): any size in, [S,S,3] uint8 out (computed on the GPU)."""
+        a = np.ascontiguousarray(_to_rgb8(image))
+        size = self.config.model_cfg.vision_cfg.image_size
+        out = np.empty((size, size, 3), dtype=np.uint8)
+        with self.session._lock:
+            self.session.check(_native.lib.clipb200_resize_rgb8(self.session.handle, a.ctypes.data, a.shape[1], a.shape[0],
+                                                               self._pp, out.ctypes.data))
         return out
 
     def embed_pixel_values(self, pixel_values: np.ndarray) -> np.ndarray:
@@ -171,7 +197,9 @@ class VisionEmbedder:
         return out
 
     def preprocess_batch(self, images: Sequence) -> np.ndarray:  # vision.rs:120-135
-        batch = self._pack(images)
+        batch, arrs = self._pack(images)
+        if batch is None:
+            batch = np.stack([self.resize(a) for a in arrs], axis=0)
         n, size = batch.shape[0], batch.shape[1]
         out = np.empty((n, 3, size, size), dtype=np.float32)
         with self.session._lock:

@@ -97,9 +97,17 @@ int64_t clipb200_engine_weight_bytes(const clipb200_engine* e);    /* HBM held b
 /* ORT-equivalent: pixel_values f32 [B,3,S,S] -> out f32 [B,D] (rows L2-normalised). src/vision.rs:105-113 */
 int clipb200_vision_embed_f32(clipb200_engine* e, const float* nchw, int64_t batch, float* out);
 /* Fast path: packed RGB8 HWC images already at the model resolution, [B,S,S,3]; normalisation
- * (src/vision.rs:235-259) runs on the GPU.  Other sizes: CLIPB200_ERR_UNSUPPORTED (GPU resize is SURVEY 8f.1). */
+ * (src/vision.rs:235-259) runs on the GPU.  Other sizes: use clipb200_vision_embed_rgb8_var. */
 int clipb200_vision_embed_rgb8(clipb200_engine* e, const uint8_t* hwc, int64_t batch, int32_t width, int32_t height,
                                const clipb200_preproc* pp, float* out);
+/* Images of arbitrary size (one pointer / width / height per image, packed RGB8 HWC): the resize of
+ * `resize_with_fast_image_resize` (src/vision.rs:164-198: antialiased CatmullRom / bilinear convolution or nearest,
+ * f64 centre-crop box unless resize_mode is squash) runs on the GPU, then normalise + tower as above. */
+int clipb200_vision_embed_rgb8_var(clipb200_engine* e, const uint8_t* const* images, const int32_t* widths,
+                                   const int32_t* heights, int64_t batch, const clipb200_preproc* pp, float* out);
+/* Only the resize: one image in, S x S x 3 RGB8 out (what src/vision.rs:197 returns). */
+int clipb200_resize_rgb8(clipb200_engine* e, const uint8_t* image, int32_t width, int32_t height,
+                         const clipb200_preproc* pp, uint8_t* out);
 /* The reference's public `preprocess_batch` (src/vision.rs:120-135): same inputs, out f32 [B,3,S,S]; bit-exact. */
 int clipb200_preprocess_rgb8(clipb200_engine* e, const uint8_t* hwc, int64_t batch, int32_t width, int32_t height,
                              const clipb200_preproc* pp, float* out_nchw);

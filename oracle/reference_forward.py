@@ -52,15 +52,18 @@ def normalize_pixels(pixels_hwc_u8: np.ndarray, mean: Sequence[float], std: Sequ
     return out
 
 
-def preprocess_batch(images_hwc_u8: Sequence[np.ndarray], image_size: int, mean, std) -> np.ndarray:
-    """vision.rs:120-135 for images that are already image_size x image_size (resize == identity, see header).
-    Empty batch -> error, as vision.rs:121-123."""
+def preprocess_batch(images_hwc_u8: Sequence[np.ndarray], image_size: int, mean, std,
+                     interpolation: str = "bicubic", resize_mode: str = "shortest") -> np.ndarray:
+    """vision.rs:120-135: resize (oracle/resize.py restates vision.rs:164-198; the identity for images that are already
+    image_size x image_size) then normalise.  Empty batch -> error, as vision.rs:121-123."""
     if len(images_hwc_u8) == 0:
         raise ValueError("Empty batch")
     out = np.zeros((len(images_hwc_u8), 3, image_size, image_size), dtype=np.float32)
     for i, im in enumerate(images_hwc_u8):
         if im.shape[0] != image_size or im.shape[1] != image_size:
-            raise NotImplementedError("oracle resize only covers at-resolution inputs (SURVEY 8f rank 1 is next)")
+            from oracle import resize as _resize
+
+            im = _resize.resize_rgb8(im, image_size, interpolation, resize_mode)
         out[i] = normalize_pixels(im, mean, std)
     return out
 
@@ -372,7 +375,9 @@ class OracleClip:
     def embed_images(self, images: Sequence[np.ndarray]) -> np.ndarray:
         pc = self.config["preprocess_cfg"]
         size = int(self.config["model_cfg"]["vision_cfg"]["image_size"])
-        return vision_forward(self.vision, preprocess_batch(images, size, pc["mean"], pc["std"]))
+        return vision_forward(self.vision, preprocess_batch(images, size, pc["mean"], pc["std"],
+                                                            pc.get("interpolation", "bicubic"),
+                                                            pc.get("resize_mode", "shortest")))
 
     def embed_texts(self, texts: Sequence[str]) -> np.ndarray:
         ids, _ = tokenize(self.model_dir, texts)
