@@ -92,9 +92,12 @@ constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;         // warp 0 TMA, wa
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 constexpr int GEMM_EPI_STAGE_BYTES = 32 * 128;                 // per epilogue warp: 32 rows x 128 B, 128B-swizzled
 
-template <int BN>
+// NCTA = 1: one CTA per 128 x BN tile.  NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile;
+// each CTA stages its own 128 rows of A and HALF of the W tile, so the shared-memory traffic per MMA (TMA fill +
+// operand read) drops from 1.5x to 1.0x of the 128 B/clk shared-memory bandwidth.
+template <int BN, int NCTA = 1>
 struct GemmCfg {
-  static constexpr int B_STAGE_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_STAGE_BYTES = (BN / NCTA) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = GEMM_A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int EPI_BYTES = GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES;  // 32 KB
   static constexpr int BAR_BYTES = 256;
@@ -103,11 +106,15 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int NCTA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                          const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, GemmEpilogue ep) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, NCTA>;
+  constexpr int TILE_M = GEMM_BM * NCTA;
+  const int rank = NCTA == 2 ? static_cast<int>(ptx::cluster_ctarank()) : 0;      // CTA within the pair
+  const int first_tile = NCTA == 2 ? static_cast<int>(ptx::cluster_id_x()) : static_cast<int>(blockIdx.x);
+  const int tile_step = NCTA == 2 ? static_cast<int>(ptx::cluster_count_x()) : static_cast<int>(gridDim.x);
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -124,7 +131,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int m_tiles = (M + TILE_M - 1) / TILE_M;
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
@@ -139,13 +146,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 32 * GEMM_EPI_WARPS);
+      ptx::mbar_init(&tmem_empty_bar[a], NCTA * GEMM_EPI_WARPS);  // one arrival per epilogue warp (of both CTAs)
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc<512>(tmem_base_ptr);
+  if (warp == 1) {
+    if (NCTA == 2) ptx::tmem_alloc_2sm<512>(tmem_base_ptr);
+    else ptx::tmem_alloc<512>(tmem_base_ptr);
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) ptx::cluster_sync();  // the peer's barriers must be initialised before anything arrives remotely
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_ptr;
 
@@ -154,28 +165,41 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          ptx::tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * GEMM_A_STAGE_BYTES, kb * GEMM_BK,
-                           m_blk * GEMM_BM);
-          ptx::tma_load_2d(&tmap_w, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, kb * GEMM_BK,
-                           n_blk * BN);
+          if (NCTA == 2) {
+            // Both CTAs' loads are credited to the LEADER's full barrier; only the leader arrives (expecting the
+            // bytes of both).  The peer never arrives: its bytes for the next phase can only land after the leader's
+            // MMAs released the slot, and a transiently negative tx-count cannot complete a phase whose single
+            // arrival is still pending.  (A remote release-arrive here costs a cluster-scope fence per k-block and
+            // serialises the peer's TMA pipeline: measured 2x slower.)
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            ptx::tma_load_2d_2sm(&tmap_a, &full_bar[stage], smem_a + stage * GEMM_A_STAGE_BYTES, kb * GEMM_BK,
+                                 m_blk * TILE_M + rank * GEMM_BM);
+            ptx::tma_load_2d_2sm(&tmap_w, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, kb * GEMM_BK,
+                                 n_blk * BN + rank * (BN / 2));
+          } else {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            ptx::tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * GEMM_A_STAGE_BYTES, kb * GEMM_BK,
+                             m_blk * GEMM_BM);
+            ptx::tma_load_2d(&tmap_w, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, kb * GEMM_BK,
+                             n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(GEMM_BM, BN);
+    if (lane == 0 && rank == 0) {  // in a pair only the leader CTA issues MMAs
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(TILE_M, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * 256);
@@ -187,13 +211,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the (>>4) address field
-            ptx::umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                              (kb | k) != 0 ? 1u : 0u);
+            if (NCTA == 2)
+              ptx::umma_bf16_ss_2sm(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                                    (kb | k) != 0 ? 1u : 0u);
+            else
+              ptx::umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                                (kb | k) != 0 ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if (NCTA == 2) ptx::umma_commit_2sm(&empty_bar[stage]);
+          else ptx::umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        // accumulator complete (each CTA of a pair holds its own 128 rows in its own TMEM)
+        if (NCTA == 2) ptx::umma_commit_2sm(&tmem_full_bar[acc]);
+        else ptx::umma_commit(&tmem_full_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -212,11 +244,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int sw = lane & 7;  // 128B-swizzle phase of this thread's staging row
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const int row_base = m_blk * GEMM_BM + quarter * 32;
+      const int row_base = m_blk * TILE_M + rank * GEMM_BM + quarter * 32;
       const uint32_t taddr_row = tmem_base + static_cast<uint32_t>(acc * 256) +
                                  (static_cast<uint32_t>(quarter * 32) << 16);
       if (EPI == EPI_BF16) {
@@ -350,7 +382,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) {  // the accumulator buffer is owned by the (leader's) MMA thread
+        if (rank == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        else ptx::mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -358,10 +394,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) ptx::cluster_sync();  // the leader's MMAs touch the peer's shared memory and TMEM until here
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<512>(tmem_base);
+    if (NCTA == 2) ptx::tmem_dealloc_2sm<512>(tmem_base);
+    else ptx::tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -401,29 +439,45 @@ inline bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint6
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int NCTA>
 inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, int M, int N,
                                  int K, const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tw, tc, M, N, K, ep);
-  return cudaGetLastError();
+  using Cfg = GemmCfg<BN, NCTA>;
+  const int tile_m = GEMM_BM * NCTA;
+  const int tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
+  const int slots = num_sms / NCTA;
+  const int groups = tiles < slots ? tiles : slots;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * NCTA);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, NCTA>, ta, tw, tc, M, N, K, ep);
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int NCTA>
 inline cudaError_t gemm_configure_t() {
-  return cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              GemmCfg<BN>::SMEM_BYTES);
+  return cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              GemmCfg<BN, NCTA>::SMEM_BYTES);
 }
 
 // Opt every instantiation into >48 KB dynamic shared memory on the CURRENT device (call once per device).
 inline cudaError_t gemm_configure_device() {
   cudaError_t e;
-#define CLIPB200_CFG(BN_)                                                   \
-  if ((e = gemm_configure_t<BN_, EPI_BF16>()) != cudaSuccess) return e;     \
-  if ((e = gemm_configure_t<BN_, EPI_RESID>()) != cudaSuccess) return e;    \
-  if ((e = gemm_configure_t<BN_, EPI_F32>()) != cudaSuccess) return e;
+#define CLIPB200_CFG(BN_)                                                      \
+  if ((e = gemm_configure_t<BN_, EPI_BF16, 1>()) != cudaSuccess) return e;     \
+  if ((e = gemm_configure_t<BN_, EPI_RESID, 1>()) != cudaSuccess) return e;    \
+  if ((e = gemm_configure_t<BN_, EPI_F32, 1>()) != cudaSuccess) return e;      \
+  if ((e = gemm_configure_t<BN_, EPI_BF16, 2>()) != cudaSuccess) return e;     \
+  if ((e = gemm_configure_t<BN_, EPI_RESID, 2>()) != cudaSuccess) return e;    \
+  if ((e = gemm_configure_t<BN_, EPI_F32, 2>()) != cudaSuccess) return e;
   CLIPB200_CFG(256)
   CLIPB200_CFG(192)
   CLIPB200_CFG(128)
@@ -447,15 +501,17 @@ inline int gemm_pick_bn(int N) {
 }
 
 // A: [M,K] bf16 (lda elements), W: [N,K] bf16 (ldw elements).  force_bn: 0 = auto.
+// force_ncta: 0 = auto (CTA pairs for large M), 1 / 2 = forced.
 inline cudaError_t gemm_bf16(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M,
                              int N, int K, int epi_mode, const GemmEpilogue& ep, int num_sms, cudaStream_t stream,
-                             int force_bn = 0) {
+                             int force_bn = 0, int force_ncta = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return cudaErrorInvalidValue;
   if ((K & 7) || (N & 7) || (lda & 7) || (ldw & 7) || (ep.ldc & 7)) return cudaErrorInvalidValue;
   const int bn = force_bn ? force_bn : gemm_pick_bn(N);
   CUtensorMap ta, tw, tc;
   if (!make_tmap_2d(&ta, A, M, K, lda, GEMM_BM, 2)) return cudaErrorUnknown;
-  if (!make_tmap_2d(&tw, W, N, K, ldw, bn, 2)) return cudaErrorUnknown;
+  const int ncta = force_ncta ? force_ncta : (M >= 2048 ? 2 : 1);
+  if (!make_tmap_2d(&tw, W, N, K, ldw, bn / ncta, 2)) return cudaErrorUnknown;
   if (epi_mode == EPI_BF16) {
     if (!make_tmap_2d(&tc, ep.out_bf16, M, N, ep.ldc, 32, 2)) return cudaErrorUnknown;
   } else if (epi_mode == EPI_RESID) {
@@ -463,11 +519,16 @@ inline cudaError_t gemm_bf16(const __nv_bfloat16* A, long long lda, const __nv_b
   } else {
     tc = ta;  // unused by the kernel in this mode
   }
-#define CLIPB200_GEMM_CASE(BN_)                                                                     \
-  if (bn == BN_) {                                                                                  \
-    if (epi_mode == EPI_BF16) return gemm_launch_t<BN_, EPI_BF16>(ta, tw, tc, M, N, K, ep, num_sms, stream);   \
-    if (epi_mode == EPI_RESID) return gemm_launch_t<BN_, EPI_RESID>(ta, tw, tc, M, N, K, ep, num_sms, stream); \
-    return gemm_launch_t<BN_, EPI_F32>(ta, tw, tc, M, N, K, ep, num_sms, stream);                       \
+#define CLIPB200_GEMM_CASE(BN_)                                                                                  \
+  if (bn == BN_ && ncta == 1) {                                                                                  \
+    if (epi_mode == EPI_BF16) return gemm_launch_t<BN_, EPI_BF16, 1>(ta, tw, tc, M, N, K, ep, num_sms, stream);   \
+    if (epi_mode == EPI_RESID) return gemm_launch_t<BN_, EPI_RESID, 1>(ta, tw, tc, M, N, K, ep, num_sms, stream); \
+    return gemm_launch_t<BN_, EPI_F32, 1>(ta, tw, tc, M, N, K, ep, num_sms, stream);                              \
+  }                                                                                                              \
+  if (bn == BN_ && ncta == 2) {                                                                                  \
+    if (epi_mode == EPI_BF16) return gemm_launch_t<BN_, EPI_BF16, 2>(ta, tw, tc, M, N, K, ep, num_sms, stream);   \
+    if (epi_mode == EPI_RESID) return gemm_launch_t<BN_, EPI_RESID, 2>(ta, tw, tc, M, N, K, ep, num_sms, stream); \
+    return gemm_launch_t<BN_, EPI_F32, 2>(ta, tw, tc, M, N, K, ep, num_sms, stream);                              \
   }
   CLIPB200_GEMM_CASE(256)
   CLIPB200_GEMM_CASE(192)

@@ -63,7 +63,7 @@ static float host_act(float x, int act) {
 }
 static float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
-static int run_case(int M, int N, int K, int epi, int act, int force_bn, bool time_it, int num_sms) {
+static int run_case(int M, int N, int K, int epi, int act, int force_bn, bool time_it, int num_sms, int ncta = 1) {
   __nv_bfloat16 *A, *W, *Cb;
   float *bias, *Cf, *Cf0, *gamma, *pos;
   const int rows_in = (epi == EPI_F32) ? 7 : 0, rows_out = 8, row_off = 1;  // CLS-style remap test
@@ -95,7 +95,7 @@ static int run_case(int M, int N, int K, int epi, int act, int force_bn, bool ti
   ep.out_f32 = Cf;
   if (epi == EPI_RESID) ep.gamma = gamma;
   if (epi == EPI_F32) { ep.pos = pos; ep.rows_in = rows_in; ep.rows_out = rows_out; ep.row_off = row_off; }
-  CK(gemm_bf16(A, K, W, K, M, N, K, epi, ep, num_sms, 0, force_bn));
+  CK(gemm_bf16(A, K, W, K, M, N, K, epi, ep, num_sms, 0, force_bn, ncta));
   CK(cudaDeviceSynchronize());
 
   // rows to verify
@@ -169,17 +169,17 @@ static int run_case(int M, int N, int K, int epi, int act, int force_bn, bool ti
   if (time_it) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) CK(gemm_bf16(A, K, W, K, M, N, K, epi, ep, num_sms, 0, force_bn));
+    for (int i = 0; i < 3; ++i) CK(gemm_bf16(A, K, W, K, M, N, K, epi, ep, num_sms, 0, force_bn, ncta));
     CK(cudaEventRecord(e0));
     const int iters = 10;
-    for (int i = 0; i < iters; ++i) CK(gemm_bf16(A, K, W, K, M, N, K, epi, ep, num_sms, 0, force_bn));
+    for (int i = 0; i < iters; ++i) CK(gemm_bf16(A, K, W, K, M, N, K, epi, ep, num_sms, 0, force_bn, ncta));
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float t; CK(cudaEventElapsedTime(&t, e0, e1));
     ms = t / iters;
   }
   const char* en = epi == EPI_BF16 ? "bf16" : (epi == EPI_RESID ? "resid" : "f32");
-  printf("%s M=%d N=%d K=%d epi=%s act=%d bn=%d max_abs=%.4g max_rel=%.4g bad=%lld", bad ? "FAIL" : "ok  ", M, N, K,
+  printf("%s cta%d M=%d N=%d K=%d epi=%s act=%d bn=%d max_abs=%.4g max_rel=%.4g bad=%lld", bad ? "FAIL" : "ok  ", ncta, M, N, K,
          en, act, force_bn ? force_bn : gemm_pick_bn(N), max_abs, max_rel, bad);
   if (time_it) printf("  %.3f ms  %.1f TFLOP/s", ms, 2.0 * M * N * K / ms * 1e-9);
   printf("\n");
@@ -199,6 +199,11 @@ int main(int argc, char** argv) {
   CK(gemm_configure_device());
   int fails = 0;
   const bool quick = argc > 1 && atoi(argv[1]) == 1;
+  if (argc > 1 && atoi(argv[1]) == 2) {  // CTA-pair tile-shape sweep
+    for (int ncta = 1; ncta <= 2; ++ncta)
+      for (int bn : {128, 192, 256}) fails += run_case(8192, 8064, 4096, EPI_BF16, ACT_NONE, bn, true, num_sms, ncta);
+    return fails;
+  }
   // smallest cases first: one tile, one k-block
   fails += run_case(128, 256, 64, EPI_BF16, ACT_NONE, 256, false, num_sms);
   fails += run_case(128, 128, 64, EPI_BF16, ACT_NONE, 128, false, num_sms);
@@ -212,6 +217,13 @@ int main(int argc, char** argv) {
   fails += run_case(389, 1152, 4304, EPI_RESID, ACT_NONE, 0, false, num_sms);
   fails += run_case(343, 768, 592, EPI_F32, ACT_NONE, 0, false, num_sms);
   fails += run_case(77 * 5, 1024, 1024, EPI_RESID, ACT_NONE, 0, false, num_sms);
+  // CTA-pair (cta_group::2) variants: one pair tile, tails, several tiles per pair
+  fails += run_case(256, 256, 64, EPI_BF16, ACT_NONE, 256, false, num_sms, 2);
+  fails += run_case(256, 128, 128, EPI_BF16, ACT_NONE, 128, false, num_sms, 2);
+  fails += run_case(256, 192, 1152, EPI_RESID, ACT_NONE, 192, false, num_sms, 2);
+  fails += run_case(389, 4304, 1152, EPI_BF16, ACT_GELU_TANH, 0, false, num_sms, 2);
+  fails += run_case(1000, 1152, 4304, EPI_RESID, ACT_NONE, 0, false, num_sms, 2);
+  fails += run_case(343, 768, 592, EPI_F32, ACT_NONE, 0, false, num_sms, 2);
   if (!quick) {
     // multi-tile persistent scheduling + perf (SO400M layer shapes at a 128-image micro-batch, M = 73728)
     const int M = 128 * 576;
@@ -223,6 +235,11 @@ int main(int argc, char** argv) {
     fails += run_case(M, 1152, 4304, EPI_RESID, ACT_NONE, 0, true, num_sms);
     fails += run_case(M, 1152, 4304, EPI_RESID, ACT_NONE, 128, true, num_sms);
     fails += run_case(8192, 8192, 8192, EPI_BF16, ACT_NONE, 256, true, num_sms);
+    fails += run_case(M, 3456, 1152, EPI_BF16, ACT_NONE, 256, true, num_sms, 2);
+    fails += run_case(M, 1152, 1152, EPI_RESID, ACT_NONE, 0, true, num_sms, 2);
+    fails += run_case(M, 4304, 1152, EPI_BF16, ACT_GELU_TANH, 256, true, num_sms, 2);
+    fails += run_case(M, 1152, 4304, EPI_RESID, ACT_NONE, 0, true, num_sms, 2);
+    fails += run_case(8192, 8192, 8192, EPI_BF16, ACT_NONE, 256, true, num_sms, 2);
   }
   printf("%s (%d failing cases)\n", fails ? "GEMM TEST FAILED" : "GEMM TEST PASSED", fails);
   return fails ? 1 : 0;
