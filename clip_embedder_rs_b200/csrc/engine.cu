@@ -424,6 +424,9 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
     return Status::Err(io ? CLIPB200_ERR_IO : CLIPB200_ERR_PARSE, err);
   }
   input_names = m.inputs;
+  if (get_encode_tiled() == nullptr)  // resolved here so that it never happens inside a graph capture
+    return Status::Err(CLIPB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+  if (const char* env = getenv("CLIPB200_NO_GRAPHS")) if (atoi(env) != 0) graph_max_n_ = 0;
   CUDA_RET(gemm_configure_device(), "configure GEMM kernels");
   CUDA_RET(flash_attention_configure_device(), "configure attention kernels");
   CUDA_RET(attn_tcgen05_configure_device(), "configure tcgen05 attention kernels");
@@ -471,6 +474,7 @@ Engine::~Engine() {
     if (out_copied_[i]) cudaEventDestroy(out_copied_[i]);
   }
   for (int i = 0; i < 16; ++i) if (user_events_[i]) cudaEventDestroy(user_events_[i]);
+  for (auto& g : graphs_) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   for (auto& p : prof_pending_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto& e : prof_free_) cudaEventDestroy(e);
   if (l2_flush_) cudaFree(l2_flush_);
@@ -732,6 +736,41 @@ Status Engine::ForwardText(int n, const int64_t* d_ids, float* d_out) {
   return Status::OK();
 }
 
+// Forward pass of one micro-batch from staging slot `slot`.  Small micro-batches are launch-bound (a ViT-B/32 image
+// is ~90 kernels of a few microseconds each), so their kernel sequence is captured once into a CUDA graph per
+// (mode, n, slot) and replayed; tensor maps are by-value kernel parameters, so the captured launches are complete.
+Status Engine::ForwardSlot(int mode, int n, int slot) {
+  auto fwd = [&]() -> Status {
+    if (mode == 0) return ForwardVision(n, static_cast<const uint8_t*>(d_in_[slot]), nullptr, d_out_[slot]);
+    if (mode == 1) return ForwardVision(n, nullptr, d_in_f32_[slot], d_out_[slot]);
+    return ForwardText(n, static_cast<const int64_t*>(d_in_[slot]), d_out_[slot]);
+  };
+  if (profile_ || n > graph_max_n_) return fwd();
+  const auto key = std::make_tuple(mode, n, slot);
+  auto it = graphs_.find(key);
+  if (it == graphs_.end()) {
+    const int64_t before = launch_count;
+    CUDA_RET(cudaStreamBeginCapture(compute_, cudaStreamCaptureModeThreadLocal), "begin graph capture");
+    Status st = fwd();
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(compute_, &graph);
+    if (!st.ok()) {
+      if (graph) cudaGraphDestroy(graph);
+      return st;
+    }
+    CUDA_RET(ce, "end graph capture");
+    GraphEntry g;
+    g.launches = launch_count - before;
+    launch_count = before;
+    ce = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CUDA_RET(ce, "instantiate graph");
+    it = graphs_.emplace(key, g).first;
+  }
+  launch_count += it->second.launches;
+  return Check(cudaGraphLaunch(it->second.exec, compute_), "graph launch");
+}
+
 // ------------------------------------------------------------------------------------------------ pipeline
 // mode 0: vision u8, 1: vision f32 NCHW, 2: text ids
 template <typename InT>
@@ -781,9 +820,7 @@ Status Engine::RunPipelined(const InT* in, int64_t batch, size_t in_elems_per_it
     CUDA_RET(cudaEventRecord(in_ready_[slot], copy_in_), "record");
     CUDA_RET(cudaStreamWaitEvent(compute_, in_ready_[slot], 0), "wait input");
     if (s >= 2) CUDA_RET(cudaStreamWaitEvent(compute_, out_copied_[slot], 0), "wait output slot");
-    if (mode == 0) st = ForwardVision(n, static_cast<const uint8_t*>(d_in[slot]), nullptr, d_out_[slot]);
-    else if (mode == 1) st = ForwardVision(n, nullptr, static_cast<const float*>(d_in[slot]), d_out_[slot]);
-    else st = ForwardText(n, static_cast<const int64_t*>(d_in[slot]), d_out_[slot]);
+    st = ForwardSlot(mode, n, slot);
     if (!st.ok()) break;
     CUDA_RET(cudaEventRecord(in_consumed_[slot], compute_), "record");
     CUDA_RET(cudaEventRecord(out_ready_[slot], compute_), "record");

@@ -121,6 +121,14 @@ class Engine {
   Status UploadConv(const OnnxModel& m, const std::string& name, int cout, int cin_g, int k, ConvW* out);
   Status UploadSe(const OnnxModel& m, const std::string& name, int C, SeW* out);
   Status FvMlp(const FvBlock& b, float* cur, int n, int Hh, int C, const float* gamma);
+  // CUDA graphs for small micro-batches (launch-bound regime): one instantiated graph per (mode, n, staging slot)
+  Status ForwardSlot(int mode, int n, int slot);
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+  };
+  std::map<std::tuple<int, int, int>, GraphEntry> graphs_;
+  int graph_max_n_ = 32;
   // resize plans (coefficient tables) cached per (width, height, interpolation, squash)
   Status GetResizePlan(int width, int height, int interpolation, bool squash, const ResizePlanDev** plan);
   Status ResizeToDevice(const uint8_t* h_img, int width, int height, const clipb200_preproc* pp, uint8_t* d_dst);
