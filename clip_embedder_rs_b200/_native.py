@@ -58,6 +58,11 @@ SIGNATURES = {
     "clipb200_text_embed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "clipb200_similarity": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_float,
                                       C.c_int, C.c_void_p]),
+    "clipb200_corpus_create": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]),
+    "clipb200_corpus_destroy": (None, [C.c_void_p]),
+    "clipb200_corpus_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "clipb200_corpus_size": (C.c_int64, [C.c_void_p]),
+    "clipb200_corpus_rank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "clipb200_vision_embed_rgb8_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Preproc),
                                                     C.c_void_p]),
     "clipb200_text_embed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),

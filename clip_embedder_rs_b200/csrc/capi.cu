@@ -219,6 +219,69 @@ int clipb200_similarity(int cuda_device, const float* A, const float* b, int64_t
   API_GUARD_END
 }
 
+struct clipb200_corpus {
+  int device = 0;
+  int64_t dim = 0, capacity = 0, size = 0;
+  float* rows = nullptr;
+  float* query = nullptr;
+  float* probs = nullptr;
+};
+
+int clipb200_corpus_create(int cuda_device, int64_t dim, int64_t capacity, clipb200_corpus** out) {
+  API_GUARD_BEGIN
+  if (out == nullptr || dim <= 0 || capacity <= 0 || dim > 0x7fffffff || capacity > 0x7fffffff)
+    return fail(CLIPB200_ERR_INVALID_ARG, "bad corpus shape");
+  *out = nullptr;
+  cudaError_t ce = cudaSetDevice(cuda_device);
+  if (ce != cudaSuccess) return fail(CLIPB200_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+  clipb200_corpus* c = new clipb200_corpus();
+  c->device = cuda_device;
+  c->dim = dim;
+  c->capacity = capacity;
+  if ((ce = cudaMalloc(&c->rows, static_cast<size_t>(capacity) * dim * 4)) != cudaSuccess ||
+      (ce = cudaMalloc(&c->query, dim * 4)) != cudaSuccess || (ce = cudaMalloc(&c->probs, capacity * 4 + 16)) != cudaSuccess) {
+    cudaFree(c->rows); cudaFree(c->query); cudaFree(c->probs);
+    delete c;
+    return fail(CLIPB200_ERR_CUDA, std::string("corpus allocation: ") + cudaGetErrorString(ce));
+  }
+  *out = c;
+  return CLIPB200_OK;
+  API_GUARD_END
+}
+void clipb200_corpus_destroy(clipb200_corpus* c) {
+  if (c == nullptr) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->rows); cudaFree(c->query); cudaFree(c->probs);
+  delete c;
+}
+int clipb200_corpus_append(clipb200_corpus* c, const float* rows, int64_t n) {
+  API_GUARD_BEGIN
+  if (c == nullptr || rows == nullptr || n < 0) return fail(CLIPB200_ERR_INVALID_ARG, "null argument");
+  if (c->size + n > c->capacity) return fail(CLIPB200_ERR_INVALID_ARG, "corpus capacity exceeded");
+  cudaError_t ce = cudaSetDevice(c->device);
+  if (ce == cudaSuccess)
+    ce = cudaMemcpy(c->rows + c->size * c->dim, rows, static_cast<size_t>(n) * c->dim * 4, cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) return fail(CLIPB200_ERR_CUDA, std::string("corpus append: ") + cudaGetErrorString(ce));
+  c->size += n;
+  return CLIPB200_OK;
+  API_GUARD_END
+}
+int64_t clipb200_corpus_size(const clipb200_corpus* c) { return c == nullptr ? 0 : c->size; }
+int clipb200_corpus_rank(clipb200_corpus* c, const float* query, float scale, float bias, int activation, float* probs) {
+  API_GUARD_BEGIN
+  if (c == nullptr || query == nullptr || probs == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null argument");
+  if (c->size == 0) return fail(CLIPB200_ERR_INVALID_ARG, "Empty batch");
+  cudaError_t ce = cudaSetDevice(c->device);
+  if (ce == cudaSuccess) ce = cudaMemcpy(c->query, query, c->dim * 4, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess)
+    ce = clipb200::launch_similarity(c->rows, c->query, static_cast<int>(c->size), static_cast<int>(c->dim), scale, bias,
+                                     activation, c->probs, nullptr, 0);
+  if (ce == cudaSuccess) ce = cudaMemcpy(probs, c->probs, c->size * 4, cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess) return fail(CLIPB200_ERR_CUDA, std::string("corpus rank: ") + cudaGetErrorString(ce));
+  return CLIPB200_OK;
+  API_GUARD_END
+}
+
 void* clipb200_host_alloc(size_t bytes) {
   void* p = nullptr;
   if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;

@@ -118,6 +118,17 @@ int clipb200_text_embed(clipb200_engine* e, const int64_t* input_ids, const int6
 int clipb200_similarity(int cuda_device, const float* A, const float* b, int64_t n, int64_t d, float scale,
                         float bias, int activation, float* probs);
 
+/* ---- corpus search tail (src/clip.rs:136-170 `rank_images` at scale) -----------------------------
+ * An embedding matrix [n, dim] kept resident in HBM; a query is one similarity pass over it (HBM-bound GEMV with the
+ * fused logit scale / bias / softmax-over-corpus or sigmoid); the stable descending sort stays on the host. */
+typedef struct clipb200_corpus clipb200_corpus;
+int clipb200_corpus_create(int cuda_device, int64_t dim, int64_t capacity, clipb200_corpus** out);
+void clipb200_corpus_destroy(clipb200_corpus* c);
+int clipb200_corpus_append(clipb200_corpus* c, const float* rows, int64_t n);   /* host rows [n, dim] */
+int64_t clipb200_corpus_size(const clipb200_corpus* c);
+int clipb200_corpus_rank(clipb200_corpus* c, const float* query, float scale, float bias, int activation,
+                         float* probs /* host [size] */);
+
 /* ---- run: device-resident buffers (benchmark "value": inputs already in HBM) --------------------------- */
 int clipb200_vision_embed_rgb8_device(clipb200_engine* e, const uint8_t* d_hwc, int64_t batch,
                                       const clipb200_preproc* pp, float* d_out);

@@ -151,3 +151,22 @@ def test_softmax_sigmoid_tail():
     assert np.allclose(cb.Clip.softmax(logits), R.softmax(logits), rtol=1e-5, atol=1e-7)
     for x in (-20.0, -1.0, 0.0, 2.5, 30.0):
         assert abs(cb.Clip.sigmoid(x) - float(R.sigmoid(x))) < 1e-6
+
+
+def test_corpus_rank_matches_rank_images(clips):
+    """The resident-corpus search tail gives the same ranking as `rank_images` on the same images."""
+    from clip_embedder_rs_b200.corpus import EmbeddingCorpus, rank_corpus
+
+    clip, model_dir = clips("tiny_siglip")
+    size = clip.vision.config.model_cfg.vision_cfg.image_size
+    imgs = random_images(23, size, seed=77)
+    corpus = EmbeddingCorpus(clip.vision.session.embed_dim, capacity=64)
+    for s in range(0, 23, 10):  # appended shard by shard, as the sharded embedder would
+        corpus.append(clip.vision.embed_images(imgs[s:s + 10]))
+    assert len(corpus) == 23
+    text = "a photo of a cat"
+    want = clip.rank_images(imgs, text)
+    got = rank_corpus(clip, corpus, text)
+    assert [i for i, _ in got] == [i for i, _ in want]
+    assert np.allclose([p for _, p in got], [p for _, p in want], rtol=1e-4, atol=1e-7)
+    assert rank_corpus(clip, corpus, text, top_k=5) == got[:5]
