@@ -5,7 +5,7 @@
 // Replaces the MatMul -> Mul -> (+mask) -> Softmax -> MatMul chain ONNX Runtime executes inside `session.run`
 // (reference src/vision.rs:108, src/text.rs:157-160).
 //
-// Persistent CTAs (2 per SM, 192 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..5 = softmax
+// Persistent CTAs (2 per SM, 192 threads): warps 0..3 = softmax, warp 4 = TMA producer, warp 5 = tcgen05.mma issuer
 // (one query row per thread).  Work item = (batch, head, 128-query tile); K/V stream through a 2-stage smem ring in
 // blocks of BKV keys.
 //   S = Q K^T   : tcgen05.mma SS, M=128, N=BKV, accumulator S in TMEM (fp32)
@@ -205,7 +205,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
       }
     ptx::fence_proxy_async_smem();
   }
-  if (warp == 0 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     ptx::prefetch_tmap(&tm_q_main);
     ptx::prefetch_tmap(&tm_kv_main);
     ptx::prefetch_tmap(&tm_out);
@@ -222,7 +222,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
     ptx::mbar_init(pv_done, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc<C::TMEM_COLS>(tmem_base_ptr);
+  if (warp == 5) ptx::tmem_alloc<C::TMEM_COLS>(tmem_base_ptr);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -235,7 +235,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
     return nb < kv_blocks_total ? nb : kv_blocks_total;
   };
 
-  if (warp == 0) {
+  if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t g = 0;   // running K/V block counter
@@ -269,7 +269,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, 0);
@@ -335,7 +335,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
     const uint32_t t_s = tmem_base + lane_base + C::COL_S;
     const uint32_t t_p = tmem_base + lane_base + C::COL_P;
     const uint32_t t_o = tmem_base + lane_base + C::COL_O;
-    uint8_t* stg = s_out + (warp - 2) * C::OUT_WARP;
+    uint8_t* stg = s_out + warp * C::OUT_WARP;
     uint32_t g = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int qt = item % p.q_tiles;
@@ -469,7 +469,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 5) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }

@@ -450,7 +450,7 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
   if (const char* env = getenv("CLIPB200_MICRO_BATCH")) if (mb_ <= 0) mb_ = atoi(env);
   if (mb_ <= 0 && fastvit_) mb_ = 64;
   if (mb_ <= 0) {
-    mb_ = 73728 / T_;  // ~72k token rows per step keeps every GEMM at >= 20 waves of 128-row tiles
+    mb_ = 147456 / T_;  // ~147k token rows per step (256 SO400M images): measured best on B200 (32..1024 swept)
     if (mb_ > 1024) mb_ = 1024;
     if (mb_ < 1) mb_ = 1;
   }
