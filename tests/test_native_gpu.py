@@ -1,0 +1,69 @@
+"""Runs the standalone native checks (built by `make gemm_test attn_test`) as part of the GPU suite:
+tests/native/gemm_test.cu — tcgen05 GEMM (1-CTA and CTA-pair modes, all epilogues, M/N/K tails) against a SIMT fp32
+reference; tests/native/attn_test.cu — tcgen05 attention against the mma.sync kernel and an fp32 SIMT reference."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+NATIVE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "native")
+
+
+@pytest.mark.parametrize("binary,arg,marker", [("gemm_test.bin", "1", "GEMM TEST PASSED"), ("attn_test.bin", None, "ATTN TEST PASSED")])
+def test_native_binary(binary, arg, marker):
+    path = os.path.join(NATIVE, binary)
+    if not os.path.exists(path):
+        pytest.fail(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    cmd = [path] + ([arg] if arg else [])
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    print(out.stdout[-3000:])
+    assert out.returncode == 0 and marker in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_loader_accepts_f16_bf16_and_identity_aliases(make_model, tmp_path):
+    """The ONNX loader's claims beyond the synthetic exporter's defaults: fp16 / bf16 initializers, inline
+    `float_data`, and exporter-style de-duplication (an `Identity` node aliasing one initializer under a second name)."""
+    import numpy as np
+
+    import clip_embedder_rs_b200 as cb
+    import onnx_proto as op
+    from conftest import cosine_rows, random_images
+
+    src = make_model("tiny_clip")
+    ref = cb.VisionEmbedder.from_local_dir(src).build()
+    imgs = random_images(3, 64, seed=9)
+    want = ref.embed_images(imgs)
+
+    m = op.read_model(os.path.join(src, "visual.onnx"))
+    dst = tmp_path / "variant"
+    dst.mkdir()
+    for f in os.listdir(src):
+        if not f.startswith("visual.onnx"):
+            os.symlink(os.path.join(src, f), dst / f)
+    w = op.ModelWriter(str(dst / "visual.onnx"), "visual")
+    w.add_input("pixel_values", op.FLOAT, ["batch_size", 3, 64, 64])
+    w.add_output("image_embeddings", op.FLOAT, ["batch_size", 64])
+    for k, v in m["metadata"].items():
+        w.add_metadata(k, v)
+    alias_src = "model.visual.transformer.resblocks.0.ln_1.bias"
+    alias_dst = "model.visual.transformer.resblocks.1.ln_1.bias"
+    for i, (name, arr) in enumerate(m["initializers"].items()):
+        arr = np.array(arr)
+        if name == alias_dst:
+            continue  # provided through the Identity node below (made equal to resblocks.0's bias)
+        if name.endswith("mlp.c_fc.weight"):  # fp16 storage
+            w._inits.append(op.tensor_proto(name, arr.astype(np.float16)))
+        elif name.endswith("attn.out_proj.weight"):  # bf16 storage (upper 16 bits of fp32, round-to-nearest-even)
+            u = arr.astype(np.float32).view(np.uint32)
+            bf = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+            w._inits.append(op.f_bytes(1, b"".join(op._varint(int(d)) for d in arr.shape)) + op.f_varint(2, op.BFLOAT16) +
+                            op.f_str(8, name) + op.f_bytes(9, bf.tobytes()))
+        else:
+            w.add_initializer(name, arr)
+    w.add_node(op.node("Identity", [alias_src], [alias_dst]))
+    w.close()
+    got = cb.VisionEmbedder.from_local_dir(dst).build().embed_images(imgs)
+    # same model up to fp16/bf16 storage rounding of two weight families and one aliased LayerNorm bias
+    assert cosine_rows(got, want).min() > 0.995
+    assert np.abs(got - want).max() > 0  # the variant really differs (alias + rounding), i.e. it was loaded
