@@ -170,3 +170,30 @@ def test_corpus_rank_matches_rank_images(clips):
     assert [i for i, _ in got] == [i for i, _ in want]
     assert np.allclose([p for _, p in got], [p for _, p in want], rtol=1e-4, atol=1e-7)
     assert rank_corpus(clip, corpus, text, top_k=5) == got[:5]
+
+
+def test_duplicate_handles_run_concurrently(clips):
+    """SURVEY 8(b) threading row: distinct handles (`duplicate()`, vision.rs:87-91) may be used concurrently from
+    different threads; each must give the same embeddings as a lone run."""
+    import threading
+
+    clip, _ = clips("tiny_siglip")
+    size = clip.vision.config.model_cfg.vision_cfg.image_size
+    imgs = random_images(40, size, seed=5)
+    want = clip.vision.embed_images(imgs)
+    twins = [clip.vision, clip.vision.duplicate(), clip.vision.duplicate()]
+    results, errors = {}, []
+
+    def work(i):
+        try:
+            for _ in range(6):
+                results[i] = twins[i].embed_images(imgs)
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(twins))]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for i in range(len(twins)):
+        assert np.array_equal(results[i], want), f"handle {i} diverged under concurrency"
