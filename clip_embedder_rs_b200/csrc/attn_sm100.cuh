@@ -5,7 +5,7 @@
 // Replaces the MatMul -> Mul -> (+mask) -> Softmax -> MatMul chain ONNX Runtime executes inside `session.run`
 // (reference src/vision.rs:108, src/text.rs:157-160).
 //
-// Persistent CTAs (2 per SM, 192 threads): warps 0..3 = softmax, warp 4 = TMA producer, warp 5 = tcgen05.mma issuer
+// Persistent CTAs (2 per SM, 320 threads): warps 0..7 = softmax (two per query row), warp 8 = TMA producer, warp 9 = MMA issuer
 // (one query row per thread).  Work item = (batch, head, 128-query tile); K/V stream through a 2-stage smem ring in
 // blocks of BKV keys.
 //   S = Q K^T   : tcgen05.mma SS, M=128, N=BKV, accumulator S in TMEM (fp32)
@@ -32,8 +32,32 @@ namespace attn {
 #define CLIPB200_ATTN_DBG 0  // profiling aid (tests/native/attn_test.cu): 1 no exp, 2 no S load, 4 no P store
 #endif
 
+#ifdef CLIPB200_ATTN_TIMING
+// profiling aid: cycles each role of CTA 0 spends waiting on each barrier (read back by tests/native/attn_test.cu)
+__device__ unsigned long long g_attn_wait[16];
+#define ATTN_TIMED_WAIT(slot, bar, par)                                          \
+  do {                                                                           \
+    const long long t0_ = clock64();                                             \
+    ptx::mbar_wait(bar, par);                                                    \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0)                              \
+      atomicAdd(&g_attn_wait[slot], (unsigned long long)(clock64() - t0_));      \
+  } while (0)
+#else
+#define ATTN_TIMED_WAIT(slot, bar, par) ptx::mbar_wait(bar, par)
+#endif
+
 constexpr int BQ = 128;
-constexpr int THREADS = 192;
+// SPLIT softmax warps share one query row (each takes BKV/SPLIT key columns): 4*SPLIT softmax warps + TMA + MMA warp.
+// SPLIT = 2 doubles the independent instruction streams per SM sub-partition (two CTAs -> four softmax warps each), which
+// is what hides the tcgen05.ld -> exp2 -> tcgen05.st latency chain; the pair exchanges its row maximum through smem.
+#ifndef CLIPB200_ATTN_SPLIT
+#define CLIPB200_ATTN_SPLIT 1
+#endif
+constexpr int SPLIT = CLIPB200_ATTN_SPLIT;
+constexpr int NSW = 4 * SPLIT;            // softmax warps
+constexpr int WARP_TMA = NSW;
+constexpr int WARP_MMA = NSW + 1;
+constexpr int THREADS = 32 * (NSW + 2);
 
 template <int HD, int BKV>
 struct Cfg {
@@ -60,8 +84,13 @@ struct Cfg {
   static constexpr int OFF_KV = (Q_MAIN + Q_REM + 1023) / 1024 * 1024;
   static constexpr int KV_STAGE_AL = (KV_STAGE + 1023) / 1024 * 1024;
   static constexpr int OFF_OUT = OFF_KV + STAGES * KV_STAGE_AL;
-  static constexpr int OFF_BAR = OFF_OUT + (4 * OUT_WARP + 127) / 128 * 128;
+  static constexpr int OFF_XCH = OFF_OUT + (4 * OUT_WARP + 127) / 128 * 128;   // row-max / row-sum exchange
+  static constexpr int XCH_BYTES = (2 * 2 + 2) * BQ * 4;
+  static constexpr int OFF_BAR = OFF_XCH + XCH_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int CW = BKV / SPLIT;          // key columns per softmax thread
+  static constexpr int OW = HDP / SPLIT;          // O columns per softmax thread (rescale / epilogue)
+  static_assert(CW % 16 == 0 && OW % 8 == 0, "split granularity");
   // TMEM columns
   static constexpr int COL_S = 0;
   static constexpr int COL_P = BKV;               // packed bf16: BKV/2 columns
@@ -153,6 +182,21 @@ __device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :
+               : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void pair_barrier(int quarter) {  // the SPLIT warps that share a row block
+  asm volatile("bar.sync %0, %1;" ::"r"(quarter + 1), "n"(32 * SPLIT) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -205,7 +249,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
       }
     ptx::fence_proxy_async_smem();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == WARP_TMA && lane == 0) {
     ptx::prefetch_tmap(&tm_q_main);
     ptx::prefetch_tmap(&tm_kv_main);
     ptx::prefetch_tmap(&tm_out);
@@ -217,12 +261,12 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
       ptx::mbar_init(&v_full[s], 1); ptx::mbar_init(&v_empty[s], 1);
     }
     ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(s_empty, 128);
-    ptx::mbar_init(p_full, 128);
+    ptx::mbar_init(s_empty, 128 * SPLIT);
+    ptx::mbar_init(p_full, 128 * SPLIT);
     ptx::mbar_init(pv_done, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 5) ptx::tmem_alloc<C::TMEM_COLS>(tmem_base_ptr);
+  if (warp == WARP_MMA) ptx::tmem_alloc<C::TMEM_COLS>(tmem_base_ptr);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -235,7 +279,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
     return nb < kv_blocks_total ? nb : kv_blocks_total;
   };
 
-  if (warp == 4) {
+  if (warp == WARP_TMA) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t g = 0;   // running K/V block counter
@@ -245,7 +289,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
         const int bh = item / p.q_tiles;
         const int h = bh % p.H, b = bh / p.H;
         const int col_q = h * HD, col_k = p.H * HD + h * HD, col_v = 2 * p.H * HD + h * HD;
-        ptx::mbar_wait(q_empty, (it & 1) ^ 1);
+        ATTN_TIMED_WAIT(0, q_empty, (it & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(q_full, C::Q_TX);
         tma_load_3d(&tm_q_main, q_full, s_q, col_q, qt * BQ, b);
         for (int pl = 0; pl < C::REM_PLANES; ++pl)
@@ -256,12 +300,12 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
           const uint32_t par = ((g >> 1) & 1) ^ 1;
           uint8_t* kt = s_kv + st * C::KV_STAGE_AL;
           uint8_t* vt = kt + C::KV_TILE;
-          ptx::mbar_wait(&k_empty[st], par);
+          ATTN_TIMED_WAIT(1, &k_empty[st], par);
           ptx::mbar_arrive_expect_tx(&k_full[st], C::KV_TX / 2);
           tma_load_3d(&tm_kv_main, &k_full[st], kt, col_k, j * BKV, b);
           for (int pl = 0; pl < C::REM_PLANES; ++pl)
             tma_load_3d(&tm_kv_rem, &k_full[st], kt + C::KV_MAIN + pl * BKV * 16, col_k + 64 + 8 * pl, j * BKV, b);
-          ptx::mbar_wait(&v_empty[st], par);
+          ATTN_TIMED_WAIT(2, &v_empty[st], par);
           ptx::mbar_arrive_expect_tx(&v_full[st], C::KV_TX / 2);
           tma_load_3d(&tm_kv_main, &v_full[st], vt, col_v, j * BKV, b);
           for (int pl = 0; pl < C::REM_PLANES; ++pl)
@@ -269,9 +313,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
         }
       }
     }
-  } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+  } else if (warp == WARP_MMA) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, uniform control flow)
+    {
       constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, 0);
       constexpr uint32_t idesc_pv_main = make_idesc(BQ, 64, 1);
       constexpr uint32_t idesc_pv_rem = make_idesc(BQ, C::REMP > 0 ? C::REMP : 16, 1);
@@ -281,102 +325,119 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
       auto issue_qk = [&](uint32_t gg) {
         const int st = gg & 1;
         const uint32_t k_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL);
-        ptx::mbar_wait(&k_full[st], (gg >> 1) & 1);
-        ptx::mbar_wait(s_empty, (gg & 1) ^ 1);
+        ATTN_TIMED_WAIT(3, &k_full[st], (gg >> 1) & 1);
+        ATTN_TIMED_WAIT(4, s_empty, (gg & 1) ^ 1);
         ptx::tc_fence_after();
+#ifdef CLIPB200_ATTN_TIMING
+        const long long tq0 = clock64();
+#endif
         const uint64_t dq = ptx::make_kmajor_sw128_desc(q_addr);
         const uint64_t dk = ptx::make_kmajor_sw128_desc(k_addr);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          ptx::umma_bf16_ss(t_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_qk,
+          ptx::umma_bf16_ss_w(t_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_qk,
                             k != 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < C::REMP / 16; ++k) {
           const uint64_t dqr = make_nosw_desc(q_addr + C::Q_MAIN + k * 2 * BQ * 16, BQ * 16, 128);
           const uint64_t dkr = make_nosw_desc(k_addr + C::KV_MAIN + k * 2 * BKV * 16, BKV * 16, 128);
-          ptx::umma_bf16_ss(t_s, dqr, dkr, idesc_qk, 1u);
+          ptx::umma_bf16_ss_w(t_s, dqr, dkr, idesc_qk, 1u);
         }
-        ptx::umma_commit(&k_empty[st]);
-        ptx::umma_commit(s_full);
+        ptx::umma_commit_w(&k_empty[st]);
+        ptx::umma_commit_w(s_full);
+#ifdef CLIPB200_ATTN_TIMING
+        if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_attn_wait[11], (unsigned long long)(clock64() - tq0));
+#endif
       };
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
         const int qt = item % p.q_tiles;
         const int nb = item_blocks(qt);
-        ptx::mbar_wait(q_full, it & 1);
+        ATTN_TIMED_WAIT(5, q_full, it & 1);
         ptx::tc_fence_after();
         issue_qk(g);
         for (int j = 0; j < nb; ++j, ++g) {
           if (j + 1 < nb) issue_qk(g + 1);             // S(j+1) overlaps softmax(j)
-          else ptx::umma_commit(q_empty);              // all QK^T of this item are issued: Q tile is free when they retire
+          else ptx::umma_commit_w(q_empty);              // all QK^T of this item are issued: Q tile is free when they retire
           const int st = g & 1;
           const uint32_t v_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL + C::KV_TILE);
-          ptx::mbar_wait(&v_full[st], (g >> 1) & 1);
-          ptx::mbar_wait(p_full, g & 1);
+          ATTN_TIMED_WAIT(6, &v_full[st], (g >> 1) & 1);
+          ATTN_TIMED_WAIT(7, p_full, g & 1);
           ptx::tc_fence_after();
+#ifdef CLIPB200_ATTN_TIMING
+          const long long tp0 = clock64();
+#endif
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k) {
             const uint32_t acc = (j | k) != 0 ? 1u : 0u;
             const uint64_t dv = make_mnmajor_sw128_desc(v_addr + k * 16 * 128);
-            umma_bf16_ts(t_o, t_p + static_cast<uint32_t>(k * 8), dv, idesc_pv_main, acc);
+            ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), dv, idesc_pv_main, acc);
             if (C::REMP > 0) {
               const uint64_t dvr = make_nosw_desc(v_addr + C::KV_MAIN + k * 16 * 16, 128, BKV * 16);
-              umma_bf16_ts(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
+              ptx::umma_bf16_ts_w(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
             }
           }
-          ptx::umma_commit(&v_empty[st]);
-          ptx::umma_commit(pv_done);
+          ptx::umma_commit_w(&v_empty[st]);
+          ptx::umma_commit_w(pv_done);
+#ifdef CLIPB200_ATTN_TIMING
+          if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_attn_wait[12], (unsigned long long)(clock64() - tp0));
+#endif
         }
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax + epilogue (warps 2..5)
-    const int quarter = warp & 3;
+    // ------------------------------------------------------------------ softmax + epilogue (warps 0..NSW-1)
+    constexpr int CW = C::CW, OW = C::OW;
+    const int quarter = warp & 3;     // TMEM lane quarter (query rows quarter*32 .. +31 of the tile)
+    const int half = warp >> 2;       // which CW-wide slice of the key columns / OW-wide slice of O this warp owns
+    const int row = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_base + C::COL_S;
-    const uint32_t t_p = tmem_base + lane_base + C::COL_P;
-    const uint32_t t_o = tmem_base + lane_base + C::COL_O;
-    uint8_t* stg = s_out + warp * C::OUT_WARP;
+    const uint32_t t_s = tmem_base + lane_base + C::COL_S + static_cast<uint32_t>(half * CW);
+    const uint32_t t_p = tmem_base + lane_base + C::COL_P + static_cast<uint32_t>(half * CW / 2);
+    const uint32_t t_o = tmem_base + lane_base + C::COL_O + static_cast<uint32_t>(half * OW);
+    uint8_t* stg = s_out + quarter * C::OUT_WARP;
+    float* xch_max = reinterpret_cast<float*>(smem + C::OFF_XCH);  // [parity][half][row]
+    float* xch_sum = xch_max + 2 * 2 * BQ;                         // [half][row]
     uint32_t g = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int qt = item % p.q_tiles;
       const int bh = item / p.q_tiles;
       const int h = bh % p.H, b = bh / p.H;
       const int nb = item_blocks(qt);
-      const int qrow = qt * BQ + quarter * 32 + lane;
+      const int qrow = qt * BQ + row;
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nb; ++j, ++g) {
-        ptx::mbar_wait(s_full, g & 1);
+        if (warp == 0 && lane == 0) { ATTN_TIMED_WAIT(8, s_full, g & 1); } else { ptx::mbar_wait(s_full, g & 1); }
         ptx::tc_fence_after();
-        float sv[BKV];
+        float sv[CW];
         {
-          // issue every TMEM load of this row before the single wait
-          uint32_t r[(BKV + 31) / 32][32];
+          // issue every TMEM load of this thread's slice before the single wait
+          uint32_t r32[CW / 32 > 0 ? CW / 32 : 1][32];
+          uint32_t r16[16];
 #pragma unroll
-          for (int c = 0; c < BKV / 32; ++c) {
+          for (int c = 0; c < CW / 32; ++c) {
             if (CLIPB200_ATTN_DBG & 2) {
 #pragma unroll
-              for (int e = 0; e < 32; ++e) r[c][e] = 0;
+              for (int e = 0; e < 32; ++e) r32[c][e] = 0x3f800000u + e;
             } else {
-              ptx::tmem_ld_32x32(t_s + static_cast<uint32_t>(c * 32), r[c]);
+              ptx::tmem_ld_32x32(t_s + static_cast<uint32_t>(c * 32), r32[c]);
             }
           }
-          if (BKV % 32 != 0) {
-            uint32_t r16[16];
-            tmem_ld_32x32_x16(t_s + static_cast<uint32_t>(BKV / 32 * 32), r16);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) r[BKV / 32][e] = r16[e];
-          }
+          if (CW % 32 != 0) tmem_ld_32x32_x16(t_s + static_cast<uint32_t>(CW / 32 * 32), r16);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < BKV; ++e) sv[e] = __uint_as_float(r[e / 32][e % 32]);
+          for (int e = 0; e < CW / 32 * 32; ++e) sv[e] = __uint_as_float(r32[e / 32][e % 32]);
+          if (CW % 32 != 0) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sv[CW / 32 * 32 + e] = __uint_as_float(r16[e]);
+          }
         }
         ptx::tc_fence_before();
         ptx::mbar_arrive(s_empty);  // S is in registers: the next QK^T may overwrite it
-        const int key0 = j * BKV;
-        const bool need_mask = (key0 + BKV > p.T) || (CAUSAL && key0 + BKV - 1 > qt * BQ + quarter * 32);
+        const int key0 = j * BKV + half * CW;
+        const bool need_mask = (key0 + CW > p.T) || (CAUSAL && key0 + CW - 1 > qt * BQ + quarter * 32);
         if (need_mask) {  // warp-uniform, only the last kv block (and the diagonal blocks of causal towers)
 #pragma unroll
-          for (int e = 0; e < BKV; ++e) {
+          for (int e = 0; e < CW; ++e) {
             const int key = key0 + e;
             if (key >= p.T || (CAUSAL && key > qrow)) sv[e] = -INFINITY;
           }
@@ -384,7 +445,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
         // row maximum on the raw scores (the scale is positive, so max(s * scale) == scale * max(s))
         float mx = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < BKV; ++e) mx = fmaxf(mx, sv[e]);
+        for (int e = 0; e < CW; ++e) mx = fmaxf(mx, sv[e]);
+        if (SPLIT == 2) {  // combine with the warp that owns the other half of this row's columns
+          float* slot = xch_max + (g & 1) * 2 * BQ;
+          slot[half * BQ + row] = mx;
+          pair_barrier(quarter);
+          mx = fmaxf(mx, slot[(half ^ 1) * BQ + row]);
+        }
         mx *= p.scale_log2e;
         // Lazy rescaling: keep the running reference maximum unless the new block maximum exceeds it by more than
         // 2^8; P then stays <= 256 (exact in the fp32 sums, fine in bf16) and O / l are rescaled only rarely.
@@ -395,9 +462,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
         const float alpha = bump ? ex2(m_run - m_use) : 1.0f;
         const float neg_m = -m_use;
         float rs0 = 0.f, rs1 = 0.f;
-        uint32_t pk[BKV / 2];
+        uint32_t pk[CW / 2];
 #pragma unroll
-        for (int e = 0; e < BKV / 2; ++e) {
+        for (int e = 0; e < CW / 2; ++e) {
           // exp2(s * scale - m): one FFMA + one MUFU per element
           const float a0 = fmaf(sv[2 * e], p.scale_log2e, neg_m), a1 = fmaf(sv[2 * e + 1], p.scale_log2e, neg_m);
           const float p0 = (CLIPB200_ATTN_DBG & 1) ? a0 * 0.001f : ex2(a0);
@@ -406,22 +473,27 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
           rs1 += p1;
           pk[e] = pack_bf16(p0, p1);
         }
-        const float rs = rs0 + rs1;
-        l_run = l_run * alpha + rs;
+        l_run = l_run * alpha + (rs0 + rs1);  // partial over this warp's columns; the halves are added in the epilogue
         m_run = m_new;
         // P(j) and the O rescale must wait until PV(j-1) has finished reading P and writing O
-        ptx::mbar_wait(pv_done, (g & 1) ^ 1);
+        if (warp == 0 && lane == 0) { ATTN_TIMED_WAIT(9, pv_done, (g & 1) ^ 1); } else { ptx::mbar_wait(pv_done, (g & 1) ^ 1); }
         ptx::tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < BKV / 32; ++c) {
+        for (int c = 0; c < CW / 32; ++c) {
           uint32_t r[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) r[e] = pk[c * 16 + e];
-          if (!(CLIPB200_ATTN_DBG & 4)) tmem_st_32x32_x16(t_p + static_cast<uint32_t>(c * 16), r);
+          tmem_st_32x32_x16(t_p + static_cast<uint32_t>(c * 16), r);
         }
-        if (j > 0 && __any_sync(0xffffffffu, bump)) {
+        if (CW % 32 != 0) {
+          uint32_t r[8];
 #pragma unroll
-          for (int c = 0; c < C::HDP / 16; ++c) {
+          for (int e = 0; e < 8; ++e) r[e] = pk[CW / 32 * 16 + e];
+          tmem_st_32x32_x8(t_p + static_cast<uint32_t>(CW / 32 * 16), r);
+        }
+        if (j > 0 && __any_sync(0xffffffffu, bump)) {  // rare: rescale this warp's slice of O
+#pragma unroll
+          for (int c = 0; c < OW / 16; ++c) {
             uint32_t r[16];
             tmem_ld_32x32_x16(t_o + static_cast<uint32_t>(c * 16), r);
             ptx::tmem_ld_wait();
@@ -429,47 +501,55 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
             for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
             tmem_st_32x32_x16(t_o + static_cast<uint32_t>(c * 16), r);
           }
+          if (OW % 16 != 0) {
+            uint32_t r[8];
+            tmem_ld_32x32_x8(t_o + static_cast<uint32_t>(OW / 16 * 16), r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+            tmem_st_32x32_x8(t_o + static_cast<uint32_t>(OW / 16 * 16), r);
+          }
         }
         tmem_st_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(p_full);
       }
-      // epilogue: wait for the last PV, normalise, store
-      ptx::mbar_wait(pv_done, (g & 1) ^ 1);
+      // epilogue: wait for the last PV, normalise, store this warp's slice of the O row
+      if (warp == 0 && lane == 0) { ATTN_TIMED_WAIT(10, pv_done, (g & 1) ^ 1); } else { ptx::mbar_wait(pv_done, (g & 1) ^ 1); }
       ptx::tc_fence_after();
-      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-      if (lane == 0) ptx::tma_store_wait_read<0>();
-      __syncwarp();
+      if (SPLIT == 2) xch_sum[half * BQ + row] = l_run;
+      if (half == 0 && lane == 0) ptx::tma_store_wait_read<0>();  // previous item's store has left the staging tile
+      if (SPLIT == 2) pair_barrier(quarter); else __syncwarp();
+      const float l_tot = SPLIT == 2 ? l_run + xch_sum[(half ^ 1) * BQ + row] : l_run;
+      const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
 #pragma unroll
-      for (int c = 0; c < (HD + 15) / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld_32x32_x16(t_o + static_cast<uint32_t>(c * 16), r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          if (c * 16 + e * 8 < HD) {
-            uint4 o;
-            o.x = pack_bf16(__uint_as_float(r[e * 8 + 0]) * inv, __uint_as_float(r[e * 8 + 1]) * inv);
-            o.y = pack_bf16(__uint_as_float(r[e * 8 + 2]) * inv, __uint_as_float(r[e * 8 + 3]) * inv);
-            o.z = pack_bf16(__uint_as_float(r[e * 8 + 4]) * inv, __uint_as_float(r[e * 8 + 5]) * inv);
-            o.w = pack_bf16(__uint_as_float(r[e * 8 + 6]) * inv, __uint_as_float(r[e * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(stg + lane * C::OUT_ROW + (c * 16 + e * 8) * 2) = o;
-          }
+      for (int c = 0; c < OW / 8; ++c) {
+        const int col = half * OW + c * 8;
+        if (col < HD) {
+          uint32_t r[8];
+          tmem_ld_32x32_x8(t_o + static_cast<uint32_t>(c * 8), r);
+          ptx::tmem_ld_wait();
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+          o.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+          o.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+          o.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+          *reinterpret_cast<uint4*>(stg + lane * C::OUT_ROW + col * 2) = o;
         }
       }
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
+      if (SPLIT == 2) pair_barrier(quarter); else __syncwarp();
+      if (half == 0 && lane == 0) {
         tma_store_3d(&tm_out, stg, h * HD, qt * BQ + quarter * 32, b);
         ptx::tma_store_commit();
       }
     }
-    if (lane == 0) ptx::tma_store_wait<0>();
+    if (half == 0 && lane == 0) ptx::tma_store_wait<0>();
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == WARP_MMA) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }

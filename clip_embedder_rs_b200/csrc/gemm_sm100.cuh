@@ -197,7 +197,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp == GEMM_WARP_MMA) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && rank == 0) {  // in a pair only the leader CTA issues MMAs
+    if (rank == 0) {  // in a pair only the leader CTA issues MMAs; whole warp in uniform control flow, one lane elected
+                      // inside each issue (keeps descriptors in uniform registers: see ptx_sm100.cuh)
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(TILE_M, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -216,20 +217,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the (>>4) address field
             if (NCTA == 2)
-              ptx::umma_bf16_ss_2sm(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+              ptx::umma_bf16_ss_2sm_w(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
                                     (kb | k) != 0 ? 1u : 0u);
             else
-              ptx::umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+              ptx::umma_bf16_ss_w(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
                                 (kb | k) != 0 ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-          if (NCTA == 2) ptx::umma_commit_2sm(&empty_bar[stage]);
-          else ptx::umma_commit(&empty_bar[stage]);
+          if (NCTA == 2) ptx::umma_commit_2sm_w(&empty_bar[stage]);
+          else ptx::umma_commit_w(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         // accumulator complete (each CTA of a pair holds its own 128 rows in its own TMEM)
-        if (NCTA == 2) ptx::umma_commit_2sm(&tmem_full_bar[acc]);
-        else ptx::umma_commit(&tmem_full_bar[acc]);
+        if (NCTA == 2) ptx::umma_commit_2sm_w(&tmem_full_bar[acc]);
+        else ptx::umma_commit_w(&tmem_full_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

@@ -143,7 +143,7 @@ int main(int argc, char** argv) {
   CK(cudaSetDevice(0));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
-  const int num_sms = prop.multiProcessorCount;
+  const int num_sms = getenv("ATTN_HALF_GRID") ? prop.multiProcessorCount / 2 : prop.multiProcessorCount;
   CK(flash_attention_configure_device());
   CK(attn_tcgen05_configure_device());
   int fails = 0;
@@ -168,6 +168,16 @@ int main(int argc, char** argv) {
   run(64, 576, 16, 96, false, true);   // 12
   run(128, 576, 18, 64, false, true);  // 13: no remainder planes (same total width as 16 x 72)
   run(128, 576, 14, 80, false, true);  // 14: two real remainder planes
+#ifdef CLIPB200_ATTN_TIMING
+  {
+    unsigned long long h[16];
+    CK(cudaMemcpyFromSymbol(h, attn::g_attn_wait, sizeof(h)));
+    const char* names[13] = {"prod q_empty", "prod k_empty", "prod v_empty", "mma k_full", "mma s_empty", "mma q_full",
+                             "mma v_full", "mma p_full", "smx s_full", "smx pv_done", "smx pv_done(epi)",
+                             "mma QK issue", "mma PV issue"};
+    for (int i = 0; i < 13; ++i) printf("  wait[%-16s] = %llu cycles\n", names[i], h[i]);
+  }
+#endif
   printf("%s (%d failing cases)\n", fails ? "ATTN TEST FAILED" : "ATTN TEST PASSED", fails);
   return fails ? 1 : 0;
 }
