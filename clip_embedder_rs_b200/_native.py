@@ -40,6 +40,7 @@ SIGNATURES = {
     "clipb200_last_error": (C.c_char_p, []),
     "clipb200_version": (C.c_char_p, []),
     "clipb200_onnx_inspect": (C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t]),
+    "clipb200_onnx_read_tensor": (C.c_int, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "clipb200_engine_num_inputs": (C.c_int, [C.c_void_p]),
     "clipb200_engine_input_name": (C.c_char_p, [C.c_void_p, C.c_int]),
     "clipb200_engine_kind": (C.c_int, [C.c_void_p]),

@@ -93,11 +93,17 @@ int clipb200_onnx_inspect(const char* onnx_path, char* json_out, size_t capacity
   };
   size_t bytes = 0;
   for (const auto& kv : m.initializers) bytes += kv.second.nbytes;
+  const size_t n_file_initializers = m.initializers.size();
+  // the same structural binding clipb200_engine_create performs for real exports (onnx_graph.h)
+  std::vector<clipb200::GraphBinding> bindings;
+  std::string graph_err;
+  const bool graph_tried = clipb200::graph_needs_recognition(m);
+  const bool graph_ok = graph_tried && clipb200::recognize_graph(&m, &graph_err, &bindings);
   std::string j = "{\"inputs\": [";
   for (size_t i = 0; i < m.inputs.size(); ++i) j += std::string(i ? ", " : "") + "\"" + esc(m.inputs[i]) + "\"";
   j += "], \"outputs\": [";
   for (size_t i = 0; i < m.outputs.size(); ++i) j += std::string(i ? ", " : "") + "\"" + esc(m.outputs[i]) + "\"";
-  j += "], \"opset\": " + std::to_string(m.opset) + ", \"num_initializers\": " + std::to_string(m.initializers.size()) +
+  j += "], \"opset\": " + std::to_string(m.opset) + ", \"num_initializers\": " + std::to_string(n_file_initializers) +
        ", \"initializer_bytes\": " + std::to_string(bytes) + ", \"num_nodes\": " + std::to_string(m.nodes.size()) +
        ", \"metadata\": {";
   bool first = true;
@@ -105,9 +111,44 @@ int clipb200_onnx_inspect(const char* onnx_path, char* json_out, size_t capacity
     j += std::string(first ? "" : ", ") + "\"" + esc(kv.first) + "\": \"" + esc(kv.second) + "\"";
     first = false;
   }
-  j += "}}";
+  j += "}, \"graph\": {\"attempted\": " + std::string(graph_tried ? "true" : "false") + ", \"recognized\": " +
+       std::string(graph_ok ? "true" : "false") + ", \"error\": \"" + esc(graph_err) + "\", \"bindings\": [";
+  for (size_t i = 0; i < bindings.size(); ++i)
+    j += std::string(i ? ", " : "") + "{\"name\": \"" + esc(bindings[i].canonical) + "\", \"source\": \"" +
+         esc(bindings[i].source) + "\", \"transposed\": " + (bindings[i].transposed ? "true" : "false") + "}";
+  j += "]}}";
   if (j.size() + 1 > capacity) return fail(CLIPB200_ERR_INVALID_ARG, "output buffer too small");
   memcpy(json_out, j.c_str(), j.size() + 1);
+  return CLIPB200_OK;
+  API_GUARD_END
+}
+
+// Parse-only: the fp32 value of one tensor exactly as clipb200_engine_create would bind it (after graph recognition,
+// canonical [out, in] layout for Linear weights).
+int clipb200_onnx_read_tensor(const char* onnx_path, const char* name, float* out, size_t capacity, int64_t* dims_out,
+                              int* rank_out) {
+  API_GUARD_BEGIN
+  if (onnx_path == nullptr || name == nullptr || rank_out == nullptr) return fail(CLIPB200_ERR_INVALID_ARG, "null argument");
+  clipb200::OnnxModel m;
+  std::string err;
+  if (!clipb200::load_onnx(onnx_path, &m, &err)) {
+    const bool io = err.find("cannot open") != std::string::npos || err.find("cannot stat") != std::string::npos ||
+                    err.find("cannot mmap") != std::string::npos || err.find("is empty") != std::string::npos;
+    return fail(io ? CLIPB200_ERR_IO : CLIPB200_ERR_PARSE, err);
+  }
+  if (clipb200::graph_needs_recognition(m) && !clipb200::recognize_graph(&m, &err, nullptr)) {
+    // not fatal: the tensor may still be present under its exported name
+  }
+  const clipb200::OnnxTensor* t = m.find(name);
+  if (t == nullptr) return fail(CLIPB200_ERR_UNSUPPORTED, std::string("tensor '") + name + "' not found" + (err.empty() ? "" : "; " + err));
+  if (t->dims.size() > 8) return fail(CLIPB200_ERR_UNSUPPORTED, "tensor rank > 8");
+  *rank_out = static_cast<int>(t->dims.size());
+  if (dims_out != nullptr) for (size_t i = 0; i < t->dims.size(); ++i) dims_out[i] = t->dims[i];
+  if (out == nullptr) return CLIPB200_OK;  // shape query
+  if (static_cast<size_t>(t->numel()) > capacity) return fail(CLIPB200_ERR_INVALID_ARG, "output buffer too small");
+  std::vector<float> v;
+  if (!clipb200::tensor_to_f32(*t, &v)) return fail(CLIPB200_ERR_UNSUPPORTED, "tensor is not f32 / f16 / bf16");
+  memcpy(out, v.data(), v.size() * 4);
   return CLIPB200_OK;
   API_GUARD_END
 }

@@ -126,6 +126,7 @@ Status Engine::UploadLinear(const OnnxModel& m, const std::string& wname, const 
     RET_IF_ERR(HostF32(m, wname, -1, &tmp));
     src = tmp.data();
   }
+  if (t->transposed) transpose = !transpose;  // canonical alias of a pre-transposed MatMul operand (onnx_graph.cc)
   const int ldk = (K + 7) & ~7;
   float* staging = nullptr;
   const size_t fbytes = static_cast<size_t>(N) * K * 4;
@@ -275,17 +276,22 @@ Status Engine::LoadVision(const OnnxModel& m) {
     RET_IF_ERR(UploadF32(m, pre + ".norm.weight", D_, &ln_post_.g));
     RET_IF_ERR(UploadF32(m, pre + ".norm.bias", D_, &ln_post_.b));
     const std::string ap = pre + ".attn_pool";
-    // the pooling query is weight-only: q = (latent @ Wq^T + bq) * hd^-0.5, folded at load time
-    std::vector<float> latent, wq, bq;
-    RET_IF_ERR(HostF32(m, ap + ".latent", D_, &latent));
-    RET_IF_ERR(HostF32(m, ap + ".q.weight", static_cast<int64_t>(D_) * D_, &wq));
-    RET_IF_ERR(HostF32(m, ap + ".q.bias", D_, &bq));
+    // the pooling query is weight-only: q = (latent @ Wq^T + bq) * hd^-0.5, folded at load time (the graph
+    // recogniser folds it from the graph itself and hands it over as `clipb200.map_query`)
     std::vector<float> q(D_);
-    const double sc = 1.0 / sqrt(static_cast<double>(hd_));
-    for (int o = 0; o < D_; ++o) {
-      double acc = bq[o];
-      for (int i = 0; i < D_; ++i) acc += static_cast<double>(wq[static_cast<size_t>(o) * D_ + i]) * latent[i];
-      q[o] = static_cast<float>(acc * sc);
+    if (m.has("clipb200.map_query")) {
+      RET_IF_ERR(HostF32(m, "clipb200.map_query", D_, &q));
+    } else {
+      std::vector<float> latent, wq, bq;
+      RET_IF_ERR(HostF32(m, ap + ".latent", D_, &latent));
+      RET_IF_ERR(HostF32(m, ap + ".q.weight", static_cast<int64_t>(D_) * D_, &wq));
+      RET_IF_ERR(HostF32(m, ap + ".q.bias", D_, &bq));
+      const double sc = 1.0 / sqrt(static_cast<double>(hd_));
+      for (int o = 0; o < D_; ++o) {
+        double acc = bq[o];
+        for (int i = 0; i < D_; ++i) acc += static_cast<double>(wq[static_cast<size_t>(o) * D_ + i]) * latent[i];
+        q[o] = static_cast<float>(acc * sc);
+      }
     }
     RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&map_q_), D_ * 4));
     CUDA_RET(cudaMemcpy(map_q_, q.data(), D_ * 4, cudaMemcpyHostToDevice), "upload pool query");
@@ -424,6 +430,10 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
     return Status::Err(io ? CLIPB200_ERR_IO : CLIPB200_ERR_PARSE, err);
   }
   input_names = m.inputs;
+  // Real exports (torch.onnx.export graphs) are bound from the graph structure; initializer-only files and graphs
+  // the recogniser does not know (FastViT) fall through to binding by open_clip / timm parameter names.
+  std::string graph_err;
+  if (graph_needs_recognition(m) && !recognize_graph(&m, &graph_err, nullptr)) graph_note_ = graph_err;
   if (get_encode_tiled() == nullptr)  // resolved here so that it never happens inside a graph capture
     return Status::Err(CLIPB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
   if (const char* env = getenv("CLIPB200_NO_GRAPHS")) if (atoi(env) != 0) graph_max_n_ = 0;
@@ -438,8 +448,11 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
   for (const std::string& n : m.inputs) if (n == "input_ids") is_text = true;
   const std::string tower = m.meta("clipb200.tower");
   if (tower == "text") is_text = true;
-  if (is_text) RET_IF_ERR(LoadText(m));
-  else RET_IF_ERR(LoadVision(m));
+  {
+    Status ls = is_text ? LoadText(m) : LoadVision(m);
+    if (!ls.ok() && !graph_note_.empty()) return Status::Err(ls.code, ls.msg + "; " + graph_note_);
+    RET_IF_ERR(ls);
+  }
   if (!fastvit_ && hd_ != 32 && hd_ != 64 && hd_ != 72 && hd_ != 80 && hd_ != 96 && hd_ != 128)
     return Status::Err(CLIPB200_ERR_UNSUPPORTED, "head_dim " + std::to_string(hd_) + " not supported");
   if (!fastvit_ && ((D_ & 7) || (mlp_ & 7) || (E_ & 7) || D_ > 2048))

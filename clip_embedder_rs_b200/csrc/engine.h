@@ -14,6 +14,7 @@
 #include <map>
 #include <tuple>
 
+#include "onnx_graph.h"
 #include "onnx_loader.h"
 #include "resize.cuh"
 
@@ -157,6 +158,7 @@ class Engine {
 
   // architecture
   std::string family_;
+  std::string graph_note_;  // why the graph recogniser declined (reported if name binding fails too)
   int S_ = 0, P_ = 0, G_ = 0, Tp_ = 0, T_ = 0, D_ = 0, L_ = 0, H_ = 0, hd_ = 0, mlp_ = 0, act_ = 0, E_ = 0;
   int K_ = 0, Kp_ = 0, vocab_ = 0;
   float eps_ = 1e-5f;

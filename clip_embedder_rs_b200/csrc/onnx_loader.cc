@@ -111,6 +111,7 @@ struct ExtRef {
 bool parse_tensor(Cursor c, OnnxTensor* t, ExtRef* ext) {
   std::vector<float> float_data;
   std::vector<int64_t> int64_data;
+  std::vector<int32_t> int32_data;
   while (!c.done()) {
     int w;
     const int f = c.key(&w);
@@ -151,6 +152,13 @@ bool parse_tensor(Cursor c, OnnxTensor* t, ExtRef* ext) {
       } else {
         c.skip(w);
       }
+    } else if (f == 5) {  // int32_data (also carries bool / int8 / uint8 / fp16 bit patterns)
+      if (w == 2) {
+        Cursor r = c.sub();
+        while (!r.done()) int32_data.push_back(static_cast<int32_t>(r.varint()));
+      } else {
+        int32_data.push_back(static_cast<int32_t>(c.varint()));
+      }
     } else if (f == 7) {  // int64_data
       if (w == 2) {
         Cursor r = c.sub();
@@ -169,6 +177,20 @@ bool parse_tensor(Cursor c, OnnxTensor* t, ExtRef* ext) {
     } else if (!int64_data.empty()) {
       t->owned.resize(int64_data.size() * 8);
       memcpy(t->owned.data(), int64_data.data(), t->owned.size());
+    } else if (!int32_data.empty()) {
+      if (t->data_type == 6) {
+        t->owned.resize(int32_data.size() * 4);
+        memcpy(t->owned.data(), int32_data.data(), t->owned.size());
+      } else if (t->data_type == 9 || t->data_type == 2 || t->data_type == 3) {
+        t->owned.resize(int32_data.size());
+        for (size_t i = 0; i < int32_data.size(); ++i) t->owned[i] = static_cast<uint8_t>(int32_data[i]);
+      } else if (t->data_type == 10 || t->data_type == 16) {
+        t->owned.resize(int32_data.size() * 2);
+        for (size_t i = 0; i < int32_data.size(); ++i) {
+          const uint16_t h = static_cast<uint16_t>(int32_data[i]);
+          memcpy(t->owned.data() + 2 * i, &h, 2);
+        }
+      }
     }
     t->data = t->owned.data();
     t->nbytes = t->owned.size();
@@ -176,12 +198,90 @@ bool parse_tensor(Cursor c, OnnxTensor* t, ExtRef* ext) {
   return c.ok;
 }
 
-void parse_value_info_name(Cursor c, std::string* name) {
+// ValueInfoProto{1 name, 2 type{1 tensor_type{1 elem_type, 2 shape{1 dim{1 dim_value | 2 dim_param}}}}}
+void parse_value_info(Cursor c, OnnxValueInfo* vi) {
+  while (!c.done()) {
+    int w;
+    const int f = c.key(&w);
+    if (f == 1 && w == 2) {
+      vi->name = c.str();
+    } else if (f == 2 && w == 2) {
+      Cursor ty = c.sub();
+      while (!ty.done()) {
+        int tw;
+        const int tf = ty.key(&tw);
+        if (tf == 1 && tw == 2) {
+          Cursor tt = ty.sub();
+          while (!tt.done()) {
+            int ew;
+            const int ef = tt.key(&ew);
+            if (ef == 1 && ew == 0) {
+              vi->elem_type = static_cast<int>(tt.varint());
+            } else if (ef == 2 && ew == 2) {
+              Cursor sh = tt.sub();
+              while (!sh.done()) {
+                int sw;
+                const int sf = sh.key(&sw);
+                if (sf == 1 && sw == 2) {
+                  Cursor d = sh.sub();
+                  int64_t value = -1;
+                  while (!d.done()) {
+                    int dw;
+                    const int df = d.key(&dw);
+                    if (df == 1 && dw == 0) value = static_cast<int64_t>(d.varint());
+                    else d.skip(dw);
+                  }
+                  vi->dims.push_back(value);
+                } else {
+                  sh.skip(sw);
+                }
+              }
+            } else {
+              tt.skip(ew);
+            }
+          }
+        } else {
+          ty.skip(tw);
+        }
+      }
+    } else {
+      c.skip(w);
+    }
+  }
+}
+
+bool parse_tensor(Cursor c, OnnxTensor* t, ExtRef* ext);
+
+void parse_attr(Cursor c, std::string* name, OnnxAttr* a) {
   while (!c.done()) {
     int w;
     const int f = c.key(&w);
     if (f == 1 && w == 2) *name = c.str();
-    else c.skip(w);
+    else if (f == 2 && w == 5) { memcpy(&a->f, c.p, 4); c.p += 4; if (a->type == 0) a->type = 1; }
+    else if (f == 3 && w == 0) { a->i = static_cast<int64_t>(c.varint()); if (a->type == 0) a->type = 2; }
+    else if (f == 4 && w == 2) { a->s = c.str(); if (a->type == 0) a->type = 3; }
+    else if (f == 5 && w == 2) {
+      a->t = std::make_shared<OnnxTensor>();
+      ExtRef ext;
+      if (!parse_tensor(c.sub(), a->t.get(), &ext) || ext.present) a->t.reset();  // constants are always inline
+      if (a->type == 0) a->type = 4;
+    } else if (f == 7) {
+      if (w == 2) {
+        Cursor r = c.sub();
+        while (r.end - r.p >= 4) { float v; memcpy(&v, r.p, 4); r.p += 4; a->floats.push_back(v); }
+      } else if (w == 5) { float v; memcpy(&v, c.p, 4); c.p += 4; a->floats.push_back(v); }
+      else c.skip(w);
+    } else if (f == 8) {
+      if (w == 2) {
+        Cursor r = c.sub();
+        while (!r.done()) a->ints.push_back(static_cast<int64_t>(r.varint()));
+      } else if (w == 0) a->ints.push_back(static_cast<int64_t>(c.varint()));
+      else c.skip(w);
+    } else if (f == 20 && w == 0) {
+      a->type = static_cast<int>(c.varint());
+    } else {
+      c.skip(w);
+    }
   }
 }
 
@@ -191,8 +291,14 @@ void parse_node(Cursor c, OnnxNode* n) {
     const int f = c.key(&w);
     if (f == 1 && w == 2) n->inputs.push_back(c.str());
     else if (f == 2 && w == 2) n->outputs.push_back(c.str());
+    else if (f == 3 && w == 2) n->name = c.str();
     else if (f == 4 && w == 2) n->op_type = c.str();
-    else c.skip(w);
+    else if (f == 5 && w == 2) {
+      std::string name;
+      OnnxAttr a;
+      parse_attr(c.sub(), &name, &a);
+      n->attrs.emplace(std::move(name), std::move(a));
+    } else c.skip(w);
   }
 }
 
@@ -233,7 +339,7 @@ bool load_onnx(const std::string& path, OnnxModel* model, std::string* err) {
   const size_t slash = path.find_last_of('/');
   if (slash != std::string::npos) dir = path.substr(0, slash);
   std::map<std::string, std::shared_ptr<MappedFile>> ext_files;
-  std::vector<std::string> graph_inputs;
+  std::vector<OnnxValueInfo> graph_inputs;
   bool saw_graph = false;
 
   Cursor c{static_cast<const uint8_t*>(mf->base), static_cast<const uint8_t*>(mf->base) + mf->size, true};
@@ -285,10 +391,10 @@ bool load_onnx(const std::string& path, OnnxModel* model, std::string* err) {
           }
           model->initializers.emplace(t.name, std::move(t));
         } else if ((gf == 11 || gf == 12) && gw == 2) {
-          std::string name;
-          parse_value_info_name(g.sub(), &name);
-          if (gf == 11) graph_inputs.push_back(name);
-          else model->outputs.push_back(name);
+          OnnxValueInfo vi;
+          parse_value_info(g.sub(), &vi);
+          if (gf == 11) graph_inputs.push_back(std::move(vi));
+          else model->outputs.push_back(vi.name);
         } else if (gf == 1 && gw == 2) {
           OnnxNode n;
           parse_node(g.sub(), &n);
@@ -341,8 +447,11 @@ bool load_onnx(const std::string& path, OnnxModel* model, std::string* err) {
     }
   }
   // Old exporters list initializers among the graph inputs; real inputs are the ones without data.
-  for (const std::string& n : graph_inputs)
-    if (!model->initializers.count(n)) model->inputs.push_back(n);
+  for (OnnxValueInfo& vi : graph_inputs) {
+    if (model->initializers.count(vi.name)) continue;
+    model->inputs.push_back(vi.name);
+    model->input_infos.push_back(std::move(vi));
+  }
   return true;
 }
 

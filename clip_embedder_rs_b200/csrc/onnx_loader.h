@@ -27,6 +27,10 @@ struct OnnxTensor {
   const uint8_t* data = nullptr;  // points into a mapped file, or into `owned`
   size_t nbytes = 0;
   std::vector<uint8_t> owned;  // float_data / int64_data fields converted to raw little-endian
+  // Set by the graph recogniser (onnx_graph.cc) on canonical-name aliases of 2-D weights: `dims` are the canonical
+  // [rows, cols] but the bytes are stored as the transpose ([cols, rows] row-major), e.g. a `Linear` weight that the
+  // exporter pre-transposed into a MatMul operand.
+  bool transposed = false;
   int64_t numel() const {
     int64_t n = 1;
     for (int64_t d : dims) n *= d;
@@ -34,14 +38,44 @@ struct OnnxTensor {
   }
 };
 
+struct OnnxAttr {
+  int type = 0;  // AttributeProto.type: 1 FLOAT, 2 INT, 3 STRING, 4 TENSOR, 6 FLOATS, 7 INTS
+  float f = 0.f;
+  int64_t i = 0;
+  std::string s;
+  std::vector<int64_t> ints;
+  std::vector<float> floats;
+  std::shared_ptr<OnnxTensor> t;
+};
+
 struct OnnxNode {
-  std::string op_type;
+  std::string op_type, name;
   std::vector<std::string> inputs, outputs;
+  std::map<std::string, OnnxAttr> attrs;
+  const OnnxAttr* attr(const std::string& k) const {
+    auto it = attrs.find(k);
+    return it == attrs.end() ? nullptr : &it->second;
+  }
+  int64_t attr_i(const std::string& k, int64_t dflt) const {
+    const OnnxAttr* a = attr(k);
+    return a ? a->i : dflt;
+  }
+  float attr_f(const std::string& k, float dflt) const {
+    const OnnxAttr* a = attr(k);
+    return a ? a->f : dflt;
+  }
+};
+
+struct OnnxValueInfo {
+  std::string name;
+  int elem_type = 0;
+  std::vector<int64_t> dims;  // -1 for symbolic (dim_param) dimensions
 };
 
 struct OnnxModel {
   std::vector<std::string> inputs;   // graph inputs that are not initializers
   std::vector<std::string> outputs;
+  std::vector<OnnxValueInfo> input_infos;  // same order as `inputs`
   std::map<std::string, OnnxTensor> initializers;
   std::map<std::string, std::string> metadata;
   std::vector<OnnxNode> nodes;

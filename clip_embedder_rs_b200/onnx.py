@@ -15,6 +15,42 @@ def _raise_engine_error(code: int) -> None:
     raise error.Ort(_native.last_error(), code)
 
 
+def inspect_onnx(path) -> dict:
+    """Parse-only description of a model file (no GPU): inputs, outputs, opset, metadata and — for files that carry
+    an executable graph — how the graph recogniser bound every parameter (`["graph"]["bindings"]`)."""
+    import json
+
+    cap = 1 << 20
+    while True:
+        buf = C.create_string_buffer(cap)
+        rc = _native.lib.clipb200_onnx_inspect(os.fspath(path).encode(), buf, cap)
+        if rc == _native.OK:
+            return json.loads(buf.value.decode())
+        if "too small" in _native.last_error() and cap < (1 << 28):
+            cap *= 4
+            continue
+        _raise_engine_error(rc)
+
+
+def read_onnx_tensor(path, name: str):
+    """fp32 value of one parameter exactly as the engine would bind it (canonical open_clip / timm name, `[out, in]`
+    layout for Linear weights), without touching a GPU."""
+    import numpy as np
+
+    dims = (C.c_int64 * 8)()
+    rank = C.c_int(0)
+    p = os.fspath(path).encode()
+    rc = _native.lib.clipb200_onnx_read_tensor(p, name.encode(), None, 0, dims, C.byref(rank))
+    if rc != _native.OK:
+        _raise_engine_error(rc)
+    shape = tuple(int(dims[i]) for i in range(rank.value))
+    out = np.empty(shape, dtype=np.float32)
+    rc = _native.lib.clipb200_onnx_read_tensor(p, name.encode(), out.ctypes.data_as(C.c_void_p), out.size, dims, C.byref(rank))
+    if rc != _native.OK:
+        _raise_engine_error(rc)
+    return out
+
+
 class OnnxSession:
     def __init__(self, path, execution_providers: Optional[Sequence] = None, device: int = 0,
                  micro_batch: int = 0, profile: bool = False):

@@ -84,6 +84,14 @@ const char* clipb200_version(void);
  * metadata) of what clipb200_engine_create would load.  Same IO / PARSE status codes as create. */
 int clipb200_onnx_inspect(const char* onnx_path, char* json_out, size_t capacity);
 
+/* Parse-only probe (no GPU needed): copies one tensor as fp32 exactly as clipb200_engine_create would bind it.
+ * For files that carry an executable graph (what `torch.onnx.export` writes, pull_onnx.py:169-181) the tensors are
+ * bound from the graph structure, not from initializer names, and are reported under the open_clip / timm
+ * parameter names with Linear weights in [out, in] layout; `clipb200_onnx_inspect` lists the bindings under
+ * "graph".  `out` may be NULL to query the shape only; `dims_out` must have room for 8 entries. */
+int clipb200_onnx_read_tensor(const char* onnx_path, const char* name, float* out, size_t capacity_elems,
+                              int64_t* dims_out, int* rank_out);
+
 /* ---- introspection (src/onnx.rs:32-46) ---------------------------------------------------------------- */
 int clipb200_engine_num_inputs(const clipb200_engine* e);
 const char* clipb200_engine_input_name(const clipb200_engine* e, int i);

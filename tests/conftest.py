@@ -34,6 +34,25 @@ def make_model(model_root):
     return _make
 
 
+@pytest.fixture(scope="session")
+def make_real_model(model_root):
+    """Model directory whose visual.onnx / text.onnx are executable graphs written by `torch.onnx.export`
+    (tools/torch_export.py), optionally with every initializer renamed to `val_<n>`."""
+    import export_synthetic as ex
+    import torch_export as te
+
+    cache = {}
+
+    def _make(config: str, seed: int = 0, anonymize: bool = False, towers=("vision", "text")) -> str:
+        key = (config, seed, anonymize, tuple(towers))
+        if key not in cache:
+            out = os.path.join(model_root, f"real_{config}_s{seed}_{'anon' if anonymize else 'named'}_{'-'.join(towers)}")
+            cache[key] = te.export_model_dir(ex.CONFIGS[config], out, seed, tuple(towers), anonymize)
+        return cache[key]
+
+    return _make
+
+
 def random_images(n: int, size: int, seed: int) -> np.ndarray:
     return np.random.default_rng(seed).integers(0, 256, size=(n, size, size, 3), dtype=np.uint8)
 
