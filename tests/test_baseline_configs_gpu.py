@@ -152,3 +152,23 @@ def test_c2_mobileclip2_s2(make_big):
     assert [l for l, _ in clip.classify(imgs[0], labels)] == [l for l, _ in o.classify(imgs[0], labels)]
     whole = cb.Clip.from_local_dir(mdir).build().vision.embed_images(imgs)  # default micro-batch
     assert np.abs(whole - got_v).max() < 2e-3
+
+
+def test_c3_so400m_real_export_full_size(make_real_model):
+    """BASELINE config C3 as the reference would receive it: a full-size `torch.onnx.export` graph (27 x 1152, MAP head,
+    1.7 GB of external fp32 weights), every initializer anonymised.  The engine binds it from graph structure; the
+    oracle ONNX interpreter executes the same file in fp32."""
+    import clip_embedder_rs_b200 as cb
+    from oracle import onnx_interp as oi
+    from oracle import reference_forward as R
+
+    mdir = make_real_model("so400m_siglip2_384", anonymize=True, towers=("vision",))
+    vis = cb.VisionEmbedder.from_local_dir(mdir).build()
+    imgs = np.random.default_rng(4).integers(0, 256, size=(3, 384, 384, 3), dtype=np.uint8)
+    pc = vis.config.preprocess_cfg
+    want = oi.OnnxSession(os.path.join(mdir, "visual.onnx")).run(
+        {"pixel_values": R.preprocess_batch(list(imgs), 384, pc.mean, pc.std)})
+    got = vis.embed_images(imgs)
+    cos = cosine_rows(got, want)
+    print(f"\n[C3 real export] cos >= {cos.min():.6f} max_abs {np.abs(got - want).max():.2e}")
+    assert got.shape == (3, 1152) and cos.min() >= COS_BAR
