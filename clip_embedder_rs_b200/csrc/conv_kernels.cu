@@ -11,6 +11,7 @@
 #include "conv_kernels.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace clipb200 {
 
@@ -163,6 +164,9 @@ static cudaError_t dw_launch(const Tin* in, int n, int H, int W, int Cin, const 
 cudaError_t launch_dwconv(const void* in, bool in_bf16, int n, int H, int W, int Cin, int K, int stride, int mult,
                           const float* w, const float* bias, bool gelu, void* out, bool out_bf16, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
+  static const bool legacy = getenv("CLIPB200_DWCONV_LEGACY") != nullptr && atoi(getenv("CLIPB200_DWCONV_LEGACY")) != 0;
+  if (!legacy && dwconv_tma_supported(in_bf16, Cin, K, stride, mult, gelu))
+    return launch_dwconv_tma(static_cast<const float*>(in), n, H, W, Cin, K, w, bias, out, out_bf16, st);
 #define CLIPB200_DW(K_, S_, M_, TI, TO, G_)                                                                     \
   if (K == K_ && stride == S_ && mult == M_ && in_bf16 == std::is_same<TI, __nv_bfloat16>::value &&             \
       out_bf16 == std::is_same<TO, __nv_bfloat16>::value && gelu == G_)                                         \

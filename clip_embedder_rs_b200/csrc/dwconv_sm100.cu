@@ -1,0 +1,150 @@
+// Stride-1 depthwise KxK convolution (K = 3 | 7) for the FastViT / MobileCLIP2 trunk, NHWC fp32 activations:
+// the RepMixer token mixer, the 7x7 depthwise conv in front of every ConvMlp and the RepCPE positional encoding
+// (83 of the 91 depthwise launches of one MobileCLIP2-S2 forward; SURVEY.md Appendix A "C2").  They replace the
+// grouped `Conv` nodes onnxruntime executes for the re-parameterised graph (reference pull_onnx.py:110-116).
+//
+// B200 design: the halo tile is fetched by ONE TMA instruction.  A 4-D tensor map over [n][H][W][C] with box
+// {32 channels, 16+K-1, 16+K-1, 1} lands a dense [y][x][c] tile in shared memory; coordinates that fall outside the
+// image (the conv's zero padding) or beyond C (channel tails such as 80 = 32+32+16) are zero-filled by the TMA unit, so
+// the kernel has no address arithmetic, no bounds checks and no load instructions for the input at all.  While the copy
+// is in flight every thread pulls its K*K taps into registers.  Lanes are channels (conflict-free shared-memory reads,
+// 128-byte coalesced stores); each warp owns two output rows of 16 pixels and keeps 2x16 accumulators in registers, so
+// one staged input row is read once and feeds both output rows (5.5 LDS per 49 FFMA for K = 7).
+#include <cuda.h>
+
+#include "conv_kernels.cuh"
+#include "gemm_sm100.cuh"  // get_encode_tiled
+#include "ptx_sm100.cuh"
+
+namespace clipb200 {
+
+namespace {
+
+constexpr int DW_TW = 16, DW_TH = 16, DW_CI = 32, DW_THREADS = 256;
+
+__device__ __forceinline__ void tma_load_4d(const void* tmap, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1,
+                                            int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+template <int K, typename Tout>
+__global__ void __launch_bounds__(DW_THREADS, 2)
+dwconv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ w /*[K*K][C]*/,
+                  const float* __restrict__ bias, Tout* __restrict__ out, int H, int W, int C, int tiles_x) {
+  constexpr int IW = DW_TW + K - 1, IH = DW_TH + K - 1;
+  extern __shared__ uint8_t dw_raw[];
+  float* tile = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dw_raw) + 127) & ~uintptr_t(127));  // [IH][IW][32]
+  __shared__ __align__(8) uint64_t bar;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.y * DW_CI, b = blockIdx.z;
+  const int ty0 = (blockIdx.x / tiles_x) * DW_TH, tx0 = (blockIdx.x % tiles_x) * DW_TW;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+    ptx::mbar_arrive_expect_tx(&bar, IH * IW * DW_CI * 4);
+    tma_load_4d(&tm_in, &bar, tile, c0, tx0 - K / 2, ty0 - K / 2, b);
+  }
+  const int c = c0 + lane;
+  const bool c_ok = c < C;
+  float wk[K * K];
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) wk[t] = c_ok ? __ldg(w + t * C + c) : 0.f;
+  const float bv = c_ok ? __ldg(bias + c) : 0.f;
+  __syncthreads();  // the barrier init is visible to everyone
+  ptx::mbar_wait(&bar, 0);
+
+  const int r0 = warp * 2;  // this warp's two output rows inside the tile
+  float acc0[DW_TW], acc1[DW_TW];
+#pragma unroll
+  for (int x = 0; x < DW_TW; ++x) acc0[x] = acc1[x] = bv;
+#pragma unroll
+  for (int iy = 0; iy < K + 1; ++iy) {  // staged rows r0 .. r0+K feed output rows r0 (taps ky = iy) and r0+1 (ky = iy-1)
+    float rv[IW];
+    const float* src = tile + ((r0 + iy) * IW) * DW_CI + lane;
+#pragma unroll
+    for (int i = 0; i < IW; ++i) rv[i] = src[i * DW_CI];
+    if (iy < K) {
+#pragma unroll
+      for (int x = 0; x < DW_TW; ++x)
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) acc0[x] = fmaf(rv[x + kx], wk[iy * K + kx], acc0[x]);
+    }
+    if (iy > 0) {
+#pragma unroll
+      for (int x = 0; x < DW_TW; ++x)
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) acc1[x] = fmaf(rv[x + kx], wk[(iy - 1) * K + kx], acc1[x]);
+    }
+  }
+  if (!c_ok) return;
+  const int oy = ty0 + r0;
+  Tout* o0 = out + ((static_cast<long long>(b) * H + oy) * W + tx0) * C + c;
+#pragma unroll
+  for (int x = 0; x < DW_TW; ++x) {
+    if (tx0 + x < W) {
+      if (oy < H) store_out(o0 + static_cast<long long>(x) * C, acc0[x]);
+      if (oy + 1 < H) store_out(o0 + (static_cast<long long>(W) + x) * C, acc1[x]);
+    }
+  }
+}
+
+bool make_tmap_nhwc_f32(CUtensorMap* tm, const float* base, int n, int H, int W, int C, int box_w, int box_h) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(n)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4,
+                           static_cast<cuuint64_t>(H) * W * C * 4};
+  cuuint32_t box[4] = {DW_CI, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int K, typename Tout>
+cudaError_t launch_t(const float* in, int n, int H, int W, int C, const float* w, const float* bias, Tout* out,
+                     cudaStream_t st) {
+  constexpr int IW = DW_TW + K - 1, IH = DW_TH + K - 1;
+  constexpr int smem = IH * IW * DW_CI * 4 + 128;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_tma_kernel<K, Tout>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  CUtensorMap tm;
+  if (!make_tmap_nhwc_f32(&tm, in, n, H, W, C, IW, IH)) return cudaErrorInvalidValue;
+  const int tiles_x = (W + DW_TW - 1) / DW_TW, tiles_y = (H + DW_TH - 1) / DW_TH;
+  dim3 grid(tiles_x * tiles_y, (C + DW_CI - 1) / DW_CI, n);
+  dwconv_tma_kernel<K, Tout><<<grid, DW_THREADS, smem, st>>>(tm, w, bias, out, H, W, C, tiles_x);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool dwconv_tma_supported(bool in_bf16, int C, int K, int stride, int mult, bool gelu) {
+  // TMA needs 16-byte global strides: C * 4 bytes per pixel -> C % 4 == 0
+  return !in_bf16 && stride == 1 && mult == 1 && !gelu && (K == 3 || K == 7) && C % 4 == 0;
+}
+
+cudaError_t launch_dwconv_tma(const float* in, int n, int H, int W, int C, int K, const float* w, const float* bias,
+                              void* out, bool out_bf16, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  if (K == 7 && out_bf16) return launch_t<7, __nv_bfloat16>(in, n, H, W, C, w, bias, static_cast<__nv_bfloat16*>(out), st);
+  if (K == 7) return launch_t<7, float>(in, n, H, W, C, w, bias, static_cast<float*>(out), st);
+  if (K == 3 && out_bf16) return launch_t<3, __nv_bfloat16>(in, n, H, W, C, w, bias, static_cast<__nv_bfloat16*>(out), st);
+  if (K == 3) return launch_t<3, float>(in, n, H, W, C, w, bias, static_cast<float*>(out), st);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace clipb200
