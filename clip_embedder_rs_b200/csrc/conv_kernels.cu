@@ -15,7 +15,18 @@
 
 namespace clipb200 {
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
+// same Abramowitz-Stegun form as gemm_sm100.cuh::gelu_erf_fast (|error| <= 4.3e-7)
+__device__ __forceinline__ float gelu_erf(float x) {
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, fabsf(x), 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752f));
+  float q = fmaf(t, 0.5307027145f, -0.7265760135f);
+  q = fmaf(t, q, 0.7107068705f);
+  q = fmaf(t, q, -0.142248368f);
+  q = fmaf(t, q, 0.127414796f);
+  const float h = q * t * e;
+  return x * (x < 0.f ? h : 1.0f - h);
+}
 __device__ __forceinline__ float ld_as_float(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void st_from_float(float* p, float v) { *p = v; }
@@ -75,12 +86,83 @@ stem_conv3x3_s2_kernel(const uint8_t* __restrict__ img_u8, const float* __restri
   *reinterpret_cast<uint4*>(out + pix * Cout + g * 8) = *reinterpret_cast<uint4*>(h);
 }
 
+// Same convolution, one thread = one output pixel x ALL output channels (Cout % 16 == 0): the 27 taps are gathered once
+// per pixel (the kernel above gathers them Cout/8 times), weights come from shared memory as warp-broadcast 16-byte
+// loads (27 x 4 LDS.128 per 16 channels x 27 FFMA), and the pixel's Cout bf16 outputs leave as 16-byte stores.
+__global__ void __launch_bounds__(128)
+stem_conv3x3_s2_pix_kernel(const uint8_t* __restrict__ img_u8, const float* __restrict__ img_f32,
+                           const float* __restrict__ lut, int S, int Cout, const float* __restrict__ w /*[27][Cout]*/,
+                           const float* __restrict__ bias, long long total_pix, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) float stem_smem[];  // [27*Cout] weights + [Cout] bias + [768] LUT
+  float* sw = stem_smem;
+  float* sb = sw + 27 * Cout;
+  float* sl = sb + Cout;
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias[i];
+  if (img_u8 != nullptr)
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) sl[i] = lut[i];
+  __syncthreads();
+  const long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (pix >= total_pix) return;
+  const int So = S >> 1;
+  const int ox = static_cast<int>(pix % So), oy = static_cast<int>((pix / So) % So);
+  const long long b = pix / (static_cast<long long>(So) * So);
+  float taps[27];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
+      const bool ok = iy >= 0 && iy < S && ix >= 0 && ix < S;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = 0.f;
+        if (ok) {
+          if (img_u8 != nullptr) v = sl[c * 256 + __ldg(img_u8 + ((b * S + iy) * S + ix) * 3 + c)];
+          else v = __ldg(img_f32 + ((b * 3 + c) * S + iy) * S + ix);
+        }
+        taps[c * 9 + ky * 3 + kx] = v;
+      }
+    }
+  __nv_bfloat16* orow = out + pix * Cout;
+  for (int c0 = 0; c0 < Cout; c0 += 16) {
+    float4 a[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a[q] = *reinterpret_cast<const float4*>(sb + c0 + 4 * q);
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      const float v = taps[t];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w4 = *reinterpret_cast<const float4*>(sw + t * Cout + c0 + 4 * q);
+        a[q].x = fmaf(v, w4.x, a[q].x); a[q].y = fmaf(v, w4.y, a[q].y);
+        a[q].z = fmaf(v, w4.z, a[q].z); a[q].w = fmaf(v, w4.w, a[q].w);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q += 2) {
+      __nv_bfloat162 h[4];
+      h[0] = __floats2bfloat162_rn(gelu_erf(a[q].x), gelu_erf(a[q].y));
+      h[1] = __floats2bfloat162_rn(gelu_erf(a[q].z), gelu_erf(a[q].w));
+      h[2] = __floats2bfloat162_rn(gelu_erf(a[q + 1].x), gelu_erf(a[q + 1].y));
+      h[3] = __floats2bfloat162_rn(gelu_erf(a[q + 1].z), gelu_erf(a[q + 1].w));
+      *reinterpret_cast<uint4*>(orow + c0 + 4 * q) = *reinterpret_cast<uint4*>(h);
+    }
+  }
+}
+
 cudaError_t launch_stem_conv3x3_s2(const uint8_t* img_u8, const float* img_f32, const float* lut, int n, int S, int Cout,
                                    const float* w27, const float* bias, __nv_bfloat16* out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   if ((Cout & 7) || (S & 1)) return cudaErrorInvalidValue;
-  const long long total = static_cast<long long>(n) * (S / 2) * (S / 2) * (Cout / 8);
   const size_t smem = (27 * Cout + Cout + 768) * sizeof(float);
+  if ((Cout & 15) == 0) {
+    const long long pixels = static_cast<long long>(n) * (S / 2) * (S / 2);
+    stem_conv3x3_s2_pix_kernel<<<static_cast<unsigned>((pixels + 127) / 128), 128, smem, st>>>(img_u8, img_f32, lut, S, Cout,
+                                                                                               w27, bias, pixels, out);
+    return cudaGetLastError();
+  }
+  const long long total = static_cast<long long>(n) * (S / 2) * (S / 2) * (Cout / 8);
   stem_conv3x3_s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, smem, st>>>(img_u8, img_f32, lut, S, Cout, w27,
                                                                                         bias, total, out);
   return cudaGetLastError();
