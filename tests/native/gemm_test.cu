@@ -204,6 +204,19 @@ int main(int argc, char** argv) {
       for (int bn : {128, 192, 256}) fails += run_case(8192, 8064, 4096, EPI_BF16, ACT_NONE, bn, true, num_sms, ncta);
     return fails;
   }
+  if (argc > 1 && atoi(argv[1]) == 3) {  // FastViT 1x1-conv shapes (MobileCLIP2-S2, 256 images): short K, epilogue-bound
+    for (int ncta = 1; ncta <= 2; ++ncta) {
+      for (int act : {ACT_NONE, ACT_GELU_ERF}) {
+        fails += run_case(65536, 960, 320, EPI_BF16, act, 0, true, num_sms, ncta);      // stage 3 fc1
+        fails += run_case(262144, 480, 160, EPI_BF16, act, 0, true, num_sms, ncta);     // stage 2 fc1
+        fails += run_case(1048576, 240, 80, EPI_BF16, act, 0, true, num_sms, ncta);     // stage 1 fc1
+      }
+      fails += run_case(65536, 320, 960, EPI_RESID, ACT_NONE, 0, true, num_sms, ncta);  // stage 3 fc2
+      fails += run_case(1048576, 80, 240, EPI_RESID, ACT_NONE, 0, true, num_sms, ncta); // stage 1 fc2
+    }
+    for (int bn : {128, 192, 256}) fails += run_case(65536, 960, 320, EPI_BF16, ACT_GELU_ERF, bn, true, num_sms, 2);
+    return fails;
+  }
   // smallest cases first: one tile, one k-block
   fails += run_case(128, 256, 64, EPI_BF16, ACT_NONE, 256, false, num_sms);
   fails += run_case(128, 128, 64, EPI_BF16, ACT_NONE, 128, false, num_sms);
