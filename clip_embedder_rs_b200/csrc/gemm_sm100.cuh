@@ -110,6 +110,12 @@ constexpr int GEMM_WARP_TMA = GEMM_EPI_WARPS;
 constexpr int GEMM_WARP_MMA = GEMM_EPI_WARPS + 1;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 constexpr int GEMM_EPI_STAGE_BYTES = 32 * 128;                 // per epilogue warp: 32 rows x 128 B, 128B-swizzled
+// staging tiles per epilogue warp: with 2 the warp fills one tile while the TMA store / reduce of the previous chunk is
+// still reading the other (cp.async.bulk.wait_group.read 1), at the price of one smem pipeline stage
+#ifndef CLIPB200_GEMM_EPI_BUFS
+#define CLIPB200_GEMM_EPI_BUFS 1
+#endif
+constexpr int GEMM_EPI_BUFS = CLIPB200_GEMM_EPI_BUFS;
 
 // NCTA = 1: one CTA per 128 x BN tile.  NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile;
 // each CTA stages its own 128 rows of A and HALF of the W tile, so the shared-memory traffic per MMA (TMA fill +
@@ -118,7 +124,7 @@ template <int BN, int NCTA = 1>
 struct GemmCfg {
   static constexpr int B_STAGE_BYTES = (BN / NCTA) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = GEMM_A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES;  // 32 KB
+  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * GEMM_EPI_BUFS * GEMM_EPI_STAGE_BYTES;  // 32 KB per buffer set
   static constexpr int BAR_BYTES = 256;
   static constexpr int BUDGET = 227 * 1024 - 1024 - BAR_BYTES - EPI_BYTES;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
@@ -260,7 +266,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int ew = warp;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int half = ew >> 2;
-    uint8_t* stg = smem_epi + ew * GEMM_EPI_STAGE_BYTES;
+    uint8_t* const stg_base = smem_epi + ew * GEMM_EPI_BUFS * GEMM_EPI_STAGE_BYTES;
+    uint8_t* stg = stg_base;
+    int stg_buf = 0;
+    auto next_stg = [&]() {  // rotate to the staging tile whose store was issued longest ago
+      if (GEMM_EPI_BUFS > 1) {
+        stg_buf = (stg_buf + 1) % GEMM_EPI_BUFS;
+        stg = stg_base + stg_buf * GEMM_EPI_STAGE_BYTES;
+      }
+    };
     const int sw = lane & 7;  // 128B-swizzle phase of this thread's staging row
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -298,7 +312,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             pk[16 + 2 * j] = pack2_act(__uint_as_float(r1[4 * j]) + b1[j].x, __uint_as_float(r1[4 * j + 1]) + b1[j].y, ep.act);
             pk[16 + 2 * j + 1] = pack2_act(__uint_as_float(r1[4 * j + 2]) + b1[j].z, __uint_as_float(r1[4 * j + 3]) + b1[j].w, ep.act);
           }
-          if (lane == 0) ptx::tma_store_wait_read<0>();  // the previous store of this warp has left the staging tile
+          next_stg();
+          if (lane == 0) ptx::tma_store_wait_read<GEMM_EPI_BUFS - 1>();  // the store that used this tile has read it
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -342,7 +357,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               }
             }
           }
-          if (lane == 0) ptx::tma_store_wait_read<0>();
+          next_stg();
+          if (lane == 0) ptx::tma_store_wait_read<GEMM_EPI_BUFS - 1>();
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
