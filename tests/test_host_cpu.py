@@ -201,3 +201,15 @@ def test_two_rank_sharding_over_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GATHER_OK" in outs[0]
+
+
+def test_cpp_host_mirror_errors_and_configs(tmp_path):
+    """include/clipb200.hpp without a GPU: `verify_model_dir` errors with the crate's messages (src/error.rs:29-37),
+    `ModelConfig` / `OpenClipConfig::from_file` (serde defaults, optional fields, JSON / IO errors), softmax / sigmoid."""
+    import subprocess
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "native", "host_api_test.bin")
+    if not os.path.exists(path):
+        pytest.fail(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    out = subprocess.run([path, "errors", str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "HOST API ERRORS PASSED" in out.stdout, out.stdout + out.stderr

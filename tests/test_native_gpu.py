@@ -67,3 +67,49 @@ def test_loader_accepts_f16_bf16_and_identity_aliases(make_model, tmp_path):
     # same model up to fp16/bf16 storage rounding of two weight families and one aliased LayerNorm bias
     assert cosine_rows(got, want).min() > 0.995
     assert np.abs(got - want).max() > 0  # the variant really differs (alias + rounding), i.e. it was loaded
+
+
+def test_cpp_host_mirror_matches_python_mirror(make_model, tmp_path):
+    """include/clipb200.hpp (C++ mirror of the crate API: Clip / VisionEmbedder / TextEmbedder, configs, errors) driven
+    by tests/native/host_api_test.cpp on the same model directory and inputs as the Python mirror: same embeddings,
+    same classify / rank_images order, same preprocess values, `Empty batch` error, working `duplicate()`."""
+    import json
+
+    import numpy as np
+
+    import clip_embedder_rs_b200 as cb
+    from conftest import random_images, random_texts
+
+    path = os.path.join(NATIVE, "host_api_test.bin")
+    if not os.path.exists(path):
+        pytest.fail(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    for config in ("tiny_clip", "tiny_siglip"):
+        mdir = make_model(config)
+        clip = cb.Clip.from_local_dir(mdir).build()
+        n, w, h = 4, 100, 80  # not the model resolution: the GPU resize path is part of the call
+        imgs = np.random.default_rng(61).integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+        texts = random_texts(5, seed=62)
+        ids, mask = clip.text.tokenize(texts)
+        lens = mask.sum(axis=1).astype(np.int64)
+        imgs.tofile(tmp_path / "images.u8")
+        ids.astype(np.int64).tofile(tmp_path / "ids.i64")
+        lens.tofile(tmp_path / "lens.i64")
+        out = subprocess.run([path, "run", mdir, str(tmp_path / "images.u8"), str(n), str(w), str(h), str(tmp_path / "ids.i64"),
+                              str(tmp_path / "lens.i64"), str(len(texts))], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        j = json.loads(out.stdout)
+        D = clip.vision.session.embed_dim
+        assert j["embed_dim"] == D and j["input_name"] == "pixel_values" and j["id_name"] == "input_ids"
+        assert j["empty_batch_error"] and j["duplicate_matches"]
+        want_v = clip.vision.embed_images(list(imgs))
+        want_t = clip.text.embed_texts(texts)
+        got_v = np.asarray(j["image_embeddings"], dtype=np.float32).reshape(n, D)
+        got_t = np.asarray(j["text_embeddings"], dtype=np.float32).reshape(len(texts), D)
+        assert np.allclose(got_v, want_v, atol=1e-6) and np.allclose(got_t, want_t, atol=1e-6), config
+        assert np.allclose(np.asarray(j["preprocess0"], dtype=np.float32), clip.vision.preprocess(imgs[0]).reshape(-1)[:64])
+        want_cls = clip.classify(imgs[0], texts)
+        assert [int(l[1:]) for l, _ in j["classify"]] == [texts.index(l) for l, _ in want_cls]
+        assert np.allclose([p for _, p in j["classify"]], [p for _, p in want_cls], atol=1e-5)
+        want_rank = clip.rank_images(list(imgs), texts[0])
+        assert [i for i, _ in j["rank_images"]] == [i for i, _ in want_rank]
+        assert abs(j["compare"] - clip.compare(imgs[0], texts[1])) < 1e-4
