@@ -13,7 +13,7 @@
 #include <cuda.h>
 
 #include "conv_kernels.cuh"
-#include "gemm_sm100.cuh"  // get_encode_tiled
+#include "tensormap.h"  // get_encode_tiled
 #include "ptx_sm100.cuh"
 
 namespace clipb200 {
@@ -41,8 +41,7 @@ __global__ void __launch_bounds__(DW_THREADS, 2)
 dwconv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ w /*[K*K][C]*/,
                   const float* __restrict__ bias, Tout* __restrict__ out, int H, int W, int C, int tiles_x) {
   constexpr int IW = DW_TW + K - 1, IH = DW_TH + K - 1;
-  extern __shared__ uint8_t dw_raw[];
-  float* tile = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dw_raw) + 127) & ~uintptr_t(127));  // [IH][IW][32]
+  extern __shared__ __align__(128) float tile[];  // [IH][IW][32]; declared aligned so the reads stay LDS (no generic LD)
   __shared__ __align__(8) uint64_t bar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = blockIdx.y * DW_CI, b = blockIdx.z;
@@ -115,7 +114,7 @@ template <int K, typename Tout>
 cudaError_t launch_t(const float* in, int n, int H, int W, int C, const float* w, const float* bias, Tout* out,
                      cudaStream_t st) {
   constexpr int IW = DW_TW + K - 1, IH = DW_TH + K - 1;
-  constexpr int smem = IH * IW * DW_CI * 4 + 128;
+  constexpr int smem = IH * IW * DW_CI * 4;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(dwconv_tma_kernel<K, Tout>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -17,6 +17,7 @@
 #include <stdint.h>
 
 #include "ptx_sm100.cuh"
+#include "tensormap.h"
 
 namespace clipb200 {
 
@@ -442,23 +443,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-inline PFN_encodeTiled get_encode_tiled() {
-  static PFN_encodeTiled fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
-  return fn;
-}
-
 // Row-major [rows, cols] tensor (cols contiguous, leading dimension ld elements), box = [box_rows, 128 bytes of
 // columns], 128-byte swizzle.  elem_bytes 2 = bf16 (64-column box), 4 = fp32 (32-column box).
 inline bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
