@@ -15,6 +15,7 @@ cudaError_t launch_stem_conv3x3_s2(const uint8_t* img_u8, const float* img_f32, 
 cudaError_t launch_dwconv(const void* in, bool in_bf16, int n, int H, int W, int Cin, int K, int stride, int mult,
                           const float* w, const float* bias, bool gelu, void* out, bool out_bf16, cudaStream_t st);
 // stride-1, multiplier-1 fp32 variants on the TMA-staged kernel (dwconv_sm100.cu); launch_dwconv routes to it
+cudaError_t dwconv_tma_configure_device();
 bool dwconv_tma_supported(bool in_bf16, int C, int K, int stride, int mult, bool gelu);
 cudaError_t launch_dwconv_tma(const float* in, int n, int H, int W, int C, int K, const float* w, const float* bias,
                               void* out, bool out_bf16, cudaStream_t st);

@@ -115,12 +115,6 @@ cudaError_t launch_t(const float* in, int n, int H, int W, int C, const float* w
                      cudaStream_t st) {
   constexpr int IW = DW_TW + K - 1, IH = DW_TH + K - 1;
   constexpr int smem = IH * IW * DW_CI * 4;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv_tma_kernel<K, Tout>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   CUtensorMap tm;
   if (!make_tmap_nhwc_f32(&tm, in, n, H, W, C, IW, IH)) return cudaErrorInvalidValue;
   const int tiles_x = (W + DW_TW - 1) / DW_TW, tiles_y = (H + DW_TH - 1) / DW_TH;
@@ -129,7 +123,22 @@ cudaError_t launch_t(const float* in, int n, int H, int W, int C, const float* w
   return cudaGetLastError();
 }
 
+template <int K, typename Tout>
+cudaError_t configure_t() {
+  constexpr int smem = (DW_TH + K - 1) * (DW_TW + K - 1) * DW_CI * 4;
+  return cudaFuncSetAttribute(dwconv_tma_kernel<K, Tout>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
 }  // namespace
+
+// opt in to > 48 KB of dynamic shared memory once per device (called from Engine::Init, never inside a graph capture)
+cudaError_t dwconv_tma_configure_device() {
+  cudaError_t e = configure_t<7, __nv_bfloat16>();
+  if (e == cudaSuccess) e = configure_t<7, float>();
+  if (e == cudaSuccess) e = configure_t<3, __nv_bfloat16>();
+  if (e == cudaSuccess) e = configure_t<3, float>();
+  return e;
+}
 
 bool dwconv_tma_supported(bool in_bf16, int C, int K, int stride, int mult, bool gelu) {
   // TMA needs 16-byte global strides: C * 4 bytes per pixel -> C % 4 == 0

@@ -8,6 +8,7 @@
 
 #include "attn_sm100.cuh"
 #include "gemm_sm100.cuh"
+#include "conv_kernels.cuh"
 #include "kernels.cuh"
 
 namespace clipb200 {
@@ -440,6 +441,7 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
   CUDA_RET(gemm_configure_device(), "configure GEMM kernels");
   CUDA_RET(flash_attention_configure_device(), "configure attention kernels");
   CUDA_RET(attn_tcgen05_configure_device(), "configure tcgen05 attention kernels");
+  CUDA_RET(dwconv_tma_configure_device(), "configure depthwise-conv kernels");
   CUDA_RET(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking), "stream");
   CUDA_RET(cudaStreamCreateWithFlags(&copy_in_, cudaStreamNonBlocking), "stream");
   CUDA_RET(cudaStreamCreateWithFlags(&copy_out_, cudaStreamNonBlocking), "stream");
