@@ -14,10 +14,24 @@ namespace {
 constexpr int64_t kMaxConst = int64_t(1) << 23;  // largest input-independent tensor that is folded to a value
 using Shape = std::vector<int64_t>;
 
+constexpr int64_t kNumelCap = int64_t(1) << 52;  // saturation value: far above anything that is ever materialised
+
+// Saturating product; a negative dimension (malformed file) also saturates so that every size check fails closed.
 int64_t numel(const Shape& s) {
   int64_t n = 1;
-  for (int64_t d : s) n *= d;
+  for (int64_t d : s) {
+    if (d < 0) return kNumelCap;
+    if (d == 0) return 0;
+    if (n > kNumelCap / d) return kNumelCap;
+    n *= d;
+  }
   return n;
+}
+
+bool shape_ok(const Shape& s) {
+  if (s.size() > 8) return false;
+  for (int64_t d : s) if (d < 0 || d > (int64_t(1) << 40)) return false;
+  return numel(s) < kNumelCap;
 }
 
 std::string shape_str(const Shape& s) {
@@ -47,6 +61,7 @@ float half_bits_to_float(uint16_t h) {
 
 bool read_tensor(const OnnxTensor& t, std::vector<double>* out) {
   const int64_t n = t.numel();
+  if (n < 0 || n > (int64_t(1) << 31)) return false;
   out->resize(static_cast<size_t>(n));
   if (n == 0) return true;
   if (t.data == nullptr) return false;
@@ -200,12 +215,21 @@ struct Analyzer {
 
   bool run() {
     if (!init_env()) return false;
-    for (size_t i = 0; i < m.nodes.size(); ++i)
-      if (!eval(static_cast<int>(i))) {
+    for (const auto& kv : env)
+      if (!shape_ok(kv.second.shape)) return fail("tensor '" + kv.first + "' has an invalid shape " + shape_str(kv.second.shape));
+    for (size_t i = 0; i < m.nodes.size(); ++i) {
+      bool ok = eval(static_cast<int>(i));
+      if (ok)
+        for (const std::string& o : m.nodes[i].outputs) {
+          AVal* v = get(o);
+          if (v != nullptr && !shape_ok(v->shape)) ok = fail("output '" + o + "' has an invalid shape " + shape_str(v->shape));
+        }
+      if (!ok) {
         if (err.empty()) err = "graph analysis failed";
         err += " (node " + std::to_string(i) + " " + m.nodes[i].op_type + " '" + m.nodes[i].name + "')";
         return false;
       }
+    }
     return true;
   }
 
@@ -322,8 +346,13 @@ struct Analyzer {
             if (i >= s.size()) return fail("Reshape: 0 beyond input rank");
             d = s[i];
           }
-          if (d == -1) neg = static_cast<int>(i);
-          else known *= d;
+          if (d == -1) {
+            if (neg >= 0) return fail("Reshape: more than one -1");
+            neg = static_cast<int>(i);
+          } else {
+            if (d < 0 || d > (int64_t(1) << 40) || (d > 0 && known > kNumelCap / d)) return fail("Reshape: invalid target dimension");
+            known *= d;
+          }
           o.push_back(d);
         }
         if (neg >= 0) {
@@ -334,6 +363,7 @@ struct Analyzer {
       } else if (op == "Flatten") {
         int64_t ax = n.attr_i("axis", 1);
         if (ax < 0) ax += static_cast<int64_t>(s.size());
+        if (ax < 0 || ax > static_cast<int64_t>(s.size())) return fail("Flatten: axis out of range");
         int64_t a = 1, b = 1;
         for (size_t i = 0; i < s.size(); ++i) (static_cast<int64_t>(i) < ax ? a : b) *= s[i];
         o = {a, b};
@@ -345,12 +375,19 @@ struct Analyzer {
           if (!present) return fail("Unsqueeze without axes");
           const int64_t r = static_cast<int64_t>(s.size() + axes.size());
           std::set<int64_t> ax;
-          for (int64_t a : axes) ax.insert(a < 0 ? a + r : a);
+          for (int64_t a : axes) {
+            const int64_t p = a < 0 ? a + r : a;
+            if (p < 0 || p >= r || !ax.insert(p).second) return fail("Unsqueeze: axis out of range or repeated");
+          }
           size_t k = 0;
           for (int64_t i = 0; i < r; ++i) o.push_back(ax.count(i) ? 1 : s[k++]);
         } else {
           std::set<int64_t> ax;
-          for (int64_t a : axes) ax.insert(a < 0 ? a + static_cast<int64_t>(s.size()) : a);
+          for (int64_t a : axes) {
+            const int64_t p = a < 0 ? a + static_cast<int64_t>(s.size()) : a;
+            if (p < 0 || p >= static_cast<int64_t>(s.size())) return fail("Squeeze: axis out of range");
+            ax.insert(p);
+          }
           for (size_t i = 0; i < s.size(); ++i) {
             const bool drop = present ? ax.count(static_cast<int64_t>(i)) > 0 : s[i] == 1;
             if (!drop) o.push_back(s[i]);
@@ -372,6 +409,11 @@ struct Analyzer {
       if (const OnnxAttr* a = n.attr("perm")) perm = a->ints;
       if (perm.empty()) for (int i = static_cast<int>(s.size()) - 1; i >= 0; --i) perm.push_back(i);
       if (perm.size() != s.size()) return fail("Transpose: perm rank mismatch");
+      {
+        std::set<int64_t> seen;
+        for (int64_t p : perm)
+          if (p < 0 || p >= static_cast<int64_t>(s.size()) || !seen.insert(p).second) return fail("Transpose: perm is not a permutation");
+      }
       AVal v;
       v.dtype = in[0]->dtype;
       v.tainted = in[0]->tainted;
@@ -401,6 +443,7 @@ struct Analyzer {
       if (xs.empty()) return fail("Concat without inputs");
       const size_t r = xs[0]->shape.size();
       if (axis < 0) axis += static_cast<int64_t>(r);
+      if (axis < 0 || axis >= static_cast<int64_t>(r)) return fail("Concat: axis out of range");
       AVal v;
       v.dtype = xs[0]->dtype;
       v.shape = xs[0]->shape;
@@ -408,6 +451,8 @@ struct Analyzer {
       bool all_data = true;
       for (AVal* x : xs) {
         if (x->shape.size() != r) return fail("Concat: rank mismatch");
+        for (size_t d = 0; d < r; ++d)
+          if (static_cast<int64_t>(d) != axis && x->shape[d] != xs[0]->shape[d]) return fail("Concat: shapes differ off the axis");
         v.shape[axis] += x->shape[axis];
         v.tainted |= x->tainted;
       }
@@ -547,6 +592,7 @@ struct Analyzer {
         v.dtype = a->t->data_type;
       }
       v.shape = t;
+      if (!shape_ok(t)) return fail("ConstantOfShape: invalid shape");
       if (numel(t) <= kMaxConst) {
         v.data.assign(static_cast<size_t>(numel(t)), val);
         v.has_data = true;
@@ -562,7 +608,9 @@ struct Analyzer {
       if (d == 0) return fail("Range: zero step");
       AVal v;
       v.dtype = in[0]->dtype;
-      const int64_t cnt = std::max<int64_t>(0, static_cast<int64_t>(ceil((b - a) / d)));
+      const double span = ceil((b - a) / d);
+      if (!(span < static_cast<double>(kMaxConst))) return fail("Range: too many elements");
+      const int64_t cnt = std::max<int64_t>(0, static_cast<int64_t>(span));
       for (int64_t i = 0; i < cnt; ++i) v.data.push_back(a + i * d);
       v.shape = {cnt};
       v.has_data = true;
@@ -740,6 +788,10 @@ struct Analyzer {
       v.dtype = in[0]->dtype;
       v.tainted = any_taint;
       v.shape = {M, N};
+      if (need(2)) {
+        Shape chk;
+        if (in[2]->shape.size() > 2 || !bshape(in[2]->shape, v.shape, &chk) || chk != v.shape) return fail("Gemm: C does not broadcast to [M, N]");
+      }
       if (!v.tainted && M * N <= kMaxConst && M * N * K <= (int64_t(1) << 28) && materialize(in[0]) && materialize(in[1]) &&
           (!need(2) || materialize(in[2]))) {
         const double alpha = n.attr_f("alpha", 1.f), beta = n.attr_f("beta", 1.f);
@@ -769,11 +821,15 @@ struct Analyzer {
       if (const OnnxAttr* a = n.attr("pads")) pads = a->ints;
       if (const OnnxAttr* a = n.attr("dilations")) dil = a->ints;
       if (strides.size() != 2 || pads.size() != 4 || dil.size() != 2) return fail("Conv: malformed attributes");
+      for (int64_t v : strides) if (v <= 0 || v > 4096) return fail("Conv: invalid stride");
+      for (int64_t v : dil) if (v <= 0 || v > 4096) return fail("Conv: invalid dilation");
+      for (int64_t v : pads) if (v < 0 || v > 4096) return fail("Conv: invalid padding");
       AVal v;
       v.dtype = in[0]->dtype;
       v.tainted = any_taint;
       v.shape = {x[0], w[0], (x[2] + pads[0] + pads[2] - dil[0] * (w[2] - 1) - 1) / strides[0] + 1,
                  (x[3] + pads[1] + pads[3] - dil[1] * (w[3] - 1) - 1) / strides[1] + 1};
+      if (v.shape[2] <= 0 || v.shape[3] <= 0) return fail("Conv: kernel larger than the padded input");
       put(n, idx, std::move(v));
       return true;
     }
@@ -793,7 +849,11 @@ struct Analyzer {
         if (n.attr_i("noop_with_empty_axes", 0) != 0) { AVal v = *in[0]; v.init = nullptr; put(n, idx, std::move(v)); return true; }
         for (size_t i = 0; i < s.size(); ++i) ax.insert(static_cast<int64_t>(i));
       }
-      for (int64_t a : axes) ax.insert(a < 0 ? a + static_cast<int64_t>(s.size()) : a);
+      for (int64_t a : axes) {
+        const int64_t p = a < 0 ? a + static_cast<int64_t>(s.size()) : a;
+        if (p < 0 || p >= static_cast<int64_t>(s.size())) return fail(op + ": axis out of range");
+        ax.insert(p);
+      }
       AVal v;
       v.dtype = (op == "ArgMax" || op == "ArgMin") ? 7 : in[0]->dtype;
       v.tainted = any_taint;
@@ -832,8 +892,18 @@ struct Analyzer {
         parts = a->ints;
       } else {
         const int64_t k = n.attr_i("num_outputs", static_cast<int64_t>(n.outputs.size()));
+        if (k <= 0 || k > 1024 || axis < 0 || axis >= static_cast<int64_t>(s.size())) return fail("Split: invalid num_outputs / axis");
         const int64_t chunk = (s[axis] + k - 1) / k;
         for (int64_t i = 0; i < k; ++i) parts.push_back(std::min(chunk, s[axis] - i * chunk));
+      }
+      if (axis < 0 || axis >= static_cast<int64_t>(s.size())) return fail("Split: axis out of range");
+      {
+        int64_t total = 0;
+        for (int64_t p : parts) {
+          if (p < 0) return fail("Split: negative part");
+          total += p;
+        }
+        if (total != s[axis] || parts.size() > 1024) return fail("Split: parts do not cover the axis");
       }
       int64_t off = 0;
       const bool can = !in[0]->tainted && numel(s) <= kMaxConst && materialize(in[0]);
@@ -1080,6 +1150,8 @@ struct Recognizer {
         int64_t axis = 0;
         if (n.inputs.size() > 3 && an.ints_of(an.get(n.inputs[3]), &ax) && ax.size() == 1) axis = ax[0];
         if (axis < 0) axis += static_cast<int64_t>(in0->shape.size());
+        if (axis < 0 || axis >= static_cast<int64_t>(in0->shape.size()) || v->shape.size() != in0->shape.size())
+          return fail("attention operand slice axis out of range");
         const int64_t len = v->shape[axis];
         int64_t s0 = st[0] < 0 ? st[0] + in0->shape[axis] : st[0];
         if (len <= 0 || s0 % len != 0) return fail("attention operand slice is not chunk aligned");
@@ -1103,6 +1175,7 @@ struct Recognizer {
     a.softmax_node = node_idx;
     a.Tq = x->shape[x->shape.size() - 2];
     a.Tk = x->shape[x->shape.size() - 1];
+    if (a.Tq <= 0 || a.Tk <= 0) return fail("Softmax over an empty tensor");
     a.heads = numel(x->shape) / (a.Tq * a.Tk);
     // back from the softmax input to QK^T
     std::string cur = sm.inputs[0];
@@ -1135,6 +1208,7 @@ struct Recognizer {
     const OnnxNode& qk = m.nodes[qk_node];
     AVal* qa = an.get(qk.inputs[0]);
     a.hd = qa->shape.back();
+    if (a.hd <= 0) return fail("attention with an empty head dimension");
     double qs = 1.0, ks = 1.0, vs = 1.0;
     AVal* qconst = nullptr;
     if (!trace_operand(qk.inputs[0], &a.q_site, &a.q_sel, &qs, &qconst)) return false;
@@ -1540,6 +1614,7 @@ struct Recognizer {
     const OnnxNode& cn = m.nodes[conv.node];
     const Shape& ws = conv.w->shape;
     const int64_t D = ws[0], P = ws[2];
+    if (D <= 0 || P <= 0) return fail("empty patch-embedding weight");
     std::vector<int64_t> strides = {1, 1}, pads = {0, 0, 0, 0};
     if (const OnnxAttr* a = cn.attr("strides")) strides = a->ints;
     if (const OnnxAttr* a = cn.attr("pads")) pads = a->ints;
@@ -1662,6 +1737,7 @@ struct Recognizer {
     if (toks.empty() || toks[0].kind != TK_EMBED) return fail("text graph does not start with a token-embedding gather: " + tok_dump(0));
     AVal* table = toks[p++].cval;
     const int64_t V = table->shape[0], D = table->shape[1];
+    if (V <= 0 || D <= 0) return fail("empty token-embedding table");
     if (p >= toks.size() || toks[p].kind != TK_POS) return fail("no positional-embedding add after the token embedding: " + tok_dump(p));
     AVal* pos = toks[p++].cval;
     const int64_t T = numel(pos->shape) / D;

@@ -359,6 +359,18 @@ bool load_onnx(const std::string& path, OnnxModel* model, std::string* err) {
             *err = "malformed TensorProto in '" + path + "'";
             return false;
           }
+          bool dims_ok = t.dims.size() <= 8;
+          {
+            int64_t prod = 1;
+            for (int64_t d : t.dims) {
+              if (d < 0 || d > (int64_t(1) << 40) || (d > 0 && prod > (int64_t(1) << 46) / d)) { dims_ok = false; break; }
+              prod *= d;
+            }
+          }
+          if (!dims_ok) {
+            *err = "initializer '" + t.name + "' has invalid dimensions";
+            return false;
+          }
           const size_t esz = dtype_size(t.data_type);
           if (esz == 0) {
             *err = "initializer '" + t.name + "' has unsupported data_type " + std::to_string(t.data_type);
@@ -378,7 +390,8 @@ bool load_onnx(const std::string& path, OnnxModel* model, std::string* err) {
               it = ext_files.emplace(ext.location, ef).first;
             }
             const size_t len = ext.length >= 0 ? static_cast<size_t>(ext.length) : want;
-            if (ext.offset < 0 || static_cast<size_t>(ext.offset) + len > it->second->size || len < want) {
+            if (ext.offset < 0 || static_cast<size_t>(ext.offset) > it->second->size ||
+                len > it->second->size - static_cast<size_t>(ext.offset) || len < want) {
               *err = "initializer '" + t.name + "' external data range is outside '" + ext.location + "'";
               return false;
             }

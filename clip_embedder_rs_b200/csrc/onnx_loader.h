@@ -31,9 +31,13 @@ struct OnnxTensor {
   // [rows, cols] but the bytes are stored as the transpose ([cols, rows] row-major), e.g. a `Linear` weight that the
   // exporter pre-transposed into a MatMul operand.
   bool transposed = false;
-  int64_t numel() const {
+  int64_t numel() const {  // -1 for malformed dims (negative / overflowing): every size comparison then fails closed
     int64_t n = 1;
-    for (int64_t d : dims) n *= d;
+    for (int64_t d : dims) {
+      if (d < 0) return -1;
+      if (d > 0 && n > (int64_t(1) << 50) / d) return -1;
+      n *= d;
+    }
     return n;
   }
 };
