@@ -46,6 +46,10 @@ WORKLOADS = {
     "vit_b32_vision": ("vit_b32", "vision", 1024, 8.82, "images/s", "ViT-B/32 vision embedding, batch 1024 per GPU"),
     "mobileclip2_vision": ("mobileclip2_s2", "vision", 256, 15.67, "images/s",
                            "MobileCLIP2-S2 (FastViT-MCi2) vision embedding, batch 256 per GPU, uint8 256x256 inputs"),
+    "mobileclip2_s3_vision": ("mobileclip2_s3", "vision", 256, 0.0, "images/s",
+                              "MobileCLIP2-S3 (FastViT-MCi3, 5 stages) vision embedding, batch 256 per GPU"),
+    "mobileclip2_s4_vision": ("mobileclip2_s4", "vision", 256, 0.0, "images/s",
+                              "MobileCLIP2-S4 (FastViT-MCi4, 5 stages) vision embedding, batch 256 per GPU"),
     "mobileclip2_text": ("mobileclip2_s2", "text", 256, 5.96, "texts/s", "MobileCLIP2-S2 text encoder, batch 256, context 77"),
     "small_vision": ("small_siglip", "vision", 256, 0.0, "images/s", "small SigLIP-shaped test tower"),
 }

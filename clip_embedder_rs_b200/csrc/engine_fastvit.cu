@@ -181,13 +181,16 @@ Status Engine::LoadFastVit(const OnnxModel& m) {
 
 Status Engine::AllocFastVitWorkspace() {
   const size_t P0 = static_cast<size_t>(S_ / 4) * (S_ / 4);
-  size_t max_pc = 0, max_hidden = 0, max_c = 0;
+  size_t max_pc = 0, max_hidden = 0, max_c = 0, max_qkv = 16;
   size_t P = P0;
   for (size_t i = 0; i < fv_stages_.size(); ++i) {
     if (i > 0) P /= 4;
     const size_t C = fv_stages_[i].C;
     max_pc = std::max(max_pc, P * C);
-    for (const FvBlock& b : fv_stages_[i].blocks) max_hidden = std::max(max_hidden, P * static_cast<size_t>(b.fc1.N));
+    for (const FvBlock& b : fv_stages_[i].blocks) {
+      max_hidden = std::max(max_hidden, P * static_cast<size_t>(b.fc1.N));
+      if (b.attn) max_qkv = std::max(max_qkv, P * 3 * C);  // 5-stage trunks (MCi3 / MCi4) have two attention stages
+    }
     max_c = std::max(max_c, C);
   }
   const size_t cf = 2 * static_cast<size_t>(fv_stages_.back().C);
@@ -202,7 +205,7 @@ Status Engine::AllocFastVitWorkspace() {
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&fv_stem_out_), mb * static_cast<size_t>(S_ / 2) * (S_ / 2) * fv_stem0_.cout * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&h_), mb * max_pc * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&mlpbuf_), mb * max_hidden * 2));
-  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&qkv_), mb * P * 3 * static_cast<size_t>(fv_stages_.back().C) * 2));
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&qkv_), mb * max_qkv * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&pooled_), mb * cf * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&proj_out_), mb * static_cast<size_t>(E_) * 4));
   return Status::OK();

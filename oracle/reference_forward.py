@@ -214,7 +214,7 @@ def vision_forward(t: Tower, pixel_values: np.ndarray, normalize: bool = True) -
 
 def _fastvit_forward(t: Tower, x: torch.Tensor) -> torch.Tensor:
     """timm FastViT (fastvit_mci2 for MobileCLIP2-S2) after `reparameterize_model` (pull_onnx.py:110-116) with eval
-    BatchNorm folded: stem (3x3 s2, dw3x3 s2, 1x1) -> 4 stages (RepMixer blocks; last stage: conditional positional
+    BatchNorm folded: stem (3x3 s2, dw3x3 s2, 1x1) -> 4 or 5 stages (RepMixer blocks; last stage(s): conditional positional
     encoding + attention blocks) with 7x7 s2 depthwise + 1x1 downsampling -> dw3x3 expansion + SE -> GAP -> Linear.
     SURVEY.md Appendix A ("C2 MobileCLIP2-S2"); architecture is upstream recall, see DESIGN.md."""
     w = t.w
@@ -251,7 +251,7 @@ def _fastvit_forward(t: Tower, x: torch.Tensor) -> torch.Tensor:
                 x = se(f"{st}.downsample.proj.0.se", x)
             x = F.gelu(x)
             x = F.gelu(conv(f"{st}.downsample.proj.1.reparam_conv", x))
-        last = i == len(dims) - 1
+        last = i >= len(dims) - int(t.meta.get("attn_stages", 1))  # attention stages (fastvit_mci3 / mci4: the last two)
         if last:
             x = conv(f"{st}.pos_emb.reparam_conv", x, groups=c)  # RepCPE, identity branch folded in
         for j in range(depth):

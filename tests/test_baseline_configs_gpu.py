@@ -172,3 +172,22 @@ def test_c3_so400m_real_export_full_size(make_real_model):
     cos = cosine_rows(got, want)
     print(f"\n[C3 real export] cos >= {cos.min():.6f} max_abs {np.abs(got - want).max():.2e}")
     assert got.shape == (3, 1152) and cos.min() >= COS_BAR
+
+
+@pytest.mark.parametrize("config", ["mobileclip2_s3", "mobileclip2_s4"])
+def test_mobileclip2_s3_s4_five_stage_fastvit(make_big, config):
+    """The other MobileCLIP2 models the reference benches (benches/model_bench.rs:10-12): 5-stage FastViT-MCi3 / MCi4
+    trunks (two attention stages at 8x8 and 4x4 tokens, ratio-4 ConvMlps) — same kernels, layout read from the file."""
+    import clip_embedder_rs_b200 as cb
+    from oracle import reference_forward as R
+
+    mdir = make_big(config, ("vision",))
+    vis = cb.VisionEmbedder.from_local_dir(mdir).build()
+    imgs = random_images(10, 256, seed=7)
+    got = vis.embed_images(imgs)
+    want = R.OracleClip(mdir, towers=("vision",)).embed_images(list(imgs[:5]))
+    cos = cosine_rows(got[:5], want)
+    spread = float((want @ want.T)[np.triu_indices(5, 1)].mean())
+    print(f"\n[{config}] vision cos min {cos.min():.6f} max_abs {np.abs(got[:5] - want).max():.2e} "
+          f"(mean cosine between different images {spread:.3f})")
+    assert cos.min() >= COS_BAR and spread < 0.98

@@ -12,7 +12,7 @@ from conftest import cosine_rows, random_images, random_texts
 pytestmark = pytest.mark.gpu
 
 COS_BAR = 0.999
-SMALL = ["tiny_clip", "tiny_clip_p14", "tiny_siglip", "tiny_mobileclip"]
+SMALL = ["tiny_clip", "tiny_clip_p14", "tiny_siglip", "tiny_mobileclip", "tiny_mobileclip5"]
 
 
 @pytest.fixture(scope="module")

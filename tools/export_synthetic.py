@@ -55,6 +55,8 @@ class VisionSpec:
     depths: tuple = ()
     se_down: tuple = ()
     mlp_ratio: int = 3
+    layer_scale: float = 0.1  # synthetic layer-scale gamma (conditioning of the random network, see fastvit_synth.py)
+    attn_stages: int = 1  # trailing stages whose token mixer is attention (+ RepCPE): 1 for MCi2, 2 for MCi3 / MCi4
 
 
 @dataclass
@@ -136,22 +138,37 @@ CONFIGS: Dict[str, ModelSpec] = {
 }
 
 
-def _mobileclip(name, image, dims, depths, embed, twidth=512, tlayers=12, theads=8, tmlp=2048):
-    """MobileCLIP2-S2 shape: re-parameterised FastViT-MCi2 trunk + 12x512 non-causal text tower."""
+def _mobileclip(name, image, dims, depths, embed, twidth=512, tlayers=12, theads=8, tmlp=2048, mlp_ratio=3,
+                attn_stages=1, timm_name="fastvit_mci2", layer_scale=0.1):
+    """MobileCLIP2 shapes: re-parameterised FastViT trunk + non-causal text tower.  S2 = MCi2
+    (4 stages, attention in the last); S3 / S4 = MCi3 / MCi4 (5 stages, attention in the last two, MLP ratio 4)."""
+    n = len(dims)
     return ModelSpec(
         name=name, embed_dim=embed,
-        vision=VisionSpec("fastvit", image, 4, dims[-1], sum(depths), dims[-1] // 32, dims[-1] * 3, "gelu", 1e-5, "avg",
-                          dims=tuple(dims), depths=tuple(depths), se_down=(False, False, True, True)),
+        vision=VisionSpec("fastvit", image, 4, dims[-1], sum(depths), dims[-1] // 32, dims[-1] * mlp_ratio, "gelu", 1e-5, "avg",
+                          dims=tuple(dims), depths=tuple(depths), se_down=tuple(i >= 2 for i in range(n)),
+                          mlp_ratio=mlp_ratio, attn_stages=attn_stages, layer_scale=layer_scale),
         text=TextSpec("custom", 77, 49408, twidth, tlayers, theads, tmlp, "gelu", 1e-5, False, "argmax", False),
         mean=[0.0, 0.0, 0.0], std=[1.0, 1.0, 1.0], interpolation="bilinear", resize_mode="shortest",
         logit_scale=100.0, logit_bias=0.0, activation_function="softmax", tokenizer_needs_lowercase=False, pad_id=0,
-        timm_model_name="fastvit_mci2")
+        timm_model_name=timm_name)
 
 
 # BASELINE.json configs[1]: MobileCLIP2-S2
 CONFIGS["mobileclip2_s2"] = _mobileclip("MobileCLIP2-S2", 256, (80, 160, 320, 640), (4, 12, 24, 4), 512)
 CONFIGS["tiny_mobileclip"] = _mobileclip("tiny-mobileclip", 64, (32, 64, 128, 256), (1, 2, 2, 2), 64, twidth=128,
                                          tlayers=2, theads=2, tmlp=512)
+# MobileCLIP2-S3 / S4 (benches/model_bench.rs:10-12): 5-stage FastViT-MCi3 / MCi4 [upstream recall: widths, depths and
+# text-tower sizes as in timm / open_clip; only the layout matters for the engine, which derives it from the file]
+CONFIGS["mobileclip2_s3"] = _mobileclip("MobileCLIP2-S3", 256, (96, 192, 384, 768, 1536), (2, 12, 24, 4, 2), 768,
+                                        twidth=768, tlayers=12, theads=12, tmlp=3072, mlp_ratio=4, attn_stages=2,
+                                        timm_name="fastvit_mci3", layer_scale=0.05)
+CONFIGS["mobileclip2_s4"] = _mobileclip("MobileCLIP2-S4", 256, (128, 256, 512, 1024, 2048), (2, 12, 24, 4, 4), 768,
+                                        twidth=768, tlayers=12, theads=12, tmlp=3072, mlp_ratio=4, attn_stages=2,
+                                        timm_name="fastvit_mci4", layer_scale=0.05)
+CONFIGS["tiny_mobileclip5"] = _mobileclip("tiny-mobileclip-5stage", 128, (16, 32, 64, 128, 256), (1, 2, 2, 2, 1), 64,
+                                          twidth=128, tlayers=2, theads=2, tmlp=512, mlp_ratio=4, attn_stages=2,
+                                          timm_name="fastvit_mci3", layer_scale=0.05)
 CONFIGS["tiny_siglip"].text.vocab_size = 49412
 CONFIGS["small_siglip"].text.vocab_size = 49412
 
@@ -432,7 +449,8 @@ def vision_meta(spec: ModelSpec) -> Dict[str, str]:
             "clipb200.heads": v.heads, "clipb200.mlp_dim": v.mlp_dim, "clipb200.act": ACT_IDS[v.act],
             "clipb200.eps": repr(v.eps), "clipb200.pool": v.pool, "clipb200.embed_dim": spec.embed_dim,
             **({"clipb200.dims": ",".join(map(str, v.dims)), "clipb200.depths": ",".join(map(str, v.depths)),
-                "clipb200.se_down": ",".join(str(int(x)) for x in v.se_down), "clipb200.mlp_ratio": v.mlp_ratio}
+                "clipb200.se_down": ",".join(str(int(x)) for x in v.se_down), "clipb200.mlp_ratio": v.mlp_ratio,
+                "clipb200.attn_stages": v.attn_stages}
                if v.family == "fastvit" else {})}
 
 

@@ -75,7 +75,8 @@ def gen_fastvit(spec, g, emit) -> None:
         # layer-scale ~0.1: with 0.3 the random network amplifies perturbations so much that even the fp32 oracle
         # with bf16-rounded GEMM operands only reaches cosine 0.989 against itself; at 0.1 it is well conditioned
         # (0.99996) while different images still map to clearly different embeddings (cosine ~0.9).
-        gm = (0.1 + 0.02 * rng.standard_normal((c, 1, 1))).astype(np.float32)
+        ls = getattr(v, "layer_scale", 0.1)  # the deeper 5-stage trunks (ratio-4 MLPs, two attention stages) need 0.05
+        gm = (ls + 0.2 * ls * rng.standard_normal((c, 1, 1))).astype(np.float32)
         emit(name, gm)
         return torch.from_numpy(gm)
 
@@ -92,7 +93,7 @@ def gen_fastvit(spec, g, emit) -> None:
                 x = se(f"{st}.downsample.proj.0.se", x, c)
             x = F.gelu(x)
             x = F.gelu(conv(f"{st}.downsample.proj.1.reparam_conv", x, c, c, 1))
-        last = i == len(v.dims) - 1
+        last = i >= len(v.dims) - getattr(v, "attn_stages", 1)  # attention stage(s): MCi2 the last one, MCi3 / MCi4 the last two
         if last:
             # RepCPE: x + dwconv7x7(x), folded into one conv (identity added to the centre tap)
             w = draw(c, 1, 7, 0.5)
