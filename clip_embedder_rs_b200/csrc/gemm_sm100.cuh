@@ -82,7 +82,8 @@ __device__ __forceinline__ float apply_act_fast(float x, int act) {
     case ACT_QUICKGELU:
       return __fdividef(x, 1.0f + __expf(-1.702f * x));
     case ACT_GELU_TANH: {
-      const float u = 0.7978845608028654f * x * fmaf(0.044715f * x, x, 1.0f);
+      // u = sqrt(2/pi) (x + 0.044715 x^3) = x * (c1 + c2 x^2): 5 FMA-pipe ops + MUFU.TANH per element
+      const float u = x * fmaf(x * x, 0.0356774081363001f, 0.7978845608028654f);
       const float hx = 0.5f * x;
       return fmaf(hx, tanh_approx(u), hx);
     }
@@ -101,16 +102,43 @@ __device__ __forceinline__ uint32_t pack2_act(float a, float b, int act) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+namespace ptx {
+__device__ __forceinline__ void tmem_ld_32x32_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+}  // namespace ptx
+
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_EPI_WARPS = 8;                             // 2 per TMEM lane quarter
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;         // warps 0..7 epilogue, warp 8 TMA, warp 9 MMA
+// Epilogue warps per output mode (measured on B200, tests/native/gemm_test.bin and its mode 3):
+//   EPI_BF16  -> 16 warps (4 per TMEM lane quarter), 32-column chunks, 64-byte staging rows with the 64B swizzle: half the
+//                registers per thread and twice the independent instruction streams hide the tcgen05.ld -> bias /
+//                activation -> st.shared -> TMA-store chain.  fc1 + GELU 1239 -> 1446 TFLOP/s, qkv 1370 -> 1454, the
+//                short-K FastViT 1x1 convs +65 %.
+//   EPI_RESID / EPI_F32 -> 8 warps (2 per quarter), 32-column chunks, 128-byte rows: with 16 warps the fp32 reduce-add
+//                would need 16-column chunks (twice the TMA reduce operations) and measured 2-7 % slower.
+// `CLIPB200_GEMM_EPI_WARPS` (8 | 16) overrides the bf16 choice for A/B runs.
+#ifndef CLIPB200_GEMM_EPI_WARPS
+#define CLIPB200_GEMM_EPI_WARPS 16
+#endif
+template <int EPI>
+struct EpiTraits {
+  static constexpr int WARPS = EPI == 0 /* EPI_BF16 */ ? CLIPB200_GEMM_EPI_WARPS : 8;
+  static constexpr int SLOTS = WARPS / 4;                 // warps per TMEM lane quarter
+  static constexpr bool NARROW = WARPS == 16;
+  static constexpr int THREADS = 32 * (WARPS + 2);        // epilogue warps, then the TMA warp, then the MMA warp
+  static constexpr int STAGE_BYTES = NARROW ? 32 * 64 : 32 * 128;  // per epilogue warp: 32 swizzled rows
+};
 // The two single-thread roles get the HIGHEST warp ids: the SM's warp arbiter favours higher warp ids, and a late
 // tcgen05.mma / TMA issue starves the tensor pipe while the math-heavy epilogue warps can always wait a few cycles.
-constexpr int GEMM_WARP_TMA = GEMM_EPI_WARPS;
-constexpr int GEMM_WARP_MMA = GEMM_EPI_WARPS + 1;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
-constexpr int GEMM_EPI_STAGE_BYTES = 32 * 128;                 // per epilogue warp: 32 rows x 128 B, 128B-swizzled
+constexpr int GEMM_EPI_STAGE_BYTES_F32MODE = 32 * 128;         // EPI_F32 transposes through a full 128-byte-row tile
 // staging tiles per epilogue warp: with 2 the warp fills one tile while the TMA store / reduce of the previous chunk is
 // still reading the other (cp.async.bulk.wait_group.read 1), at the price of one smem pipeline stage
 #ifndef CLIPB200_GEMM_EPI_BUFS
@@ -121,11 +149,12 @@ constexpr int GEMM_EPI_BUFS = CLIPB200_GEMM_EPI_BUFS;
 // NCTA = 1: one CTA per 128 x BN tile.  NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile;
 // each CTA stages its own 128 rows of A and HALF of the W tile, so the shared-memory traffic per MMA (TMA fill +
 // operand read) drops from 1.5x to 1.0x of the 128 B/clk shared-memory bandwidth.
-template <int BN, int NCTA = 1>
+template <int BN, int NCTA = 1, int EPI = 0>
 struct GemmCfg {
   static constexpr int B_STAGE_BYTES = (BN / NCTA) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = GEMM_A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * GEMM_EPI_BUFS * GEMM_EPI_STAGE_BYTES;  // 32 KB per buffer set
+  static constexpr int EPI_WARP_BYTES = EPI == 2 /* EPI_F32 */ ? GEMM_EPI_STAGE_BYTES_F32MODE : GEMM_EPI_BUFS * EpiTraits<EPI>::STAGE_BYTES;
+  static constexpr int EPI_BYTES = EpiTraits<EPI>::WARPS * EPI_WARP_BYTES;  // 32 KB in every mode
   static constexpr int BAR_BYTES = 256;
   static constexpr int BUDGET = 227 * 1024 - 1024 - BAR_BYTES - EPI_BYTES;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
@@ -133,10 +162,12 @@ struct GemmCfg {
 };
 
 template <int BN, int EPI, int NCTA>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(EpiTraits<EPI>::THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                          const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, GemmEpilogue ep) {
-  using Cfg = GemmCfg<BN, NCTA>;
+  using Cfg = GemmCfg<BN, NCTA, EPI>;
+  using ET = EpiTraits<EPI>;
+  constexpr int GEMM_WARP_TMA = ET::WARPS, GEMM_WARP_MMA = ET::WARPS + 1;
   constexpr int TILE_M = GEMM_BM * NCTA;
   const int rank = NCTA == 2 ? static_cast<int>(ptx::cluster_ctarank()) : 0;      // CTA within the pair
   const int first_tile = NCTA == 2 ? static_cast<int>(ptx::cluster_id_x()) : static_cast<int>(blockIdx.x);
@@ -172,7 +203,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], NCTA * GEMM_EPI_WARPS);  // one arrival per epilogue warp (of both CTAs)
+      ptx::mbar_init(&tmem_empty_bar[a], NCTA * ET::WARPS);  // one arrival per epilogue warp (of both CTAs)
     }
     ptx::fence_mbar_init();
   }
@@ -266,14 +297,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // reads the staging tile back transposed and stores 4 rows x 128 B per warp instruction.
     const int ew = warp;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int half = ew >> 2;
-    uint8_t* const stg_base = smem_epi + ew * GEMM_EPI_BUFS * GEMM_EPI_STAGE_BYTES;
+    const int half = ew >> 2;  // slot of this warp among the ET::SLOTS warps of its lane quarter
+    uint8_t* const stg_base = smem_epi + ew * Cfg::EPI_WARP_BYTES;
     uint8_t* stg = stg_base;
     int stg_buf = 0;
     auto next_stg = [&]() {  // rotate to the staging tile whose store was issued longest ago
       if (GEMM_EPI_BUFS > 1) {
         stg_buf = (stg_buf + 1) % GEMM_EPI_BUFS;
-        stg = stg_base + stg_buf * GEMM_EPI_STAGE_BYTES;
+        stg = stg_base + stg_buf * ET::STAGE_BYTES;
       }
     };
     const int sw = lane & 7;  // 128B-swizzle phase of this thread's staging row
@@ -286,9 +317,77 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int row_base = m_blk * TILE_M + rank * GEMM_BM + quarter * 32;
       const uint32_t taddr_row = tmem_base + static_cast<uint32_t>(acc * 256) +
                                  (static_cast<uint32_t>(quarter * 32) << 16);
-      if (EPI == EPI_BF16) {
+      if (EPI == EPI_BF16 && ET::NARROW) {
+        // 16 epilogue warps: 32-column chunks, 64-byte staging rows (SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3)
+        const int sw64 = (lane >> 1) & 3;
 #pragma unroll 1
-        for (int c = half; c < BN / 64; c += 2) {
+        for (int c = half; c < BN / 32; c += ET::SLOTS) {
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 >= N) break;  // warp-uniform
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr_row + static_cast<uint32_t>(c * 32), r);
+          float4 b[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.bias != nullptr && n0 + 4 * j < N) b[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
+          }
+          ptx::tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            pk[2 * j] = pack2_act(__uint_as_float(r[4 * j]) + b[j].x, __uint_as_float(r[4 * j + 1]) + b[j].y, ep.act);
+            pk[2 * j + 1] = pack2_act(__uint_as_float(r[4 * j + 2]) + b[j].z, __uint_as_float(r[4 * j + 3]) + b[j].w, ep.act);
+          }
+          if (lane == 0) ptx::tma_store_wait_read<0>();  // the previous store of this warp has left the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ sw64) << 4)) =
+                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmap_c, stg, n0, row_base);
+            ptx::tma_store_commit();
+          }
+        }
+      } else if (EPI == EPI_RESID && ET::NARROW) {
+        const int sw64 = (lane >> 1) & 3;
+#pragma unroll 1
+        for (int c = half; c < BN / 16; c += ET::SLOTS) {
+          const int n0 = n_blk * BN + c * 16;
+          if (n0 >= N) break;  // warp-uniform
+          uint32_t r[16];
+          ptx::tmem_ld_32x32_x16(taddr_row + static_cast<uint32_t>(c * 16), r);
+          float4 b4[4], g4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            g4[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (n0 + 4 * j < N) {
+              if (ep.bias != nullptr) b4[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
+              if (ep.gamma != nullptr) g4[j] = __ldg(reinterpret_cast<const float4*>(ep.gamma + n0) + j);
+            }
+          }
+          ptx::tmem_ld_wait();
+          if (lane == 0) ptx::tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ sw64) << 4)) =
+                make_float4((__uint_as_float(r[4 * j + 0]) + b4[j].x) * g4[j].x, (__uint_as_float(r[4 * j + 1]) + b4[j].y) * g4[j].y,
+                            (__uint_as_float(r[4 * j + 2]) + b4[j].z) * g4[j].z, (__uint_as_float(r[4 * j + 3]) + b4[j].w) * g4[j].w);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_reduce_add_2d(&tmap_c, stg, n0, row_base);  // x[rows, cols] += tile, done in L2
+            ptx::tma_store_commit();
+          }
+        }
+      } else if (EPI == EPI_BF16) {
+#pragma unroll 1
+        for (int c = half; c < BN / 64; c += ET::SLOTS) {
           const int n0 = n_blk * BN + c * 64;
           if (n0 >= N) break;  // warp-uniform
           uint32_t r0[32], r1[32];
@@ -329,7 +428,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
       } else if (EPI == EPI_RESID) {
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < BN / 32; c += ET::SLOTS) {
           const int n0 = n_blk * BN + c * 32;
           if (n0 >= N) break;  // warp-uniform
           uint32_t r[32];
@@ -375,7 +474,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       } else {
         const int colq = lane & 7, rsub = lane >> 3;
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < BN / 32; c += ET::SLOTS) {
           const int n0 = n_blk * BN + c * 32;
           if (n0 >= N) break;  // warp-uniform
           uint32_t r[32];
@@ -446,30 +545,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 // Row-major [rows, cols] tensor (cols contiguous, leading dimension ld elements), box = [box_rows, 128 bytes of
 // columns], 128-byte swizzle.  elem_bytes 2 = bf16 (64-column box), 4 = fp32 (32-column box).
 inline bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                         uint32_t box_rows, int elem_bytes) {
+                         uint32_t box_rows, int elem_bytes, int inner_bytes = 128) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (enc == nullptr) return false;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * static_cast<uint64_t>(elem_bytes)};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), box_rows};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(inner_bytes / elem_bytes), box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
 template <int BN, int EPI, int NCTA>
 inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, int M, int N,
                                  int K, const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, NCTA>;
+  using Cfg = GemmCfg<BN, NCTA, EPI>;
   const int tile_m = GEMM_BM * NCTA;
   const int tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
   const int slots = num_sms / NCTA;
   const int groups = tiles < slots ? tiles : slots;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(groups * NCTA);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(EpiTraits<EPI>::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -485,7 +585,7 @@ inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, c
 template <int BN, int EPI, int NCTA>
 inline cudaError_t gemm_configure_t() {
   return cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              GemmCfg<BN, NCTA>::SMEM_BYTES);
+                              GemmCfg<BN, NCTA, EPI>::SMEM_BYTES);
 }
 
 // Opt every instantiation into >48 KB dynamic shared memory on the CURRENT device (call once per device).
@@ -533,9 +633,9 @@ inline cudaError_t gemm_bf16(const __nv_bfloat16* A, long long lda, const __nv_b
   const int ncta = force_ncta ? force_ncta : (M >= 2048 ? 2 : 1);
   if (!make_tmap_2d(&tw, W, N, K, ldw, bn / ncta, 2)) return cudaErrorUnknown;
   if (epi_mode == EPI_BF16) {
-    if (!make_tmap_2d(&tc, ep.out_bf16, M, N, ep.ldc, 32, 2)) return cudaErrorUnknown;
+    if (!make_tmap_2d(&tc, ep.out_bf16, M, N, ep.ldc, 32, 2, EpiTraits<EPI_BF16>::NARROW ? 64 : 128)) return cudaErrorUnknown;
   } else if (epi_mode == EPI_RESID) {
-    if (!make_tmap_2d(&tc, ep.out_f32, M, N, ep.ldc, 32, 4)) return cudaErrorUnknown;
+    if (!make_tmap_2d(&tc, ep.out_f32, M, N, ep.ldc, 32, 4, EpiTraits<EPI_RESID>::NARROW ? 64 : 128)) return cudaErrorUnknown;
   } else {
     tc = ta;  // unused by the kernel in this mode
   }

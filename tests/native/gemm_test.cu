@@ -217,6 +217,10 @@ int main(int argc, char** argv) {
     for (int bn : {128, 192, 256}) fails += run_case(65536, 960, 320, EPI_BF16, ACT_GELU_ERF, bn, true, num_sms, 2);
     return fails;
   }
+  if (argc > 1 && atoi(argv[1]) == 4) {  // one short-K, epilogue-heavy launch for ncu (FastViT stage-1 fc1 + GELU)
+    const int ncta = argc > 2 ? atoi(argv[2]) : 1;
+    return run_case(1048576, 240, 80, EPI_BF16, ACT_GELU_ERF, 0, false, num_sms, ncta);
+  }
   // smallest cases first: one tile, one k-block
   fails += run_case(128, 256, 64, EPI_BF16, ACT_NONE, 256, false, num_sms);
   fails += run_case(128, 128, 64, EPI_BF16, ACT_NONE, 128, false, num_sms);
