@@ -371,15 +371,15 @@ def main():
     gemm_tflops = res["prof"]["gemm_flops"] / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     total_kernel_ms = sum(v for k, v in res["prof"]["ms"].items() if k not in ("h2d", "d2h"))
     # DRAM bytes per GEMM launch from the committed ncu --set full capture of one SO400M layer at this micro-batch
-    # (profiles/r01c_ncu_summary.md); the algorithmic bytes of the same launches are stated beside it.
+    # (profiles/r01d_ncu_summary.md); the algorithmic bytes of the same launches are stated beside it.
     traffic, traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01c_gemm_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01d_gemm_traffic.json")
     if args.workload == "so400m_vision" and args.micro_batch in (0, 256) and os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
         traffic = tj["mean_dram_bytes_per_gemm_launch"]
         traffic_note = ("mean dram__bytes_read+write per layer-GEMM launch (qkv, proj, fc1, fc2 at M=147456), "
-                        "profiles/r01c_gemm_traffic.json; algorithmic bytes of the same launches: 1.83e9")
+                        "profiles/r01d_gemm_traffic.json; algorithmic bytes of the same launches: 1.83e9")
     roofline = {
         "bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of the timed steps)",
         "achieved": gemm_tflops, "peak": pk["sustained"], "unit": "TFLOP/s",
