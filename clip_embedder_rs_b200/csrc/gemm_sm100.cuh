@@ -127,11 +127,14 @@ constexpr int GEMM_BK = 64;
 #ifndef CLIPB200_GEMM_EPI_WARPS
 #define CLIPB200_GEMM_EPI_WARPS 16
 #endif
+#ifndef CLIPB200_GEMM_RESID_WARPS
+#define CLIPB200_GEMM_RESID_WARPS 8
+#endif
 template <int EPI>
 struct EpiTraits {
-  static constexpr int WARPS = EPI == 0 /* EPI_BF16 */ ? CLIPB200_GEMM_EPI_WARPS : 8;
+  static constexpr int WARPS = EPI == 0 /* EPI_BF16 */ ? CLIPB200_GEMM_EPI_WARPS : (EPI == 1 ? CLIPB200_GEMM_RESID_WARPS : 8);
   static constexpr int SLOTS = WARPS / 4;                 // warps per TMEM lane quarter
-  static constexpr bool NARROW = WARPS == 16;
+  static constexpr bool NARROW = WARPS == 16 && EPI == 0;
   static constexpr int THREADS = 32 * (WARPS + 2);        // epilogue warps, then the TMA warp, then the MMA warp
   static constexpr int STAGE_BYTES = NARROW ? 32 * 64 : 32 * 128;  // per epilogue warp: 32 swizzled rows
 };
