@@ -143,8 +143,9 @@ bool parse_tensor(Cursor c, OnnxTensor* t, ExtRef* ext) {
         const size_t n = static_cast<size_t>(r.end - r.p) / 4;
         const size_t old = float_data.size();
         float_data.resize(old + n);
-        memcpy(float_data.data() + old, r.p, n * 4);
+        if (n > 0) memcpy(float_data.data() + old, r.p, n * 4);
       } else if (w == 5) {
+        if (c.end - c.p < 4) { c.ok = false; break; }
         float v;
         memcpy(&v, c.p, 4);
         c.p += 4;
@@ -257,7 +258,12 @@ void parse_attr(Cursor c, std::string* name, OnnxAttr* a) {
     int w;
     const int f = c.key(&w);
     if (f == 1 && w == 2) *name = c.str();
-    else if (f == 2 && w == 5) { memcpy(&a->f, c.p, 4); c.p += 4; if (a->type == 0) a->type = 1; }
+    else if (f == 2 && w == 5) {
+      if (c.end - c.p < 4) { c.ok = false; break; }
+      memcpy(&a->f, c.p, 4);
+      c.p += 4;
+      if (a->type == 0) a->type = 1;
+    }
     else if (f == 3 && w == 0) { a->i = static_cast<int64_t>(c.varint()); if (a->type == 0) a->type = 2; }
     else if (f == 4 && w == 2) { a->s = c.str(); if (a->type == 0) a->type = 3; }
     else if (f == 5 && w == 2) {
@@ -269,8 +275,13 @@ void parse_attr(Cursor c, std::string* name, OnnxAttr* a) {
       if (w == 2) {
         Cursor r = c.sub();
         while (r.end - r.p >= 4) { float v; memcpy(&v, r.p, 4); r.p += 4; a->floats.push_back(v); }
-      } else if (w == 5) { float v; memcpy(&v, c.p, 4); c.p += 4; a->floats.push_back(v); }
-      else c.skip(w);
+      } else if (w == 5) {
+        if (c.end - c.p < 4) { c.ok = false; break; }
+        float v;
+        memcpy(&v, c.p, 4);
+        c.p += 4;
+        a->floats.push_back(v);
+      } else c.skip(w);
     } else if (f == 8) {
       if (w == 2) {
         Cursor r = c.sub();

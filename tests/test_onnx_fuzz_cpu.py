@@ -77,7 +77,7 @@ def test_mutated_graphs_never_crash_the_library(make_real_model, tmp_path, confi
     assert out.returncode == 0 and "INSPECT DONE" in out.stdout, (out.returncode, out.stdout[-500:], out.stderr[-1500:])
 
 
-def test_mutated_graphs_under_address_and_ub_sanitizers(make_real_model, tmp_path):
+def test_mutated_graphs_under_address_and_ub_sanitizers(make_real_model, make_model, tmp_path):
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
@@ -94,6 +94,8 @@ def test_mutated_graphs_under_address_and_ub_sanitizers(make_real_model, tmp_pat
         mdir = make_real_model(config, anonymize=(config == "tiny_siglip"))
         paths += _write_corpus(mdir, fname, str(tmp_path / f"corpus_{config}_{fname}"), 120, seed)
         paths.append(os.path.join(mdir, fname))  # and the unmodified file: must be recognised
+    # initializer-only files (tools/export_synthetic.py): the loader alone (typed data fields, external-data records)
+    paths += _write_corpus(make_model("tiny_clip"), "visual.onnx", str(tmp_path / "corpus_synthetic"), 120, 6)
     for i in range(0, len(paths), 64):
         out = subprocess.run([exe] + paths[i:i + 64], capture_output=True, text=True, errors="replace", timeout=600)
         assert out.returncode == 0 and "FUZZ HARNESS DONE" in out.stdout, (paths[i:i + 64][:2], out.stderr[-3000:])
