@@ -66,6 +66,21 @@ extern "C" {
                            out: *mut f32) -> c_int;
     fn clipb200_similarity(device: c_int, a: *const f32, b: *const f32, n: i64, d: i64, scale: f32, bias: f32,
                            activation: c_int, probs: *mut f32) -> c_int;
+    fn clipb200_resize_rgb8(e: *mut RawEngine, image: *const u8, w: i32, h: i32, pp: *const Preproc, out: *mut u8) -> c_int;
+    fn clipb200_preprocess_rgb8(e: *mut RawEngine, hwc: *const u8, batch: i64, w: i32, h: i32, pp: *const Preproc,
+                                out_nchw: *mut f32) -> c_int;
+    fn clipb200_onnx_inspect(path: *const c_char, json_out: *mut c_char, capacity: usize) -> c_int;
+    fn clipb200_corpus_create(device: c_int, dim: i64, capacity: i64, out: *mut *mut RawCorpus) -> c_int;
+    fn clipb200_corpus_destroy(c: *mut RawCorpus);
+    fn clipb200_corpus_append(c: *mut RawCorpus, rows: *const f32, n: i64) -> c_int;
+    fn clipb200_corpus_size(c: *const RawCorpus) -> i64;
+    fn clipb200_corpus_rank(c: *mut RawCorpus, query: *const f32, scale: f32, bias: f32, activation: c_int,
+                            probs: *mut f32) -> c_int;
+}
+
+#[repr(C)]
+pub struct RawCorpus {
+    _private: [u8; 0],
 }
 
 /// Engine failure; maps onto `ClipError::Ort(String)` upstream.
@@ -163,9 +178,79 @@ impl Engine {
     }
 }
 
+impl Engine {
+    /// `resize_with_fast_image_resize` (src/vision.rs:164-198) on the GPU: one RGB8 image in, `S x S x 3` RGB8 out.
+    pub fn resize_rgb8(&mut self, pixels: &[u8], width: u32, height: u32, pp: &Preproc) -> Result<Vec<u8>, EngineError> {
+        let s = self.image_size();
+        let mut out = vec![0u8; s * s * 3];
+        check(unsafe { clipb200_resize_rgb8(self.raw, pixels.as_ptr(), width as i32, height as i32, pp, out.as_mut_ptr()) })?;
+        Ok(out)
+    }
+
+    /// `preprocess_batch` (src/vision.rs:120-135) for images already at the model resolution: f32 [B,3,S,S], bit-exact.
+    pub fn preprocess_rgb8(&mut self, hwc: &[u8], batch: usize, pp: &Preproc) -> Result<Vec<f32>, EngineError> {
+        let s = self.image_size();
+        let mut out = vec![0f32; batch * 3 * s * s];
+        check(unsafe {
+            clipb200_preprocess_rgb8(self.raw, hwc.as_ptr(), batch as i64, s as i32, s as i32, pp, out.as_mut_ptr())
+        })?;
+        Ok(out)
+    }
+}
+
 impl Drop for Engine {
     fn drop(&mut self) {
         unsafe { clipb200_engine_destroy(self.raw) }
+    }
+}
+
+/// Parse-only description (JSON) of a model file, including how the graph recogniser bound every parameter.
+pub fn inspect(onnx_path: impl AsRef<Path>) -> Result<String, EngineError> {
+    let path = CString::new(onnx_path.as_ref().to_string_lossy().as_bytes())
+        .map_err(|e| EngineError { code: 1, message: e.to_string() })?;
+    let mut buf = vec![0u8; 1 << 22];
+    check(unsafe { clipb200_onnx_inspect(path.as_ptr(), buf.as_mut_ptr().cast::<c_char>(), buf.len()) })?;
+    let end = buf.iter().position(|&b| b == 0).unwrap_or(buf.len());
+    Ok(String::from_utf8_lossy(&buf[..end]).into_owned())
+}
+
+/// HBM-resident embedding matrix for `rank_images` over corpora that do not fit one call (src/clip.rs:136-170).
+pub struct Corpus {
+    raw: *mut RawCorpus,
+    dim: usize,
+}
+
+unsafe impl Send for Corpus {}
+
+impl Corpus {
+    pub fn new(cuda_device: i32, dim: usize, capacity: usize) -> Result<Self, EngineError> {
+        let mut raw = std::ptr::null_mut();
+        check(unsafe { clipb200_corpus_create(cuda_device, dim as i64, capacity as i64, &mut raw) })?;
+        Ok(Self { raw, dim })
+    }
+    pub fn len(&self) -> usize {
+        unsafe { clipb200_corpus_size(self.raw) as usize }
+    }
+    pub fn is_empty(&self) -> bool {
+        self.len() == 0
+    }
+    /// Appends `rows.len() / dim` embeddings (row-major).
+    pub fn append(&mut self, rows: &[f32]) -> Result<(), EngineError> {
+        check(unsafe { clipb200_corpus_append(self.raw, rows.as_ptr(), (rows.len() / self.dim) as i64) })
+    }
+    /// One fused similarity pass over the corpus; the stable descending sort stays with the caller (clip.rs:167).
+    pub fn rank(&mut self, query: &[f32], scale: f32, bias: f32, sigmoid: bool) -> Result<Vec<f32>, EngineError> {
+        let mut probs = vec![0f32; self.len()];
+        check(unsafe {
+            clipb200_corpus_rank(self.raw, query.as_ptr(), scale, bias, c_int::from(sigmoid), probs.as_mut_ptr())
+        })?;
+        Ok(probs)
+    }
+}
+
+impl Drop for Corpus {
+    fn drop(&mut self) {
+        unsafe { clipb200_corpus_destroy(self.raw) }
     }
 }
 
