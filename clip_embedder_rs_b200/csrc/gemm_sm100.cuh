@@ -608,11 +608,13 @@ inline cudaError_t gemm_configure_device() {
   return cudaSuccess;
 }
 
-inline int gemm_pick_bn(int N) {
-  // minimise (padded columns) x (relative cost per column of that tile width, measured on B200: the wider tile
-  // re-reads A less often and needs less smem bandwidth per MMA: 256 -> 1.00, 192 -> 1.055, 128 -> 1.14)
+inline int gemm_pick_bn(int N, int K) {
+  // minimise (padded columns) x (relative cost per column of that tile width).  Measured on B200 with CTA pairs
+  // (tests/native/gemm_test.bin 5, M = 147456): the 256-wide tile re-reads A less often and needs less shared-memory
+  // bandwidth per MMA; per column the 192-wide tile costs 1.10x at K = 4304 and 1.15x at K = 1152 (so N = 1152 takes
+  // 256-wide tiles with 10 % padding when K is short, 192-wide ones when K is long), the 128-wide tile 1.25x.
   const int cands[3] = {256, 192, 128};
-  const double factor[3] = {1.0, 1.055, 1.14};
+  const double factor[3] = {1.0, K <= 2048 ? 1.15 : 1.10, 1.25};
   int best = 256;
   double best_cost = -1.0;
   for (int i = 0; i < 3; ++i) {
@@ -630,7 +632,7 @@ inline cudaError_t gemm_bf16(const __nv_bfloat16* A, long long lda, const __nv_b
                              int force_bn = 0, int force_ncta = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return cudaErrorInvalidValue;
   if ((K & 7) || (N & 7) || (lda & 7) || (ldw & 7) || (ep.ldc & 7)) return cudaErrorInvalidValue;
-  const int bn = force_bn ? force_bn : gemm_pick_bn(N);
+  const int bn = force_bn ? force_bn : gemm_pick_bn(N, K);
   CUtensorMap ta, tw, tc;
   if (!make_tmap_2d(&ta, A, M, K, lda, GEMM_BM, 2)) return cudaErrorUnknown;
   const int ncta = force_ncta ? force_ncta : (M >= 2048 ? 2 : 1);

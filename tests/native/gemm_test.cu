@@ -180,7 +180,7 @@ static int run_case(int M, int N, int K, int epi, int act, int force_bn, bool ti
   }
   const char* en = epi == EPI_BF16 ? "bf16" : (epi == EPI_RESID ? "resid" : "f32");
   printf("%s cta%d M=%d N=%d K=%d epi=%s act=%d bn=%d max_abs=%.4g max_rel=%.4g bad=%lld", bad ? "FAIL" : "ok  ", ncta, M, N, K,
-         en, act, force_bn ? force_bn : gemm_pick_bn(N), max_abs, max_rel, bad);
+         en, act, force_bn ? force_bn : gemm_pick_bn(N, K), max_abs, max_rel, bad);
   if (time_it) printf("  %.3f ms  %.1f TFLOP/s", ms, 2.0 * M * N * K / ms * 1e-9);
   printf("\n");
   fflush(stdout);
@@ -220,6 +220,20 @@ int main(int argc, char** argv) {
   if (argc > 1 && atoi(argv[1]) == 4) {  // one short-K, epilogue-heavy launch for ncu (FastViT stage-1 fc1 + GELU)
     const int ncta = argc > 2 ? atoi(argv[2]) : 1;
     return run_case(1048576, 240, 80, EPI_BF16, ACT_GELU_ERF, 0, false, num_sms, ncta);
+  }
+  if (argc > 1 && atoi(argv[1]) == 5) {  // tile-width sweep on the SO400M / DFN5B-text / giant-opt layer shapes (CTA pairs)
+    const int M = 256 * 576;
+    for (int bn : {128, 192, 256}) {
+      fails += run_case(M, 3456, 1152, EPI_BF16, ACT_NONE, bn, true, num_sms, 2);
+      fails += run_case(M, 1152, 1152, EPI_RESID, ACT_NONE, bn, true, num_sms, 2);
+      fails += run_case(M, 4304, 1152, EPI_BF16, ACT_GELU_TANH, bn, true, num_sms, 2);
+      fails += run_case(M, 1152, 4304, EPI_RESID, ACT_NONE, bn, true, num_sms, 2);
+      fails += run_case(M, 3072, 1024, EPI_BF16, ACT_NONE, bn, true, num_sms, 2);
+      fails += run_case(M, 1024, 4096, EPI_RESID, ACT_NONE, bn, true, num_sms, 2);
+      fails += run_case(M, 4608, 1536, EPI_BF16, ACT_NONE, bn, true, num_sms, 2);
+      fails += run_case(M, 1536, 6144, EPI_RESID, ACT_NONE, bn, true, num_sms, 2);
+    }
+    return fails;
   }
   // smallest cases first: one tile, one k-block
   fails += run_case(128, 256, 64, EPI_BF16, ACT_NONE, 256, false, num_sms);
