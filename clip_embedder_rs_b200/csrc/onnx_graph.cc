@@ -771,7 +771,6 @@ struct Analyzer {
               for (int64_t j = 0; j < N; ++j) po[i * N + j] += x * pb[k * N + j];
             }
         });
-        if (bo.empty()) { /* for_each on a rank-0 shape visits the single element */ }
         v.has_data = true;
       }
       put(n, idx, std::move(v));
@@ -949,7 +948,7 @@ struct LinearSite {
 struct AttnSite {
   int softmax_node = -1;
   int64_t heads = 0, Tq = 0, Tk = 0, hd = 0;
-  double scale = 1.0, q_side_scale = 1.0;
+  double scale = 1.0;  // product of the scalar factors between the projections and the softmax input
   int mask = 0;  // 0 none, 1 causal
   int q_site = -1, k_site = -1, v_site = -1;
   int q_sel = -1, k_sel = -1, v_sel = -1;  // chunk index inside a fused projection (-1 unknown / not fused)
@@ -1215,10 +1214,7 @@ struct Recognizer {
     if (a.q_site < 0) {
       if (qconst == nullptr) return fail("query operand has no recognisable source");
       a.q_const = true;
-      a.q_val = an.get(qk.inputs[0]);  // value as it enters the product (input-independent)
-      qs = 1.0;
-      // scalars applied on the constant side are already inside q_val
-      a.q_side_scale = 1.0;
+      a.q_val = an.get(qk.inputs[0]);  // value as it enters the product: query-side scalars are already folded in
     }
     if (!trace_operand(qk.inputs[1], &a.k_site, &a.k_sel, &ks, nullptr)) return false;
     if (a.k_site < 0) return fail("key operand does not come from a projection");
