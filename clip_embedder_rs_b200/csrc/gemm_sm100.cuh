@@ -167,7 +167,10 @@ struct GemmCfg {
 template <int BN, int EPI, int NCTA>
 __global__ void __launch_bounds__(EpiTraits<EPI>::THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                         const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, GemmEpilogue ep) {
+                         const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_wt,
+                         int M, int N, int K, int n_tail, GemmEpilogue ep) {
+  // n_tail = 128: the last column tile is only 128 wide (N = 1152 = 4 x 256 + 128, N = 3456 = 13 x 256 + 128): its W
+  // box comes from `tmap_wt` and its MMAs use N = 128, so the tail costs half a tile instead of a padded full one.
   using Cfg = GemmCfg<BN, NCTA, EPI>;
   using ET = EpiTraits<EPI>;
   constexpr int GEMM_WARP_TMA = ET::WARPS, GEMM_WARP_MMA = ET::WARPS + 1;
@@ -229,23 +232,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          const bool tail_tile = n_tail != 0 && n_blk == n_tiles - 1;
+          const int b_bytes = tail_tile ? (n_tail / NCTA) * GEMM_BK * 2 : Cfg::B_STAGE_BYTES;
+          const CUtensorMap* tw = tail_tile ? &tmap_wt : &tmap_w;
           if (NCTA == 2) {
             // Both CTAs' loads are credited to the LEADER's full barrier; only the leader arrives (expecting the
             // bytes of both).  The peer never arrives: its bytes for the next phase can only land after the leader's
             // MMAs released the slot, and a transiently negative tx-count cannot complete a phase whose single
             // arrival is still pending.  (A remote release-arrive here costs a cluster-scope fence per k-block and
             // serialises the peer's TMA pipeline: measured 2x slower.)
-            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * (GEMM_A_STAGE_BYTES + b_bytes));
             ptx::tma_load_2d_2sm(&tmap_a, &full_bar[stage], smem_a + stage * GEMM_A_STAGE_BYTES, kb * GEMM_BK,
                                  m_blk * TILE_M + rank * GEMM_BM);
-            ptx::tma_load_2d_2sm(&tmap_w, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, kb * GEMM_BK,
-                                 n_blk * BN + rank * (BN / 2));
+            ptx::tma_load_2d_2sm(tw, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, kb * GEMM_BK,
+                                 n_blk * BN + rank * ((tail_tile ? n_tail : BN) / 2));
           } else {
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], GEMM_A_STAGE_BYTES + b_bytes);
             ptx::tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * GEMM_A_STAGE_BYTES, kb * GEMM_BK,
                              m_blk * GEMM_BM);
-            ptx::tma_load_2d(&tmap_w, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, kb * GEMM_BK,
-                             n_blk * BN);
+            ptx::tma_load_2d(tw, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, kb * GEMM_BK, n_blk * BN);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -255,7 +260,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ------------------------------------------------------------ MMA issuer
     if (rank == 0) {  // in a pair only the leader CTA issues MMAs; whole warp in uniform control flow, one lane elected
                       // inside each issue (keeps descriptors in uniform registers: see ptx_sm100.cuh)
-      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(TILE_M, BN);
+      constexpr uint32_t idesc_full = ptx::make_idesc_bf16_f32(TILE_M, BN);
+      constexpr uint32_t idesc_tail = ptx::make_idesc_bf16_f32(TILE_M, 128);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -263,6 +269,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
+        const uint32_t idesc = (n_tail != 0 && tile % n_tiles == n_tiles - 1) ? idesc_tail : idesc_full;
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * 256);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
@@ -563,8 +570,9 @@ inline bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint6
 }
 
 template <int BN, int EPI, int NCTA>
-inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, int M, int N,
-                                 int K, const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
+inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc,
+                                 const CUtensorMap& twt, int n_tail, int M, int N, int K, const GemmEpilogue& ep,
+                                 int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, NCTA, EPI>;
   const int tile_m = GEMM_BM * NCTA;
   const int tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
@@ -582,7 +590,7 @@ inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, NCTA>, ta, tw, tc, M, N, K, ep);
+  return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, NCTA>, ta, tw, tc, twt, M, N, K, n_tail, ep);
 }
 
 template <int BN, int EPI, int NCTA>
@@ -619,11 +627,16 @@ inline int gemm_pick_bn(int N, int K) {
   double best_cost = -1.0;
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
-    const double cost = static_cast<double>((N + bn - 1) / bn) * bn * factor[i];
+    double cost = static_cast<double>((N + bn - 1) / bn) * bn * factor[i];
+    // 256-wide tiles with a 128-wide tail tile (gemm_tail_cols): the tail costs 128 columns at the narrow-tile rate
+    if (bn == 256 && N % 256 != 0 && N % 256 <= 128) cost = static_cast<double>(N / 256) * 256 + 128 * factor[2];
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
 }
+
+// Width of the last column tile when it is narrower than BN (only BN = 256 supports it): 128 if the remainder of N fits.
+inline int gemm_tail_cols(int N, int bn) { return (bn == 256 && N % 256 != 0 && N % 256 <= 128) ? 128 : 0; }
 
 // A: [M,K] bf16 (lda elements), W: [N,K] bf16 (ldw elements).  force_bn: 0 = auto.
 // force_ncta: 0 = auto (CTA pairs for large M), 1 / 2 = forced.
@@ -637,6 +650,9 @@ inline cudaError_t gemm_bf16(const __nv_bfloat16* A, long long lda, const __nv_b
   if (!make_tmap_2d(&ta, A, M, K, lda, GEMM_BM, 2)) return cudaErrorUnknown;
   const int ncta = force_ncta ? force_ncta : (M >= 2048 ? 2 : 1);
   if (!make_tmap_2d(&tw, W, N, K, ldw, bn / ncta, 2)) return cudaErrorUnknown;
+  const int n_tail = gemm_tail_cols(N, bn);
+  CUtensorMap twt = tw;
+  if (n_tail != 0 && !make_tmap_2d(&twt, W, N, K, ldw, n_tail / ncta, 2)) return cudaErrorUnknown;
   if (epi_mode == EPI_BF16) {
     if (!make_tmap_2d(&tc, ep.out_bf16, M, N, ep.ldc, 32, 2, EpiTraits<EPI_BF16>::NARROW ? 64 : 128)) return cudaErrorUnknown;
   } else if (epi_mode == EPI_RESID) {
@@ -646,14 +662,14 @@ inline cudaError_t gemm_bf16(const __nv_bfloat16* A, long long lda, const __nv_b
   }
 #define CLIPB200_GEMM_CASE(BN_)                                                                                  \
   if (bn == BN_ && ncta == 1) {                                                                                  \
-    if (epi_mode == EPI_BF16) return gemm_launch_t<BN_, EPI_BF16, 1>(ta, tw, tc, M, N, K, ep, num_sms, stream);   \
-    if (epi_mode == EPI_RESID) return gemm_launch_t<BN_, EPI_RESID, 1>(ta, tw, tc, M, N, K, ep, num_sms, stream); \
-    return gemm_launch_t<BN_, EPI_F32, 1>(ta, tw, tc, M, N, K, ep, num_sms, stream);                              \
+    if (epi_mode == EPI_BF16) return gemm_launch_t<BN_, EPI_BF16, 1>(ta, tw, tc, twt, n_tail, M, N, K, ep, num_sms, stream);   \
+    if (epi_mode == EPI_RESID) return gemm_launch_t<BN_, EPI_RESID, 1>(ta, tw, tc, twt, n_tail, M, N, K, ep, num_sms, stream); \
+    return gemm_launch_t<BN_, EPI_F32, 1>(ta, tw, tc, twt, n_tail, M, N, K, ep, num_sms, stream);                              \
   }                                                                                                              \
   if (bn == BN_ && ncta == 2) {                                                                                  \
-    if (epi_mode == EPI_BF16) return gemm_launch_t<BN_, EPI_BF16, 2>(ta, tw, tc, M, N, K, ep, num_sms, stream);   \
-    if (epi_mode == EPI_RESID) return gemm_launch_t<BN_, EPI_RESID, 2>(ta, tw, tc, M, N, K, ep, num_sms, stream); \
-    return gemm_launch_t<BN_, EPI_F32, 2>(ta, tw, tc, M, N, K, ep, num_sms, stream);                              \
+    if (epi_mode == EPI_BF16) return gemm_launch_t<BN_, EPI_BF16, 2>(ta, tw, tc, twt, n_tail, M, N, K, ep, num_sms, stream);   \
+    if (epi_mode == EPI_RESID) return gemm_launch_t<BN_, EPI_RESID, 2>(ta, tw, tc, twt, n_tail, M, N, K, ep, num_sms, stream); \
+    return gemm_launch_t<BN_, EPI_F32, 2>(ta, tw, tc, twt, n_tail, M, N, K, ep, num_sms, stream);                              \
   }
   CLIPB200_GEMM_CASE(256)
   CLIPB200_GEMM_CASE(192)
