@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ptx_sm100.cuh"
 #include "tensormap.h"
@@ -616,6 +617,15 @@ inline cudaError_t gemm_configure_device() {
   return cudaSuccess;
 }
 
+// Width of the last column tile when it is narrower than BN (only BN = 256 supports it): 128 if the remainder of N fits.
+inline bool gemm_tail_enabled() {  // CLIPB200_GEMM_NO_TAIL=1 pads the last tile instead (A/B runs on one box)
+  static const bool on = !(getenv("CLIPB200_GEMM_NO_TAIL") != nullptr && atoi(getenv("CLIPB200_GEMM_NO_TAIL")) != 0);
+  return on;
+}
+inline int gemm_tail_cols(int N, int bn) {
+  return (gemm_tail_enabled() && bn == 256 && N % 256 != 0 && N % 256 <= 128) ? 128 : 0;
+}
+
 inline int gemm_pick_bn(int N, int K) {
   // minimise (padded columns) x (relative cost per column of that tile width).  Measured on B200 with CTA pairs
   // (tests/native/gemm_test.bin 5, M = 147456): the 256-wide tile re-reads A less often and needs less shared-memory
@@ -629,14 +639,11 @@ inline int gemm_pick_bn(int N, int K) {
     const int bn = cands[i];
     double cost = static_cast<double>((N + bn - 1) / bn) * bn * factor[i];
     // 256-wide tiles with a 128-wide tail tile (gemm_tail_cols): the tail costs 128 columns at the narrow-tile rate
-    if (bn == 256 && N % 256 != 0 && N % 256 <= 128) cost = static_cast<double>(N / 256) * 256 + 128 * factor[2];
+    if (gemm_tail_cols(N, bn) != 0) cost = static_cast<double>(N / 256) * 256 + 128 * factor[2];
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
 }
-
-// Width of the last column tile when it is narrower than BN (only BN = 256 supports it): 128 if the remainder of N fits.
-inline int gemm_tail_cols(int N, int bn) { return (bn == 256 && N % 256 != 0 && N % 256 <= 128) ? 128 : 0; }
 
 // A: [M,K] bf16 (lda elements), W: [N,K] bf16 (ldw elements).  force_bn: 0 = auto.
 // force_ncta: 0 = auto (CTA pairs for large M), 1 / 2 = forced.
