@@ -221,6 +221,14 @@ int main(int argc, char** argv) {
     const int ncta = argc > 2 ? atoi(argv[2]) : 1;
     return run_case(1048576, 240, 80, EPI_BF16, ACT_GELU_ERF, 0, false, num_sms, ncta);
   }
+  if (argc > 1 && atoi(argv[1]) == 6) {  // what does the fp32 reduce-add epilogue cost?  same shapes, bf16 store instead
+    const int M = 256 * 576;
+    fails += run_case(M, 1152, 4304, EPI_RESID, ACT_NONE, 0, true, num_sms, 2);
+    fails += run_case(M, 1152, 4304, EPI_BF16, ACT_NONE, 0, true, num_sms, 2);
+    fails += run_case(M, 1152, 1152, EPI_RESID, ACT_NONE, 0, true, num_sms, 2);
+    fails += run_case(M, 1152, 1152, EPI_BF16, ACT_NONE, 0, true, num_sms, 2);
+    return fails;
+  }
   if (argc > 1 && atoi(argv[1]) == 5) {  // tile-width sweep on the SO400M / DFN5B-text / giant-opt layer shapes (CTA pairs)
     const int M = 256 * 576;
     for (int bn : {128, 192, 256}) {
