@@ -249,6 +249,10 @@ cudaError_t launch_dwconv(const void* in, bool in_bf16, int n, int H, int W, int
   static const bool legacy = getenv("CLIPB200_DWCONV_LEGACY") != nullptr && atoi(getenv("CLIPB200_DWCONV_LEGACY")) != 0;
   if (!legacy && dwconv_tma_supported(in_bf16, Cin, K, stride, mult, gelu))
     return launch_dwconv_tma(static_cast<const float*>(in), n, H, W, Cin, K, w, bias, out, out_bf16, st);
+  if (!legacy) {
+    cudaError_t e = cudaSuccess;
+    if (launch_dwconv_tma_gen(in, in_bf16, n, H, W, Cin, K, stride, mult, w, bias, gelu, out, out_bf16, st, &e)) return e;
+  }
 #define CLIPB200_DW(K_, S_, M_, TI, TO, G_)                                                                     \
   if (K == K_ && stride == S_ && mult == M_ && in_bf16 == std::is_same<TI, __nv_bfloat16>::value &&             \
       out_bf16 == std::is_same<TO, __nv_bfloat16>::value && gelu == G_)                                         \

@@ -19,6 +19,9 @@ cudaError_t dwconv_tma_configure_device();
 bool dwconv_tma_supported(bool in_bf16, int C, int K, int stride, int mult, bool gelu);
 cudaError_t launch_dwconv_tma(const float* in, int n, int H, int W, int C, int K, const float* w, const float* bias,
                               void* out, bool out_bf16, cudaStream_t st);
+bool launch_dwconv_tma_gen(const void* in, bool in_bf16, int n, int H, int W, int C, int K, int stride, int mult,
+                           const float* w, const float* bias, bool gelu, void* out, bool out_bf16, cudaStream_t st,
+                           cudaError_t* err);
 cudaError_t launch_gap(const float* x, int n, int P, int C, float* out, cudaStream_t st);
 cudaError_t launch_se_mlp(const float* s, int n, int C, int R, const float* w1, const float* b1, const float* w2,
                           const float* b2, float* gate, cudaStream_t st);

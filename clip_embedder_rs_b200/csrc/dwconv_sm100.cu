@@ -123,6 +123,115 @@ cudaError_t launch_t(const float* in, int n, int H, int W, int C, const float* w
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Strided and / or channel-multiplying variants (stem depthwise 3x3 s2 on bf16, the 7x7 s2 x2 downsampling convs, the
+// final 3x3 x2 expansion): same TMA-staged halo tile, one output row of 16 pixels per warp.  Lanes are OUTPUT channels;
+// with a channel multiplier of 2 two neighbouring lanes read the same input channel (a shared-memory broadcast), so the
+// staged tile only holds 32 / MULT input channels.
+template <int K, int STRIDE, int MULT, typename Tin, typename Tout, bool GELU>
+struct DwGen {
+  static constexpr int TW = 16, TH = 8, CI = 32 / MULT;
+  static constexpr int IW = (TW - 1) * STRIDE + K, IH = (TH - 1) * STRIDE + K;
+  static constexpr int SMEM = IH * IW * CI * static_cast<int>(sizeof(Tin));
+};
+
+__device__ __forceinline__ float load_in(const float* p) { return *p; }
+__device__ __forceinline__ float load_in(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float gelu_erf_dw(float x) {  // Abramowitz-Stegun form, same as gemm_sm100.cuh::gelu_erf_fast
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, fabsf(x), 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752f));
+  float q = fmaf(t, 0.5307027145f, -0.7265760135f);
+  q = fmaf(t, q, 0.7107068705f);
+  q = fmaf(t, q, -0.142248368f);
+  q = fmaf(t, q, 0.127414796f);
+  const float h = q * t * e;
+  return x * (x < 0.f ? h : 1.0f - h);
+}
+
+template <int K, int STRIDE, int MULT, typename Tin, typename Tout, bool GELU>
+__global__ void __launch_bounds__(DW_THREADS, 2)
+dwconv_tma_gen_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ w /*[K*K][Cout]*/,
+                      const float* __restrict__ bias, Tout* __restrict__ out, int Ho, int Wo, int Cout, int tiles_x) {
+  using G = DwGen<K, STRIDE, MULT, Tin, Tout, GELU>;
+  extern __shared__ __align__(128) uint8_t gen_tile_raw[];
+  const Tin* tile = reinterpret_cast<const Tin*>(gen_tile_raw);  // [IH][IW][CI]
+  __shared__ __align__(8) uint64_t bar;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.y * 32, b = blockIdx.z;  // first OUTPUT channel of this block
+  const int ty0 = (blockIdx.x / tiles_x) * G::TH, tx0 = (blockIdx.x % tiles_x) * G::TW;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+    ptx::mbar_arrive_expect_tx(&bar, G::SMEM);
+    tma_load_4d(&tm_in, &bar, gen_tile_raw, c0 / MULT, tx0 * STRIDE - K / 2, ty0 * STRIDE - K / 2, b);
+  }
+  const int oc = c0 + lane;
+  const bool c_ok = oc < Cout;
+  float wk[K * K];
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) wk[t] = c_ok ? __ldg(w + t * Cout + oc) : 0.f;
+  const float bv = c_ok ? __ldg(bias + oc) : 0.f;
+  __syncthreads();
+  ptx::mbar_wait(&bar, 0);
+  const int cl = lane / MULT;  // input channel inside the staged tile
+  float acc[G::TW];
+#pragma unroll
+  for (int x = 0; x < G::TW; ++x) acc[x] = bv;
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    float rv[G::IW];
+    const Tin* src = tile + ((warp * STRIDE + ky) * G::IW) * G::CI + cl;
+#pragma unroll
+    for (int i = 0; i < G::IW; ++i) rv[i] = load_in(src + i * G::CI);
+#pragma unroll
+    for (int x = 0; x < G::TW; ++x)
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) acc[x] = fmaf(rv[x * STRIDE + kx], wk[ky * K + kx], acc[x]);
+  }
+  const int oy = ty0 + warp;
+  if (!c_ok || oy >= Ho) return;
+  Tout* o0 = out + ((static_cast<long long>(b) * Ho + oy) * Wo + tx0) * Cout + oc;
+#pragma unroll
+  for (int x = 0; x < G::TW; ++x)
+    if (tx0 + x < Wo) store_out(o0 + static_cast<long long>(x) * Cout, GELU ? gelu_erf_dw(acc[x]) : acc[x]);
+}
+
+template <typename Tin>
+bool make_tmap_nhwc(CUtensorMap* tm, const Tin* base, int n, int H, int W, int C, int box_c, int box_w, int box_h) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return false;
+  const cuuint64_t es = sizeof(Tin);
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(n)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * es, static_cast<cuuint64_t>(W) * C * es,
+                           static_cast<cuuint64_t>(H) * W * C * es};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tm, sizeof(Tin) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+             const_cast<Tin*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int K, int STRIDE, int MULT, typename Tin, typename Tout, bool GELU>
+cudaError_t launch_gen(const Tin* in, int n, int H, int W, int C, const float* w, const float* bias, Tout* out,
+                       cudaStream_t st) {
+  using G = DwGen<K, STRIDE, MULT, Tin, Tout, GELU>;
+  const int Ho = (H + 2 * (K / 2) - K) / STRIDE + 1, Wo = (W + 2 * (K / 2) - K) / STRIDE + 1, Cout = C * MULT;
+  CUtensorMap tm;
+  if (!make_tmap_nhwc<Tin>(&tm, in, n, H, W, C, G::CI, G::IW, G::IH)) return cudaErrorInvalidValue;
+  const int tiles_x = (Wo + G::TW - 1) / G::TW, tiles_y = (Ho + G::TH - 1) / G::TH;
+  dim3 grid(tiles_x * tiles_y, (Cout + 31) / 32, n);
+  dwconv_tma_gen_kernel<K, STRIDE, MULT, Tin, Tout, GELU><<<grid, DW_THREADS, G::SMEM, st>>>(tm, w, bias, out, Ho, Wo, Cout, tiles_x);
+  return cudaGetLastError();
+}
+
+template <int K, int STRIDE, int MULT, typename Tin, typename Tout, bool GELU>
+cudaError_t configure_gen() {
+  return cudaFuncSetAttribute(dwconv_tma_gen_kernel<K, STRIDE, MULT, Tin, Tout, GELU>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, DwGen<K, STRIDE, MULT, Tin, Tout, GELU>::SMEM);
+}
+
 template <int K, typename Tout>
 cudaError_t configure_t() {
   constexpr int smem = (DW_TH + K - 1) * (DW_TW + K - 1) * DW_CI * 4;
@@ -137,7 +246,38 @@ cudaError_t dwconv_tma_configure_device() {
   if (e == cudaSuccess) e = configure_t<7, float>();
   if (e == cudaSuccess) e = configure_t<3, __nv_bfloat16>();
   if (e == cudaSuccess) e = configure_t<3, float>();
+  if (e == cudaSuccess) e = configure_gen<3, 2, 1, __nv_bfloat16, __nv_bfloat16, true>();
+  if (e == cudaSuccess) e = configure_gen<7, 2, 2, float, __nv_bfloat16, true>();
+  if (e == cudaSuccess) e = configure_gen<7, 2, 2, float, float, false>();
+  if (e == cudaSuccess) e = configure_gen<3, 1, 2, float, float, false>();
   return e;
+}
+
+// The strided / multiplier combinations of the FastViT trunk; false = not one of them (caller falls back).
+bool launch_dwconv_tma_gen(const void* in, bool in_bf16, int n, int H, int W, int C, int K, int stride, int mult,
+                           const float* w, const float* bias, bool gelu, void* out, bool out_bf16, cudaStream_t st,
+                           cudaError_t* err) {
+  const size_t es = in_bf16 ? 2 : 4;
+  if ((C * es) % 16 != 0 || (H % stride) != 0 || (W % stride) != 0) return false;  // TMA stride rule; even sizes
+  if (K == 3 && stride == 2 && mult == 1 && in_bf16 && out_bf16 && gelu) {
+    *err = launch_gen<3, 2, 1, __nv_bfloat16, __nv_bfloat16, true>(static_cast<const __nv_bfloat16*>(in), n, H, W, C, w, bias,
+                                                                    static_cast<__nv_bfloat16*>(out), st);
+    return true;
+  }
+  if (K == 7 && stride == 2 && mult == 2 && !in_bf16 && out_bf16 && gelu) {
+    *err = launch_gen<7, 2, 2, float, __nv_bfloat16, true>(static_cast<const float*>(in), n, H, W, C, w, bias,
+                                                           static_cast<__nv_bfloat16*>(out), st);
+    return true;
+  }
+  if (K == 7 && stride == 2 && mult == 2 && !in_bf16 && !out_bf16 && !gelu) {
+    *err = launch_gen<7, 2, 2, float, float, false>(static_cast<const float*>(in), n, H, W, C, w, bias, static_cast<float*>(out), st);
+    return true;
+  }
+  if (K == 3 && stride == 1 && mult == 2 && !in_bf16 && !out_bf16 && !gelu) {
+    *err = launch_gen<3, 1, 2, float, float, false>(static_cast<const float*>(in), n, H, W, C, w, bias, static_cast<float*>(out), st);
+    return true;
+  }
+  return false;
 }
 
 bool dwconv_tma_supported(bool in_bf16, int C, int K, int stride, int mult, bool gelu) {
