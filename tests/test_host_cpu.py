@@ -213,3 +213,32 @@ def test_cpp_host_mirror_errors_and_configs(tmp_path):
         pytest.fail(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
     out = subprocess.run([path, "errors", str(tmp_path)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and "HOST API ERRORS PASSED" in out.stdout, out.stdout + out.stderr
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The JSON lines committed under profiles/ (what `bench.py` printed on a B200) carry every key the driver reads:
+    the base contract, `e2e`, `gpu_launches`, `clocks`, `roofline` (with `traffic`) and `cpu_baseline`; the reference arm
+    carries `impl` and a zero-copy `e2e`."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    own = json.loads(open(os.path.join(root, "profiles", "r01_bench_final.json")).read())
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in own, k
+    assert own["unit"] == "images/s" and own["higher_is_better"] is True and own["scaling"] == "weak"
+    assert own["vs_baseline"] is None and own["dtype"] == "bf16" and own["data"] == "synthetic"
+    assert "workload" in own["config"] and "model" not in own["config"]
+    assert own["warmup"] >= 3 and own["gpu_launches"] > 0
+    assert set(own["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert own["e2e"]["h2d_bytes_per_step"] == 1024 * 384 * 384 * 3 and own["e2e"]["d2h_bytes_per_step"] == 1024 * 1152 * 4
+    assert abs(own["e2e"]["value"] - own["value"]) / own["value"] < 0.05
+    r = own["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is not None and 0.5 < r["frac"] < 1.0
+    assert set(own["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(own["clocks"]["reasons"])
+    c = own["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    ref = json.loads(open(os.path.join(root, "profiles", "r01_bench_reference_arm.json")).read())
+    assert ref["impl"] == "reference" and ref["metric"] == own["metric"] and ref["unit"] == own["unit"]
+    assert ref["config"]["workload"] == own["config"]["workload"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["d2h_bytes_per_step"] == 0 and ref["e2e"]["value"] == ref["value"]
