@@ -169,6 +169,7 @@ struct Analyzer {
   const OnnxModel& m;
   std::unordered_map<std::string, AVal> env;
   std::string err;
+  int64_t batch0 = 1;  // batch the graph is analysed at: 1 for a dynamic batch axis, else the exported batch
 
   explicit Analyzer(const OnnxModel& model) : m(model) {}
 
@@ -205,7 +206,8 @@ struct Analyzer {
           if (i != 0) return fail("graph input '" + vi.name + "' has a dynamic dimension other than the batch axis");
           v.shape[i] = 1;
         }
-      if (!v.shape.empty() && vi.dims[0] > 0) v.shape[0] = 1;  // fixed-batch exports are analysed at batch 1 too
+      // a fixed-batch export (no dynamic_axes) bakes its batch into Reshape constants: analyse it at that batch
+      if (!v.shape.empty()) batch0 = v.shape[0];
       v.dtype = vi.elem_type ? vi.elem_type : 1;
       v.tainted = true;
       env[vi.name] = std::move(v);
@@ -1175,7 +1177,7 @@ struct Recognizer {
     a.Tq = x->shape[x->shape.size() - 2];
     a.Tk = x->shape[x->shape.size() - 1];
     if (a.Tq <= 0 || a.Tk <= 0) return fail("Softmax over an empty tensor");
-    a.heads = numel(x->shape) / (a.Tq * a.Tk);
+    a.heads = numel(x->shape) / (a.Tq * a.Tk) / (an.batch0 > 0 ? an.batch0 : 1);
     // back from the softmax input to QK^T
     std::string cur = sm.inputs[0];
     int qk_node = -1;
@@ -1412,6 +1414,22 @@ struct Recognizer {
     }
     AVal tmp = *v;
     if (!materialize(&tmp)) return fail("'" + name + "' is not a foldable constant");
+    add_tensor(make_owned(name, dims, tmp.data), v->init_name.empty() ? "<folded constant>" : v->init_name, false);
+    return true;
+  }
+
+  // Constants that the exporter expanded along a FIXED batch axis (class token, attention-pool query of a graph
+  // exported without dynamic_axes): every batch copy must be identical; emit the first one.
+  bool emit_batch_constant(const std::string& name, AVal* v, const Shape& dims) {
+    const int64_t want = numel(dims), b = an.batch0;
+    if (v == nullptr || b <= 1 || numel(v->shape) != want * b) return emit_plain(name, v, dims);
+    AVal tmp = *v;
+    if (!materialize(&tmp)) return fail("'" + name + "' is not a foldable constant");
+    for (int64_t r = 1; r < b; ++r)
+      for (int64_t i = 0; i < want; ++i)
+        if (tmp.data[static_cast<size_t>(r * want + i)] != tmp.data[static_cast<size_t>(i)])
+          return fail("'" + name + "' differs between the batch copies of a fixed-batch export");
+    tmp.data.resize(static_cast<size_t>(want));
     add_tensor(make_owned(name, dims, tmp.data), v->init_name.empty() ? "<folded constant>" : v->init_name, false);
     return true;
   }
@@ -1670,7 +1688,13 @@ struct Recognizer {
         if (!emit_stacked(ap + ".kv.weight", ap + ".kv.bias", {a.k_site, a.v_site}, D)) return false;
       } else return fail("attention-pool head: expected 1 or 2 key/value projections");
       AVal q = *a.q_val;
-      if (!materialize(&q) || numel(q.shape) != D) return fail("attention-pool query is not a foldable [1, H, 1, hd] constant");
+      if (!materialize(&q) || (numel(q.shape) != D && numel(q.shape) != D * an.batch0))
+        return fail("attention-pool query is not a foldable [1, H, 1, hd] constant");
+      if (numel(q.shape) != D) {  // fixed-batch export: identical copies along the batch axis
+        for (int64_t i = D; i < numel(q.shape); ++i)
+          if (q.data[static_cast<size_t>(i)] != q.data[static_cast<size_t>(i % D)]) return fail("attention-pool query differs between batch copies");
+        q.data.resize(static_cast<size_t>(D));
+      }
       // a.scale holds the scalars on the key side and behind QK^T; the engine applies none, so fold all of it into q
       std::vector<double> qd(q.data);
       const double want = 1.0 / sqrt(static_cast<double>(a.hd));
@@ -1711,7 +1735,7 @@ struct Recognizer {
       if (head.K != D || head.bias != nullptr) return fail("output projection must be a bias-free D->E matrix");
       E = head.N;
       if (!emit_weight(pre + ".conv1.weight", conv, true, ws)) return false;
-      if (!emit_plain(pre + ".class_embedding", cls, {D})) return false;
+      if (!emit_batch_constant(pre + ".class_embedding", cls, {D})) return false;
       if (T * D != numel(pos->shape)) return fail("positional embedding size");
       if (!emit_plain(pre + ".positional_embedding", pos, {T, D})) return false;
       if (!emit_ln(pre + ".ln_pre", ln_pre, D, &c.eps)) return false;

@@ -9,8 +9,9 @@ the check SURVEY.md §8(c) asks for ("so the file, not the module, is what gets 
 architectures and only follows the graph.
 
 **parity unpinned** in the sense of the task statement: it has not been run against onnxruntime itself (absent).  It
-is pinned against torch: every graph in the tests was produced by `torch.onnx.export` from an `nn.Module`, and the
-interpreter must reproduce that module's own fp32 output (`tests/test_onnx_graph_cpu.py`).
+is pinned against torch (every graph in the tests was produced by `torch.onnx.export` from an `nn.Module`, and the
+interpreter must reproduce that module's own fp32 output) and against an independent ONNX runtime that is in the image,
+OpenCV DNN, executing the same files (`tests/test_onnx_graph_cpu.py`).
 
 Only the operators that `torch.onnx.export` emits for the CLIP / SigLIP / ViT towers are implemented; anything else
 raises `NotImplementedError` naming the operator.

@@ -20,6 +20,11 @@ restatement cannot be checked against the reference's own outputs.  What it foll
 
 The forward passes read their weights from the SAME `visual.onnx` / `text.onnx` (+ `.onnx.data`) files that the
 engine loads, through the independent Python reader in `tools/onnx_proto.py`.
+
+What it IS checked against (tests/test_oracle_cpu.py, tests/test_onnx_graph_cpu.py): HF transformers' independent CLIP /
+SiglipModel implementations loaded with the same weights; real `torch.onnx.export` graphs of the same models executed by
+`oracle/onnx_interp.py`; and the same exported files executed by a third-party ONNX runtime that is in the image, OpenCV
+DNN (vision towers incl. the SigLIP MAP head, SigLIP text; 1e-5).  None of these is onnxruntime, hence the label above.
 """
 from __future__ import annotations
 

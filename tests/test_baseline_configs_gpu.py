@@ -191,3 +191,39 @@ def test_mobileclip2_s3_s4_five_stage_fastvit(make_big, config):
     print(f"\n[{config}] vision cos min {cos.min():.6f} max_abs {np.abs(got[:5] - want).max():.2e} "
           f"(mean cosine between different images {spread:.3f})")
     assert cos.min() >= COS_BAR and spread < 0.98
+
+
+def test_c3_so400m_against_opencv_dnn_full_size(tmp_path):
+    """BASELINE config C3 at full size against an independent ONNX runtime: the SO400M tower exported by
+    `torch.onnx.export` with the batch baked in (OpenCV's importer cannot infer a dynamic batch) and weights inline is
+    executed by OpenCV DNN on the CPU and by the engine on the GPU.  onnxruntime itself is not available in this image;
+    this is the closest third-party stand-in for the reference's `session.run`."""
+    cv2 = pytest.importorskip("cv2")
+    import ctypes as C
+
+    import torch
+
+    import export_synthetic as ex
+    import torch_export as te
+    from clip_embedder_rs_b200 import _native
+    from clip_embedder_rs_b200.onnx import OnnxSession
+    from oracle import reference_forward as R
+
+    spec = ex.CONFIGS["so400m_siglip2_384"]
+    model = te.build_model(spec, 0, towers=("vision",))
+    imgs = np.random.default_rng(4).integers(0, 256, size=(2, 384, 384, 3), dtype=np.uint8)
+    feed = R.preprocess_batch(list(imgs), 384, spec.mean, spec.std)
+    path = str(tmp_path / "visual.onnx")
+    te.export_tower(te.VisualWrapper(model), torch.from_numpy(feed), path, "pixel_values", "image_embeddings",
+                    dynamic_batch=False, external_data=False)
+    del model
+    net = cv2.dnn.readNetFromONNX(path)
+    net.setInput(feed, "pixel_values")
+    want = net.forward()
+    del net
+    s = OnnxSession(path)
+    got = np.empty_like(want)
+    s.check(_native.lib.clipb200_vision_embed_f32(s.handle, feed.ctypes.data_as(C.c_void_p), 2, got.ctypes.data_as(C.c_void_p)))
+    cos = cosine_rows(got, want)
+    print(f"\n[C3 vs OpenCV DNN] cos >= {cos.min():.6f} max_abs {np.abs(got - want).max():.2e}")
+    assert want.shape == (2, 1152) and cos.min() >= COS_BAR

@@ -214,3 +214,49 @@ def test_unrecognised_graph_is_reported_not_guessed(tmp_path):
 def test_initializer_only_files_skip_the_recogniser(make_model):
     j = inspect_onnx(os.path.join(make_model("tiny_clip"), "visual.onnx"))
     assert not j["graph"]["attempted"] and j["num_nodes"] == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# An independent ONNX runtime.  onnxruntime (what the reference links) is not in this image, but OpenCV's DNN module is:
+# a third-party ONNX importer + CPU executor that shares no code with torch, with this repo's interpreter or with the
+# engine.  It cannot shape-infer a dynamic batch axis, so the towers are exported with the batch baked in (no
+# dynamic_axes) and weights inline; the CLIP text tower's argmax pooling (Range / Flatten / Gather arithmetic) is beyond
+# its Gather, so text is checked on the SigLIP tower (last-token pooling).
+def _export_static(tmp_path, config, tower):
+    spec = ex.CONFIGS[config]
+    model = te.build_model(spec, 0)
+    path = str(tmp_path / f"{config}_{tower}_static.onnx")
+    if tower == "vision":
+        s = spec.vision.image_size
+        feed = np.random.default_rng(7).standard_normal((2, 3, s, s)).astype(np.float32)
+        wrapper, in_name, out_name = te.VisualWrapper(model), "pixel_values", "image_embeddings"
+    else:
+        feed = np.random.default_rng(8).integers(1, spec.text.vocab_size - 2, (2, spec.text.context_length)).astype(np.int64)
+        wrapper, in_name, out_name = te.TextWrapper(model), "input_ids", "text_embeddings"
+    te.export_tower(wrapper, torch.from_numpy(feed), path, in_name, out_name, dynamic_batch=False, external_data=False)
+    with torch.no_grad():
+        want = wrapper(torch.from_numpy(feed)).numpy()
+    return path, in_name, feed, want
+
+
+@pytest.mark.parametrize("config,tower", [("tiny_clip", "vision"), ("tiny_siglip", "vision"), ("tiny_siglip", "text")])
+def test_opencv_dnn_runs_the_same_file(tmp_path, make_model, config, tower):
+    cv2 = pytest.importorskip("cv2")
+    path, in_name, feed, want = _export_static(tmp_path, config, tower)
+    net = cv2.dnn.readNetFromONNX(path)
+    net.setInput(feed, in_name)
+    got_cv = net.forward()
+    got_interp = oi.OnnxSession(path).run({in_name: feed})
+    synth = make_model(config)
+    got_oracle = (R.vision_forward(R.Tower(os.path.join(synth, "visual.onnx")), feed) if tower == "vision"
+                  else R.text_forward(R.Tower(os.path.join(synth, "text.onnx")), feed))
+    assert got_cv.shape == want.shape
+    # four implementations of the same file / weights: torch module, OpenCV DNN, the oracle interpreter, the functional oracle
+    assert np.abs(got_cv - want).max() < 2e-6
+    assert np.abs(got_cv - got_interp).max() < 2e-6
+    assert np.abs(got_cv - got_oracle).max() < 1e-5
+    # and the engine's recogniser binds the fixed-batch graph too (class token / pool query expanded along batch 2)
+    j = inspect_onnx(path)
+    assert j["graph"]["recognized"], j["graph"]["error"]
+    spec = ex.CONFIGS[config]
+    assert int(j["metadata"]["clipb200.heads"]) == (spec.vision.heads if tower == "vision" else spec.text.heads)

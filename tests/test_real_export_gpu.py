@@ -88,3 +88,27 @@ def test_third_party_export_hf_clip_vision_on_gpu(tmp_path):
     cos = cosine_rows(out, want)
     print(f"\n[hf clip vision] cos >= {cos.min():.6f} max abs {np.abs(out - want).max():.2e}")
     assert cos.min() >= COS_BAR
+
+
+@pytest.mark.parametrize("config", ["tiny_clip", "tiny_siglip"])
+def test_engine_matches_opencv_dnn_on_the_same_file(tmp_path, config):
+    """The engine against an independent ONNX runtime (OpenCV DNN) executing the very same exported file (fixed batch,
+    inline weights): the closest stand-in for the reference's onnxruntime that this image offers."""
+    cv2 = pytest.importorskip("cv2")
+    import ctypes as C
+
+    from clip_embedder_rs_b200 import _native
+    from clip_embedder_rs_b200.onnx import OnnxSession
+    from test_onnx_graph_cpu import _export_static
+
+    path, in_name, feed, _ = _export_static(tmp_path, config, "vision")
+    net = cv2.dnn.readNetFromONNX(path)
+    net.setInput(feed, in_name)
+    want = net.forward()
+    s = OnnxSession(path)
+    out = np.empty_like(want)
+    s.check(_native.lib.clipb200_vision_embed_f32(s.handle, feed.ctypes.data_as(C.c_void_p), feed.shape[0],
+                                                  out.ctypes.data_as(C.c_void_p)))
+    cos = cosine_rows(out, want)
+    print(f"\n[{config} vs OpenCV DNN] cos >= {cos.min():.6f} max abs {np.abs(out - want).max():.2e}")
+    assert cos.min() >= COS_BAR

@@ -28,6 +28,7 @@ from __future__ import annotations
 import argparse
 import math
 import os
+import shutil
 import sys
 import tempfile
 import warnings
@@ -395,15 +396,21 @@ def repack(src_path: str, dst_path: str, anonymize: bool = False, metadata: Opti
 
 
 def export_tower(module: nn.Module, dummy: torch.Tensor, path: str, in_name: str, out_name: str,
-                 anonymize: bool = False) -> None:
+                 anonymize: bool = False, dynamic_batch: bool = True, external_data: bool = True) -> None:
+    """`dynamic_batch=False` bakes the dummy batch into the graph (what `torch.onnx.export` does without
+    `dynamic_axes`); `external_data=False` keeps the exporter's file as it is, weights inline — the form OpenCV's DNN
+    importer (an independent ONNX runtime, used as a cross-check in the tests) can read."""
     _patch_exporter()
+    kw = dict(dynamic_axes={in_name: {0: "batch_size"}, out_name: {0: "batch_size"}}) if dynamic_batch else {}
     with tempfile.TemporaryDirectory() as tmp, warnings.catch_warnings():
         warnings.simplefilter("ignore")
         raw = os.path.join(tmp, "raw.onnx")
         torch.onnx.export(module, dummy, raw, input_names=[in_name], output_names=[out_name],
-                          dynamic_axes={in_name: {0: "batch_size"}, out_name: {0: "batch_size"}},
-                          opset_version=18, do_constant_folding=True, dynamo=False)
-        repack(raw, path, anonymize=anonymize)
+                          opset_version=18, do_constant_folding=True, dynamo=False, **kw)
+        if external_data or anonymize:
+            repack(raw, path, anonymize=anonymize)
+        else:
+            shutil.copyfile(raw, path)
 
 
 def export_model_dir(spec: ex.ModelSpec, out_dir: str, seed: int = 0, towers=("vision", "text"),
