@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "gemm_sm100.cuh"  // get_encode_tiled
 #include "ptx_sm100.cuh"
@@ -29,7 +30,8 @@ namespace clipb200 {
 namespace attn {
 
 #ifndef CLIPB200_ATTN_DBG
-#define CLIPB200_ATTN_DBG 0  // profiling aid (tests/native/attn_test.cu): 1 no exp, 2 no S load, 4 no P store
+#define CLIPB200_ATTN_DBG 0  // profiling aid (tests/native/attn_test.cu): 1 no exp, 2 no S load, 4 no P store,
+                             // 8 no remainder-plane MMAs, 16 no PV MMAs, 32 no QK MMAs (results wrong by construction)
 #endif
 
 #ifdef CLIPB200_ATTN_TIMING
@@ -208,6 +210,279 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// ---- softmax arithmetic options (measured with tests/native/attn_test.cu; defaults = the fastest measured) -------------
+// CLIPB200_ATTN_POLY_NUM / _DEN: of every DEN element pairs, NUM take exp2 on the FMA pipe (Cody-Waite split + degree-3
+// minimax polynomial in packed f32x2 arithmetic: FFMA2 / FADD2 + one LEA per element, relative error 7.5e-5, far below
+// the bf16 rounding of P) instead of MUFU.EX2.  The softmax warps are bound by the 16 exp2/clk/SM MUFU rate at head dim
+// 72, so moving a fraction of the exponentials to the (otherwise ~half idle) FMA pipe shortens their critical path.
+#ifndef CLIPB200_ATTN_POLY_NUM
+#define CLIPB200_ATTN_POLY_NUM 1
+#endif
+#ifndef CLIPB200_ATTN_POLY_DEN
+#define CLIPB200_ATTN_POLY_DEN 4
+#endif
+// CLIPB200_ATTN_PACKED: scale-and-shift (FFMA2) and row sums (FADD2) of the MUFU elements in packed f32x2 as well.
+#ifndef CLIPB200_ATTN_PACKED
+#define CLIPB200_ATTN_PACKED 1
+#endif
+// CLIPB200_ATTN_ELECT_ARRIVE: one lane per softmax warp arrives on s_empty / p_full (barrier count = warps) instead of
+// all 32 lanes (count = threads): 31 fewer same-address shared-memory atomics per warp and barrier.
+#ifndef CLIPB200_ATTN_ELECT_ARRIVE
+#define CLIPB200_ATTN_ELECT_ARRIVE 1
+#endif
+// CLIPB200_ATTN_LDPIPE: the S tile is read from TMEM in 32-column chunks and the row maximum of chunk c is taken while
+// chunk c+1 is in flight (TMEM reads run at 64 B/clk, so 96 columns take ~190 cycles that would otherwise be exposed).
+#ifndef CLIPB200_ATTN_LDPIPE
+#define CLIPB200_ATTN_LDPIPE 1
+#endif
+// CLIPB200_ATTN_MAXTREE: row maximum with four independent FMNMX3 chains instead of one 48-deep dependent chain.
+#ifndef CLIPB200_ATTN_MAXTREE
+#define CLIPB200_ATTN_MAXTREE 1
+#endif
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for a pair of arguments x <= ~9 without the MUFU: x = n + f with n = round(x), f in [-0.5, 0.5];
+// 2^f by a degree-3 minimax polynomial, 2^n by adding n to the exponent field (the rounded integer sits in the low
+// mantissa bits of x + 1.5 * 2^23).  Arguments are clamped at -125 so the exponent field cannot wrap: masked (-inf)
+// scores come out as 2^-125 ~ 2e-38 instead of 0, which no bf16 / fp32 sum can see next to the row maximum's 2^0.
+__device__ __forceinline__ void exp2_poly_pair(uint64_t x, float& p0, float& p1) {
+  float x0, x1;
+  unpack2(x, x0, x1);
+  x = pack2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  const uint64_t xf = add2(x, pack2(12582912.f, 12582912.f));
+  const uint64_t xi = add2(xf, pack2(-12582912.f, -12582912.f));
+  const uint64_t fr = fma2(xi, pack2(-1.f, -1.f), x);
+  uint64_t p = fma2(pack2(0.0551716648f, 0.0551716648f), fr, pack2(0.2426111251f, 0.2426111251f));
+  p = fma2(p, fr, pack2(0.6932609677f, 0.6932609677f));
+  p = fma2(p, fr, pack2(0.9999280572f, 0.9999280572f));
+  float q0, q1, f0, f1;
+  unpack2(p, q0, q1);
+  unpack2(xf, f0, f1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(f0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(f1) << 23));
+}
+
+// Per-thread view of one query tile's softmax pipeline (shared by the one-tile and the two-tile kernels).
+struct SmxCtx {
+  uint64_t *s_full, *s_empty, *p_full, *pv_done;
+  uint32_t t_s, t_p, t_o;   // TMEM addresses of this thread's S / P / O slices (lane quarter and column slice applied)
+  uint8_t* stg;             // this warp's [32][HD] bf16 output staging tile
+  float *xch_max, *xch_sum; // SPLIT == 2 exchange buffers
+  bool timed;               // this warp feeds the CLIPB200_ATTN_TIMING counters
+};
+
+// Softmax + epilogue of ONE work item (nb key/value blocks of one 128-query tile) for one softmax thread.
+// `g` is the tile's running block counter (parity of s_full / s_empty / p_full / pv_done).
+template <int HD, int BKV, bool CAUSAL>
+__device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, const CUtensorMap* tm_out, int qt, int h,
+                                             int b, int nb, uint32_t& g, int quarter, int half, int lane) {
+  using C = Cfg<HD, BKV>;
+  constexpr int CW = C::CW, OW = C::OW;
+  const int row = quarter * 32 + lane;
+  const int qrow = qt * BQ + row;
+  float m_run = -INFINITY, l_run = 0.f;
+  for (int j = 0; j < nb; ++j, ++g) {
+    if (cx.timed && lane == 0) { ATTN_TIMED_WAIT(8, cx.s_full, g & 1); } else { ptx::mbar_wait(cx.s_full, g & 1); }
+    ptx::tc_fence_after();
+    float sv[CW];
+    float mx_pipe[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // LDPIPE: maxima of the chunks already read
+    if (CLIPB200_ATTN_LDPIPE && CW % 32 == 0 && !(CLIPB200_ATTN_DBG & 2)) {
+      // chunk c+1 is requested before the maximum of chunk c is taken (tcgen05.wait::ld waits for every outstanding
+      // load, so at most one chunk is in flight while the previous one is being reduced)
+      uint32_t r32[CW / 32][32];
+      ptx::tmem_ld_32x32(cx.t_s, r32[0]);
+#pragma unroll
+      for (int c = 0; c < CW / 32; ++c) {
+        ptx::tmem_ld_wait();
+        if (c + 1 < CW / 32) ptx::tmem_ld_32x32(cx.t_s + static_cast<uint32_t>((c + 1) * 32), r32[c + 1]);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          sv[c * 32 + e] = __uint_as_float(r32[c][e]);
+          mx_pipe[(e >> 1) & 3] = fmaxf(mx_pipe[(e >> 1) & 3], sv[c * 32 + e]);
+        }
+      }
+    } else {
+      // issue every TMEM load of this thread's slice before the single wait
+      uint32_t r32[CW / 32 > 0 ? CW / 32 : 1][32];
+      uint32_t r16[16];
+#pragma unroll
+      for (int c = 0; c < CW / 32; ++c) {
+        if (CLIPB200_ATTN_DBG & 2) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) r32[c][e] = 0x3f800000u + e;
+        } else {
+          ptx::tmem_ld_32x32(cx.t_s + static_cast<uint32_t>(c * 32), r32[c]);
+        }
+      }
+      if (CW % 32 != 0) tmem_ld_32x32_x16(cx.t_s + static_cast<uint32_t>(CW / 32 * 32), r16);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < CW / 32 * 32; ++e) sv[e] = __uint_as_float(r32[e / 32][e % 32]);
+      if (CW % 32 != 0) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) sv[CW / 32 * 32 + e] = __uint_as_float(r16[e]);
+      }
+    }
+    ptx::tc_fence_before();
+    // S is in registers: the next QK^T may overwrite it
+    if (CLIPB200_ATTN_ELECT_ARRIVE) { if (lane == 0) ptx::mbar_arrive(cx.s_empty); } else { ptx::mbar_arrive(cx.s_empty); }
+    const int key0 = j * BKV + half * CW;
+    const bool need_mask = (key0 + CW > p.T) || (CAUSAL && key0 + CW - 1 > qt * BQ + quarter * 32);
+    if (need_mask) {  // warp-uniform, only the last kv block (and the diagonal blocks of causal towers)
+#pragma unroll
+      for (int e = 0; e < CW; ++e) {
+        const int key = key0 + e;
+        if (key >= p.T || (CAUSAL && key > qrow)) sv[e] = -INFINITY;
+      }
+    }
+    // row maximum on the raw scores (the scale is positive, so max(s * scale) == scale * max(s))
+    float mx = -INFINITY;
+    if (CLIPB200_ATTN_LDPIPE && CW % 32 == 0 && !(CLIPB200_ATTN_DBG & 2) && !need_mask) {
+      mx = fmaxf(fmaxf(mx_pipe[0], mx_pipe[1]), fmaxf(mx_pipe[2], mx_pipe[3]));
+    } else if (CLIPB200_ATTN_MAXTREE) {
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int e = 0; e < CW; ++e) m4[(e >> 1) & 3] = fmaxf(m4[(e >> 1) & 3], sv[e]);
+      mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < CW; ++e) mx = fmaxf(mx, sv[e]);
+    }
+    if (SPLIT == 2) {  // combine with the warp that owns the other half of this row's columns
+      float* slot = cx.xch_max + (g & 1) * 2 * BQ;
+      slot[half * BQ + row] = mx;
+      pair_barrier(quarter);
+      mx = fmaxf(mx, slot[(half ^ 1) * BQ + row]);
+    }
+    mx *= p.scale_log2e;
+    // Lazy rescaling: keep the running reference maximum unless the new block maximum exceeds it by more than
+    // 2^8; P then stays <= 256 (exact in the fp32 sums, fine in bf16) and O / l are rescaled only rarely.
+    // The result is mathematically identical because O and l always share the same reference maximum.
+    const bool bump = (mx > m_run + 8.0f) || (m_run == -INFINITY);
+    const float m_new = bump ? mx : m_run;
+    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+    const float alpha = bump ? ex2(m_run - m_use) : 1.0f;
+    const float neg_m = -m_use;
+    float rs0 = 0.f, rs1 = 0.f;
+    uint32_t pk[CW / 2];
+    const uint64_t scale2 = pack2(p.scale_log2e, p.scale_log2e), negm2 = pack2(neg_m, neg_m);
+    uint64_t rs2 = pack2(0.f, 0.f);
+#pragma unroll
+    for (int e = 0; e < CW / 2; ++e) {
+      // exp2(s * scale - m): one FFMA + one MUFU per element, or (POLY_NUM of every POLY_DEN pairs) the packed
+      // FMA-pipe polynomial
+      float p0, p1;
+      if (CLIPB200_ATTN_POLY_NUM > 0 && (e % CLIPB200_ATTN_POLY_DEN) >= CLIPB200_ATTN_POLY_DEN - CLIPB200_ATTN_POLY_NUM) {
+        exp2_poly_pair(fma2(pack2(sv[2 * e], sv[2 * e + 1]), scale2, negm2), p0, p1);
+      } else if (CLIPB200_ATTN_PACKED) {
+        float a0, a1;
+        unpack2(fma2(pack2(sv[2 * e], sv[2 * e + 1]), scale2, negm2), a0, a1);
+        p0 = ex2(a0);
+        p1 = ex2(a1);
+      } else {
+        const float a0 = fmaf(sv[2 * e], p.scale_log2e, neg_m), a1 = fmaf(sv[2 * e + 1], p.scale_log2e, neg_m);
+        p0 = (CLIPB200_ATTN_DBG & 1) ? a0 * 0.001f : ex2(a0);
+        p1 = (CLIPB200_ATTN_DBG & 1) ? a1 * 0.001f : ex2(a1);
+      }
+      if (CLIPB200_ATTN_PACKED) {
+        rs2 = add2(rs2, pack2(p0, p1));
+      } else {
+        rs0 += p0;
+        rs1 += p1;
+      }
+      pk[e] = pack_bf16(p0, p1);
+    }
+    if (CLIPB200_ATTN_PACKED) unpack2(rs2, rs0, rs1);
+    l_run = l_run * alpha + (rs0 + rs1);  // partial over this warp's columns; the halves are added in the epilogue
+    m_run = m_new;
+    // P(j) and the O rescale must wait until PV(j-1) has finished reading P and writing O
+    if (cx.timed && lane == 0) { ATTN_TIMED_WAIT(9, cx.pv_done, (g & 1) ^ 1); } else { ptx::mbar_wait(cx.pv_done, (g & 1) ^ 1); }
+    ptx::tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < CW / 32; ++c) {
+      uint32_t r[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) r[e] = pk[c * 16 + e];
+      if (CLIPB200_ATTN_DBG & 4) { if (r[0] == 0x12345678u && r[7] == 0x9abcdef0u) tmem_st_32x32_x16(cx.t_p + static_cast<uint32_t>(c * 16), r); }
+      else tmem_st_32x32_x16(cx.t_p + static_cast<uint32_t>(c * 16), r);
+    }
+    if (CW % 32 != 0) {
+      uint32_t r[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = pk[CW / 32 * 16 + e];
+      tmem_st_32x32_x8(cx.t_p + static_cast<uint32_t>(CW / 32 * 16), r);
+    }
+    if (j > 0 && __any_sync(0xffffffffu, bump)) {  // rare: rescale this warp's slice of O
+#pragma unroll
+      for (int c = 0; c < OW / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32_x16(cx.t_o + static_cast<uint32_t>(c * 16), r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+        tmem_st_32x32_x16(cx.t_o + static_cast<uint32_t>(c * 16), r);
+      }
+      if (OW % 16 != 0) {
+        uint32_t r[8];
+        tmem_ld_32x32_x8(cx.t_o + static_cast<uint32_t>(OW / 16 * 16), r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+        tmem_st_32x32_x8(cx.t_o + static_cast<uint32_t>(OW / 16 * 16), r);
+      }
+    }
+    tmem_st_wait();
+    ptx::tc_fence_before();
+    if (CLIPB200_ATTN_ELECT_ARRIVE) { if (lane == 0) ptx::mbar_arrive(cx.p_full); } else { ptx::mbar_arrive(cx.p_full); }
+  }
+  // epilogue: wait for the last PV, normalise, store this warp's slice of the O row
+  if (cx.timed && lane == 0) { ATTN_TIMED_WAIT(10, cx.pv_done, (g & 1) ^ 1); } else { ptx::mbar_wait(cx.pv_done, (g & 1) ^ 1); }
+  ptx::tc_fence_after();
+  if (SPLIT == 2) cx.xch_sum[half * BQ + row] = l_run;
+  if (half == 0 && lane == 0) ptx::tma_store_wait_read<0>();  // previous item's store has left the staging tile
+  if (SPLIT == 2) pair_barrier(quarter); else __syncwarp();
+  const float l_tot = SPLIT == 2 ? l_run + cx.xch_sum[(half ^ 1) * BQ + row] : l_run;
+  const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+#pragma unroll
+  for (int c = 0; c < OW / 8; ++c) {
+    const int col = half * OW + c * 8;
+    if (col < HD) {
+      uint32_t r[8];
+      tmem_ld_32x32_x8(cx.t_o + static_cast<uint32_t>(c * 8), r);
+      ptx::tmem_ld_wait();
+      uint4 o;
+      o.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+      o.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+      o.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+      o.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+      *reinterpret_cast<uint4*>(cx.stg + lane * C::OUT_ROW + col * 2) = o;
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::fence_proxy_async_smem();
+  if (SPLIT == 2) pair_barrier(quarter); else __syncwarp();
+  if (half == 0 && lane == 0) {
+    tma_store_3d(tm_out, cx.stg, h * HD, qt * BQ + quarter * 32, b);
+    ptx::tma_store_commit();
+  }
+}
+
 template <int HD, int BKV, bool CAUSAL>
 __global__ void __launch_bounds__(THREADS, 2)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_constant__ CUtensorMap tm_q_rem,
@@ -261,8 +536,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
       ptx::mbar_init(&v_full[s], 1); ptx::mbar_init(&v_empty[s], 1);
     }
     ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(s_empty, 128 * SPLIT);
-    ptx::mbar_init(p_full, 128 * SPLIT);
+    ptx::mbar_init(s_empty, CLIPB200_ATTN_ELECT_ARRIVE ? NSW : 128 * SPLIT);
+    ptx::mbar_init(p_full, CLIPB200_ATTN_ELECT_ARRIVE ? NSW : 128 * SPLIT);
     ptx::mbar_init(pv_done, 1);
     ptx::fence_mbar_init();
   }
@@ -334,11 +609,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
         const uint64_t dq = ptx::make_kmajor_sw128_desc(q_addr);
         const uint64_t dk = ptx::make_kmajor_sw128_desc(k_addr);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < ((CLIPB200_ATTN_DBG & 32) ? 0 : 4); ++k)
           ptx::umma_bf16_ss_w(t_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_qk,
                             k != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < C::REMP / 16; ++k) {
+        for (int k = 0; k < ((CLIPB200_ATTN_DBG & (8 | 32)) ? 0 : C::REMP / 16); ++k) {
           const uint64_t dqr = make_nosw_desc(q_addr + C::Q_MAIN + k * 2 * BQ * 16, BQ * 16, 128);
           const uint64_t dkr = make_nosw_desc(k_addr + C::KV_MAIN + k * 2 * BKV * 16, BKV * 16, 128);
           ptx::umma_bf16_ss_w(t_s, dqr, dkr, idesc_qk, 1u);
@@ -367,11 +642,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
           const long long tp0 = clock64();
 #endif
 #pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
+          for (int k = 0; k < ((CLIPB200_ATTN_DBG & 16) ? 0 : BKV / 16); ++k) {
             const uint32_t acc = (j | k) != 0 ? 1u : 0u;
             const uint64_t dv = make_mnmajor_sw128_desc(v_addr + k * 16 * 128);
             ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), dv, idesc_pv_main, acc);
-            if (C::REMP > 0) {
+            if (C::REMP > 0 && !(CLIPB200_ATTN_DBG & 8)) {
               const uint64_t dvr = make_nosw_desc(v_addr + C::KV_MAIN + k * 16 * 16, 128, BKV * 16);
               ptx::umma_bf16_ts_w(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
             }
@@ -389,161 +664,23 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
     constexpr int CW = C::CW, OW = C::OW;
     const int quarter = warp & 3;     // TMEM lane quarter (query rows quarter*32 .. +31 of the tile)
     const int half = warp >> 2;       // which CW-wide slice of the key columns / OW-wide slice of O this warp owns
-    const int row = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_base + C::COL_S + static_cast<uint32_t>(half * CW);
-    const uint32_t t_p = tmem_base + lane_base + C::COL_P + static_cast<uint32_t>(half * CW / 2);
-    const uint32_t t_o = tmem_base + lane_base + C::COL_O + static_cast<uint32_t>(half * OW);
-    uint8_t* stg = s_out + quarter * C::OUT_WARP;
-    float* xch_max = reinterpret_cast<float*>(smem + C::OFF_XCH);  // [parity][half][row]
-    float* xch_sum = xch_max + 2 * 2 * BQ;                         // [half][row]
+    SmxCtx ctx;
+    ctx.s_full = s_full; ctx.s_empty = s_empty; ctx.p_full = p_full; ctx.pv_done = pv_done;
+    ctx.t_s = tmem_base + lane_base + C::COL_S + static_cast<uint32_t>(half * CW);
+    ctx.t_p = tmem_base + lane_base + C::COL_P + static_cast<uint32_t>(half * CW / 2);
+    ctx.t_o = tmem_base + lane_base + C::COL_O + static_cast<uint32_t>(half * OW);
+    ctx.stg = s_out + quarter * C::OUT_WARP;
+    ctx.xch_max = reinterpret_cast<float*>(smem + C::OFF_XCH);  // [parity][half][row]
+    ctx.xch_sum = ctx.xch_max + 2 * 2 * BQ;                     // [half][row]
+    ctx.timed = warp == 0;
     uint32_t g = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int qt = item % p.q_tiles;
       const int bh = item / p.q_tiles;
       const int h = bh % p.H, b = bh / p.H;
       const int nb = item_blocks(qt);
-      const int qrow = qt * BQ + row;
-      float m_run = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < nb; ++j, ++g) {
-        if (warp == 0 && lane == 0) { ATTN_TIMED_WAIT(8, s_full, g & 1); } else { ptx::mbar_wait(s_full, g & 1); }
-        ptx::tc_fence_after();
-        float sv[CW];
-        {
-          // issue every TMEM load of this thread's slice before the single wait
-          uint32_t r32[CW / 32 > 0 ? CW / 32 : 1][32];
-          uint32_t r16[16];
-#pragma unroll
-          for (int c = 0; c < CW / 32; ++c) {
-            if (CLIPB200_ATTN_DBG & 2) {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) r32[c][e] = 0x3f800000u + e;
-            } else {
-              ptx::tmem_ld_32x32(t_s + static_cast<uint32_t>(c * 32), r32[c]);
-            }
-          }
-          if (CW % 32 != 0) tmem_ld_32x32_x16(t_s + static_cast<uint32_t>(CW / 32 * 32), r16);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < CW / 32 * 32; ++e) sv[e] = __uint_as_float(r32[e / 32][e % 32]);
-          if (CW % 32 != 0) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) sv[CW / 32 * 32 + e] = __uint_as_float(r16[e]);
-          }
-        }
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(s_empty);  // S is in registers: the next QK^T may overwrite it
-        const int key0 = j * BKV + half * CW;
-        const bool need_mask = (key0 + CW > p.T) || (CAUSAL && key0 + CW - 1 > qt * BQ + quarter * 32);
-        if (need_mask) {  // warp-uniform, only the last kv block (and the diagonal blocks of causal towers)
-#pragma unroll
-          for (int e = 0; e < CW; ++e) {
-            const int key = key0 + e;
-            if (key >= p.T || (CAUSAL && key > qrow)) sv[e] = -INFINITY;
-          }
-        }
-        // row maximum on the raw scores (the scale is positive, so max(s * scale) == scale * max(s))
-        float mx = -INFINITY;
-#pragma unroll
-        for (int e = 0; e < CW; ++e) mx = fmaxf(mx, sv[e]);
-        if (SPLIT == 2) {  // combine with the warp that owns the other half of this row's columns
-          float* slot = xch_max + (g & 1) * 2 * BQ;
-          slot[half * BQ + row] = mx;
-          pair_barrier(quarter);
-          mx = fmaxf(mx, slot[(half ^ 1) * BQ + row]);
-        }
-        mx *= p.scale_log2e;
-        // Lazy rescaling: keep the running reference maximum unless the new block maximum exceeds it by more than
-        // 2^8; P then stays <= 256 (exact in the fp32 sums, fine in bf16) and O / l are rescaled only rarely.
-        // The result is mathematically identical because O and l always share the same reference maximum.
-        const bool bump = (mx > m_run + 8.0f) || (m_run == -INFINITY);
-        const float m_new = bump ? mx : m_run;
-        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-        const float alpha = bump ? ex2(m_run - m_use) : 1.0f;
-        const float neg_m = -m_use;
-        float rs0 = 0.f, rs1 = 0.f;
-        uint32_t pk[CW / 2];
-#pragma unroll
-        for (int e = 0; e < CW / 2; ++e) {
-          // exp2(s * scale - m): one FFMA + one MUFU per element
-          const float a0 = fmaf(sv[2 * e], p.scale_log2e, neg_m), a1 = fmaf(sv[2 * e + 1], p.scale_log2e, neg_m);
-          const float p0 = (CLIPB200_ATTN_DBG & 1) ? a0 * 0.001f : ex2(a0);
-          const float p1 = (CLIPB200_ATTN_DBG & 1) ? a1 * 0.001f : ex2(a1);
-          rs0 += p0;
-          rs1 += p1;
-          pk[e] = pack_bf16(p0, p1);
-        }
-        l_run = l_run * alpha + (rs0 + rs1);  // partial over this warp's columns; the halves are added in the epilogue
-        m_run = m_new;
-        // P(j) and the O rescale must wait until PV(j-1) has finished reading P and writing O
-        if (warp == 0 && lane == 0) { ATTN_TIMED_WAIT(9, pv_done, (g & 1) ^ 1); } else { ptx::mbar_wait(pv_done, (g & 1) ^ 1); }
-        ptx::tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < CW / 32; ++c) {
-          uint32_t r[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) r[e] = pk[c * 16 + e];
-          tmem_st_32x32_x16(t_p + static_cast<uint32_t>(c * 16), r);
-        }
-        if (CW % 32 != 0) {
-          uint32_t r[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) r[e] = pk[CW / 32 * 16 + e];
-          tmem_st_32x32_x8(t_p + static_cast<uint32_t>(CW / 32 * 16), r);
-        }
-        if (j > 0 && __any_sync(0xffffffffu, bump)) {  // rare: rescale this warp's slice of O
-#pragma unroll
-          for (int c = 0; c < OW / 16; ++c) {
-            uint32_t r[16];
-            tmem_ld_32x32_x16(t_o + static_cast<uint32_t>(c * 16), r);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-            tmem_st_32x32_x16(t_o + static_cast<uint32_t>(c * 16), r);
-          }
-          if (OW % 16 != 0) {
-            uint32_t r[8];
-            tmem_ld_32x32_x8(t_o + static_cast<uint32_t>(OW / 16 * 16), r);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 8; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-            tmem_st_32x32_x8(t_o + static_cast<uint32_t>(OW / 16 * 16), r);
-          }
-        }
-        tmem_st_wait();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(p_full);
-      }
-      // epilogue: wait for the last PV, normalise, store this warp's slice of the O row
-      if (warp == 0 && lane == 0) { ATTN_TIMED_WAIT(10, pv_done, (g & 1) ^ 1); } else { ptx::mbar_wait(pv_done, (g & 1) ^ 1); }
-      ptx::tc_fence_after();
-      if (SPLIT == 2) xch_sum[half * BQ + row] = l_run;
-      if (half == 0 && lane == 0) ptx::tma_store_wait_read<0>();  // previous item's store has left the staging tile
-      if (SPLIT == 2) pair_barrier(quarter); else __syncwarp();
-      const float l_tot = SPLIT == 2 ? l_run + xch_sum[(half ^ 1) * BQ + row] : l_run;
-      const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
-#pragma unroll
-      for (int c = 0; c < OW / 8; ++c) {
-        const int col = half * OW + c * 8;
-        if (col < HD) {
-          uint32_t r[8];
-          tmem_ld_32x32_x8(t_o + static_cast<uint32_t>(c * 8), r);
-          ptx::tmem_ld_wait();
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
-          o.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
-          o.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
-          o.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
-          *reinterpret_cast<uint4*>(stg + lane * C::OUT_ROW + col * 2) = o;
-        }
-      }
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async_smem();
-      if (SPLIT == 2) pair_barrier(quarter); else __syncwarp();
-      if (half == 0 && lane == 0) {
-        tma_store_3d(&tm_out, stg, h * HD, qt * BQ + quarter * 32, b);
-        ptx::tma_store_commit();
-      }
+      softmax_item<HD, BKV, CAUSAL>(ctx, p, &tm_out, qt, h, b, nb, g, quarter, half, lane);
     }
     if (half == 0 && lane == 0) ptx::tma_store_wait<0>();
   }
@@ -552,6 +689,263 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
   if (warp == WARP_MMA) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---- two-tile kernel ------------------------------------------------------------------------------------------------
+// One CTA per SM owns TWO 128-query tiles of the same (batch, head) and streams K/V ONCE for both: the one-tile kernel
+// re-reads every K/V block once per query tile (5x for T = 576), which makes it L2-bandwidth / TMA-latency bound — with
+// every MMA and all softmax arithmetic removed it still takes 82 % of its full run time (tests/native/attn_test.cu,
+// CLIPB200_ATTN_DBG=63).  Here the pair shares a 4-deep K/V ring (3 loads per (b, h) instead of 5 at T = 576), each tile
+// keeps its own Q buffer, S / P / O columns (256 of the CTA's 512 TMEM columns), four softmax warps and its own
+// MMA-issuing warp, so the two tiles run as independent pipelines that only meet at the ring's empty barriers
+// (count 2: a tile that does not need a block — odd tail tile, causal upper blocks — arrives without issuing MMAs).
+constexpr int PAIR_WARP_TMA = 8;
+constexpr int PAIR_WARP_MMA0 = 9;   // + tile index
+constexpr int PAIR_THREADS = 32 * 11;
+
+template <int HD, int BKV>
+struct PairCfg {
+  using C = Cfg<HD, BKV>;
+  static constexpr int STAGES = 4;
+  static constexpr int Q_TILE_AL = (C::Q_MAIN + C::Q_REM + 1023) / 1024 * 1024;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_KV = 2 * Q_TILE_AL;
+  static constexpr int OUT_TILE = (4 * C::OUT_WARP + 127) / 128 * 128;
+  static constexpr int OFF_OUT = OFF_KV + STAGES * C::KV_STAGE_AL;
+  static constexpr int OFF_BAR = OFF_OUT + 2 * OUT_TILE;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int TILE_COLS = 256;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(C::COL_O + C::HDP <= TILE_COLS, "TMEM budget per tile");
+};
+
+template <int HD, int BKV, bool CAUSAL>
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
+attn_fwd_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_constant__ CUtensorMap tm_q_rem,
+                             const __grid_constant__ CUtensorMap tm_kv_main, const __grid_constant__ CUtensorMap tm_kv_rem,
+                             const __grid_constant__ CUtensorMap tm_out, Params p) {
+  using C = Cfg<HD, BKV>;
+  using PC = PairCfg<HD, BKV>;
+  constexpr int ST = PC::STAGES;
+  extern __shared__ uint8_t attn_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem + PC::OFF_Q;
+  uint8_t* s_kv = smem + PC::OFF_KV;
+  uint8_t* s_out = smem + PC::OFF_OUT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PC::OFF_BAR);
+  uint64_t* q_full = bars + 0;     // [2] per tile
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* s_full = bars + 4;     // [2]
+  uint64_t* s_empty = bars + 6;    // [2]
+  uint64_t* p_full = bars + 8;     // [2]
+  uint64_t* pv_done = bars + 10;   // [2]
+  uint64_t* k_full = bars + 12;    // [ST] shared ring
+  uint64_t* k_empty = bars + 16;   // [ST] count 2: both tiles release a slot
+  uint64_t* v_full = bars + 20;    // [ST]
+  uint64_t* v_empty = bars + 24;   // [ST]
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 28);
+  static_assert(ST == 4, "barrier carve assumes a 4-deep ring");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv_blocks_total = (p.T + BKV - 1) / BKV;
+  const int n_pairs = (p.q_tiles + 1) / 2;
+
+  if (C::REMP_PLANES > C::REM_PLANES) {  // zero the padding chunk planes TMA never writes
+    for (int t = 0; t < 2; ++t)
+      for (int i = threadIdx.x; i < (C::REMP_PLANES - C::REM_PLANES) * BQ; i += PAIR_THREADS)
+        reinterpret_cast<uint4*>(s_q + t * PC::Q_TILE_AL + C::Q_MAIN + C::REM_PLANES * BQ * 16)[i] = make_uint4(0, 0, 0, 0);
+    for (int st = 0; st < ST; ++st)
+      for (int kv = 0; kv < 2; ++kv) {
+        uint8_t* tile = s_kv + st * C::KV_STAGE_AL + kv * C::KV_TILE;
+        for (int i = threadIdx.x; i < (C::REMP_PLANES - C::REM_PLANES) * BKV; i += PAIR_THREADS)
+          reinterpret_cast<uint4*>(tile + C::KV_MAIN + C::REM_PLANES * BKV * 16)[i] = make_uint4(0, 0, 0, 0);
+      }
+    ptx::fence_proxy_async_smem();
+  }
+  if (warp == PAIR_WARP_TMA && lane == 0) {
+    ptx::prefetch_tmap(&tm_q_main);
+    ptx::prefetch_tmap(&tm_kv_main);
+    ptx::prefetch_tmap(&tm_out);
+    if (C::REM > 0) { ptx::prefetch_tmap(&tm_q_rem); ptx::prefetch_tmap(&tm_kv_rem); }
+    for (int t = 0; t < 2; ++t) {
+      ptx::mbar_init(&q_full[t], 1);
+      ptx::mbar_init(&q_empty[t], 1);
+      ptx::mbar_init(&s_full[t], 1);
+      ptx::mbar_init(&s_empty[t], CLIPB200_ATTN_ELECT_ARRIVE ? 4 : 128);
+      ptx::mbar_init(&p_full[t], CLIPB200_ATTN_ELECT_ARRIVE ? 4 : 128);
+      ptx::mbar_init(&pv_done[t], 1);
+    }
+    for (int s = 0; s < ST; ++s) {
+      ptx::mbar_init(&k_full[s], 1); ptx::mbar_init(&k_empty[s], 2);
+      ptx::mbar_init(&v_full[s], 1); ptx::mbar_init(&v_empty[s], 2);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == PAIR_WARP_MMA0) ptx::tmem_alloc<PC::TMEM_COLS>(tmem_base_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  auto item_blocks = [&](int qt) {
+    if (!CAUSAL) return kv_blocks_total;
+    const int last_q = qt * BQ + BQ - 1;
+    const int nb = last_q / BKV + 1;
+    return nb < kv_blocks_total ? nb : kv_blocks_total;
+  };
+
+  if (warp == PAIR_WARP_TMA) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t g = 0;              // running K/V block counter of the shared ring
+      uint32_t itq[2] = {0, 0};    // Q tiles loaded so far, per tile slot
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int qp = item % n_pairs;
+        const int bh = item / n_pairs;
+        const int h = bh % p.H, b = bh / p.H;
+        const int col_q = h * HD, col_k = p.H * HD + h * HD, col_v = 2 * p.H * HD + h * HD;
+        const bool valid1 = 2 * qp + 1 < p.q_tiles;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t == 1 && !valid1) break;
+          const int qt = 2 * qp + t;
+          uint8_t* qs = s_q + t * PC::Q_TILE_AL;
+          ptx::mbar_wait(&q_empty[t], (itq[t] & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&q_full[t], C::Q_TX);
+          tma_load_3d(&tm_q_main, &q_full[t], qs, col_q, qt * BQ, b);
+          for (int pl = 0; pl < C::REM_PLANES; ++pl)
+            tma_load_3d(&tm_q_rem, &q_full[t], qs + C::Q_MAIN + pl * BQ * 16, col_q + 64 + 8 * pl, qt * BQ, b);
+          ++itq[t];
+        }
+        const int nb = item_blocks(valid1 ? 2 * qp + 1 : 2 * qp);
+        for (int j = 0; j < nb; ++j, ++g) {
+          const int st = g & (ST - 1);
+          const uint32_t par = ((g / ST) & 1) ^ 1;
+          uint8_t* kt = s_kv + st * C::KV_STAGE_AL;
+          uint8_t* vt = kt + C::KV_TILE;
+          ptx::mbar_wait(&k_empty[st], par);
+          ptx::mbar_arrive_expect_tx(&k_full[st], C::KV_TX / 2);
+          tma_load_3d(&tm_kv_main, &k_full[st], kt, col_k, j * BKV, b);
+          for (int pl = 0; pl < C::REM_PLANES; ++pl)
+            tma_load_3d(&tm_kv_rem, &k_full[st], kt + C::KV_MAIN + pl * BKV * 16, col_k + 64 + 8 * pl, j * BKV, b);
+          ptx::mbar_wait(&v_empty[st], par);
+          ptx::mbar_arrive_expect_tx(&v_full[st], C::KV_TX / 2);
+          tma_load_3d(&tm_kv_main, &v_full[st], vt, col_v, j * BKV, b);
+          for (int pl = 0; pl < C::REM_PLANES; ++pl)
+            tma_load_3d(&tm_kv_rem, &v_full[st], vt + C::KV_MAIN + pl * BKV * 16, col_v + 64 + 8 * pl, j * BKV, b);
+        }
+      }
+    }
+  } else if (warp >= PAIR_WARP_MMA0) {
+    // ------------------------------------------------------------------ MMA issuer of tile t (whole warp, uniform)
+    const int t = warp - PAIR_WARP_MMA0;
+    constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, 0);
+    constexpr uint32_t idesc_pv_main = make_idesc(BQ, 64, 1);
+    constexpr uint32_t idesc_pv_rem = make_idesc(BQ, C::REMP > 0 ? C::REMP : 16, 1);
+    const uint32_t t_tile = tmem_base + static_cast<uint32_t>(t * PC::TILE_COLS);
+    const uint32_t t_s = t_tile + C::COL_S, t_p = t_tile + C::COL_P, t_o = t_tile + C::COL_O;
+    const uint32_t q_addr = ptx::smem_u32(s_q + t * PC::Q_TILE_AL);
+    uint32_t g = 0;    // ring position (advances for every block of every item, needed or not)
+    uint32_t gt = 0;   // blocks this tile has processed (parity of its S / P barriers)
+    uint32_t itq = 0;  // Q tiles this tile has consumed
+    auto issue_qk = [&](uint32_t gg, uint32_t ggt) {
+      const int st = gg & (ST - 1);
+      const uint32_t k_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL);
+      ptx::mbar_wait(&k_full[st], (gg / ST) & 1);
+      ptx::mbar_wait(&s_empty[t], (ggt & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint64_t dq = ptx::make_kmajor_sw128_desc(q_addr);
+      const uint64_t dk = ptx::make_kmajor_sw128_desc(k_addr);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        ptx::umma_bf16_ss_w(t_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_qk,
+                            k != 0 ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < C::REMP / 16; ++k) {
+        const uint64_t dqr = make_nosw_desc(q_addr + C::Q_MAIN + k * 2 * BQ * 16, BQ * 16, 128);
+        const uint64_t dkr = make_nosw_desc(k_addr + C::KV_MAIN + k * 2 * BKV * 16, BKV * 16, 128);
+        ptx::umma_bf16_ss_w(t_s, dqr, dkr, idesc_qk, 1u);
+      }
+      ptx::umma_commit_w(&k_empty[st]);
+      ptx::umma_commit_w(&s_full[t]);
+    };
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int qp = item % n_pairs;
+      const bool valid1 = 2 * qp + 1 < p.q_tiles;
+      const bool valid = t == 0 || valid1;
+      const int nb_item = item_blocks(valid1 ? 2 * qp + 1 : 2 * qp);
+      const int nb = valid ? item_blocks(2 * qp + t) : 0;
+      if (valid) {
+        ptx::mbar_wait(&q_full[t], itq & 1);
+        ++itq;
+        ptx::tc_fence_after();
+        issue_qk(g, gt);
+        for (int j = 0; j < nb; ++j, ++g, ++gt) {
+          if (j + 1 < nb) issue_qk(g + 1, gt + 1);        // S(j+1) overlaps softmax(j)
+          else ptx::umma_commit_w(&q_empty[t]);           // every QK^T of this item is issued
+          const int st = g & (ST - 1);
+          const uint32_t v_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL + C::KV_TILE);
+          ptx::mbar_wait(&v_full[st], (g / ST) & 1);
+          ptx::mbar_wait(&p_full[t], gt & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {
+            const uint32_t acc = (j | k) != 0 ? 1u : 0u;
+            const uint64_t dv = make_mnmajor_sw128_desc(v_addr + k * 16 * 128);
+            ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), dv, idesc_pv_main, acc);
+            if (C::REMP > 0) {
+              const uint64_t dvr = make_nosw_desc(v_addr + C::KV_MAIN + k * 16 * 16, 128, BKV * 16);
+              ptx::umma_bf16_ts_w(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
+            }
+          }
+          ptx::umma_commit_w(&v_empty[st]);
+          ptx::umma_commit_w(&pv_done[t]);
+        }
+      }
+      // ring slots this tile does not read (absent odd tile; causal blocks above this tile's diagonal) still need its
+      // release.  Waiting for the slot's full barrier first keeps the arrival in the right phase of the empty barrier.
+      for (int j = nb; j < nb_item; ++j, ++g) {
+        const int st = g & (ST - 1);
+        const uint32_t par = (g / ST) & 1;
+        ptx::mbar_wait(&k_full[st], par);
+        if (lane == 0) ptx::mbar_arrive(&k_empty[st]);
+        ptx::mbar_wait(&v_full[st], par);
+        if (lane == 0) ptx::mbar_arrive(&v_empty[st]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue: warps 4t .. 4t+3 own tile t
+    const int t = warp >> 2;
+    const int quarter = warp & 3;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_tile = tmem_base + static_cast<uint32_t>(t * PC::TILE_COLS) + lane_base;
+    SmxCtx ctx;
+    ctx.s_full = &s_full[t]; ctx.s_empty = &s_empty[t]; ctx.p_full = &p_full[t]; ctx.pv_done = &pv_done[t];
+    ctx.t_s = t_tile + C::COL_S;
+    ctx.t_p = t_tile + C::COL_P;
+    ctx.t_o = t_tile + C::COL_O;
+    ctx.stg = s_out + t * PC::OUT_TILE + quarter * C::OUT_WARP;
+    ctx.xch_max = nullptr;
+    ctx.xch_sum = nullptr;
+    ctx.timed = warp == 0;
+    uint32_t gt = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int qp = item % n_pairs;
+      const int bh = item / n_pairs;
+      const int h = bh % p.H, b = bh / p.H;
+      const int qt = 2 * qp + t;
+      if (qt >= p.q_tiles) continue;
+      softmax_item<HD, BKV, CAUSAL>(ctx, p, &tm_out, qt, h, b, item_blocks(qt), gt, quarter, 0, lane);
+    }
+    if (lane == 0) ptx::tma_store_wait<0>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == PAIR_WARP_MMA0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<PC::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -590,8 +984,36 @@ inline cudaError_t launch_t(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B,
   attn_fwd_tcgen05_kernel<HD, BKV, CAUSAL><<<grid, THREADS, C::SMEM_BYTES, st>>>(q_main, q_rem, kv_main, kv_rem, o_map, p);
   return cudaGetLastError();
 }
+template <int HD, int BKV, bool CAUSAL>
+inline cudaError_t launch_pair_t(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int num_sms,
+                                 cudaStream_t st) {
+  using C = Cfg<HD, BKV>;
+  using PC = PairCfg<HD, BKV>;
+  CUtensorMap q_main, q_rem, kv_main, kv_rem, o_map;
+  const uint64_t cols = 3ull * H * HD;
+  if (!make_tmap_3d(&q_main, qkv, cols, T, B, 64, BQ, true)) return cudaErrorUnknown;
+  if (!make_tmap_3d(&kv_main, qkv, cols, T, B, 64, BKV, true)) return cudaErrorUnknown;
+  if (!make_tmap_3d(&q_rem, qkv, cols, T, B, 8, BQ, false)) return cudaErrorUnknown;
+  if (!make_tmap_3d(&kv_rem, qkv, cols, T, B, 8, BKV, false)) return cudaErrorUnknown;
+  if (!make_tmap_3d(&o_map, out, static_cast<uint64_t>(H) * HD, T, B, HD, 32, false)) return cudaErrorUnknown;
+  Params p;
+  p.T = T; p.H = H; p.B = B;
+  p.q_tiles = (T + BQ - 1) / BQ;
+  p.n_items = ((p.q_tiles + 1) / 2) * H * B;   // work item = a pair of query tiles of one (batch, head)
+  p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  const int grid = p.n_items < num_sms ? p.n_items : num_sms;
+  attn_fwd_tcgen05_pair_kernel<HD, BKV, CAUSAL><<<grid, PAIR_THREADS, PC::SMEM_BYTES, st>>>(q_main, q_rem, kv_main, kv_rem,
+                                                                                         o_map, p);
+  return cudaGetLastError();
+}
 template <int HD, int BKV>
 inline cudaError_t configure_t() {
+  cudaError_t ep = cudaFuncSetAttribute(attn_fwd_tcgen05_pair_kernel<HD, BKV, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<HD, BKV>::SMEM_BYTES);
+  if (ep != cudaSuccess) return ep;
+  ep = cudaFuncSetAttribute(attn_fwd_tcgen05_pair_kernel<HD, BKV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            PairCfg<HD, BKV>::SMEM_BYTES);
+  if (ep != cudaSuccess) return ep;
   cudaError_t e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<HD, BKV, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HD, BKV>::SMEM_BYTES);
   if (e != cudaSuccess) return e;
@@ -615,10 +1037,18 @@ inline bool attn_tcgen05_supported(int hd) { return hd == 64 || hd == 72 || hd =
 inline cudaError_t attn_tcgen05(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, bool causal,
                                 int num_sms, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
+  // Sequences of two or more query tiles go to the two-tile kernel (K/V streamed once per tile pair);
+  // CLIPB200_ATTN_ONE_TILE=1 forces the one-tile kernel (A/B measurements).
+  static const bool one_tile_only = attn::SPLIT != 1 || getenv("CLIPB200_ATTN_ONE_TILE") != nullptr;
+  const bool pair = !one_tile_only && T > attn::BQ;
 #define CLIPB200_ATTN_CASE(HD_, BKV_)                                                             \
-  if (hd == HD_)                                                                                  \
+  if (hd == HD_) {                                                                                \
+    if (pair)                                                                                     \
+      return causal ? attn::launch_pair_t<HD_, BKV_, true>(qkv, out, B, T, H, num_sms, st)        \
+                    : attn::launch_pair_t<HD_, BKV_, false>(qkv, out, B, T, H, num_sms, st);      \
     return causal ? attn::launch_t<HD_, BKV_, true>(qkv, out, B, T, H, num_sms, st)               \
-                  : attn::launch_t<HD_, BKV_, false>(qkv, out, B, T, H, num_sms, st);
+                  : attn::launch_t<HD_, BKV_, false>(qkv, out, B, T, H, num_sms, st);             \
+  }
   // kv block: 96 keys (576 = 6 x 96 exactly); 64 for head dim 96 so that two CTAs still fit in one SM's shared memory
   CLIPB200_ATTN_CASE(64, 96)
   CLIPB200_ATTN_CASE(72, 96)

@@ -70,7 +70,29 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 }
 // Bounded wait: a pipeline barrier that does not flip within a few seconds means a protocol bug; trap instead of
 // hanging the device.  The slow path sleeps inside try_wait, so waiting warps do not compete for issue slots.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef CLIPB200_MBAR_TESTWAIT   // experiment: non-suspending poll (test_wait) instead of try_wait
+  {
+    uint32_t spins = 0;
+    while (!mbar_test_wait(bar, parity)) {
+      if (++spins > 400000000u) __trap();
+    }
+    return;
+  }
+#endif
   if (mbar_try_wait(bar, parity)) return;
   uint32_t tries = 0;
 #ifdef CLIPB200_MBAR_SPIN
