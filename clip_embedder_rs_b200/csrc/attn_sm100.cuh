@@ -5,13 +5,19 @@
 // Replaces the MatMul -> Mul -> (+mask) -> Softmax -> MatMul chain ONNX Runtime executes inside `session.run`
 // (reference src/vision.rs:108, src/text.rs:157-160).
 //
-// Persistent CTAs (2 per SM, 320 threads): warps 0..7 = softmax (two per query row), warp 8 = TMA producer, warp 9 = MMA issuer
-// (one query row per thread).  Work item = (batch, head, 128-query tile); K/V stream through a 2-stage smem ring in
+// Persistent CTAs (2 per SM, 192 threads): warps 0..3 = softmax (one query row per thread), warp 4 = TMA producer,
+// warp 5 = MMA issuer.  Work item = (batch, head, 128-query tile); K/V stream through a 2- or 3-stage smem ring in
 // blocks of BKV keys.
 //   S = Q K^T   : tcgen05.mma SS, M=128, N=BKV, accumulator S in TMEM (fp32)
-//   softmax     : tcgen05.ld S -> registers, online max / exp2 / sum in fp32, P written back to TMEM as packed bf16
+//   softmax     : tcgen05.ld S -> registers, online max / exp2 / sum in fp32 (packed f32x2 arithmetic, a quarter of the
+//                 exponentials as an FMA-pipe polynomial), P written back to TMEM as packed bf16
 //   O += P V    : tcgen05.mma with the A operand (P) read from TMEM, V from smem as an MN-major operand
 //   epilogue    : O / l -> bf16 -> smem -> TMA store
+// Two protocols between the MMA warp and the softmax warps (template parameter DB, chosen per head dim by measurement):
+// one S tile + separate P tile with s_full / s_empty / p_full / pv_done hand-offs, or two S tiles with P written in
+// place (see Cfg).  Measured with every MMA and all softmax arithmetic removed (CLIPB200_ATTN_DBG=63), the kernel still
+// takes 82 % of its run time: it is bound by the latency of the tcgen05.mma -> commit -> mbarrier -> tcgen05.ld round
+// trips of each key block, not by MUFU, tensor or L2 throughput (profiles/r01g_attn_summary.md).
 // Head dims that are not a multiple of 64 (72, 80, 96) are split into a 64-wide part (128-byte-swizzled tiles) and a
 // remainder of 8-element chunk planes (no-swizzle "interleaved" tiles, zero plane appended when the remainder is not
 // a multiple of 16), so neither the GEMMs nor HBM ever see padding.
@@ -61,7 +67,13 @@ constexpr int WARP_TMA = NSW;
 constexpr int WARP_MMA = NSW + 1;
 constexpr int THREADS = 32 * (NSW + 2);
 
-template <int HD, int BKV>
+// DB = double-buffered S: two S tiles in TMEM with P(j) written in place over S(j) (packed bf16 in its first BKV/2
+// columns).  QK^T of block j+2 is issued right after PV of block j (same buffer, ordered by the tensor pipe's in-order
+// execution), so the MMA warp never waits for the softmax warps to pick S up and the softmax warps never wait for a PV
+// to retire before storing P: the two barrier round trips that serialised every block of the single-S protocol
+// (s_full -> s_empty -> QK and p_full -> pv_done -> P store; with all arithmetic removed that skeleton alone took 82 % of
+// the kernel's run time) overlap with the arithmetic instead.
+template <int HD, int BKV, bool DB = false>
 struct Cfg {
   static_assert(HD >= 64 && HD % 8 == 0 && HD <= 128, "head dim");
   static_assert(BKV % 16 == 0 && BKV >= 32 && BKV <= 128, "kv block");
@@ -78,7 +90,7 @@ struct Cfg {
   static constexpr int KV_STAGE = 2 * KV_TILE;
   static constexpr int KV_TX = 2 * (KV_MAIN + REM_PLANES * BKV * 16);  // bytes TMA delivers per stage
   static constexpr int Q_TX = Q_MAIN + REM_PLANES * BQ * 16;
-  static constexpr int STAGES = 2;
+  static constexpr int STAGES = (DB && HD < 96) ? 3 : 2;   // 3 where two CTAs still fit in one SM's shared memory
   static constexpr int OUT_ROW = HD * 2;                 // bytes
   static constexpr int OUT_WARP = 32 * OUT_ROW;
   // smem carve (offsets from a 1024-aligned base)
@@ -94,9 +106,10 @@ struct Cfg {
   static constexpr int OW = HDP / SPLIT;          // O columns per softmax thread (rescale / epilogue)
   static_assert(CW % 16 == 0 && OW % 8 == 0, "split granularity");
   // TMEM columns
-  static constexpr int COL_S = 0;
-  static constexpr int COL_P = BKV;               // packed bf16: BKV/2 columns
-  static constexpr int COL_O = BKV + BKV / 2;
+  static constexpr int COL_S = 0;                 // DB: buffer i at COL_S + i * BKV
+  static constexpr int COL_P = DB ? 0 : BKV;      // packed bf16: BKV/2 columns (DB: in place over the S buffer)
+  static constexpr int COL_O = DB ? 2 * BKV : BKV + BKV / 2;
+  static_assert(!DB || SPLIT == 1, "P aliases S: one softmax warp must own all columns of its rows");
   static constexpr int TMEM_COLS = 256;
   static_assert(COL_O + HDP <= TMEM_COLS, "TMEM budget (2 CTAs per SM -> 256 columns each)");
   static_assert(KV_MAIN % 1024 == 0, "swizzle atom alignment");
@@ -228,12 +241,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // CLIPB200_ATTN_ELECT_ARRIVE: one lane per softmax warp arrives on s_empty / p_full (barrier count = warps) instead of
 // all 32 lanes (count = threads): 31 fewer same-address shared-memory atomics per warp and barrier.
 #ifndef CLIPB200_ATTN_ELECT_ARRIVE
-#define CLIPB200_ATTN_ELECT_ARRIVE 1
+#define CLIPB200_ATTN_ELECT_ARRIVE 0   // measured: no gain (634 -> 633 TFLOP/s at head dim 72)
 #endif
 // CLIPB200_ATTN_LDPIPE: the S tile is read from TMEM in 32-column chunks and the row maximum of chunk c is taken while
 // chunk c+1 is in flight (TMEM reads run at 64 B/clk, so 96 columns take ~190 cycles that would otherwise be exposed).
 #ifndef CLIPB200_ATTN_LDPIPE
-#define CLIPB200_ATTN_LDPIPE 1
+#define CLIPB200_ATTN_LDPIPE 0         // measured: no gain (634 -> 631 TFLOP/s): the S read is not on the critical path
 #endif
 // CLIPB200_ATTN_MAXTREE: row maximum with four independent FMNMX3 chains instead of one 48-deep dependent chain.
 #ifndef CLIPB200_ATTN_MAXTREE
@@ -289,16 +302,21 @@ struct SmxCtx {
 
 // Softmax + epilogue of ONE work item (nb key/value blocks of one 128-query tile) for one softmax thread.
 // `g` is the tile's running block counter (parity of s_full / s_empty / p_full / pv_done).
-template <int HD, int BKV, bool CAUSAL>
+template <int HD, int BKV, bool CAUSAL, bool DB>
 __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, const CUtensorMap* tm_out, int qt, int h,
                                              int b, int nb, uint32_t& g, int quarter, int half, int lane) {
-  using C = Cfg<HD, BKV>;
+  using C = Cfg<HD, BKV, DB>;
   constexpr int CW = C::CW, OW = C::OW;
   const int row = quarter * 32 + lane;
   const int qrow = qt * BQ + row;
   float m_run = -INFINITY, l_run = 0.f;
   for (int j = 0; j < nb; ++j, ++g) {
-    if (cx.timed && lane == 0) { ATTN_TIMED_WAIT(8, cx.s_full, g & 1); } else { ptx::mbar_wait(cx.s_full, g & 1); }
+    // DB: block g lives in S buffer g & 1; every per-buffer barrier completes one phase per two blocks
+    const int buf = DB ? static_cast<int>(g & 1) : 0;
+    const uint32_t par = DB ? ((g >> 1) & 1) : (g & 1);
+    const uint32_t t_s = cx.t_s + static_cast<uint32_t>(buf * BKV);
+    const uint32_t t_p = DB ? t_s : cx.t_p;
+    if (cx.timed && lane == 0) { ATTN_TIMED_WAIT(8, &cx.s_full[buf], par); } else { ptx::mbar_wait(&cx.s_full[buf], par); }
     ptx::tc_fence_after();
     float sv[CW];
     float mx_pipe[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // LDPIPE: maxima of the chunks already read
@@ -306,11 +324,11 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
       // chunk c+1 is requested before the maximum of chunk c is taken (tcgen05.wait::ld waits for every outstanding
       // load, so at most one chunk is in flight while the previous one is being reduced)
       uint32_t r32[CW / 32][32];
-      ptx::tmem_ld_32x32(cx.t_s, r32[0]);
+      ptx::tmem_ld_32x32(t_s, r32[0]);
 #pragma unroll
       for (int c = 0; c < CW / 32; ++c) {
         ptx::tmem_ld_wait();
-        if (c + 1 < CW / 32) ptx::tmem_ld_32x32(cx.t_s + static_cast<uint32_t>((c + 1) * 32), r32[c + 1]);
+        if (c + 1 < CW / 32) ptx::tmem_ld_32x32(t_s + static_cast<uint32_t>((c + 1) * 32), r32[c + 1]);
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           sv[c * 32 + e] = __uint_as_float(r32[c][e]);
@@ -327,10 +345,10 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
 #pragma unroll
           for (int e = 0; e < 32; ++e) r32[c][e] = 0x3f800000u + e;
         } else {
-          ptx::tmem_ld_32x32(cx.t_s + static_cast<uint32_t>(c * 32), r32[c]);
+          ptx::tmem_ld_32x32(t_s + static_cast<uint32_t>(c * 32), r32[c]);
         }
       }
-      if (CW % 32 != 0) tmem_ld_32x32_x16(cx.t_s + static_cast<uint32_t>(CW / 32 * 32), r16);
+      if (CW % 32 != 0) tmem_ld_32x32_x16(t_s + static_cast<uint32_t>(CW / 32 * 32), r16);
       ptx::tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < CW / 32 * 32; ++e) sv[e] = __uint_as_float(r32[e / 32][e % 32]);
@@ -341,7 +359,9 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
     }
     ptx::tc_fence_before();
     // S is in registers: the next QK^T may overwrite it
-    if (CLIPB200_ATTN_ELECT_ARRIVE) { if (lane == 0) ptx::mbar_arrive(cx.s_empty); } else { ptx::mbar_arrive(cx.s_empty); }
+    if (!DB) {
+      if (CLIPB200_ATTN_ELECT_ARRIVE) { if (lane == 0) ptx::mbar_arrive(cx.s_empty); } else { ptx::mbar_arrive(cx.s_empty); }
+    }
     const int key0 = j * BKV + half * CW;
     const bool need_mask = (key0 + CW > p.T) || (CAUSAL && key0 + CW - 1 > qt * BQ + quarter * 32);
     if (need_mask) {  // warp-uniform, only the last kv block (and the diagonal blocks of causal towers)
@@ -412,23 +432,30 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
     l_run = l_run * alpha + (rs0 + rs1);  // partial over this warp's columns; the halves are added in the epilogue
     m_run = m_new;
     // P(j) and the O rescale must wait until PV(j-1) has finished reading P and writing O
-    if (cx.timed && lane == 0) { ATTN_TIMED_WAIT(9, cx.pv_done, (g & 1) ^ 1); } else { ptx::mbar_wait(cx.pv_done, (g & 1) ^ 1); }
-    ptx::tc_fence_after();
+    // DB: P(j) overwrites this thread's own (already loaded) S(j) columns, nothing to wait for
+    const bool rescale = j > 0 && __any_sync(0xffffffffu, bump);
+    // the previous block's PV: buffer (g - 1) & 1, phase (g - 1) >> 1
+    uint64_t* prev_done = DB ? &cx.pv_done[(g - 1) & 1] : cx.pv_done;
+    const uint32_t prev_par = DB ? (((g - 1) >> 1) & 1) : ((g & 1) ^ 1);
+    if (!DB || rescale) {
+      if (cx.timed && lane == 0) { ATTN_TIMED_WAIT(9, prev_done, prev_par); } else { ptx::mbar_wait(prev_done, prev_par); }
+      ptx::tc_fence_after();
+    }
 #pragma unroll
     for (int c = 0; c < CW / 32; ++c) {
       uint32_t r[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) r[e] = pk[c * 16 + e];
-      if (CLIPB200_ATTN_DBG & 4) { if (r[0] == 0x12345678u && r[7] == 0x9abcdef0u) tmem_st_32x32_x16(cx.t_p + static_cast<uint32_t>(c * 16), r); }
-      else tmem_st_32x32_x16(cx.t_p + static_cast<uint32_t>(c * 16), r);
+      if (CLIPB200_ATTN_DBG & 4) { if (r[0] == 0x12345678u && r[7] == 0x9abcdef0u) tmem_st_32x32_x16(t_p + static_cast<uint32_t>(c * 16), r); }
+      else tmem_st_32x32_x16(t_p + static_cast<uint32_t>(c * 16), r);
     }
     if (CW % 32 != 0) {
       uint32_t r[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) r[e] = pk[CW / 32 * 16 + e];
-      tmem_st_32x32_x8(cx.t_p + static_cast<uint32_t>(CW / 32 * 16), r);
+      tmem_st_32x32_x8(t_p + static_cast<uint32_t>(CW / 32 * 16), r);
     }
-    if (j > 0 && __any_sync(0xffffffffu, bump)) {  // rare: rescale this warp's slice of O
+    if (rescale) {  // rare: rescale this warp's slice of O
 #pragma unroll
       for (int c = 0; c < OW / 16; ++c) {
         uint32_t r[16];
@@ -449,10 +476,14 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
     }
     tmem_st_wait();
     ptx::tc_fence_before();
-    if (CLIPB200_ATTN_ELECT_ARRIVE) { if (lane == 0) ptx::mbar_arrive(cx.p_full); } else { ptx::mbar_arrive(cx.p_full); }
+    if (CLIPB200_ATTN_ELECT_ARRIVE) { if (lane == 0) ptx::mbar_arrive(&cx.p_full[buf]); } else { ptx::mbar_arrive(&cx.p_full[buf]); }
   }
   // epilogue: wait for the last PV, normalise, store this warp's slice of the O row
-  if (cx.timed && lane == 0) { ATTN_TIMED_WAIT(10, cx.pv_done, (g & 1) ^ 1); } else { ptx::mbar_wait(cx.pv_done, (g & 1) ^ 1); }
+  {
+    uint64_t* last_done = DB ? &cx.pv_done[(g - 1) & 1] : cx.pv_done;
+    const uint32_t last_par = DB ? (((g - 1) >> 1) & 1) : ((g & 1) ^ 1);
+    if (cx.timed && lane == 0) { ATTN_TIMED_WAIT(10, last_done, last_par); } else { ptx::mbar_wait(last_done, last_par); }
+  }
   ptx::tc_fence_after();
   if (SPLIT == 2) cx.xch_sum[half * BQ + row] = l_run;
   if (half == 0 && lane == 0) ptx::tma_store_wait_read<0>();  // previous item's store has left the staging tile
@@ -483,12 +514,13 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
   }
 }
 
-template <int HD, int BKV, bool CAUSAL>
+template <int HD, int BKV, bool CAUSAL, bool DB>
 __global__ void __launch_bounds__(THREADS, 2)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_constant__ CUtensorMap tm_q_rem,
                         const __grid_constant__ CUtensorMap tm_kv_main, const __grid_constant__ CUtensorMap tm_kv_rem,
                         const __grid_constant__ CUtensorMap tm_out, Params p) {
-  using C = Cfg<HD, BKV>;
+  using C = Cfg<HD, BKV, DB>;
+  constexpr int ST = C::STAGES;
   extern __shared__ uint8_t attn_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_q = smem + C::OFF_Q;
@@ -499,15 +531,16 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
   uint64_t* q_empty = bars + 1;
   // K and V have separate full/empty barriers: a K slot is released as soon as its QK^T retires (long before the
   // matching PV), so the next K tile is prefetched about two iterations ahead even with a 2-deep ring.
-  uint64_t* k_full = bars + 2;    // [2]
-  uint64_t* k_empty = bars + 4;   // [2]
-  uint64_t* v_full = bars + 6;    // [2]
-  uint64_t* v_empty = bars + 8;   // [2]
-  uint64_t* s_full = bars + 10;
-  uint64_t* s_empty = bars + 11;
-  uint64_t* p_full = bars + 12;
-  uint64_t* pv_done = bars + 13;
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* k_full = bars + 2;     // [ST <= 3]
+  uint64_t* k_empty = bars + 5;    // [ST]
+  uint64_t* v_full = bars + 8;     // [ST]
+  uint64_t* v_empty = bars + 11;   // [ST]
+  uint64_t* s_full = bars + 14;    // [2]  (single-S protocol: [0] only, likewise p_full / pv_done)
+  uint64_t* p_full = bars + 16;    // [2]
+  uint64_t* pv_done = bars + 18;   // [2]
+  uint64_t* s_empty = bars + 20;   // single-S protocol only
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 21);
+  static_assert(ST <= 3, "barrier carve");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv_blocks_total = (p.T + BKV - 1) / BKV;
@@ -531,14 +564,16 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
     if (C::REM > 0) { ptx::prefetch_tmap(&tm_q_rem); ptx::prefetch_tmap(&tm_kv_rem); }
     ptx::mbar_init(q_full, 1);
     ptx::mbar_init(q_empty, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < ST; ++s) {
       ptx::mbar_init(&k_full[s], 1); ptx::mbar_init(&k_empty[s], 1);
       ptx::mbar_init(&v_full[s], 1); ptx::mbar_init(&v_empty[s], 1);
     }
-    ptx::mbar_init(s_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&p_full[i], CLIPB200_ATTN_ELECT_ARRIVE ? NSW : 128 * SPLIT);
+      ptx::mbar_init(&pv_done[i], 1);
+    }
     ptx::mbar_init(s_empty, CLIPB200_ATTN_ELECT_ARRIVE ? NSW : 128 * SPLIT);
-    ptx::mbar_init(p_full, CLIPB200_ATTN_ELECT_ARRIVE ? NSW : 128 * SPLIT);
-    ptx::mbar_init(pv_done, 1);
     ptx::fence_mbar_init();
   }
   if (warp == WARP_MMA) ptx::tmem_alloc<C::TMEM_COLS>(tmem_base_ptr);
@@ -571,8 +606,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
           tma_load_3d(&tm_q_rem, q_full, s_q + C::Q_MAIN + pl * BQ * 16, col_q + 64 + 8 * pl, qt * BQ, b);
         const int nb = item_blocks(qt);
         for (int j = 0; j < nb; ++j, ++g) {
-          const int st = g & 1;
-          const uint32_t par = ((g >> 1) & 1) ^ 1;
+          const int st = g % ST;
+          const uint32_t par = ((g / ST) & 1) ^ 1;
           uint8_t* kt = s_kv + st * C::KV_STAGE_AL;
           uint8_t* vt = kt + C::KV_TILE;
           ATTN_TIMED_WAIT(1, &k_empty[st], par);
@@ -590,7 +625,72 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
     }
   } else if (warp == WARP_MMA) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, uniform control flow)
-    {
+    if (DB) {
+      constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, 0);
+      constexpr uint32_t idesc_pv_main = make_idesc(BQ, 64, 1);
+      constexpr uint32_t idesc_pv_rem = make_idesc(BQ, C::REMP > 0 ? C::REMP : 16, 1);
+      const uint32_t t_o = tmem_base + C::COL_O;
+      const uint32_t q_addr = ptx::smem_u32(s_q);
+      uint32_t g = 0, it = 0;
+      // S(gg) = Q K(gg)^T into S buffer gg & 1.  No wait on the softmax warps: the buffer's previous contents (P of block
+      // gg - 2) were consumed by PV(gg - 2), which this warp issued earlier and the tensor pipe executes first.
+      auto issue_qk = [&](uint32_t gg) {
+        const int st = gg % ST;
+        const int buf = gg & 1;
+        const uint32_t k_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL);
+        const uint32_t t_s = tmem_base + C::COL_S + static_cast<uint32_t>(buf * BKV);
+        ATTN_TIMED_WAIT(3, &k_full[st], (gg / ST) & 1);
+        ptx::tc_fence_after();
+        const uint64_t dq = ptx::make_kmajor_sw128_desc(q_addr);
+        const uint64_t dk = ptx::make_kmajor_sw128_desc(k_addr);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          ptx::umma_bf16_ss_w(t_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_qk,
+                              k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < C::REMP / 16; ++k) {
+          const uint64_t dqr = make_nosw_desc(q_addr + C::Q_MAIN + k * 2 * BQ * 16, BQ * 16, 128);
+          const uint64_t dkr = make_nosw_desc(k_addr + C::KV_MAIN + k * 2 * BKV * 16, BKV * 16, 128);
+          ptx::umma_bf16_ss_w(t_s, dqr, dkr, idesc_qk, 1u);
+        }
+        ptx::umma_commit_w(&k_empty[st]);
+        ptx::umma_commit_w(&s_full[buf]);
+      };
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int qt = item % p.q_tiles;
+        const int nb = item_blocks(qt);
+        ATTN_TIMED_WAIT(5, q_full, it & 1);
+        ptx::tc_fence_after();
+        issue_qk(g);
+        if (nb > 1) issue_qk(g + 1);
+        if (nb <= 2) ptx::umma_commit_w(q_empty);        // every QK^T of this item is issued: Q is free when they retire
+        for (int j = 0; j < nb; ++j, ++g) {
+          const int st = g % ST;
+          const int buf = g & 1;
+          const uint32_t v_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL + C::KV_TILE);
+          const uint32_t t_p = tmem_base + C::COL_S + static_cast<uint32_t>(buf * BKV);   // P(j) in place over S(j)
+          ATTN_TIMED_WAIT(6, &v_full[st], (g / ST) & 1);
+          ATTN_TIMED_WAIT(7, &p_full[buf], (g >> 1) & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {
+            const uint32_t acc = (j | k) != 0 ? 1u : 0u;
+            const uint64_t dv = make_mnmajor_sw128_desc(v_addr + k * 16 * 128);
+            ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), dv, idesc_pv_main, acc);
+            if (C::REMP > 0) {
+              const uint64_t dvr = make_nosw_desc(v_addr + C::KV_MAIN + k * 16 * 16, 128, BKV * 16);
+              ptx::umma_bf16_ts_w(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
+            }
+          }
+          ptx::umma_commit_w(&v_empty[st]);
+          ptx::umma_commit_w(&pv_done[buf]);
+          if (j + 2 < nb) {
+            issue_qk(g + 2);                               // reuses S buffer `buf` behind PV(j)
+            if (j + 3 == nb) ptx::umma_commit_w(q_empty);
+          }
+        }
+      }
+    } else {
       constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, 0);
       constexpr uint32_t idesc_pv_main = make_idesc(BQ, 64, 1);
       constexpr uint32_t idesc_pv_rem = make_idesc(BQ, C::REMP > 0 ? C::REMP : 16, 1);
@@ -666,7 +766,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
     const int half = warp >> 2;       // which CW-wide slice of the key columns / OW-wide slice of O this warp owns
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     SmxCtx ctx;
-    ctx.s_full = s_full; ctx.s_empty = s_empty; ctx.p_full = p_full; ctx.pv_done = pv_done;
+    ctx.s_full = s_full; ctx.s_empty = s_empty; ctx.p_full = p_full; ctx.pv_done = pv_done;   // [2] each but s_empty
     ctx.t_s = tmem_base + lane_base + C::COL_S + static_cast<uint32_t>(half * CW);
     ctx.t_p = tmem_base + lane_base + C::COL_P + static_cast<uint32_t>(half * CW / 2);
     ctx.t_o = tmem_base + lane_base + C::COL_O + static_cast<uint32_t>(half * OW);
@@ -680,7 +780,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
       const int bh = item / p.q_tiles;
       const int h = bh % p.H, b = bh / p.H;
       const int nb = item_blocks(qt);
-      softmax_item<HD, BKV, CAUSAL>(ctx, p, &tm_out, qt, h, b, nb, g, quarter, half, lane);
+      softmax_item<HD, BKV, CAUSAL, DB>(ctx, p, &tm_out, qt, h, b, nb, g, quarter, half, lane);
     }
     if (half == 0 && lane == 0) ptx::tma_store_wait<0>();
   }
@@ -689,263 +789,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
   if (warp == WARP_MMA) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
-  }
-}
-
-// ---- two-tile kernel ------------------------------------------------------------------------------------------------
-// One CTA per SM owns TWO 128-query tiles of the same (batch, head) and streams K/V ONCE for both: the one-tile kernel
-// re-reads every K/V block once per query tile (5x for T = 576), which makes it L2-bandwidth / TMA-latency bound — with
-// every MMA and all softmax arithmetic removed it still takes 82 % of its full run time (tests/native/attn_test.cu,
-// CLIPB200_ATTN_DBG=63).  Here the pair shares a 4-deep K/V ring (3 loads per (b, h) instead of 5 at T = 576), each tile
-// keeps its own Q buffer, S / P / O columns (256 of the CTA's 512 TMEM columns), four softmax warps and its own
-// MMA-issuing warp, so the two tiles run as independent pipelines that only meet at the ring's empty barriers
-// (count 2: a tile that does not need a block — odd tail tile, causal upper blocks — arrives without issuing MMAs).
-constexpr int PAIR_WARP_TMA = 8;
-constexpr int PAIR_WARP_MMA0 = 9;   // + tile index
-constexpr int PAIR_THREADS = 32 * 11;
-
-template <int HD, int BKV>
-struct PairCfg {
-  using C = Cfg<HD, BKV>;
-  static constexpr int STAGES = 4;
-  static constexpr int Q_TILE_AL = (C::Q_MAIN + C::Q_REM + 1023) / 1024 * 1024;
-  static constexpr int OFF_Q = 0;
-  static constexpr int OFF_KV = 2 * Q_TILE_AL;
-  static constexpr int OUT_TILE = (4 * C::OUT_WARP + 127) / 128 * 128;
-  static constexpr int OFF_OUT = OFF_KV + STAGES * C::KV_STAGE_AL;
-  static constexpr int OFF_BAR = OFF_OUT + 2 * OUT_TILE;
-  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
-  static constexpr int TMEM_COLS = 512;
-  static constexpr int TILE_COLS = 256;
-  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-  static_assert(C::COL_O + C::HDP <= TILE_COLS, "TMEM budget per tile");
-};
-
-template <int HD, int BKV, bool CAUSAL>
-__global__ void __launch_bounds__(PAIR_THREADS, 1)
-attn_fwd_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_constant__ CUtensorMap tm_q_rem,
-                             const __grid_constant__ CUtensorMap tm_kv_main, const __grid_constant__ CUtensorMap tm_kv_rem,
-                             const __grid_constant__ CUtensorMap tm_out, Params p) {
-  using C = Cfg<HD, BKV>;
-  using PC = PairCfg<HD, BKV>;
-  constexpr int ST = PC::STAGES;
-  extern __shared__ uint8_t attn_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_q = smem + PC::OFF_Q;
-  uint8_t* s_kv = smem + PC::OFF_KV;
-  uint8_t* s_out = smem + PC::OFF_OUT;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PC::OFF_BAR);
-  uint64_t* q_full = bars + 0;     // [2] per tile
-  uint64_t* q_empty = bars + 2;    // [2]
-  uint64_t* s_full = bars + 4;     // [2]
-  uint64_t* s_empty = bars + 6;    // [2]
-  uint64_t* p_full = bars + 8;     // [2]
-  uint64_t* pv_done = bars + 10;   // [2]
-  uint64_t* k_full = bars + 12;    // [ST] shared ring
-  uint64_t* k_empty = bars + 16;   // [ST] count 2: both tiles release a slot
-  uint64_t* v_full = bars + 20;    // [ST]
-  uint64_t* v_empty = bars + 24;   // [ST]
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 28);
-  static_assert(ST == 4, "barrier carve assumes a 4-deep ring");
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kv_blocks_total = (p.T + BKV - 1) / BKV;
-  const int n_pairs = (p.q_tiles + 1) / 2;
-
-  if (C::REMP_PLANES > C::REM_PLANES) {  // zero the padding chunk planes TMA never writes
-    for (int t = 0; t < 2; ++t)
-      for (int i = threadIdx.x; i < (C::REMP_PLANES - C::REM_PLANES) * BQ; i += PAIR_THREADS)
-        reinterpret_cast<uint4*>(s_q + t * PC::Q_TILE_AL + C::Q_MAIN + C::REM_PLANES * BQ * 16)[i] = make_uint4(0, 0, 0, 0);
-    for (int st = 0; st < ST; ++st)
-      for (int kv = 0; kv < 2; ++kv) {
-        uint8_t* tile = s_kv + st * C::KV_STAGE_AL + kv * C::KV_TILE;
-        for (int i = threadIdx.x; i < (C::REMP_PLANES - C::REM_PLANES) * BKV; i += PAIR_THREADS)
-          reinterpret_cast<uint4*>(tile + C::KV_MAIN + C::REM_PLANES * BKV * 16)[i] = make_uint4(0, 0, 0, 0);
-      }
-    ptx::fence_proxy_async_smem();
-  }
-  if (warp == PAIR_WARP_TMA && lane == 0) {
-    ptx::prefetch_tmap(&tm_q_main);
-    ptx::prefetch_tmap(&tm_kv_main);
-    ptx::prefetch_tmap(&tm_out);
-    if (C::REM > 0) { ptx::prefetch_tmap(&tm_q_rem); ptx::prefetch_tmap(&tm_kv_rem); }
-    for (int t = 0; t < 2; ++t) {
-      ptx::mbar_init(&q_full[t], 1);
-      ptx::mbar_init(&q_empty[t], 1);
-      ptx::mbar_init(&s_full[t], 1);
-      ptx::mbar_init(&s_empty[t], CLIPB200_ATTN_ELECT_ARRIVE ? 4 : 128);
-      ptx::mbar_init(&p_full[t], CLIPB200_ATTN_ELECT_ARRIVE ? 4 : 128);
-      ptx::mbar_init(&pv_done[t], 1);
-    }
-    for (int s = 0; s < ST; ++s) {
-      ptx::mbar_init(&k_full[s], 1); ptx::mbar_init(&k_empty[s], 2);
-      ptx::mbar_init(&v_full[s], 1); ptx::mbar_init(&v_empty[s], 2);
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp == PAIR_WARP_MMA0) ptx::tmem_alloc<PC::TMEM_COLS>(tmem_base_ptr);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_ptr;
-
-  auto item_blocks = [&](int qt) {
-    if (!CAUSAL) return kv_blocks_total;
-    const int last_q = qt * BQ + BQ - 1;
-    const int nb = last_q / BKV + 1;
-    return nb < kv_blocks_total ? nb : kv_blocks_total;
-  };
-
-  if (warp == PAIR_WARP_TMA) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t g = 0;              // running K/V block counter of the shared ring
-      uint32_t itq[2] = {0, 0};    // Q tiles loaded so far, per tile slot
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int qp = item % n_pairs;
-        const int bh = item / n_pairs;
-        const int h = bh % p.H, b = bh / p.H;
-        const int col_q = h * HD, col_k = p.H * HD + h * HD, col_v = 2 * p.H * HD + h * HD;
-        const bool valid1 = 2 * qp + 1 < p.q_tiles;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (t == 1 && !valid1) break;
-          const int qt = 2 * qp + t;
-          uint8_t* qs = s_q + t * PC::Q_TILE_AL;
-          ptx::mbar_wait(&q_empty[t], (itq[t] & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&q_full[t], C::Q_TX);
-          tma_load_3d(&tm_q_main, &q_full[t], qs, col_q, qt * BQ, b);
-          for (int pl = 0; pl < C::REM_PLANES; ++pl)
-            tma_load_3d(&tm_q_rem, &q_full[t], qs + C::Q_MAIN + pl * BQ * 16, col_q + 64 + 8 * pl, qt * BQ, b);
-          ++itq[t];
-        }
-        const int nb = item_blocks(valid1 ? 2 * qp + 1 : 2 * qp);
-        for (int j = 0; j < nb; ++j, ++g) {
-          const int st = g & (ST - 1);
-          const uint32_t par = ((g / ST) & 1) ^ 1;
-          uint8_t* kt = s_kv + st * C::KV_STAGE_AL;
-          uint8_t* vt = kt + C::KV_TILE;
-          ptx::mbar_wait(&k_empty[st], par);
-          ptx::mbar_arrive_expect_tx(&k_full[st], C::KV_TX / 2);
-          tma_load_3d(&tm_kv_main, &k_full[st], kt, col_k, j * BKV, b);
-          for (int pl = 0; pl < C::REM_PLANES; ++pl)
-            tma_load_3d(&tm_kv_rem, &k_full[st], kt + C::KV_MAIN + pl * BKV * 16, col_k + 64 + 8 * pl, j * BKV, b);
-          ptx::mbar_wait(&v_empty[st], par);
-          ptx::mbar_arrive_expect_tx(&v_full[st], C::KV_TX / 2);
-          tma_load_3d(&tm_kv_main, &v_full[st], vt, col_v, j * BKV, b);
-          for (int pl = 0; pl < C::REM_PLANES; ++pl)
-            tma_load_3d(&tm_kv_rem, &v_full[st], vt + C::KV_MAIN + pl * BKV * 16, col_v + 64 + 8 * pl, j * BKV, b);
-        }
-      }
-    }
-  } else if (warp >= PAIR_WARP_MMA0) {
-    // ------------------------------------------------------------------ MMA issuer of tile t (whole warp, uniform)
-    const int t = warp - PAIR_WARP_MMA0;
-    constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, 0);
-    constexpr uint32_t idesc_pv_main = make_idesc(BQ, 64, 1);
-    constexpr uint32_t idesc_pv_rem = make_idesc(BQ, C::REMP > 0 ? C::REMP : 16, 1);
-    const uint32_t t_tile = tmem_base + static_cast<uint32_t>(t * PC::TILE_COLS);
-    const uint32_t t_s = t_tile + C::COL_S, t_p = t_tile + C::COL_P, t_o = t_tile + C::COL_O;
-    const uint32_t q_addr = ptx::smem_u32(s_q + t * PC::Q_TILE_AL);
-    uint32_t g = 0;    // ring position (advances for every block of every item, needed or not)
-    uint32_t gt = 0;   // blocks this tile has processed (parity of its S / P barriers)
-    uint32_t itq = 0;  // Q tiles this tile has consumed
-    auto issue_qk = [&](uint32_t gg, uint32_t ggt) {
-      const int st = gg & (ST - 1);
-      const uint32_t k_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL);
-      ptx::mbar_wait(&k_full[st], (gg / ST) & 1);
-      ptx::mbar_wait(&s_empty[t], (ggt & 1) ^ 1);
-      ptx::tc_fence_after();
-      const uint64_t dq = ptx::make_kmajor_sw128_desc(q_addr);
-      const uint64_t dk = ptx::make_kmajor_sw128_desc(k_addr);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        ptx::umma_bf16_ss_w(t_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_qk,
-                            k != 0 ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < C::REMP / 16; ++k) {
-        const uint64_t dqr = make_nosw_desc(q_addr + C::Q_MAIN + k * 2 * BQ * 16, BQ * 16, 128);
-        const uint64_t dkr = make_nosw_desc(k_addr + C::KV_MAIN + k * 2 * BKV * 16, BKV * 16, 128);
-        ptx::umma_bf16_ss_w(t_s, dqr, dkr, idesc_qk, 1u);
-      }
-      ptx::umma_commit_w(&k_empty[st]);
-      ptx::umma_commit_w(&s_full[t]);
-    };
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int qp = item % n_pairs;
-      const bool valid1 = 2 * qp + 1 < p.q_tiles;
-      const bool valid = t == 0 || valid1;
-      const int nb_item = item_blocks(valid1 ? 2 * qp + 1 : 2 * qp);
-      const int nb = valid ? item_blocks(2 * qp + t) : 0;
-      if (valid) {
-        ptx::mbar_wait(&q_full[t], itq & 1);
-        ++itq;
-        ptx::tc_fence_after();
-        issue_qk(g, gt);
-        for (int j = 0; j < nb; ++j, ++g, ++gt) {
-          if (j + 1 < nb) issue_qk(g + 1, gt + 1);        // S(j+1) overlaps softmax(j)
-          else ptx::umma_commit_w(&q_empty[t]);           // every QK^T of this item is issued
-          const int st = g & (ST - 1);
-          const uint32_t v_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL + C::KV_TILE);
-          ptx::mbar_wait(&v_full[st], (g / ST) & 1);
-          ptx::mbar_wait(&p_full[t], gt & 1);
-          ptx::tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
-            const uint32_t acc = (j | k) != 0 ? 1u : 0u;
-            const uint64_t dv = make_mnmajor_sw128_desc(v_addr + k * 16 * 128);
-            ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), dv, idesc_pv_main, acc);
-            if (C::REMP > 0) {
-              const uint64_t dvr = make_nosw_desc(v_addr + C::KV_MAIN + k * 16 * 16, 128, BKV * 16);
-              ptx::umma_bf16_ts_w(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
-            }
-          }
-          ptx::umma_commit_w(&v_empty[st]);
-          ptx::umma_commit_w(&pv_done[t]);
-        }
-      }
-      // ring slots this tile does not read (absent odd tile; causal blocks above this tile's diagonal) still need its
-      // release.  Waiting for the slot's full barrier first keeps the arrival in the right phase of the empty barrier.
-      for (int j = nb; j < nb_item; ++j, ++g) {
-        const int st = g & (ST - 1);
-        const uint32_t par = (g / ST) & 1;
-        ptx::mbar_wait(&k_full[st], par);
-        if (lane == 0) ptx::mbar_arrive(&k_empty[st]);
-        ptx::mbar_wait(&v_full[st], par);
-        if (lane == 0) ptx::mbar_arrive(&v_empty[st]);
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax + epilogue: warps 4t .. 4t+3 own tile t
-    const int t = warp >> 2;
-    const int quarter = warp & 3;
-    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t t_tile = tmem_base + static_cast<uint32_t>(t * PC::TILE_COLS) + lane_base;
-    SmxCtx ctx;
-    ctx.s_full = &s_full[t]; ctx.s_empty = &s_empty[t]; ctx.p_full = &p_full[t]; ctx.pv_done = &pv_done[t];
-    ctx.t_s = t_tile + C::COL_S;
-    ctx.t_p = t_tile + C::COL_P;
-    ctx.t_o = t_tile + C::COL_O;
-    ctx.stg = s_out + t * PC::OUT_TILE + quarter * C::OUT_WARP;
-    ctx.xch_max = nullptr;
-    ctx.xch_sum = nullptr;
-    ctx.timed = warp == 0;
-    uint32_t gt = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int qp = item % n_pairs;
-      const int bh = item / n_pairs;
-      const int h = bh % p.H, b = bh / p.H;
-      const int qt = 2 * qp + t;
-      if (qt >= p.q_tiles) continue;
-      softmax_item<HD, BKV, CAUSAL>(ctx, p, &tm_out, qt, h, b, item_blocks(qt), gt, quarter, 0, lane);
-    }
-    if (lane == 0) ptx::tma_store_wait<0>();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == PAIR_WARP_MMA0) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc<PC::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -964,10 +807,10 @@ inline bool make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t cols, uint6
   return r == CUDA_SUCCESS;
 }
 
-template <int HD, int BKV, bool CAUSAL>
+template <int HD, int BKV, bool CAUSAL, bool DB>
 inline cudaError_t launch_t(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int num_sms,
                             cudaStream_t st) {
-  using C = Cfg<HD, BKV>;
+  using C = Cfg<HD, BKV, DB>;
   CUtensorMap q_main, q_rem, kv_main, kv_rem, o_map;
   const uint64_t cols = 3ull * H * HD;
   if (!make_tmap_3d(&q_main, qkv, cols, T, B, 64, BQ, true)) return cudaErrorUnknown;
@@ -981,54 +824,36 @@ inline cudaError_t launch_t(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B,
   p.n_items = p.q_tiles * H * B;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   const int grid = p.n_items < 2 * num_sms ? p.n_items : 2 * num_sms;
-  attn_fwd_tcgen05_kernel<HD, BKV, CAUSAL><<<grid, THREADS, C::SMEM_BYTES, st>>>(q_main, q_rem, kv_main, kv_rem, o_map, p);
+  attn_fwd_tcgen05_kernel<HD, BKV, CAUSAL, DB><<<grid, THREADS, C::SMEM_BYTES, st>>>(q_main, q_rem, kv_main, kv_rem, o_map, p);
   return cudaGetLastError();
 }
-template <int HD, int BKV, bool CAUSAL>
-inline cudaError_t launch_pair_t(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int num_sms,
-                                 cudaStream_t st) {
-  using C = Cfg<HD, BKV>;
-  using PC = PairCfg<HD, BKV>;
-  CUtensorMap q_main, q_rem, kv_main, kv_rem, o_map;
-  const uint64_t cols = 3ull * H * HD;
-  if (!make_tmap_3d(&q_main, qkv, cols, T, B, 64, BQ, true)) return cudaErrorUnknown;
-  if (!make_tmap_3d(&kv_main, qkv, cols, T, B, 64, BKV, true)) return cudaErrorUnknown;
-  if (!make_tmap_3d(&q_rem, qkv, cols, T, B, 8, BQ, false)) return cudaErrorUnknown;
-  if (!make_tmap_3d(&kv_rem, qkv, cols, T, B, 8, BKV, false)) return cudaErrorUnknown;
-  if (!make_tmap_3d(&o_map, out, static_cast<uint64_t>(H) * HD, T, B, HD, 32, false)) return cudaErrorUnknown;
-  Params p;
-  p.T = T; p.H = H; p.B = B;
-  p.q_tiles = (T + BQ - 1) / BQ;
-  p.n_items = ((p.q_tiles + 1) / 2) * H * B;   // work item = a pair of query tiles of one (batch, head)
-  p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
-  const int grid = p.n_items < num_sms ? p.n_items : num_sms;
-  attn_fwd_tcgen05_pair_kernel<HD, BKV, CAUSAL><<<grid, PAIR_THREADS, PC::SMEM_BYTES, st>>>(q_main, q_rem, kv_main, kv_rem,
-                                                                                         o_map, p);
-  return cudaGetLastError();
-}
-template <int HD, int BKV>
+template <int HD, int BKV, bool DB>
 inline cudaError_t configure_t() {
-  cudaError_t ep = cudaFuncSetAttribute(attn_fwd_tcgen05_pair_kernel<HD, BKV, false>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<HD, BKV>::SMEM_BYTES);
-  if (ep != cudaSuccess) return ep;
-  ep = cudaFuncSetAttribute(attn_fwd_tcgen05_pair_kernel<HD, BKV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            PairCfg<HD, BKV>::SMEM_BYTES);
-  if (ep != cudaSuccess) return ep;
-  cudaError_t e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<HD, BKV, false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HD, BKV>::SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<HD, BKV, false, DB>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HD, BKV, DB>::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<HD, BKV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              Cfg<HD, BKV>::SMEM_BYTES);
+  return cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<HD, BKV, true, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              Cfg<HD, BKV, DB>::SMEM_BYTES);
 }
+
+// Double-buffered S needs one softmax warp per row block (P aliases S); the SPLIT == 2 experiment keeps the single-S
+// protocol.
+constexpr bool kDoubleS = SPLIT == 1;
 
 }  // namespace attn
 
 inline cudaError_t attn_tcgen05_configure_device() {
   cudaError_t e;
-  if ((e = attn::configure_t<64, 96>()) != cudaSuccess) return e;
-  if ((e = attn::configure_t<72, 96>()) != cudaSuccess) return e;
-  if ((e = attn::configure_t<80, 96>()) != cudaSuccess) return e;
-  if ((e = attn::configure_t<96, 64>()) != cudaSuccess) return e;
+  if ((e = attn::configure_t<64, 96, false>()) != cudaSuccess) return e;
+  if ((e = attn::configure_t<72, 96, false>()) != cudaSuccess) return e;
+  if ((e = attn::configure_t<80, 96, false>()) != cudaSuccess) return e;
+  if ((e = attn::configure_t<96, 64, false>()) != cudaSuccess) return e;
+  if (attn::kDoubleS) {
+    if ((e = attn::configure_t<64, 96, attn::kDoubleS>()) != cudaSuccess) return e;
+    if ((e = attn::configure_t<72, 64, attn::kDoubleS>()) != cudaSuccess) return e;
+    if ((e = attn::configure_t<80, 64, attn::kDoubleS>()) != cudaSuccess) return e;
+    if ((e = attn::configure_t<96, 64, attn::kDoubleS>()) != cudaSuccess) return e;
+  }
   return cudaSuccess;
 }
 inline bool attn_tcgen05_supported(int hd) { return hd == 64 || hd == 72 || hd == 80 || hd == 96; }
@@ -1037,23 +862,30 @@ inline bool attn_tcgen05_supported(int hd) { return hd == 64 || hd == 72 || hd =
 inline cudaError_t attn_tcgen05(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, bool causal,
                                 int num_sms, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  // Sequences of two or more query tiles go to the two-tile kernel (K/V streamed once per tile pair);
-  // CLIPB200_ATTN_ONE_TILE=1 forces the one-tile kernel (A/B measurements).
-  static const bool one_tile_only = attn::SPLIT != 1 || getenv("CLIPB200_ATTN_ONE_TILE") != nullptr;
-  const bool pair = !one_tile_only && T > attn::BQ;
-#define CLIPB200_ATTN_CASE(HD_, BKV_)                                                             \
-  if (hd == HD_) {                                                                                \
-    if (pair)                                                                                     \
-      return causal ? attn::launch_pair_t<HD_, BKV_, true>(qkv, out, B, T, H, num_sms, st)        \
-                    : attn::launch_pair_t<HD_, BKV_, false>(qkv, out, B, T, H, num_sms, st);      \
-    return causal ? attn::launch_t<HD_, BKV_, true>(qkv, out, B, T, H, num_sms, st)               \
-                  : attn::launch_t<HD_, BKV_, false>(qkv, out, B, T, H, num_sms, st);             \
+  // CLIPB200_ATTN_SINGLE_S=1 selects the single-S protocol (A/B measurements against the double-buffered default)
+  static const bool single_s = !attn::kDoubleS || getenv("CLIPB200_ATTN_SINGLE_S") != nullptr;
+#define CLIPB200_ATTN_CASE(HD_, BKV_, DB_)                                                             \
+  if (hd == HD_)                                                                                       \
+    return causal ? attn::launch_t<HD_, BKV_, true, DB_>(qkv, out, B, T, H, num_sms, st)               \
+                  : attn::launch_t<HD_, BKV_, false, DB_>(qkv, out, B, T, H, num_sms, st);
+  // Which protocol per head dim is a measurement (tests/native/attn_test.cu, B = 128 / 64, T = 576, profiles/r01g_*):
+  //   hd 64: double-buffered S, 96-key blocks   616 TFLOP/s  (single S: 589)
+  //   hd 72: single S, 96-key blocks            634          (double S needs 64-key blocks to fit 256 TMEM columns: 617)
+  //   hd 80: single S, 96-key blocks            678          (double S: 667)
+  //   hd 96: double-buffered S, 64-key blocks   689          (single S: 680)
+  if (!single_s) {
+    CLIPB200_ATTN_CASE(64, 96, attn::kDoubleS)
+    CLIPB200_ATTN_CASE(96, 64, attn::kDoubleS)
   }
-  // kv block: 96 keys (576 = 6 x 96 exactly); 64 for head dim 96 so that two CTAs still fit in one SM's shared memory
-  CLIPB200_ATTN_CASE(64, 96)
-  CLIPB200_ATTN_CASE(72, 96)
-  CLIPB200_ATTN_CASE(80, 96)
-  CLIPB200_ATTN_CASE(96, 64)
+  if (getenv("CLIPB200_ATTN_DOUBLE_S") != nullptr && attn::kDoubleS) {   // A/B switch for the other two head dims
+    CLIPB200_ATTN_CASE(72, 64, attn::kDoubleS)
+    CLIPB200_ATTN_CASE(80, 64, attn::kDoubleS)
+  }
+  // single-S kv block: 96 keys (576 = 6 x 96 exactly); 64 for head dim 96 so that two CTAs fit in one SM's shared memory
+  CLIPB200_ATTN_CASE(64, 96, false)
+  CLIPB200_ATTN_CASE(72, 96, false)
+  CLIPB200_ATTN_CASE(80, 96, false)
+  CLIPB200_ATTN_CASE(96, 64, false)
 #undef CLIPB200_ATTN_CASE
   return cudaErrorInvalidValue;
 }

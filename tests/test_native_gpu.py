@@ -21,6 +21,20 @@ def test_native_binary(binary, arg, marker):
     assert out.returncode == 0 and marker in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+@pytest.mark.parametrize("switch", ["CLIPB200_ATTN_SINGLE_S", "CLIPB200_ATTN_DOUBLE_S"])
+def test_attention_protocol_switches(switch):
+    """The tcgen05 attention kernel has two MMA <-> softmax hand-off protocols (one S tile, or two S tiles with P written
+    in place) and picks one per head dim by measurement; the environment switches force the other one, and every
+    correctness case (head dims 64 / 72 / 80 / 96, kv tails, causal, multi-tile, persistent loop) must pass with it."""
+    path = os.path.join(NATIVE, "attn_test.bin")
+    if not os.path.exists(path):
+        pytest.fail(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    env = dict(os.environ, **{switch: "1"})
+    for case in range(11):   # cases 0..10 are the correctness cases, 11+ the timed ones
+        out = subprocess.run([path, str(case)], capture_output=True, text=True, timeout=120, env=env)
+        assert out.returncode == 0 and "ATTN TEST PASSED" in out.stdout, (case, out.stdout[-2000:] + out.stderr[-2000:])
+
+
 def test_loader_accepts_f16_bf16_and_identity_aliases(make_model, tmp_path):
     """The ONNX loader's claims beyond the synthetic exporter's defaults: fp16 / bf16 initializers, inline
     `float_data`, and exporter-style de-duplication (an `Identity` node aliasing one initializer under a second name)."""

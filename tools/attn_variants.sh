@@ -1,5 +1,5 @@
 cd tests/native/variants
-run() { echo "== $*"; timeout 90 "$@" | sed 's/max|tc-mma|=\([0-9.e-]*\) max|tc-fp32|=\([0-9.e-]*\)/d=\1 \2/'; }
-run ./attn_P0.bin
-CLIPB200_ATTN_ONE_TILE=1 run ./attn_P0.bin 11
-for v in P3 PN P2; do for c in 11 13 12; do run ./attn_$v.bin $c | grep -v TEST; done; done
+run() { echo "== $*"; timeout 90 "$@" | grep -v "mismatch\|TEST" | sed 's/max|tc-mma.*bad=[0-9]*//'; }
+for d in 0 1 2 3 4 5 7; do run ./attn_Y$d.bin 11; run ./attn_Y$d.bin 13; done
+ATTN_HALF_GRID=1 run ./attn_Y0.bin 11
+ATTN_HALF_GRID=1 run ./attn_Y7.bin 11
