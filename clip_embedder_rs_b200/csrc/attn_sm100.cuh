@@ -542,7 +542,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 21);
   static_assert(ST <= 3, "barrier carve");
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a lane-0 broadcast: ptxas then treats it (and every role branch on it) as warp-uniform and keeps
+  // the MMA warp's descriptors / TMEM addresses in uniform registers instead of moving each tcgen05.mma operand with R2UR
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int kv_blocks_total = (p.T + BKV - 1) / BKV;
 
   // zero the padding chunk planes (TMA never writes them) of Q and of both K/V stages
@@ -580,7 +582,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);   // warp-uniform (see `warp` above)
 
   auto item_blocks = [&](int qt) {
     if (!CAUSAL) return kv_blocks_total;

@@ -193,7 +193,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]   epilogue -> MMA
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-  const int warp = threadIdx.x >> 5;
+  // lane-0 broadcast: ptxas then knows the warp index (and every role branch on it) is warp-uniform, so the MMA warp's
+  // descriptors and TMEM addresses live in uniform registers instead of being moved with R2UR before every tcgen05.mma
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int m_tiles = (M + TILE_M - 1) / TILE_M;
   const int n_tiles = (N + BN - 1) / BN;
@@ -222,7 +224,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (NCTA == 2) ptx::cluster_sync();  // the peer's barriers must be initialised before anything arrives remotely
   else __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);
 
   if (warp == GEMM_WARP_TMA) {
     // ------------------------------------------------------------ TMA producer
