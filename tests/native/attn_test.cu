@@ -168,6 +168,8 @@ int main(int argc, char** argv) {
   run(64, 576, 16, 96, false, true);   // 12
   run(128, 576, 18, 64, false, true);  // 13: no remainder planes (same total width as 16 x 72)
   run(128, 576, 14, 80, false, true);  // 14: two real remainder planes
+  run(32, 2304, 16, 72, false, true);  // 15: 24 key blocks per item (per-block vs per-item cost, with 16)
+  run(256, 288, 16, 72, false, true);  // 16: 3 key blocks per item
 #ifdef CLIPB200_ATTN_TIMING
   {
     unsigned long long h[16];
