@@ -21,6 +21,17 @@ def test_native_binary(binary, arg, marker):
     assert out.returncode == 0 and marker in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+def test_mma_latency_microbenchmark_runs():
+    """tests/native/mma_latency_test.cu (per-instruction tcgen05.mma cost, commit and mbarrier hand-off latencies quoted in
+    DESIGN.md section 3.2) runs to completion: a protocol error in it would trap or hang, not print the end marker."""
+    path = os.path.join(NATIVE, "mma_latency_test.bin")
+    if not os.path.exists(path):
+        pytest.fail(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    out = subprocess.run([path], capture_output=True, text=True, timeout=120)
+    print(out.stdout[-3000:])
+    assert out.returncode == 0 and "MMA LATENCY TEST DONE" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 @pytest.mark.parametrize("switch", ["CLIPB200_ATTN_SINGLE_S", "CLIPB200_ATTN_DOUBLE_S"])
 def test_attention_protocol_switches(switch):
     """The tcgen05 attention kernel has two MMA <-> softmax hand-off protocols (one S tile, or two S tiles with P written
