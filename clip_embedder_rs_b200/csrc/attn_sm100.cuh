@@ -879,7 +879,8 @@ inline cudaError_t attn_tcgen05(const __nv_bfloat16* qkv, __nv_bfloat16* out, in
     CLIPB200_ATTN_CASE(64, 96, attn::kDoubleS)
     CLIPB200_ATTN_CASE(96, 64, attn::kDoubleS)
   }
-  if (getenv("CLIPB200_ATTN_DOUBLE_S") != nullptr && attn::kDoubleS) {   // A/B switch for the other two head dims
+  static const bool force_double_s = attn::kDoubleS && getenv("CLIPB200_ATTN_DOUBLE_S") != nullptr;
+  if (force_double_s) {   // A/B switch for the other two head dims
     CLIPB200_ATTN_CASE(72, 64, attn::kDoubleS)
     CLIPB200_ATTN_CASE(80, 64, attn::kDoubleS)
   }
