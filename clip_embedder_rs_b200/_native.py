@@ -64,6 +64,22 @@ SIGNATURES = {
     "clipb200_corpus_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "clipb200_corpus_size": (C.c_int64, [C.c_void_p]),
     "clipb200_corpus_rank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "clipb200_pool_create": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int32, C.POINTER(Opts), C.POINTER(C.c_void_p)]),
+    "clipb200_pool_destroy": (None, [C.c_void_p]),
+    "clipb200_pool_size": (C.c_int, [C.c_void_p]),
+    "clipb200_pool_device": (C.c_int, [C.c_void_p, C.c_int]),
+    "clipb200_pool_kind": (C.c_int, [C.c_void_p]),
+    "clipb200_pool_embed_dim": (C.c_int64, [C.c_void_p]),
+    "clipb200_pool_image_size": (C.c_int64, [C.c_void_p]),
+    "clipb200_pool_context_length": (C.c_int64, [C.c_void_p]),
+    "clipb200_pool_num_inputs": (C.c_int, [C.c_void_p]),
+    "clipb200_pool_input_name": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "clipb200_pool_launch_count": (C.c_int64, [C.c_void_p]),
+    "clipb200_pool_vision_embed_rgb8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                                  C.POINTER(Preproc), C.c_void_p]),
+    "clipb200_pool_vision_embed_rgb8_var": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                                      C.POINTER(Preproc), C.c_void_p]),
+    "clipb200_pool_text_embed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "clipb200_vision_embed_rgb8_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Preproc),
                                                     C.c_void_p]),
     "clipb200_text_embed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),

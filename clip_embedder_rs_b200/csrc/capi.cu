@@ -30,6 +30,9 @@ static int done(const Status& s) {
   return s.code;
 }
 
+// shared with pool.cu: sets this thread's message and returns the code
+int clipb200_set_last_error(int code, const std::string& msg) { return fail(code, msg); }
+
 #define API_GUARD_BEGIN try {
 #define API_GUARD_END                                                        \
   }                                                                          \

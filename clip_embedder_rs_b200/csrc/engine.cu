@@ -5,6 +5,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 
 #include "attn_sm100.cuh"
 #include "gemm_sm100.cuh"
@@ -433,8 +435,23 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
   input_names = m.inputs;
   // Real exports (torch.onnx.export graphs) are bound from the graph structure; initializer-only files and graphs
   // the recogniser does not know (FastViT) fall through to binding by open_clip / timm parameter names.
+  // A file with an executable graph is bound ONLY from that graph: guessing hyper-parameters (activation, eps, heads,
+  // causal mask, pooling) from parameter names would load such a file and return silently wrong embeddings where
+  // onnxruntime executes what the graph says.  The one family bound by name is the re-parameterised FastViT trunk
+  // (identified by its stem parameter), whose conv graph the recogniser does not parse.
   std::string graph_err;
-  if (graph_needs_recognition(m) && !recognize_graph(&m, &graph_err, nullptr)) graph_note_ = graph_err;
+  if (graph_needs_recognition(m) && !recognize_graph(&m, &graph_err, nullptr)) {
+    if (!m.has("model.visual.trunk.stem.0.reparam_conv.weight"))
+      return Status::Err(CLIPB200_ERR_UNSUPPORTED, onnx_path + ": " + graph_err);
+    graph_note_ = graph_err;
+  }
+  // src/text.rs:156-161 feeds an attention_mask when the graph declares one.  pull_onnx.py's TextWrapper never does;
+  // a graph that does uses the mask in a way only its nodes define, so it is refused instead of being ignored.
+  for (const std::string& n : m.inputs)
+    if (n == "attention_mask")
+      return Status::Err(CLIPB200_ERR_UNSUPPORTED,
+                         onnx_path + ": the graph declares an attention_mask input; this engine only runs text towers "
+                                     "whose padding is handled inside the graph (pull_onnx.py:61-68)");
   if (get_encode_tiled() == nullptr)  // resolved here so that it never happens inside a graph capture
     return Status::Err(CLIPB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
   if (const char* env = getenv("CLIPB200_NO_GRAPHS")) if (atoi(env) != 0) graph_max_n_ = 0;
@@ -493,8 +510,16 @@ Engine::~Engine() {
   for (auto& p : prof_pending_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto& e : prof_free_) cudaEventDestroy(e);
   if (l2_flush_) cudaFree(l2_flush_);
-  if (rs_src_) cudaFree(rs_src_);
-  if (rs_tmp_) cudaFree(rs_tmp_);
+  for (ResizeStage& rs : rs_stage_) {
+    if (rs.h_src) cudaFreeHost(rs.h_src);
+    if (rs.h_arena) cudaFreeHost(rs.h_arena);
+    if (rs.h_jobs) cudaFreeHost(rs.h_jobs);
+    if (rs.d_src) cudaFree(rs.d_src);
+    if (rs.d_tmp) cudaFree(rs.d_tmp);
+    if (rs.d_arena) cudaFree(rs.d_arena);
+    if (rs.d_jobs) cudaFree(rs.d_jobs);
+    if (rs.free_ev) cudaEventDestroy(rs.free_ev);
+  }
   if (compute_) cudaStreamDestroy(compute_);
   if (copy_in_) cudaStreamDestroy(copy_in_);
   if (copy_out_) cudaStreamDestroy(copy_out_);
@@ -881,7 +906,7 @@ Status Engine::VisionEmbedRgb8(const uint8_t* hwc, int64_t batch, int width, int
   if (hwc == nullptr || out == nullptr) return Status::Err(CLIPB200_ERR_INVALID_ARG, "null buffer");
   if (width != S_ || height != S_)
     return Status::Err(CLIPB200_ERR_UNSUPPORTED, "images must already be " + std::to_string(S_) + "x" + std::to_string(S_) +
-                                                     " (GPU resize is not implemented yet)");
+                                                     "; use clipb200_vision_embed_rgb8_var / clipb200_resize_rgb8 for other sizes");
   CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
   RET_IF_ERR(SetPreproc(pp));
   return RunPipelined<uint8_t>(hwc, batch, static_cast<size_t>(S_) * S_ * 3, out, device_buffers, 0);
@@ -895,7 +920,7 @@ Status Engine::PreprocessRgb8(const uint8_t* hwc, int64_t batch, int width, int 
   if (hwc == nullptr || out_nchw == nullptr) return Status::Err(CLIPB200_ERR_INVALID_ARG, "null buffer");
   if (width != S_ || height != S_)
     return Status::Err(CLIPB200_ERR_UNSUPPORTED, "images must already be " + std::to_string(S_) + "x" + std::to_string(S_) +
-                                                     " (GPU resize is not implemented yet)");
+                                                     "; use clipb200_vision_embed_rgb8_var / clipb200_resize_rgb8 for other sizes");
   CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
   RET_IF_ERR(SetPreproc(pp));
   const size_t px = static_cast<size_t>(S_) * S_ * 3;
@@ -920,76 +945,232 @@ Status Engine::PreprocessRgb8(const uint8_t* hwc, int64_t batch, int width, int 
   return Check(e, "preprocess");
 }
 
-Status Engine::GetResizePlan(int width, int height, int interpolation, bool squash, const ResizePlanDev** plan) {
-  const auto key = std::make_tuple(width, height, interpolation, squash ? 1 : 0);
-  auto it = resize_plans_.find(key);
-  if (it != resize_plans_.end()) {
-    *plan = &it->second;
-    return Status::OK();
-  }
-  double left, top, cw, ch;
-  resize_crop_box(width, height, S_, squash, &left, &top, &cw, &ch);
-  ResizePlanDev p;
-  p.left = left; p.top = top; p.sx = cw / S_; p.sy = ch / S_;
-  if (interpolation > 1) {
-    p.nearest = true;  // ResizeAlg::Nearest (vision.rs:179)
-  } else {
-    ResizeAxis ax = make_resize_axis(width, left, left + cw, S_, interpolation);
-    ResizeAxis ay = make_resize_axis(height, top, top + ch, S_, interpolation);
-    int y_first = height, y_last = 0;
-    for (int o = 0; o < S_; ++o) {
-      y_first = std::min(y_first, ay.start[o]);
-      y_last = std::max(y_last, ay.start[o] + ay.size[o]);
+// ------------------------------------------------------------------------------------------------ arbitrary sizes
+const Engine::AxisEntry& Engine::GetAxis(int in_size, double in0, double in1, int interpolation) {
+  AxisKey key;
+  key.in_size = in_size;
+  key.interp = interpolation;
+  memcpy(&key.in0_bits, &in0, 8);
+  memcpy(&key.in1_bits, &in1, 8);
+  auto it = axis_cache_.find(key);
+  if (it == axis_cache_.end()) {
+    // bounded LRU: a long-running service sees arbitrarily many photo sizes
+    constexpr size_t kMaxEntries = 512, kMaxBytes = size_t(64) << 20;
+    while (!axis_cache_.empty() && (axis_cache_.size() >= kMaxEntries || axis_cache_bytes_ > kMaxBytes)) {
+      auto victim = axis_cache_.begin();
+      for (auto i = axis_cache_.begin(); i != axis_cache_.end(); ++i)
+        if (i->second.tick < victim->second.tick) victim = i;
+      axis_cache_bytes_ -= victim->second.bytes;
+      axis_cache_.erase(victim);
     }
-    p.y_first = y_first;
-    p.rows = y_last - y_first;
-    p.xwindow = ax.window; p.ywindow = ay.window; p.xprecision = ax.precision; p.yprecision = ay.precision;
-    auto up_i = [&](const std::vector<int32_t>& v, int** d) -> Status {
-      RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(d), v.size() * 4));
-      return Check(cudaMemcpy(*d, v.data(), v.size() * 4, cudaMemcpyHostToDevice), "upload resize plan");
-    };
-    auto up_w = [&](const std::vector<int16_t>& v, int16_t** d) -> Status {
-      RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(d), v.size() * 2));
-      return Check(cudaMemcpy(*d, v.data(), v.size() * 2, cudaMemcpyHostToDevice), "upload resize plan");
-    };
-    RET_IF_ERR(up_i(ax.start, &p.xstart)); RET_IF_ERR(up_i(ax.size, &p.xsize)); RET_IF_ERR(up_w(ax.w, &p.xw));
-    RET_IF_ERR(up_i(ay.start, &p.ystart)); RET_IF_ERR(up_i(ay.size, &p.ysize)); RET_IF_ERR(up_w(ay.w, &p.yw));
+    AxisEntry e;
+    e.axis = make_resize_axis(in_size, in0, in1, S_, interpolation);
+    e.first = in_size;
+    e.last = 0;
+    for (int o = 0; o < S_; ++o) {
+      e.first = std::min(e.first, e.axis.start[o]);
+      e.last = std::max(e.last, e.axis.start[o] + e.axis.size[o]);
+    }
+    e.bytes = e.axis.w.size() * 2 + static_cast<size_t>(S_) * 8 + sizeof(AxisEntry);
+    axis_cache_bytes_ += e.bytes;
+    it = axis_cache_.emplace(key, std::move(e)).first;
   }
-  auto ins = resize_plans_.emplace(key, p);
-  *plan = &ins.first->second;
+  it->second.tick = ++axis_tick_;
+  return it->second;
+}
+
+Status Engine::GrowStage(ResizeStage* st, size_t src, size_t tmp, size_t arena_words, size_t jobs) {
+  if (st->free_ev == nullptr) CUDA_RET(cudaEventCreateWithFlags(&st->free_ev, cudaEventDisableTiming), "event");
+  const bool grow = src > st->src_cap || tmp > st->tmp_cap || arena_words > st->arena_cap || jobs > st->jobs_cap;
+  if (!grow) return Status::OK();
+  CUDA_RET(cudaStreamSynchronize(copy_in_), "sync before growing the resize staging");
+  auto round_up = [](size_t v, size_t q) { return (v + q - 1) / q * q; };
+  if (src > st->src_cap) {
+    if (st->h_src) cudaFreeHost(st->h_src);
+    if (st->d_src) cudaFree(st->d_src);
+    st->h_src = nullptr; st->d_src = nullptr; st->src_cap = 0;
+    const size_t cap = round_up(src, size_t(16) << 20);
+    CUDA_RET(cudaHostAlloc(reinterpret_cast<void**>(&st->h_src), cap, cudaHostAllocDefault), "pinned resize source staging");
+    CUDA_RET(cudaMalloc(reinterpret_cast<void**>(&st->d_src), cap), "resize source buffer");
+    st->src_cap = cap;
+  }
+  if (tmp > st->tmp_cap) {
+    if (st->d_tmp) cudaFree(st->d_tmp);
+    st->d_tmp = nullptr; st->tmp_cap = 0;
+    const size_t cap = round_up(tmp, size_t(4) << 20);
+    CUDA_RET(cudaMalloc(reinterpret_cast<void**>(&st->d_tmp), cap), "resize intermediate buffer");
+    st->tmp_cap = cap;
+  }
+  if (arena_words > st->arena_cap) {
+    if (st->h_arena) cudaFreeHost(st->h_arena);
+    if (st->d_arena) cudaFree(st->d_arena);
+    st->h_arena = nullptr; st->d_arena = nullptr; st->arena_cap = 0;
+    const size_t cap = round_up(arena_words, size_t(1) << 18);
+    CUDA_RET(cudaHostAlloc(reinterpret_cast<void**>(&st->h_arena), cap * 4, cudaHostAllocDefault), "pinned coefficient arena");
+    CUDA_RET(cudaMalloc(reinterpret_cast<void**>(&st->d_arena), cap * 4), "coefficient arena");
+    st->arena_cap = cap;
+  }
+  if (jobs > st->jobs_cap) {
+    if (st->h_jobs) cudaFreeHost(st->h_jobs);
+    if (st->d_jobs) cudaFree(st->d_jobs);
+    st->h_jobs = nullptr; st->d_jobs = nullptr; st->jobs_cap = 0;
+    const size_t cap = round_up(jobs, 256);
+    CUDA_RET(cudaHostAlloc(reinterpret_cast<void**>(&st->h_jobs), cap * sizeof(ResizeJob), cudaHostAllocDefault), "pinned resize jobs");
+    CUDA_RET(cudaMalloc(reinterpret_cast<void**>(&st->d_jobs), cap * sizeof(ResizeJob)), "resize jobs");
+    st->jobs_cap = cap;
+  }
   return Status::OK();
 }
 
-// host image -> (upload) -> resized S x S RGB8 at d_dst, on the compute stream
-Status Engine::ResizeToDevice(const uint8_t* h_img, int width, int height, const clipb200_preproc* pp, uint8_t* d_dst) {
-  if (width <= 0 || height <= 0 || width > 32768 || height > 32768)
-    return Status::Err(CLIPB200_ERR_INVALID_ARG, "bad image size");
-  const size_t src_bytes = static_cast<size_t>(width) * height * 3;
-  if (width == S_ && height == S_) {  // the convolution is the identity at the model resolution
-    return Check(cudaMemcpyAsync(d_dst, h_img, src_bytes, cudaMemcpyHostToDevice, compute_), "H2D copy");
+// Copies a list of (dst, src, bytes) with up to 8 host threads: one core moves ~10 GB/s from pageable memory, a photo
+// is tens of MB, and PCIe takes > 50 GB/s, so a single-threaded staging copy would be the bottleneck of the whole path.
+namespace {
+struct CopyPiece {
+  uint8_t* dst;
+  const uint8_t* src;
+  size_t bytes;
+};
+void parallel_copy(const std::vector<CopyPiece>& pieces) {
+  constexpr size_t kChunk = size_t(4) << 20;
+  std::vector<CopyPiece> chunks;
+  size_t total = 0;
+  for (const CopyPiece& p : pieces) {
+    total += p.bytes;
+    for (size_t o = 0; o < p.bytes; o += kChunk) chunks.push_back({p.dst + o, p.src + o, std::min(kChunk, p.bytes - o)});
   }
-  const ResizePlanDev* plan = nullptr;
-  RET_IF_ERR(GetResizePlan(width, height, pp->interpolation, pp->resize_mode == 1, &plan));
-  if (src_bytes > rs_src_bytes_) {
-    CUDA_RET(cudaStreamSynchronize(compute_), "sync");
-    if (rs_src_) cudaFree(rs_src_);
-    rs_src_ = nullptr;
-    CUDA_RET(cudaMalloc(reinterpret_cast<void**>(&rs_src_), src_bytes), "resize source buffer");
-    rs_src_bytes_ = src_bytes;
+  unsigned hw = std::thread::hardware_concurrency();
+  const size_t threads = std::min<size_t>({size_t(8), hw > 1 ? hw : 1, chunks.size()});
+  if (total < (size_t(8) << 20) || threads <= 1) {
+    for (const CopyPiece& c : chunks) memcpy(c.dst, c.src, c.bytes);
+    return;
   }
-  const size_t tmp_bytes = static_cast<size_t>(std::max(plan->rows, 1)) * S_ * 3;
-  if (tmp_bytes > rs_tmp_bytes_) {
-    CUDA_RET(cudaStreamSynchronize(compute_), "sync");
-    if (rs_tmp_) cudaFree(rs_tmp_);
-    rs_tmp_ = nullptr;
-    CUDA_RET(cudaMalloc(reinterpret_cast<void**>(&rs_tmp_), tmp_bytes), "resize temp buffer");
-    rs_tmp_bytes_ = tmp_bytes;
+  std::atomic<size_t> next(0);
+  auto work = [&]() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= chunks.size()) return;
+      memcpy(chunks[i].dst, chunks[i].src, chunks[i].bytes);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (size_t t = 1; t < threads; ++t) pool.emplace_back(work);
+  work();
+  for (std::thread& t : pool) t.join();
+}
+}  // namespace
+
+// Takes as many of the `count` images as fit one staging group (at least one), stages them through pinned memory,
+// copies them and their coefficient tables to the device and resizes them into d_dst[i * S*S*3] with two launches,
+// everything on the copy-in stream: the caller's compute stream keeps running the previous micro-batch's tower.
+Status Engine::ResizeGroupToDevice(const uint8_t* const* imgs, const int32_t* widths, const int32_t* heights, int count,
+                                   const clipb200_preproc* pp, uint8_t* d_dst, int* consumed) {
+  const size_t px = static_cast<size_t>(S_) * S_ * 3;
+  const bool squash = pp->resize_mode == 1;
+  std::vector<ResizeJob> jobs;
+  std::vector<int32_t> arena;
+  std::vector<CopyPiece> pieces;
+  std::map<AxisKey, int> placed;  // axis -> word offset of its `start` table in this group's arena
+  size_t src_bytes = 0, tmp_bytes = 0;
+  int max_rows = 0;
+  auto place_axis = [&](int in_size, double in0, double in1, int* start, int* size, int* w, int* window, int* precision,
+                        int* first, int* last) {
+    const AxisEntry& e = GetAxis(in_size, in0, in1, pp->interpolation);
+    AxisKey key;
+    key.in_size = in_size;
+    key.interp = pp->interpolation;
+    memcpy(&key.in0_bits, &in0, 8);
+    memcpy(&key.in1_bits, &in1, 8);
+    auto it = placed.find(key);
+    if (it == placed.end()) {
+      const int off = static_cast<int>(arena.size());
+      arena.insert(arena.end(), e.axis.start.begin(), e.axis.start.end());
+      arena.insert(arena.end(), e.axis.size.begin(), e.axis.size.end());
+      const size_t wwords = (e.axis.w.size() + 1) / 2;
+      const size_t at = arena.size();
+      arena.resize(at + wwords, 0);
+      memcpy(&arena[at], e.axis.w.data(), e.axis.w.size() * 2);
+      it = placed.emplace(key, off).first;
+    }
+    *start = it->second;
+    *size = it->second + S_;
+    *w = it->second + 2 * S_;
+    *window = e.axis.window;
+    *precision = e.axis.precision;
+    *first = e.first;
+    *last = e.last;
+  };
+  int n = 0;
+  for (; n < count; ++n) {
+    const int W = widths[n], H = heights[n];
+    if (imgs[n] == nullptr) return Status::Err(CLIPB200_ERR_INVALID_ARG, "null image pointer");
+    if (W <= 0 || H <= 0 || W > 32768 || H > 32768) return Status::Err(CLIPB200_ERR_INVALID_ARG, "bad image size");
+    const size_t bytes = static_cast<size_t>(W) * H * 3;
+    if (n > 0 && (src_bytes + bytes > rs_group_bytes_ || arena.size() > (size_t(8) << 20))) break;
+    ResizeJob j;
+    memset(&j, 0, sizeof(j));
+    j.W = W;
+    j.H = H;
+    j.src_off = static_cast<long long>(src_bytes);
+    j.dst_off = static_cast<long long>(static_cast<size_t>(n) * px);
+    j.tmp_off = static_cast<long long>(tmp_bytes);
+    size_t first_row = 0, n_rows = static_cast<size_t>(H);  // source rows that have to travel
+    if (W == S_ && H == S_) {
+      j.mode = 2;  // the convolution is the identity at the model resolution (and the crop box is the whole image)
+    } else {
+      double left, top, cw, ch;
+      resize_crop_box(W, H, S_, squash, &left, &top, &cw, &ch);
+      if (pp->interpolation > 1) {
+        j.mode = 1;  // ResizeAlg::Nearest (vision.rs:179)
+        j.left = left; j.top = top; j.sx = cw / S_; j.sy = ch / S_;
+      } else {
+        j.mode = 0;
+        int xf, xl, yf, yl;
+        place_axis(W, left, left + cw, &j.xstart, &j.xsize, &j.xw, &j.xwindow, &j.xprecision, &xf, &xl);
+        place_axis(H, top, top + ch, &j.ystart, &j.ysize, &j.yw, &j.ywindow, &j.yprecision, &yf, &yl);
+        // only the rows the vertical pass reads cross PCIe (a centre crop of a portrait photo skips the rest)
+        first_row = static_cast<size_t>(yf);
+        n_rows = static_cast<size_t>(std::max(yl - yf, 0));
+        j.y_first = yf;  // staged row r is source row yf + r
+        j.rows = static_cast<int>(n_rows);
+        tmp_bytes += n_rows * S_ * 3;
+        max_rows = std::max(max_rows, j.rows);
+      }
+    }
+    const size_t staged = n_rows * W * 3;
+    pieces.push_back({nullptr, imgs[n] + first_row * W * 3, staged});
+    src_bytes += (staged + 15) & ~size_t(15);
+    jobs.push_back(j);
   }
-  CUDA_RET(cudaMemcpyAsync(rs_src_, h_img, src_bytes, cudaMemcpyHostToDevice, compute_), "H2D copy");
-  ProfBegin(PC_PRE, compute_);
-  cudaError_t e = launch_resize(rs_src_, width, height, S_, *plan, rs_tmp_, d_dst, compute_);
-  ProfEnd(PC_PRE, compute_);
-  return Check(e, "resize");
+  *consumed = n;
+  ResizeStage* st = &rs_stage_[rs_groups_++ & 1];
+  if (st->in_flight) CUDA_RET(cudaEventSynchronize(st->free_ev), "wait resize staging");
+  RET_IF_ERR(GrowStage(st, src_bytes, tmp_bytes, arena.size(), jobs.size()));
+  {
+    size_t off = 0;
+    for (size_t i = 0; i < pieces.size(); ++i) {
+      pieces[i].dst = st->h_src + off;
+      off += (pieces[i].bytes + 15) & ~size_t(15);
+    }
+    parallel_copy(pieces);
+  }
+  memcpy(st->h_jobs, jobs.data(), jobs.size() * sizeof(ResizeJob));
+  if (!arena.empty()) memcpy(st->h_arena, arena.data(), arena.size() * 4);
+  ProfBegin(PC_H2D, copy_in_);
+  cudaError_t e = cudaMemcpyAsync(st->d_src, st->h_src, src_bytes, cudaMemcpyHostToDevice, copy_in_);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(st->d_jobs, st->h_jobs, jobs.size() * sizeof(ResizeJob), cudaMemcpyHostToDevice, copy_in_);
+  if (e == cudaSuccess && !arena.empty())
+    e = cudaMemcpyAsync(st->d_arena, st->h_arena, arena.size() * 4, cudaMemcpyHostToDevice, copy_in_);
+  ProfEnd(PC_H2D, copy_in_);
+  CUDA_RET(e, "H2D copy");
+  ProfBegin(PC_PRE, copy_in_);
+  e = launch_resize_batched(st->d_src, st->d_jobs, st->d_arena, n, S_, max_rows, st->d_tmp, d_dst, copy_in_);
+  ProfEnd(PC_PRE, copy_in_);
+  if (max_rows > 0) ++launch_count;  // two launches per group (ProfBegin counted one)
+  CUDA_RET(e, "resize");
+  CUDA_RET(cudaEventRecord(st->free_ev, copy_in_), "record");
+  st->in_flight = true;
+  return Status::OK();
 }
 
 Status Engine::ResizeRgb8(const uint8_t* img, int width, int height, const clipb200_preproc* pp, uint8_t* out) {
@@ -997,33 +1178,71 @@ Status Engine::ResizeRgb8(const uint8_t* img, int width, int height, const clipb
   if (img == nullptr || out == nullptr || pp == nullptr) return Status::Err(CLIPB200_ERR_INVALID_ARG, "null buffer");
   CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
   uint8_t* dst = static_cast<uint8_t*>(d_in_[0]);
-  RET_IF_ERR(ResizeToDevice(img, width, height, pp, dst));
-  CUDA_RET(cudaMemcpyAsync(out, dst, static_cast<size_t>(S_) * S_ * 3, cudaMemcpyDeviceToHost, compute_), "D2H copy");
-  CUDA_RET(cudaStreamSynchronize(compute_), "sync");
+  const int32_t w = width, h = height;
+  int consumed = 0;
+  RET_IF_ERR(ResizeGroupToDevice(&img, &w, &h, 1, pp, dst, &consumed));
+  CUDA_RET(cudaMemcpyAsync(out, dst, static_cast<size_t>(S_) * S_ * 3, cudaMemcpyDeviceToHost, copy_in_), "D2H copy");
+  CUDA_RET(cudaStreamSynchronize(copy_in_), "sync");
   return Status::OK();
 }
 
+// embed_images(&[DynamicImage]) for photos of any size (vision.rs:102-117 with the resize of :164-198 on the GPU).
+// Same three-stream pipeline as RunPipelined: while the tower of micro-batch i runs on the compute stream, the host
+// stages micro-batch i+1's photos group by group and the copy-in stream uploads and resizes them into the other slot.
 Status Engine::VisionEmbedRgb8Var(const uint8_t* const* imgs, const int32_t* widths, const int32_t* heights, int64_t batch,
                                   const clipb200_preproc* pp, float* out) {
   if (kind != CLIPB200_KIND_VISION) return Status::Err(CLIPB200_ERR_INVALID_ARG, "not a vision engine");
   if (batch <= 0) return Status::Err(CLIPB200_ERR_INVALID_ARG, "Empty batch");
-  if (imgs == nullptr || widths == nullptr || heights == nullptr || out == nullptr)
+  if (imgs == nullptr || widths == nullptr || heights == nullptr || out == nullptr || pp == nullptr)
     return Status::Err(CLIPB200_ERR_INVALID_ARG, "null buffer");
   CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
   RET_IF_ERR(SetPreproc(pp));
   const size_t px = static_cast<size_t>(S_) * S_ * 3;
-  for (int64_t s = 0; s * mb_ < batch; ++s) {
+  cudaPointerAttributes attr;
+  const bool out_pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  const int64_t steps = (batch + mb_ - 1) / mb_;
+  Status st = Status::OK();
+  for (int64_t s = 0; s < steps && st.ok(); ++s) {
+    const int slot = static_cast<int>(s & 1);
     const int n = static_cast<int>(std::min<int64_t>(mb_, batch - s * mb_));
-    uint8_t* slot = static_cast<uint8_t*>(d_in_[0]);
-    for (int i = 0; i < n; ++i) {
+    if (s >= 2) CUDA_RET(cudaStreamWaitEvent(copy_in_, in_consumed_[slot], 0), "wait consumed");
+    uint8_t* d_slot = static_cast<uint8_t*>(d_in_[slot]);
+    for (int i = 0; i < n && st.ok();) {
       const int64_t g = s * mb_ + i;
-      if (imgs[g] == nullptr) return Status::Err(CLIPB200_ERR_INVALID_ARG, "null image pointer");
-      RET_IF_ERR(ResizeToDevice(imgs[g], widths[g], heights[g], pp, slot + static_cast<size_t>(i) * px));
+      int consumed = 0;
+      st = ResizeGroupToDevice(imgs + g, widths + g, heights + g, n - i, pp, d_slot + static_cast<size_t>(i) * px, &consumed);
+      i += consumed;
     }
-    RET_IF_ERR(ForwardVision(n, slot, nullptr, d_out_[0]));
-    CUDA_RET(cudaMemcpyAsync(out + static_cast<size_t>(s) * mb_ * E_, d_out_[0], static_cast<size_t>(n) * E_ * 4,
-                             cudaMemcpyDeviceToHost, compute_), "D2H copy");
-    CUDA_RET(cudaStreamSynchronize(compute_), "sync");
+    if (!st.ok()) break;
+    CUDA_RET(cudaEventRecord(in_ready_[slot], copy_in_), "record");
+    CUDA_RET(cudaStreamWaitEvent(compute_, in_ready_[slot], 0), "wait input");
+    if (s >= 2) CUDA_RET(cudaStreamWaitEvent(compute_, out_copied_[slot], 0), "wait output slot");
+    st = ForwardSlot(0, n, slot);
+    if (!st.ok()) break;
+    CUDA_RET(cudaEventRecord(in_consumed_[slot], compute_), "record");
+    CUDA_RET(cudaEventRecord(out_ready_[slot], compute_), "record");
+    CUDA_RET(cudaStreamWaitEvent(copy_out_, out_ready_[slot], 0), "wait output");
+    ProfBegin(PC_D2H, copy_out_);
+    cudaError_t e = cudaMemcpyAsync(out_pinned ? out + static_cast<size_t>(s) * mb_ * E_ : h_out_[slot], d_out_[slot],
+                                    static_cast<size_t>(n) * E_ * 4, cudaMemcpyDeviceToHost, copy_out_);
+    ProfEnd(PC_D2H, copy_out_);
+    CUDA_RET(e, "D2H copy");
+    CUDA_RET(cudaEventRecord(out_copied_[slot], copy_out_), "record");
+    if (!out_pinned && s >= 1) {  // drain the previous step's output while this one runs
+      const int ps = static_cast<int>((s - 1) & 1);
+      const int pn = static_cast<int>(std::min<int64_t>(mb_, batch - (s - 1) * mb_));
+      CUDA_RET(cudaEventSynchronize(out_copied_[ps]), "wait D2H");
+      memcpy(out + static_cast<size_t>(s - 1) * mb_ * E_, h_out_[ps], static_cast<size_t>(pn) * E_ * 4);
+    }
+  }
+  Status sync = Synchronize();
+  if (!st.ok()) return st;
+  RET_IF_ERR(sync);
+  if (!out_pinned) {
+    const int64_t s = steps - 1;
+    const int n = static_cast<int>(std::min<int64_t>(mb_, batch - s * mb_));
+    memcpy(out + static_cast<size_t>(s) * mb_ * E_, h_out_[s & 1], static_cast<size_t>(n) * E_ * 4);
   }
   return Status::OK();
 }

@@ -13,6 +13,7 @@
 #include "../../include/clipb200.h"
 #include <map>
 #include <tuple>
+#include <utility>
 
 #include "onnx_graph.h"
 #include "onnx_loader.h"
@@ -130,12 +131,43 @@ class Engine {
   };
   std::map<std::tuple<int, int, int>, GraphEntry> graphs_;
   int graph_max_n_ = 32;
-  // resize plans (coefficient tables) cached per (width, height, interpolation, squash)
-  Status GetResizePlan(int width, int height, int interpolation, bool squash, const ResizePlanDev** plan);
-  Status ResizeToDevice(const uint8_t* h_img, int width, int height, const clipb200_preproc* pp, uint8_t* d_dst);
-  std::map<std::tuple<int, int, int, int>, ResizePlanDev> resize_plans_;
-  uint8_t *rs_src_ = nullptr, *rs_tmp_ = nullptr;
-  size_t rs_src_bytes_ = 0, rs_tmp_bytes_ = 0;
+  // ---- arbitrary-size images (vision.rs:164-198 on the GPU) ----
+  // Coefficient tables are cached on the HOST per axis (source extent, crop interval, filter): the x and y tables of an
+  // image are independent, a photo corpus has far fewer distinct axes than distinct sizes, and nothing per size lives
+  // in HBM.  The cache is an LRU bounded by entries and bytes.
+  struct AxisKey {
+    int in_size, interp;
+    uint64_t in0_bits, in1_bits;
+    bool operator<(const AxisKey& o) const {
+      return std::tie(in_size, interp, in0_bits, in1_bits) < std::tie(o.in_size, o.interp, o.in0_bits, o.in1_bits);
+    }
+  };
+  struct AxisEntry {
+    ResizeAxis axis;
+    uint64_t tick = 0;
+    size_t bytes = 0;
+    int first = 0, last = 0;  // union of the source windows [first, last)
+  };
+  std::map<AxisKey, AxisEntry> axis_cache_;
+  uint64_t axis_tick_ = 0;
+  size_t axis_cache_bytes_ = 0;
+  const AxisEntry& GetAxis(int in_size, double in0, double in1, int interpolation);
+  // Images are resized in groups of bounded source bytes; two staging sets (pinned host + device: sources, coefficient
+  // arena, jobs, intermediate) alternate so the host fills one while the copy stream drains the other.
+  struct ResizeStage {
+    uint8_t *h_src = nullptr, *d_src = nullptr, *d_tmp = nullptr;
+    int32_t *h_arena = nullptr, *d_arena = nullptr;
+    ResizeJob *h_jobs = nullptr, *d_jobs = nullptr;
+    size_t src_cap = 0, tmp_cap = 0, arena_cap = 0, jobs_cap = 0;
+    cudaEvent_t free_ev = nullptr;
+    bool in_flight = false;
+  };
+  ResizeStage rs_stage_[2];
+  uint64_t rs_groups_ = 0;
+  size_t rs_group_bytes_ = size_t(192) << 20;
+  Status ResizeGroupToDevice(const uint8_t* const* imgs, const int32_t* widths, const int32_t* heights, int count,
+                             const clipb200_preproc* pp, uint8_t* d_dst, int* consumed);
+  Status GrowStage(ResizeStage* st, size_t src, size_t tmp, size_t arena_words, size_t jobs);
   bool fastvit_ = false;
   ConvW fv_stem0_, fv_stem1_, fv_final_;
   LinearW fv_stem2_;

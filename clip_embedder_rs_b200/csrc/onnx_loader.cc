@@ -338,6 +338,26 @@ std::string OnnxModel::meta(const std::string& key, const std::string& dflt) con
   return it == metadata.end() ? dflt : it->second;
 }
 
+// A relative path whose components never step out of the directory it is joined to.
+static bool external_location_is_safe(const std::string& loc) {
+  if (loc.empty() || loc[0] == '/' || loc[0] == '\\' || loc.find('\0') != std::string::npos) return false;
+  if (loc.size() >= 2 && loc[1] == ':') return false;  // drive letter
+  size_t i = 0;
+  int depth = 0;
+  while (i <= loc.size()) {
+    size_t j = loc.find_first_of("/\\", i);
+    if (j == std::string::npos) j = loc.size();
+    const std::string part = loc.substr(i, j - i);
+    if (part == "..") {
+      if (--depth < 0) return false;
+    } else if (!part.empty() && part != ".") {
+      ++depth;
+    }
+    i = j + 1;
+  }
+  return depth > 0;
+}
+
 bool load_onnx(const std::string& path, OnnxModel* model, std::string* err) {
   auto mf = map_file(path, err);
   if (!mf) return false;
@@ -391,6 +411,13 @@ bool load_onnx(const std::string& path, OnnxModel* model, std::string* err) {
           if (ext.present) {
             if (ext.location.empty()) {
               *err = "initializer '" + t.name + "' has external data without a location";
+              return false;
+            }
+            // onnxruntime refuses external-data locations that leave the model directory; so does this loader (an
+            // untrusted .onnx must not be able to map /etc/... or ../secrets through `location`)
+            if (!external_location_is_safe(ext.location)) {
+              *err = "initializer '" + t.name + "' external data location '" + ext.location +
+                     "' is absolute or escapes the model directory";
               return false;
             }
             auto it = ext_files.find(ext.location);

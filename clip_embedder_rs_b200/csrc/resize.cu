@@ -3,7 +3,8 @@
 // box for every resize_mode except "squash".  Arithmetic follows fast_image_resize 6.0.0's U8x3 path as recalled
 // (Pillow-SIMD scheme): f64 weights normalised per output pixel, converted to i16 at the largest precision that
 // keeps the biggest weight below 2^15, integer accumulation, u8 intermediate between the horizontal and the vertical
-// pass.  The coefficient tables are built on the host (tiny) and cached per source size; the passes are HBM-bound.
+// pass.  The coefficient tables are built on the host (tiny, cached per axis by the engine) and travel with each group of
+// images; a whole group is resized by two launches (blockIdx.z = image); the passes are HBM-bound.
 #include "resize.cuh"
 
 #include <math.h>
@@ -78,67 +79,66 @@ ResizeAxis make_resize_axis(int in_size, double in0, double in1, int out_size, i
   return ax;
 }
 
-// horizontal pass: src [H, W, 3] rows y_first.. -> tmp [rows, S, 3]
+// ---- batched variants: blockIdx.z = image of the group ------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-resize_h_kernel(const uint8_t* __restrict__ src, int W, int y_first, int rows, int S, const int* __restrict__ start,
-                const int* __restrict__ size, const int16_t* __restrict__ w, int window, int precision,
-                uint8_t* __restrict__ tmp) {
+resize_h_batched_kernel(const uint8_t* __restrict__ src, const ResizeJob* __restrict__ jobs,
+                        const int32_t* __restrict__ arena, int S, uint8_t* __restrict__ tmp) {
+  const ResizeJob& j = jobs[blockIdx.z];
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
-  if (ox >= S || r >= rows) return;
-  const uint8_t* row = src + (static_cast<long long>(y_first + r) * W + start[ox]) * 3;
-  const int16_t* ww = w + static_cast<long long>(ox) * window;
-  const int n = size[ox];
-  const int half = precision > 0 ? (1 << (precision - 1)) : 0;
+  if (j.mode != 0 || ox >= S || r >= j.rows) return;
+  const int x0 = arena[j.xstart + ox], n = arena[j.xsize + ox];
+  const uint8_t* row = src + j.src_off + (static_cast<long long>(r) * j.W + x0) * 3;  // staged row r = source row y_first + r
+  const int16_t* ww = reinterpret_cast<const int16_t*>(arena + j.xw) + static_cast<long long>(ox) * j.xwindow;
+  const int half = j.xprecision > 0 ? (1 << (j.xprecision - 1)) : 0;
   int a0 = half, a1 = half, a2 = half;
   for (int i = 0; i < n; ++i) {
     const int c = ww[i];
     a0 += row[3 * i] * c; a1 += row[3 * i + 1] * c; a2 += row[3 * i + 2] * c;
   }
-  uint8_t* o = tmp + (static_cast<long long>(r) * S + ox) * 3;
-  o[0] = static_cast<uint8_t>(min(max(a0 >> precision, 0), 255));
-  o[1] = static_cast<uint8_t>(min(max(a1 >> precision, 0), 255));
-  o[2] = static_cast<uint8_t>(min(max(a2 >> precision, 0), 255));
+  uint8_t* o = tmp + j.tmp_off + (static_cast<long long>(r) * S + ox) * 3;
+  o[0] = static_cast<uint8_t>(min(max(a0 >> j.xprecision, 0), 255));
+  o[1] = static_cast<uint8_t>(min(max(a1 >> j.xprecision, 0), 255));
+  o[2] = static_cast<uint8_t>(min(max(a2 >> j.xprecision, 0), 255));
 }
-// vertical pass: tmp [rows, S, 3] -> dst [S, S, 3]
 __global__ void __launch_bounds__(256)
-resize_v_kernel(const uint8_t* __restrict__ tmp, int y_first, int S, const int* __restrict__ start,
-                const int* __restrict__ size, const int16_t* __restrict__ w, int window, int precision,
-                uint8_t* __restrict__ dst) {
+resize_v_batched_kernel(const uint8_t* __restrict__ src, const uint8_t* __restrict__ tmp,
+                        const ResizeJob* __restrict__ jobs, const int32_t* __restrict__ arena, int S,
+                        uint8_t* __restrict__ dst) {
+  const ResizeJob& j = jobs[blockIdx.z];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over S*3 bytes of one output row
   const int oy = blockIdx.y;
   if (idx >= S * 3) return;
-  const int16_t* ww = w + static_cast<long long>(oy) * window;
-  const int n = size[oy];
-  const uint8_t* col = tmp + static_cast<long long>(start[oy] - y_first) * S * 3 + idx;
-  int acc = precision > 0 ? (1 << (precision - 1)) : 0;
+  uint8_t* out = dst + j.dst_off + static_cast<long long>(oy) * S * 3 + idx;
+  if (j.mode == 2) {  // already at the model resolution: the convolution is the identity
+    *out = src[j.src_off + static_cast<long long>(oy) * S * 3 + idx];
+    return;
+  }
+  if (j.mode == 1) {  // ResizeAlg::Nearest (vision.rs:179)
+    const int ox = idx / 3, c = idx - ox * 3;
+    const int x = min(static_cast<int>(floor(j.left + (ox + 0.5) * j.sx)), j.W - 1);
+    const int y = min(static_cast<int>(floor(j.top + (oy + 0.5) * j.sy)), j.H - 1);
+    *out = src[j.src_off + (static_cast<long long>(y) * j.W + x) * 3 + c];
+    return;
+  }
+  const int y0 = arena[j.ystart + oy], n = arena[j.ysize + oy];
+  const int16_t* ww = reinterpret_cast<const int16_t*>(arena + j.yw) + static_cast<long long>(oy) * j.ywindow;
+  const uint8_t* col = tmp + j.tmp_off + static_cast<long long>(y0 - j.y_first) * S * 3 + idx;
+  int acc = j.yprecision > 0 ? (1 << (j.yprecision - 1)) : 0;
   for (int i = 0; i < n; ++i) acc += col[static_cast<long long>(i) * S * 3] * static_cast<int>(ww[i]);
-  dst[static_cast<long long>(oy) * S * 3 + idx] = static_cast<uint8_t>(min(max(acc >> precision, 0), 255));
-}
-__global__ void __launch_bounds__(256)
-resize_nearest_kernel(const uint8_t* __restrict__ src, int W, int H, int S, double left, double top, double sx, double sy,
-                      uint8_t* __restrict__ dst) {
-  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
-  if (ox >= S) return;
-  const int x = min(static_cast<int>(floor(left + (ox + 0.5) * sx)), W - 1);
-  const int y = min(static_cast<int>(floor(top + (oy + 0.5) * sy)), H - 1);
-  const uint8_t* p = src + (static_cast<long long>(y) * W + x) * 3;
-  uint8_t* o = dst + (static_cast<long long>(oy) * S + ox) * 3;
-  o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+  *out = static_cast<uint8_t>(min(max(acc >> j.yprecision, 0), 255));
 }
 
-cudaError_t launch_resize(const uint8_t* d_src, int W, int H, int S, const ResizePlanDev& plan, uint8_t* d_tmp, uint8_t* d_dst,
-                          cudaStream_t st) {
-  if (plan.nearest) {
-    resize_nearest_kernel<<<dim3((S + 255) / 256, S), 256, 0, st>>>(d_src, W, H, S, plan.left, plan.top, plan.sx, plan.sy, d_dst);
-    return cudaGetLastError();
+cudaError_t launch_resize_batched(const uint8_t* d_src, const ResizeJob* d_jobs, const int32_t* d_arena, int n, int S,
+                                  int max_rows, uint8_t* d_tmp, uint8_t* d_dst, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  if (n > 65535 || max_rows > 65535) return cudaErrorInvalidValue;
+  if (max_rows > 0) {
+    resize_h_batched_kernel<<<dim3((S + 255) / 256, max_rows, n), 256, 0, st>>>(d_src, d_jobs, d_arena, S, d_tmp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
   }
-  resize_h_kernel<<<dim3((S + 255) / 256, plan.rows), 256, 0, st>>>(d_src, W, plan.y_first, plan.rows, S, plan.xstart, plan.xsize,
-                                                                     plan.xw, plan.xwindow, plan.xprecision, d_tmp);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  resize_v_kernel<<<dim3((S * 3 + 255) / 256, S), 256, 0, st>>>(d_tmp, plan.y_first, S, plan.ystart, plan.ysize, plan.yw,
-                                                                 plan.ywindow, plan.yprecision, d_dst);
+  resize_v_batched_kernel<<<dim3((S * 3 + 255) / 256, S, n), 256, 0, st>>>(d_src, d_tmp, d_jobs, d_arena, S, d_dst);
   return cudaGetLastError();
 }
 

@@ -12,19 +12,23 @@ struct ResizeAxis {  // host-side coefficient table of one axis
   std::vector<int16_t> w;  // [out][window]
   int window = 0, precision = 0;
 };
-struct ResizePlanDev {  // device-resident plan for one (source size, target size, filter, crop mode)
-  bool nearest = false;
-  int *xstart = nullptr, *xsize = nullptr, *ystart = nullptr, *ysize = nullptr;
-  int16_t *xw = nullptr, *yw = nullptr;
-  int xwindow = 0, ywindow = 0, xprecision = 0, yprecision = 0;
-  int y_first = 0, rows = 0;
-  double left = 0, top = 0, sx = 1, sy = 1;
+// One image of a batched resize (clipb200_vision_embed_rgb8_var): offsets into the group's source staging buffer, its
+// coefficient arena (int32 words: per axis `start[S]`, `size[S]`, then `w[S][window]` as int16) and its intermediate.
+struct ResizeJob {
+  long long src_off, tmp_off, dst_off;  // bytes
+  int W, H;
+  int mode;                             // 0 two-pass convolution, 1 nearest, 2 copy (already S x S)
+  int y_first, rows;                    // source rows [y_first, y_first + rows) are staged at src_off (mode 0)
+  int xstart, xsize, xw, ystart, ysize, yw;  // word offsets into the arena
+  int xwindow, ywindow, xprecision, yprecision;
+  double left, top, sx, sy;             // nearest only
 };
+// Resizes `n` images with two launches (horizontal pass into d_tmp, vertical pass / nearest / copy into d_dst).
+// `max_rows` = the largest job.rows of the group (grid height of the horizontal pass).
+cudaError_t launch_resize_batched(const uint8_t* d_src, const ResizeJob* d_jobs, const int32_t* d_arena, int n, int S,
+                                  int max_rows, uint8_t* d_tmp, uint8_t* d_dst, cudaStream_t st);
 
 void resize_crop_box(int width, int height, int size, bool squash, double* left, double* top, double* cw, double* ch);
 ResizeAxis make_resize_axis(int in_size, double in0, double in1, int out_size, int interpolation /*0 cubic, 1 linear*/);
-// d_src [H,W,3] u8 -> d_dst [S,S,3] u8; d_tmp holds plan.rows * S * 3 bytes
-cudaError_t launch_resize(const uint8_t* d_src, int W, int H, int S, const ResizePlanDev& plan, uint8_t* d_tmp, uint8_t* d_dst,
-                          cudaStream_t st);
 
 }  // namespace clipb200

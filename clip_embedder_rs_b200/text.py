@@ -35,7 +35,7 @@ class TextEmbedder:
 
     @classmethod
     def _load(cls, model_dir: Path, execution_providers=None, device: int = 0, micro_batch: int = 0,
-              profile: bool = False) -> "TextEmbedder":
+              profile: bool = False, devices=None) -> "TextEmbedder":
         try:
             from tokenizers import Tokenizer
         except ImportError as e:  # pragma: no cover
@@ -43,7 +43,7 @@ class TextEmbedder:
         model_manager.verify_model_dir(model_dir)
         self = cls.__new__(cls)
         self.model_config = ModelConfig.from_file(model_dir / "model_config.json")
-        self.session = OnnxSession(model_dir / "text.onnx", execution_providers, device, micro_batch, profile)
+        self.session = OnnxSession(model_dir / "text.onnx", execution_providers, device, micro_batch, profile, devices)
         self.config = OpenClipConfig.from_file(model_dir / "open_clip_config.json")
         try:
             tokenizer = Tokenizer.from_file(str(model_dir / "tokenizer.json"))
@@ -64,7 +64,7 @@ class TextEmbedder:
         self._id_name = id_name
         self._mask_name: Optional[str] = self.session.find_input(["attention_mask"])
         self.model_dir = Path(model_dir)
-        self._kw = dict(device=device, micro_batch=micro_batch, profile=profile)
+        self._kw = dict(device=device, micro_batch=micro_batch, profile=profile, devices=devices)
         return self
 
     def duplicate(self) -> "TextEmbedder":  # text.rs:104-108
@@ -104,7 +104,5 @@ class TextEmbedder:
         if mask is not None:
             mask = np.ascontiguousarray(mask, dtype=np.int64)
             mptr = mask.ctypes.data
-        with self.session._lock:
-            self.session.check(_native.lib.clipb200_text_embed(self.session.handle, ids.ctypes.data, mptr,
-                                                               ids.shape[0], ids.shape[1], out.ctypes.data))
+        self.session.run_ids(ids.ctypes.data, mptr, ids.shape[0], ids.shape[1], out.ctypes.data)
         return out

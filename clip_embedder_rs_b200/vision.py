@@ -51,6 +51,12 @@ class _Builder:
         self._kw["device"] = int(index)
         return self
 
+    def devices(self, indices: Sequence[int]):
+        """In-process multi-GPU pool: one replica per listed CUDA device (`[]` = all visible), batches split row-wise
+        (what N `duplicate()`s of vision.rs:87-91 and a caller-side split would do)."""
+        self._kw["devices"] = [int(i) for i in indices]
+        return self
+
     def micro_batch(self, n: int):
         self._kw["micro_batch"] = int(n)
         return self
@@ -108,10 +114,10 @@ class VisionEmbedder:
 
     @classmethod
     def _load(cls, model_dir: Path, execution_providers=None, device: int = 0, micro_batch: int = 0,
-              profile: bool = False) -> "VisionEmbedder":
+              profile: bool = False, devices=None) -> "VisionEmbedder":
         model_manager.verify_model_dir(model_dir)
         self = cls.__new__(cls)
-        self.session = OnnxSession(model_dir / "visual.onnx", execution_providers, device, micro_batch, profile)
+        self.session = OnnxSession(model_dir / "visual.onnx", execution_providers, device, micro_batch, profile, devices)
         self.config = OpenClipConfig.from_file(model_dir / "open_clip_config.json")
         self.model_config = ModelConfig.from_file(model_dir / "model_config.json")
         name = self.session.find_input(["pixel_values", "input"])
@@ -119,7 +125,7 @@ class VisionEmbedder:
             raise error.Config("Could not find vision input node")
         self.input_name = name
         self.model_dir = Path(model_dir)
-        self._kw = dict(device=device, micro_batch=micro_batch, profile=profile)
+        self._kw = dict(device=device, micro_batch=micro_batch, profile=profile, devices=devices)
         pc = self.config.preprocess_cfg
         self._pp = _native.Preproc((pc.mean[0], pc.mean[1], pc.mean[2]), (pc.std[0], pc.std[1], pc.std[2]),
                                    _INTERP.get(pc.interpolation, 2), _RESIZE.get(pc.resize_mode, 0))
@@ -135,7 +141,8 @@ class VisionEmbedder:
         if isinstance(images, np.ndarray) and images.ndim == 4:
             if images.dtype != np.uint8 or images.shape[3] != 3:
                 raise error.Image(f"Image error: expected uint8 [B,H,W,3], got {images.dtype} {images.shape}")
-            return images
+            # the engine reads packed RGB through raw pointers: a strided view (rgba[..., :3], a flip) must be copied
+            return np.ascontiguousarray(images)
         return [np.ascontiguousarray(_to_rgb8(im)) for im in images]
 
     def _pack(self, images: Sequence):
@@ -161,15 +168,12 @@ class VisionEmbedder:
         batch, arrs = self._pack(images)
         n = len(arrs)
         out = np.empty((n, self.session.embed_dim), dtype=np.float32)
-        with self.session._lock:
-            if batch is not None:
-                size = batch.shape[1]
-                self.session.check(_native.lib.clipb200_vision_embed_rgb8(
-                    self.session.handle, batch.ctypes.data, n, size, size, self._pp, out.ctypes.data))
-            else:  # arbitrary sizes: resize (vision.rs:164-198) on the GPU
-                ptrs, ws, hs = self._pointer_arrays(arrs)
-                self.session.check(_native.lib.clipb200_vision_embed_rgb8_var(
-                    self.session.handle, ptrs, ws.ctypes.data, hs.ctypes.data, n, self._pp, out.ctypes.data))
+        if batch is not None:
+            size = batch.shape[1]
+            self.session.run_rgb8(batch.ctypes.data, n, size, size, self._pp, out.ctypes.data)
+        else:  # arbitrary sizes: resize (vision.rs:164-198) on the GPU
+            ptrs, ws, hs = self._pointer_arrays(arrs)
+            self.session.run_rgb8_var(ptrs, ws.ctypes.data, hs.ctypes.data, n, self._pp, out.ctypes.data)
         return out
 
     def resize(self, image) -> np.ndarray:

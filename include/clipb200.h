@@ -119,7 +119,9 @@ int clipb200_resize_rgb8(clipb200_engine* e, const uint8_t* image, int32_t width
 /* The reference's public `preprocess_batch` (src/vision.rs:120-135): same inputs, out f32 [B,3,S,S]; bit-exact. */
 int clipb200_preprocess_rgb8(clipb200_engine* e, const uint8_t* hwc, int64_t batch, int32_t width, int32_t height,
                              const clipb200_preproc* pp, float* out_nchw);
-/* input_ids i64 [B,ctx] (attention_mask accepted and ignored, like graphs without that input: src/text.rs:156-161) */
+/* input_ids i64 [B,ctx].  Graphs written by pull_onnx.py have no attention_mask input (padding is handled inside the
+ * graph: argmax / last-token pooling, src/text.rs:156-161 then passes none) and the pointer is not read; a graph that
+ * DOES declare an attention_mask input is refused by clipb200_engine_create with CLIPB200_ERR_UNSUPPORTED. */
 int clipb200_text_embed(clipb200_engine* e, const int64_t* input_ids, const int64_t* attention_mask_or_null,
                         int64_t batch, int64_t ctx, float* out);
 /* probs[i] = act( fma(dot(A[i,:], b), scale, bias) ), softmax taken over all n rows.  src/clip.rs:102-121 */
@@ -136,6 +138,32 @@ int clipb200_corpus_append(clipb200_corpus* c, const float* rows, int64_t n);   
 int64_t clipb200_corpus_size(const clipb200_corpus* c);
 int clipb200_corpus_rank(clipb200_corpus* c, const float* query, float scale, float bias, int activation,
                          float* probs /* host [size] */);
+
+/* ---- in-process multi-GPU pool: `duplicate()` (src/vision.rs:87-91, src/text.rs:104-108, src/clip.rs:69-73) for the
+ * GPUs of one box.  One engine replica and one host thread per device; a call splits the batch into contiguous row
+ * ranges (the first batch % n replicas take one extra row), every replica runs its own H2D / compute / D2H pipeline
+ * and writes its embeddings straight into its rows of `out`.  No collective on the data path.  `devices` NULL or
+ * n_devices <= 0 = all visible devices.  Results are bit-identical to a single engine's (same kernels, rows are
+ * independent).  A pool handle is not re-entrant, like an engine handle. */
+typedef struct clipb200_pool clipb200_pool;
+int clipb200_pool_create(const char* onnx_path, const int32_t* devices, int32_t n_devices,
+                         const clipb200_opts* opts_or_null, clipb200_pool** out);
+void clipb200_pool_destroy(clipb200_pool* p);
+int clipb200_pool_size(const clipb200_pool* p);                 /* number of replicas */
+int clipb200_pool_device(const clipb200_pool* p, int replica);  /* CUDA device index of a replica, -1 if out of range */
+int clipb200_pool_kind(const clipb200_pool* p);
+int64_t clipb200_pool_embed_dim(const clipb200_pool* p);
+int64_t clipb200_pool_image_size(const clipb200_pool* p);
+int64_t clipb200_pool_context_length(const clipb200_pool* p);
+int clipb200_pool_num_inputs(const clipb200_pool* p);           /* src/onnx.rs:32-46 on replica 0 */
+const char* clipb200_pool_input_name(const clipb200_pool* p, int i);
+int64_t clipb200_pool_launch_count(const clipb200_pool* p);     /* kernels launched by all replicas so far */
+int clipb200_pool_vision_embed_rgb8(clipb200_pool* p, const uint8_t* hwc, int64_t batch, int32_t width, int32_t height,
+                                    const clipb200_preproc* pp, float* out);
+int clipb200_pool_vision_embed_rgb8_var(clipb200_pool* p, const uint8_t* const* images, const int32_t* widths,
+                                        const int32_t* heights, int64_t batch, const clipb200_preproc* pp, float* out);
+int clipb200_pool_text_embed(clipb200_pool* p, const int64_t* input_ids, const int64_t* attention_mask_or_null,
+                             int64_t batch, int64_t ctx, float* out);
 
 /* ---- run: device-resident buffers (benchmark "value": inputs already in HBM) --------------------------- */
 int clipb200_vision_embed_rgb8_device(clipb200_engine* e, const uint8_t* d_hwc, int64_t batch,
