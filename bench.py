@@ -52,6 +52,8 @@ WORKLOADS = {
                               "MobileCLIP2-S4 (FastViT-MCi4, 5 stages) vision embedding, batch 256 per GPU"),
     "mobileclip2_text": ("mobileclip2_s2", "text", 256, 5.96, "texts/s", "MobileCLIP2-S2 text encoder, batch 256, context 77"),
     "small_vision": ("small_siglip", "vision", 256, 0.0, "images/s", "small SigLIP-shaped test tower"),
+    "so400m_photos": ("so400m_siglip2_384", "vision", 56, 518.94, "images/s",
+                      "ViT-SO400M-16-SigLIP2-384 embed_images on photo-sized inputs (GPU resize included)"),
 }
 
 
@@ -210,6 +212,176 @@ def run_reference_arm(args, wl, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# Sizes of the reference's example photos (assets/img/*.jpg, width x height): the inputs `embed_images(&[DynamicImage])`
+# sees in its README / integration test.  Content is synthetic; only the sizes matter for resize + PCIe cost.
+PHOTO_SIZES = [(4608, 3456), (2592, 1944), (5312, 2988), (4160, 2336), (4608, 3456), (1944, 2592), (2592, 1456)]
+
+
+def pinned_u8(lib, nbytes):
+    import numpy as np
+
+    p = lib.clipb200_host_alloc(nbytes)
+    if not p:
+        raise RuntimeError("pinned allocation failed")
+    return p, np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
+
+def run_pool(args):
+    """`--pool`: ONE host process drives N GPUs through the in-process pool (clipb200_pool_*), the deployment shape of a
+    Rust drop-in (one `VisionEmbedder` serving a caller's batch).  End to end only: pinned host uint8 in, host fp32
+    out, every replica running its own H2D / compute / D2H pipeline.  Not the driver's scaling line (that stays
+    torchrun); results go to profiles/r02_pool_*gpu.json."""
+    import numpy as np
+
+    import clip_embedder_rs_b200 as cb
+    from clip_embedder_rs_b200 import _native
+
+    lib = _native.lib
+    config, tower, batch, gflop, unit, desc = WORKLOADS[args.workload]
+    if args.batch > 0:
+        batch = args.batch
+    n = args.gpus
+    mdir = model_dir_for(config, (tower,), 0, 1, lambda: None)
+    t0 = time.perf_counter()
+    build = cb.VisionEmbedder if tower == "vision" else cb.TextEmbedder
+    emb = build.from_local_dir(mdir).micro_batch(args.micro_batch).devices(list(range(n))).build()
+    load_s = time.perf_counter() - t0
+    sess = emb.session
+    E = sess.embed_dim
+    total = batch * n  # weak scaling: 1024 images per GPU, one caller-side batch of N*1024
+    rng = np.random.default_rng(4)
+    if tower == "vision":
+        size = sess.image_size
+        item = size * size * 3
+        h_in, host = pinned_u8(lib, total * item)
+        block = rng.integers(0, 256, size=min(len(host), 1 << 28), dtype=np.uint8)
+        for o in range(0, len(host), len(block)):
+            host[o:o + len(block)] = block[:len(host) - o]
+    else:
+        ctx = sess.context_length
+        item = ctx * 8
+        h_in, raw = pinned_u8(lib, total * item)
+        host = raw.view(np.int64).reshape(total, ctx)
+        host[:] = 0
+        lens = rng.integers(4, ctx - 1, size=total)
+        host[:, 0] = 49406
+        for i in range(total):
+            host[i, 1:lens[i]] = rng.integers(1, 49000, size=lens[i] - 1)
+            host[i, lens[i]] = 49407
+    h_out, out_raw = pinned_u8(lib, total * E * 4)
+
+    def step():
+        if tower == "vision":
+            sess.run_rgb8(h_in, total, size, size, emb._pp, h_out)
+        else:
+            sess.run_ids(h_in, None, total, ctx, h_out)
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    l0 = sess.launch_count
+    sampler = ClockSampler(0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    clocks = sampler.stop()
+    out = out_raw.view(np.float32).reshape(total, E)
+    norm_err = float(np.abs(np.linalg.norm(out[:: max(1, total // 64)], axis=1) - 1.0).max())
+    value = total * args.steps / el
+    line = {"mode": "pool", "metric": f"{args.workload} {unit} (one process, in-process pool)", "value": value, "unit": unit,
+            "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+            "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": desc, "per_gpu_batch": batch, "global_batch": total,
+                       "parallelism": f"one host process, {n} replicas, one host thread per replica, rows split "
+                                      "contiguously, no collective",
+                       "host_cores": os.cpu_count(), "pool_load_s": load_s},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": total * item, "d2h_bytes_per_step": total * E * 4},
+            "h2d_gb_per_s": total * item * args.steps / el / 1e9,
+            "per_gpu": value / n, "gpu_launches": sess.launch_count - l0, "clocks": clocks, "out_norm_err": norm_err}
+    print(json.dumps(line), flush=True)
+    sess.close()
+
+
+def run_photos(args):
+    """`--workload so400m_photos`: `embed_images(&[DynamicImage])` on photo-sized inputs (the sizes of the reference's
+    assets/img JPEGs, synthetic content, pageable host memory like a decoded `DynamicImage`): staging, H2D, GPU resize
+    (vision.rs:164-198), normalise and tower, all inside the timed region.  Reports images/s, the PCIe floor of the
+    same bytes, and the CPU oracle's resize rate next to the reference README's 10-20 ms per image."""
+    import numpy as np
+
+    import clip_embedder_rs_b200 as cb
+    from clip_embedder_rs_b200 import _native
+
+    lib = _native.lib
+    mdir = model_dir_for("so400m_siglip2_384", ("vision",), 0, 1, lambda: None)
+    emb = cb.VisionEmbedder.from_local_dir(mdir).micro_batch(args.micro_batch).profile(True).build()
+    sess = emb.session
+    rng = np.random.default_rng(4)
+    base = {}
+    for (w, h) in set(PHOTO_SIZES):  # one random texture per size, shifted per image (generation is not what is timed)
+        base[(w, h)] = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    imgs = []
+    for i in range(args.photos):
+        w, h = PHOTO_SIZES[i % len(PHOTO_SIZES)]
+        imgs.append(np.ascontiguousarray(np.roll(base[(w, h)], i * 17, axis=1)))
+    src_bytes = sum(a.nbytes for a in imgs)
+    for _ in range(max(1, min(args.warmup, 2))):
+        emb.embed_images(imgs)
+    sess.profile(reset=True)
+    l0 = sess.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = emb.embed_images(imgs)
+    el = time.perf_counter() - t0
+    prof = sess.profile(reset=True)
+    value = len(imgs) * args.steps / el
+    # PCIe floor: the same bytes from pinned memory, one plain H2D copy
+    h_p, host = pinned_u8(lib, 1 << 28)
+    d_p = lib.clipb200_device_alloc(0, 1 << 28)
+    lib.clipb200_memcpy_h2d(0, d_p, h_p, 1 << 28)
+    t1 = time.perf_counter()
+    for _ in range(4):
+        lib.clipb200_memcpy_h2d(0, d_p, h_p, 1 << 28)
+    pcie = 4 * (1 << 28) / (time.perf_counter() - t1)
+    # staging floor: one host thread copying the same photos pageable -> pinned
+    t1 = time.perf_counter()
+    n_st = 0
+    for a in imgs[:8]:
+        m = min(a.nbytes, 1 << 28)
+        host[:m] = a.reshape(-1)[:m]
+        n_st += m
+    memcpy_1t = n_st / (time.perf_counter() - t1)
+    # CPU baseline: the oracle's restatement of resize_with_fast_image_resize on the same photos
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import resize as RZ
+
+        t1 = time.perf_counter()
+        k = 0
+        for a in imgs[:2]:
+            RZ.resize_rgb8(a, 384, "bicubic", "squash")
+            k += 1
+        cpu_el = time.perf_counter() - t1
+        cpu = {"value": k / cpu_el, "unit": "images/s (resize only)", "cores": 1, "kind": "port",
+               "sample": f"{k} photos, oracle/resize.py (numpy) in {cpu_el:.1f} s; the reference README quotes 10-20 ms "
+                         "per image for its preprocessing on the author's CPU"}
+    ms = prof["ms"]
+    line = {"metric": "SigLIP2-SO400M-384 images/sec from photo-sized inputs (resize on the GPU)", "value": value,
+            "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"ViT-SO400M-16-SigLIP2-384 embed_images on {len(imgs)} photo-sized RGB8 images per step "
+                                   f"(sizes of the reference's assets/img: {sorted(set(PHOTO_SIZES))}), pageable host memory",
+                       "mean_photo_mb": src_bytes / len(imgs) / 1e6},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": src_bytes, "d2h_bytes_per_step": len(imgs) * out.shape[1] * 4},
+            "h2d_gb_per_s": src_bytes * args.steps / el / 1e9,
+            "pcie_floor": {"measured_h2d_gb_per_s": pcie / 1e9, "images_per_s": pcie / (src_bytes / len(imgs))},
+            "staging_floor_one_thread": {"memcpy_gb_per_s": memcpy_1t / 1e9, "images_per_s": memcpy_1t / (src_bytes / len(imgs))},
+            "kernel_ms_per_step": {k: v / args.steps for k, v in ms.items()},
+            "gpu_launches": sess.launch_count - l0, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    sess.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,6 +393,10 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text", action="store_true", help="skip the secondary text-encoder measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling and MobileCLIP2 extra keys")
+    ap.add_argument("--pool", action="store_true",
+                    help="ONE process feeding --gpus N devices through the in-process pool (clipb200_pool_*), no torchrun")
+    ap.add_argument("--photos", type=int, default=56, help="photos per step of --workload so400m_photos")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     wl = WORKLOADS[args.workload]
@@ -228,6 +404,12 @@ def main():
 
     if args.impl == "reference":
         run_reference_arm(args, wl, rank, world)
+        return
+    if args.workload == "so400m_photos":
+        run_photos(args)
+        return
+    if args.pool:
+        run_pool(args)
         return
 
     import numpy as np
@@ -265,10 +447,12 @@ def main():
     lib = _native.lib
     pk = peaks()
 
-    def measure(workload_name: str, steps: int, warmup: int, with_e2e: bool):
+    def measure(workload_name: str, steps: int, warmup: int, with_e2e: bool, batch_override: int = 0):
         config, tower, batch, gflop, unit, desc = WORKLOADS[workload_name]
         if args.batch > 0 and workload_name == args.workload:
             batch = args.batch
+        if batch_override > 0:
+            batch = batch_override
         mdir = model_dir_for(config, (tower,), rank, world, barrier)
         dev = local_rank
         if tower == "vision":
@@ -340,7 +524,7 @@ def main():
         prof = sess.profile(reset=True)
         launches = sess.launch_count - launches0
         dev_ms = max_over_ranks(ms.value)
-        res = {"unit": unit, "desc": desc, "batch": batch, "ms_per_step": dev_ms / steps,
+        res = {"unit": unit, "desc": desc, "batch": batch, "ms_per_step": dev_ms / steps, "steps": steps,
                "value": world * batch * steps / (dev_ms * 1e-3), "launches": launches, "prof": prof,
                "clocks": clocks, "gflop": gflop, "h2d": in_bytes, "d2h": out_bytes,
                "weight_bytes": sess.weight_bytes}
@@ -407,16 +591,63 @@ def main():
             cpu_baseline = {"value": None, "unit": unit, "cores": os.cpu_count(), "kind": "port",
                             "sample": f"failed: {e}"}
 
+    def class_rooflines(r):
+        """GEMM class in TFLOP/s and depthwise-conv class in GB/s from the live per-class CUDA-event times."""
+        ms, out = r["prof"]["ms"], {}
+        if ms["gemm"] > 0:
+            tf = r["prof"]["gemm_flops"] / (ms["gemm"] * 1e-3) / 1e12
+            out["gemm"] = {"bound": "tensor", "achieved": tf, "peak": pk["sustained"], "unit": "TFLOP/s",
+                           "frac": tf / pk["sustained"], "ms_per_step": ms["gemm"] / r["steps"]}
+        if ms.get("dwconv", 0) > 0:
+            gbs = r["prof"]["conv_bytes"] / (ms["dwconv"] * 1e-3) / 1e9
+            out["dwconv"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                             "ms_per_step": ms["dwconv"] / r["steps"],
+                             "note": "algorithmic bytes (input + output once) of every depthwise conv launch"}
+        out["kernel_ms_per_step"] = {k: v / r["steps"] for k, v in ms.items()}
+        return out
+
+    # BASELINE config 4 (DFN5B text, batch 8192 per GPU) at every N
     text_extra = None
-    if args.workload == "so400m_vision" and world == 1 and not args.no_text:
+    if args.workload == "so400m_vision" and not args.no_text:
         try:
             tres, _ = measure("dfn5b_text", max(2, args.steps // 2), 2, with_e2e=True)
-            tf = tres["value"] * tres["gflop"] * 1e9 / 1e12
-            text_extra = {"workload": tres["desc"], "value": tres["value"], "unit": tres["unit"],
+            tf = tres["value"] / world * tres["gflop"] * 1e9 / 1e12
+            text_extra = {"workload": tres["desc"], "value": tres["value"], "unit": tres["unit"], "n_gpus": world,
                           "e2e": tres.get("e2e_value"), "ms_per_step": tres["ms_per_step"],
                           "tflops_per_gpu": tf, "frac_of_sustained_peak": tf / pk["sustained"]}
         except Exception as e:  # pragma: no cover
             text_extra = {"error": str(e)}
+
+    # BASELINE config 3 read as strong scaling: a global batch of 1024 split over the N GPUs
+    strong_extra = None
+    if args.workload == "so400m_vision" and world > 1 and not args.no_extras:
+        try:
+            per_gpu = max(1, 1024 // world)
+            sres, _ = measure("so400m_vision", args.steps, max(1, args.warmup), with_e2e=True, batch_override=per_gpu)
+            strong_extra = {"global_batch": per_gpu * world, "per_gpu_batch": per_gpu, "value": sres["value"],
+                            "unit": sres["unit"], "e2e": sres.get("e2e_value"), "ms_per_step": sres["ms_per_step"],
+                            "vs_weak_same_run": sres["value"] / res["value"],
+                            "note": "fixed total work: every GPU embeds 1024/N images per step (half a micro-batch at "
+                                    "N=8); vs_weak_same_run = this throughput / the weak-scaling value of this run"}
+        except Exception as e:  # pragma: no cover
+            strong_extra = {"error": str(e)}
+
+    # BASELINE config 2: MobileCLIP2-S2 vision + text, batch 256, one GPU
+    mobile_extra = None
+    if args.workload == "so400m_vision" and world == 1 and not args.no_extras:
+        try:
+            mv, _ = measure("mobileclip2_vision", max(3, args.steps), 3, with_e2e=True)
+            mt, _ = measure("mobileclip2_text", max(3, args.steps), 3, with_e2e=True)
+            mobile_extra = {
+                "vision": {"workload": mv["desc"], "value": mv["value"], "unit": mv["unit"], "e2e": mv.get("e2e_value"),
+                           "ms_per_step": mv["ms_per_step"], "gpu_launches": mv["launches"],
+                           "tflops": mv["value"] * mv["gflop"] * 1e9 / 1e12, "roofline": class_rooflines(mv)},
+                "text": {"workload": mt["desc"], "value": mt["value"], "unit": mt["unit"], "e2e": mt.get("e2e_value"),
+                         "ms_per_step": mt["ms_per_step"], "gpu_launches": mt["launches"],
+                         "tflops": mt["value"] * mt["gflop"] * 1e9 / 1e12, "roofline": class_rooflines(mt)},
+            }
+        except Exception as e:  # pragma: no cover
+            mobile_extra = {"error": str(e)}
 
     if rank == 0:
         line = {
@@ -437,6 +668,8 @@ def main():
             "whole_step": whole,
             "cpu_baseline": cpu_baseline,
             "text": text_extra,
+            "strong": strong_extra,
+            "mobileclip2": mobile_extra,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -14,7 +14,7 @@ OK, ERR_INVALID_ARG, ERR_IO, ERR_PARSE, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3, 
 KIND_VISION, KIND_TEXT = 0, 1
 ACT_SOFTMAX, ACT_SIGMOID = 0, 1
 PROF_CLASSES = 8
-PROF_NAMES = ("gemm", "attention", "layernorm", "preprocess", "misc", "h2d", "d2h", "reserved")
+PROF_NAMES = ("gemm", "attention", "layernorm", "preprocess", "misc", "h2d", "d2h", "dwconv")
 
 
 class Opts(C.Structure):
@@ -28,7 +28,7 @@ class Preproc(C.Structure):
 
 class Profile(C.Structure):
     _fields_ = [("ms", C.c_double * PROF_CLASSES), ("launches", C.c_int64 * PROF_CLASSES),
-                ("gemm_flops", C.c_double)]
+                ("gemm_flops", C.c_double), ("conv_bytes", C.c_double)]
 
 
 LIB_PATH = Path(__file__).resolve().parent / "libclipb200.so"
@@ -64,6 +64,8 @@ SIGNATURES = {
     "clipb200_corpus_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "clipb200_corpus_size": (C.c_int64, [C.c_void_p]),
     "clipb200_corpus_rank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "clipb200_corpus_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_int,
+                                         C.c_void_p, C.c_void_p]),
     "clipb200_pool_create": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int32, C.POINTER(Opts), C.POINTER(C.c_void_p)]),
     "clipb200_pool_destroy": (None, [C.c_void_p]),
     "clipb200_pool_size": (C.c_int, [C.c_void_p]),

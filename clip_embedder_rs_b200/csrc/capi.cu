@@ -4,12 +4,14 @@
 
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 #include <string>
 
 #include "../../include/clipb200.h"
 #include "engine.h"
 #include "kernels.cuh"
+#include "search.cuh"
 
 using clipb200::Engine;
 using clipb200::Status;
@@ -265,15 +267,32 @@ int clipb200_similarity(int cuda_device, const float* A, const float* b, int64_t
 
 struct clipb200_corpus {
   int device = 0;
-  int64_t dim = 0, capacity = 0, size = 0;
-  float* rows = nullptr;
+  int64_t dim = 0, capacity = 0, cap8 = 0, size = 0;
+  float* rows = nullptr;            // [capacity, dim] fp32 (single-query GEMV path)
+  __nv_bfloat16* split = nullptr;   // [cap8, 2 dim] bf16 (hi | lo): the GEMM operand of clipb200_corpus_search
   float* query = nullptr;
   float* probs = nullptr;
+  // search scratch, grown on demand
+  float* d_queries = nullptr;
+  __nv_bfloat16 *q_hihi = nullptr, *q_lo = nullptr;
+  float* logits = nullptr;
+  float2* stats = nullptr;
+  unsigned long long *keys_a = nullptr, *keys_b = nullptr;
+  long long* d_index = nullptr;
+  float* d_prob = nullptr;
+  int64_t q_cap = 0, key_cap = 0, out_cap = 0;
+  void free_search() {
+    cudaFree(d_queries); cudaFree(q_hihi); cudaFree(q_lo); cudaFree(logits); cudaFree(stats);
+    cudaFree(keys_a); cudaFree(keys_b); cudaFree(d_index); cudaFree(d_prob);
+    d_queries = nullptr; q_hihi = q_lo = nullptr; logits = nullptr; stats = nullptr; keys_a = keys_b = nullptr;
+    d_index = nullptr; d_prob = nullptr;
+    q_cap = key_cap = out_cap = 0;
+  }
 };
 
 int clipb200_corpus_create(int cuda_device, int64_t dim, int64_t capacity, clipb200_corpus** out) {
   API_GUARD_BEGIN
-  if (out == nullptr || dim <= 0 || capacity <= 0 || dim > 0x7fffffff || capacity > 0x7fffffff)
+  if (out == nullptr || dim <= 0 || capacity <= 0 || dim > 0x7fffffff || capacity > 0x7ffffff0)
     return fail(CLIPB200_ERR_INVALID_ARG, "bad corpus shape");
   *out = nullptr;
   cudaError_t ce = cudaSetDevice(cuda_device);
@@ -282,9 +301,13 @@ int clipb200_corpus_create(int cuda_device, int64_t dim, int64_t capacity, clipb
   c->device = cuda_device;
   c->dim = dim;
   c->capacity = capacity;
+  c->cap8 = (capacity + 7) & ~int64_t(7);
+  const size_t split_bytes = static_cast<size_t>(c->cap8) * dim * 2 * 2;
   if ((ce = cudaMalloc(&c->rows, static_cast<size_t>(capacity) * dim * 4)) != cudaSuccess ||
+      (ce = cudaMalloc(&c->split, split_bytes)) != cudaSuccess ||
+      (ce = cudaMemset(c->split, 0, split_bytes)) != cudaSuccess ||  // rows beyond `size` take part in the last N tile
       (ce = cudaMalloc(&c->query, dim * 4)) != cudaSuccess || (ce = cudaMalloc(&c->probs, capacity * 4 + 16)) != cudaSuccess) {
-    cudaFree(c->rows); cudaFree(c->query); cudaFree(c->probs);
+    cudaFree(c->rows); cudaFree(c->split); cudaFree(c->query); cudaFree(c->probs);
     delete c;
     return fail(CLIPB200_ERR_CUDA, std::string("corpus allocation: ") + cudaGetErrorString(ce));
   }
@@ -295,7 +318,8 @@ int clipb200_corpus_create(int cuda_device, int64_t dim, int64_t capacity, clipb
 void clipb200_corpus_destroy(clipb200_corpus* c) {
   if (c == nullptr) return;
   cudaSetDevice(c->device);
-  cudaFree(c->rows); cudaFree(c->query); cudaFree(c->probs);
+  cudaFree(c->rows); cudaFree(c->split); cudaFree(c->query); cudaFree(c->probs);
+  c->free_search();
   delete c;
 }
 int clipb200_corpus_append(clipb200_corpus* c, const float* rows, int64_t n) {
@@ -303,8 +327,11 @@ int clipb200_corpus_append(clipb200_corpus* c, const float* rows, int64_t n) {
   if (c == nullptr || rows == nullptr || n < 0) return fail(CLIPB200_ERR_INVALID_ARG, "null argument");
   if (c->size + n > c->capacity) return fail(CLIPB200_ERR_INVALID_ARG, "corpus capacity exceeded");
   cudaError_t ce = cudaSetDevice(c->device);
+  float* dst = c->rows + c->size * c->dim;
+  if (ce == cudaSuccess) ce = cudaMemcpy(dst, rows, static_cast<size_t>(n) * c->dim * 4, cudaMemcpyHostToDevice);
   if (ce == cudaSuccess)
-    ce = cudaMemcpy(c->rows + c->size * c->dim, rows, static_cast<size_t>(n) * c->dim * 4, cudaMemcpyHostToDevice);
+    ce = clipb200::launch_split_corpus_rows(dst, n, static_cast<int>(c->dim), c->split + c->size * c->dim * 2, nullptr);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(nullptr);
   if (ce != cudaSuccess) return fail(CLIPB200_ERR_CUDA, std::string("corpus append: ") + cudaGetErrorString(ce));
   c->size += n;
   return CLIPB200_OK;
@@ -322,6 +349,64 @@ int clipb200_corpus_rank(clipb200_corpus* c, const float* query, float scale, fl
                                      activation, c->probs, nullptr, 0);
   if (ce == cudaSuccess) ce = cudaMemcpy(probs, c->probs, c->size * 4, cudaMemcpyDeviceToHost);
   if (ce != cudaSuccess) return fail(CLIPB200_ERR_CUDA, std::string("corpus rank: ") + cudaGetErrorString(ce));
+  return CLIPB200_OK;
+  API_GUARD_END
+}
+
+// `rank_images` (src/clip.rs:136-170) for n_queries text embeddings at once: logits [Q, n] on the tcgen05 GEMM
+// (split-bf16 operands, fp32-grade), softmax-over-corpus / sigmoid and the top-k selection on the GPU.
+int clipb200_corpus_search(clipb200_corpus* c, const float* queries, int64_t n_queries, int64_t k, float scale, float bias,
+                           int activation, int64_t* top_index, float* top_prob) {
+  API_GUARD_BEGIN
+  if (c == nullptr || queries == nullptr || top_index == nullptr || top_prob == nullptr)
+    return fail(CLIPB200_ERR_INVALID_ARG, "null argument");
+  if (c->size == 0 || n_queries <= 0) return fail(CLIPB200_ERR_INVALID_ARG, "Empty batch");
+  if (k <= 0 || k > 2048 || k > c->size) return fail(CLIPB200_ERR_INVALID_ARG, "k must be in [1, min(2048, corpus size)]");
+  if (c->dim % 8 != 0) return fail(CLIPB200_ERR_UNSUPPORTED, "corpus search needs an embedding width that is a multiple of 8");
+  if (activation < 0 || activation > 2) return fail(CLIPB200_ERR_INVALID_ARG, "bad activation");
+  cudaError_t ce = cudaSetDevice(c->device);
+  if (ce != cudaSuccess) return fail(CLIPB200_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+  const int D = static_cast<int>(c->dim);
+  const int N = static_cast<int>(c->size);
+  const int N8 = (N + 7) & ~7;                   // GEMM column count; rows [N, N8) of `split` are zero
+  const long long ld = N8;
+  constexpr int64_t kQueryBlock = 128;           // one GEMM row tile per pass over the corpus
+  const size_t keys = clipb200::search_scratch_keys(N, static_cast<int>(k));
+  if (c->q_cap < kQueryBlock || c->key_cap < static_cast<int64_t>(keys) || c->out_cap < k) {
+    c->free_search();
+    const size_t Q = kQueryBlock;
+    if ((ce = cudaMalloc(&c->d_queries, Q * D * 4)) != cudaSuccess || (ce = cudaMalloc(&c->q_hihi, Q * D * 2 * 2)) != cudaSuccess ||
+        (ce = cudaMalloc(&c->q_lo, Q * D * 2)) != cudaSuccess ||
+        (ce = cudaMalloc(&c->logits, Q * static_cast<size_t>(c->cap8) * 4)) != cudaSuccess ||
+        (ce = cudaMalloc(&c->stats, Q * sizeof(float2))) != cudaSuccess ||
+        (ce = cudaMalloc(&c->keys_a, Q * keys * 8 + 8)) != cudaSuccess || (ce = cudaMalloc(&c->keys_b, Q * keys * 8 + 8)) != cudaSuccess ||
+        (ce = cudaMalloc(&c->d_index, Q * k * 8)) != cudaSuccess || (ce = cudaMalloc(&c->d_prob, Q * k * 4)) != cudaSuccess) {
+      c->free_search();
+      return fail(CLIPB200_ERR_CUDA, std::string("corpus search scratch: ") + cudaGetErrorString(ce));
+    }
+    c->q_cap = kQueryBlock;
+    c->key_cap = static_cast<int64_t>(keys);
+    c->out_cap = k;
+  }
+  for (int64_t q0 = 0; q0 < n_queries && ce == cudaSuccess; q0 += kQueryBlock) {
+    const int nq = static_cast<int>(std::min<int64_t>(kQueryBlock, n_queries - q0));
+    ce = cudaMemcpyAsync(c->d_queries, queries + q0 * D, static_cast<size_t>(nq) * D * 4, cudaMemcpyHostToDevice, nullptr);
+    if (ce == cudaSuccess) ce = clipb200::launch_split_queries(c->d_queries, nq, D, c->q_hihi, c->q_lo, nullptr);
+    // logits = q_hi.(c_hi + c_lo) over K = 2D, then += q_lo.c_hi over the first D columns of the same corpus rows
+    if (ce == cudaSuccess)
+      ce = clipb200::gemm_bf16_f32out(c->q_hihi, 2 * D, c->split, 2 * D, nq, N8, 2 * D, c->logits, ld, false, nullptr);
+    if (ce == cudaSuccess)
+      ce = clipb200::gemm_bf16_f32out(c->q_lo, D, c->split, 2 * D, nq, N8, D, c->logits, ld, true, nullptr);
+    if (ce == cudaSuccess)
+      ce = clipb200::launch_search_topk(c->logits, ld, nq, N, static_cast<int>(k), scale, bias, activation, c->stats,
+                                        c->keys_a, c->keys_b, c->d_index, c->d_prob, nullptr);
+    if (ce == cudaSuccess)
+      ce = cudaMemcpyAsync(top_index + q0 * k, c->d_index, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, nullptr);
+    if (ce == cudaSuccess)
+      ce = cudaMemcpyAsync(top_prob + q0 * k, c->d_prob, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, nullptr);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(nullptr);
+  }
+  if (ce != cudaSuccess) return fail(CLIPB200_ERR_CUDA, std::string("corpus search: ") + cudaGetErrorString(ce));
   return CLIPB200_OK;
   API_GUARD_END
 }

@@ -12,6 +12,7 @@
 #include "gemm_sm100.cuh"
 #include "conv_kernels.cuh"
 #include "kernels.cuh"
+#include "search.cuh"
 
 namespace clipb200 {
 
@@ -46,6 +47,26 @@ static float half_to_float(uint16_t h) {
   float f;
   memcpy(&f, &bits, 4);
   return f;
+}
+
+// the corpus search (capi.cu / search.cu) reaches the GEMM through this plain function
+cudaError_t gemm_bf16_f32out(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N,
+                             int K, float* out, long long ldc, bool accumulate, cudaStream_t st) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  static std::atomic<unsigned long long> configured(0);  // bit per device
+  if (dev < 64 && !(configured.load() & (1ull << dev))) {
+    if (get_encode_tiled() == nullptr) return cudaErrorNotSupported;
+    if ((e = gemm_configure_device()) != cudaSuccess) return e;
+    configured.fetch_or(1ull << dev);
+  }
+  int sms = 0;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  GemmEpilogue ep;
+  ep.out_f32 = out;
+  ep.ldc = ldc;
+  return gemm_bf16(A, lda, W, ldw, M, N, K, accumulate ? EPI_RESID : EPI_F32, ep, sms, st);
 }
 
 // ------------------------------------------------------------------------------------------------ create
@@ -527,7 +548,7 @@ Engine::~Engine() {
 
 // ------------------------------------------------------------------------------------------------ profiling
 void Engine::ProfBegin(int cls, cudaStream_t st) {
-  if (cls < PC_H2D) ++launch_count;  // kernels only; the two copy classes are DMA transfers
+  if (cls < PC_H2D || cls == PC_CONV) ++launch_count;  // kernels only; the two copy classes are DMA transfers
   if (!profile_) return;
   ProfPair p;
   p.cls = cls;

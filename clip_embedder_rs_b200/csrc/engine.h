@@ -48,7 +48,7 @@ struct BlockW {
   LinearW qkv, proj, fc1, fc2;
 };
 
-enum ProfClass { PC_GEMM = 0, PC_ATTN = 1, PC_LN = 2, PC_PRE = 3, PC_MISC = 4, PC_H2D = 5, PC_D2H = 6 };
+enum ProfClass { PC_GEMM = 0, PC_ATTN = 1, PC_LN = 2, PC_PRE = 3, PC_MISC = 4, PC_H2D = 5, PC_D2H = 6, PC_CONV = 7 };
 
 class Engine {
  public:
@@ -123,6 +123,8 @@ class Engine {
   Status UploadConv(const OnnxModel& m, const std::string& name, int cout, int cin_g, int k, ConvW* out);
   Status UploadSe(const OnnxModel& m, const std::string& name, int C, SeW* out);
   Status FvMlp(const FvBlock& b, float* cur, int n, int Hh, int C, const float* gamma);
+  cudaError_t DwConv(const void* in, bool in_bf16, int n, int H, int W, int Cin, int K, int stride, int mult,
+                     const float* w, const float* bias, bool gelu, void* out, bool out_bf16);
   // CUDA graphs for small micro-batches (launch-bound regime): one instantiated graph per (mode, n, staging slot)
   Status ForwardSlot(int mode, int n, int slot);
   struct GraphEntry {

@@ -211,12 +211,25 @@ Status Engine::AllocFastVitWorkspace() {
   return Status::OK();
 }
 
+// depthwise conv with its own profile class: device time + algorithmic bytes (input once + output once), so the
+// bench can state the achieved GB/s of the conv stages next to the GEMM class's TFLOP/s
+cudaError_t Engine::DwConv(const void* in, bool in_bf16, int n, int H, int W, int Cin, int K, int stride, int mult,
+                           const float* w, const float* bias, bool gelu, void* out, bool out_bf16) {
+  ProfBegin(PC_CONV, compute_);
+  cudaError_t e = launch_dwconv(in, in_bf16, n, H, W, Cin, K, stride, mult, w, bias, gelu, out, out_bf16, compute_);
+  ProfEnd(PC_CONV, compute_);
+  if (profile_) {
+    const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    prof_acc_.conv_bytes += static_cast<double>(n) * H * W * Cin * (in_bf16 ? 2 : 4) +
+                            static_cast<double>(n) * Ho * Wo * Cin * mult * (out_bf16 ? 2 : 4);
+  }
+  return e;
+}
+
 // ConvMlp: x += gamma * fc2(gelu(fc1(dwconv7x7(x))))
 Status Engine::FvMlp(const FvBlock& b, float* cur, int n, int Hh, int C, const float* gamma) {
   const int rows = n * Hh * Hh;
-  ProfBegin(PC_PRE, compute_);
-  cudaError_t e = launch_dwconv(cur, false, n, Hh, Hh, C, 7, 1, 1, b.mlp_dw.w, b.mlp_dw.b, false, h_, true, compute_);
-  ProfEnd(PC_PRE, compute_);
+  cudaError_t e = DwConv(cur, false, n, Hh, Hh, C, 7, 1, 1, b.mlp_dw.w, b.mlp_dw.b, false, h_, true);
   CUDA_RET(e, "depthwise 7x7");
   GemmEpilogue e1;
   e1.out_bf16 = mlpbuf_;
@@ -239,9 +252,7 @@ Status Engine::ForwardFastVit(int n, const uint8_t* d_u8, const float* d_f32, fl
   e = launch_stem_conv3x3_s2(d_u8, d_f32, lut_, n, S_, d0, fv_stem0_.w, fv_stem0_.b, fv_stem_out_, compute_);
   ProfEnd(PC_PRE, compute_);
   CUDA_RET(e, "stem conv");
-  ProfBegin(PC_PRE, compute_);
-  e = launch_dwconv(fv_stem_out_, true, n, Hh, Hh, d0, 3, 2, 1, fv_stem1_.w, fv_stem1_.b, true, h_, true, compute_);
-  ProfEnd(PC_PRE, compute_);
+  e = DwConv(fv_stem_out_, true, n, Hh, Hh, d0, 3, 2, 1, fv_stem1_.w, fv_stem1_.b, true, h_, true);
   CUDA_RET(e, "stem depthwise");
   Hh /= 2;
   float* cur = fv_xa_;
@@ -259,9 +270,7 @@ Status Engine::ForwardFastVit(int n, const uint8_t* d_u8, const float* d_f32, fl
     if (st.down) {
       const int Ho = Hh / 2;
       if (st.down_se) {
-        ProfBegin(PC_PRE, compute_);
-        e = launch_dwconv(cur, false, n, Hh, Hh, C, 7, 2, 2, st.down_dw.w, st.down_dw.b, false, fv_tmp_, false, compute_);
-        ProfEnd(PC_PRE, compute_);
+              e = DwConv(cur, false, n, Hh, Hh, C, 7, 2, 2, st.down_dw.w, st.down_dw.b, false, fv_tmp_, false);
         CUDA_RET(e, "downsample depthwise");
         ProfBegin(PC_MISC, compute_);
         e = launch_gap(fv_tmp_, n, Ho * Ho, st.C, fv_s_, compute_);
@@ -270,9 +279,7 @@ Status Engine::ForwardFastVit(int n, const uint8_t* d_u8, const float* d_f32, fl
         ProfEnd(PC_MISC, compute_);
         CUDA_RET(e, "downsample squeeze-excite");
       } else {
-        ProfBegin(PC_PRE, compute_);
-        e = launch_dwconv(cur, false, n, Hh, Hh, C, 7, 2, 2, st.down_dw.w, st.down_dw.b, true, h_, true, compute_);
-        ProfEnd(PC_PRE, compute_);
+              e = DwConv(cur, false, n, Hh, Hh, C, 7, 2, 2, st.down_dw.w, st.down_dw.b, true, h_, true);
         CUDA_RET(e, "downsample depthwise");
       }
       Hh = Ho;
@@ -284,18 +291,14 @@ Status Engine::ForwardFastVit(int n, const uint8_t* d_u8, const float* d_f32, fl
       RET_IF_ERR(Gemm(h_, C, st.down_pw, n * Hh * Hh, EPI_F32, &ep));
     }
     if (st.cpe) {
-      ProfBegin(PC_PRE, compute_);
-      e = launch_dwconv(cur, false, n, Hh, Hh, C, 7, 1, 1, st.cpe_dw.w, st.cpe_dw.b, false, other, false, compute_);
-      ProfEnd(PC_PRE, compute_);
+          e = DwConv(cur, false, n, Hh, Hh, C, 7, 1, 1, st.cpe_dw.w, st.cpe_dw.b, false, other, false);
       CUDA_RET(e, "positional encoding");
       std::swap(cur, other);
     }
     const int rows = n * Hh * Hh;
     for (const FvBlock& b : st.blocks) {
       if (!b.attn) {
-        ProfBegin(PC_PRE, compute_);
-        e = launch_dwconv(cur, false, n, Hh, Hh, C, 3, 1, 1, b.mixer.w, b.mixer.b, false, other, false, compute_);
-        ProfEnd(PC_PRE, compute_);
+              e = DwConv(cur, false, n, Hh, Hh, C, 3, 1, 1, b.mixer.w, b.mixer.b, false, other, false);
         CUDA_RET(e, "token mixer");
         std::swap(cur, other);
         RET_IF_ERR(FvMlp(b, cur, n, Hh, C, b.gamma));
@@ -323,9 +326,7 @@ Status Engine::ForwardFastVit(int n, const uint8_t* d_u8, const float* d_f32, fl
   }
   // final_conv (dw3x3, x2 channels) -> SE -> GELU -> global average pool -> head -> L2 normalise
   const int cf = 2 * C, P = Hh * Hh;
-  ProfBegin(PC_PRE, compute_);
-  e = launch_dwconv(cur, false, n, Hh, Hh, C, 3, 1, 2, fv_final_.w, fv_final_.b, false, fv_tmp_, false, compute_);
-  ProfEnd(PC_PRE, compute_);
+  e = DwConv(cur, false, n, Hh, Hh, C, 3, 1, 2, fv_final_.w, fv_final_.b, false, fv_tmp_, false);
   CUDA_RET(e, "final conv");
   ProfBegin(PC_MISC, compute_);
   e = launch_gap(fv_tmp_, n, P, cf, fv_s_, compute_);

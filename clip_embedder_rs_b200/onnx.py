@@ -170,7 +170,7 @@ class OnnxSession:
         self.check(_native.lib.clipb200_engine_profile(self.handle, C.byref(p), 1 if reset else 0))
         return {"ms": {n: p.ms[i] for i, n in enumerate(_native.PROF_NAMES)},
                 "launches": {n: int(p.launches[i]) for i, n in enumerate(_native.PROF_NAMES)},
-                "gemm_flops": p.gemm_flops}
+                "gemm_flops": p.gemm_flops, "conv_bytes": p.conv_bytes}
 
     def close(self) -> None:
         h, self._h = getattr(self, "_h", None), None

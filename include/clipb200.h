@@ -69,8 +69,9 @@ typedef struct clipb200_preproc {
 #define CLIPB200_PROF_CLASSES 8
 typedef struct clipb200_profile {
   double ms[CLIPB200_PROF_CLASSES];        /* 0 gemm, 1 attention, 2 layernorm, 3 preprocess, 4 pool/misc,  */
-  int64_t launches[CLIPB200_PROF_CLASSES]; /* 5 h2d copy, 6 d2h copy, 7 reserved                            */
+  int64_t launches[CLIPB200_PROF_CLASSES]; /* 5 h2d copy, 6 d2h copy, 7 depthwise conv (FastViT stages)     */
   double gemm_flops;                       /* algorithmic 2*M*N*K of the timed GEMM launches (no padding)   */
+  double conv_bytes;                       /* algorithmic bytes (input + output once) of the timed depthwise convs */
 } clipb200_profile;
 
 /* ---- lifetime (src/onnx.rs:14-29) ------------------------------------------------------------------- */
@@ -129,8 +130,9 @@ int clipb200_similarity(int cuda_device, const float* A, const float* b, int64_t
                         float bias, int activation, float* probs);
 
 /* ---- corpus search tail (src/clip.rs:136-170 `rank_images` at scale) -----------------------------
- * An embedding matrix [n, dim] kept resident in HBM; a query is one similarity pass over it (HBM-bound GEMV with the
- * fused logit scale / bias / softmax-over-corpus or sigmoid); the stable descending sort stays on the host. */
+ * An embedding matrix [n, dim] kept resident in HBM.  clipb200_corpus_rank: one query, one similarity pass (HBM-bound
+ * GEMV with the fused logit scale / bias / softmax-over-corpus or sigmoid), all n probabilities returned and the
+ * stable descending sort left to the host.  clipb200_corpus_search (below): many queries, GEMM + GPU top-k. */
 typedef struct clipb200_corpus clipb200_corpus;
 int clipb200_corpus_create(int cuda_device, int64_t dim, int64_t capacity, clipb200_corpus** out);
 void clipb200_corpus_destroy(clipb200_corpus* c);
@@ -138,6 +140,14 @@ int clipb200_corpus_append(clipb200_corpus* c, const float* rows, int64_t n);   
 int64_t clipb200_corpus_size(const clipb200_corpus* c);
 int clipb200_corpus_rank(clipb200_corpus* c, const float* query, float scale, float bias, int activation,
                          float* probs /* host [size] */);
+
+/* `rank_images` for n_queries query embeddings at once (queries [n_queries, dim], host): logits [n_queries, size] in ONE
+ * pass over the corpus on the tcgen05 GEMM (fp32 values split into bf16 hi + lo parts: fp32-grade dot products),
+ * mul_add(scale, bias), softmax over the whole corpus / sigmoid / raw, and the per-query top-k on the GPU.  Returns, per
+ * query, the first k entries of the reference's stable descending sort (src/clip.rs:167: ties keep the lower index
+ * first): top_index / top_prob are host [n_queries, k].  1 <= k <= min(2048, size); dim must be a multiple of 8. */
+int clipb200_corpus_search(clipb200_corpus* c, const float* queries, int64_t n_queries, int64_t k, float scale,
+                           float bias, int activation, int64_t* top_index, float* top_prob);
 
 /* ---- in-process multi-GPU pool: `duplicate()` (src/vision.rs:87-91, src/text.rs:104-108, src/clip.rs:69-73) for the
  * GPUs of one box.  One engine replica and one host thread per device; a call splits the batch into contiguous row

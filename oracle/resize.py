@@ -14,7 +14,10 @@ What is restated here is that crate's published algorithm as recalled (it is the
   * `ResizeAlg::Nearest`: src = floor(in0 + (out + 0.5) * scale).
 
 `tests/test_resize_cpu.py` cross-checks it against Pillow (same windows and kernels, 22-bit instead of <=15-bit
-coefficients): at most 1 LSB apart on the reference's photos and on noise.
+coefficients): at most 1 LSB apart on structured noise and — `test_reference_photos_against_pillow`, which opens
+`/root/reference/assets/img/*.jpg` — on the reference's seven example photos at 224 / 256 / 384 px, centre-cropped
+and squashed; `tests/test_resize_gpu.py::test_reference_photos_bit_exact` holds the GPU kernels to this oracle byte
+for byte on the same photos.
 """
 from __future__ import annotations
 

@@ -72,3 +72,21 @@ def cosine_rows(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     a = a.astype(np.float64)
     b = b.astype(np.float64)
     return (a * b).sum(-1) / (np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1))
+
+
+REF_PHOTO_DIRS = ("/root/reference/assets/img", os.path.join(ROOT, "tests", "_ref_assets"))
+
+
+def reference_photos():
+    """The reference's own example photos (`/root/reference/assets/img/*.jpg`, what its README and integration test
+    embed).  They are not part of this repository: `__graft_entry__.build()` copies them into the git-ignored
+    `tests/_ref_assets/` when the reference checkout is present, which is how they reach the GPU box.  Returns
+    [(name, uint8 [H,W,3])], decoded with Pillow like `image::open(..).to_rgb8()` (vision.rs:171)."""
+    from PIL import Image
+
+    for d in REF_PHOTO_DIRS:
+        if os.path.isdir(d):
+            names = sorted(f for f in os.listdir(d) if f.lower().endswith((".jpg", ".jpeg", ".png")))
+            if names:
+                return [(n, np.asarray(Image.open(os.path.join(d, n)).convert("RGB"))) for n in names]
+    return []

@@ -84,6 +84,32 @@ def test_c3_so400m_vision(make_big):
     assert np.abs(emb2.embed_images(imgs) - got).max() < 2e-3
 
 
+def test_c3_so400m_vision_at_the_benchmarked_shape(make_big):
+    """The shape bench.py times: 1024 seed-4 images through `clipb200_vision_embed_rgb8` at the default micro-batch
+    (256 images = 147 456 token rows, four pipelined micro-batches over the two staging slots).  Rows at the start, the
+    end and both sides of every micro-batch boundary against the CPU oracle; every row against a micro-batch-8 run of
+    the same engine code (different tile / wave decomposition of every GEMM, CUDA-graph replay instead of direct
+    launches)."""
+    import clip_embedder_rs_b200 as cb
+    from oracle import reference_forward as R
+
+    mdir = make_big("so400m_siglip2_384", ("vision",))
+    imgs = random_images(1024, 384, seed=4)
+    emb = cb.VisionEmbedder.from_local_dir(mdir).build()
+    got = emb.embed_images(imgs)
+    assert got.shape == (1024, 1152) and np.all(np.abs(np.linalg.norm(got, axis=1) - 1.0) < 1e-3)
+    rows = [0, 255, 256, 511, 767, 1023]
+    want = R.OracleClip(mdir, towers=("vision",)).embed_images(list(imgs[rows]))
+    cos = cosine_rows(got[rows], want)
+    print(f"\n[C3 @ B=1024, micro-batch 256] rows {rows}: cos min {cos.min():.6f} max_abs {np.abs(got[rows] - want).max():.2e}")
+    assert cos.min() >= COS_BAR
+    del emb
+    small = cb.VisionEmbedder.from_local_dir(mdir).micro_batch(8).build().embed_images(imgs)
+    d = np.abs(small - got).max()
+    print(f"[C3 @ B=1024] micro-batch 256 vs micro-batch 8, all rows: max_abs {d:.2e}")
+    assert d < 2e-3
+
+
 def test_c4_dfn5b_text(make_big):
     import clip_embedder_rs_b200 as cb
     from oracle import reference_forward as R

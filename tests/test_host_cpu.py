@@ -36,7 +36,7 @@ def test_struct_layouts_match_header():
     from clip_embedder_rs_b200 import _native
 
     assert C.sizeof(_native.Opts) == 32 and C.sizeof(_native.Preproc) == 32
-    assert C.sizeof(_native.Profile) == 8 * 8 + 8 * 8 + 8
+    assert C.sizeof(_native.Profile) == 8 * 8 + 8 * 8 + 8 + 8
 
 
 def test_onnx_inspect_and_loader_errors(make_model, tmp_path):

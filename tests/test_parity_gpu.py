@@ -172,6 +172,75 @@ def test_corpus_rank_matches_rank_images(clips):
     assert rank_corpus(clip, corpus, text, top_k=5) == got[:5]
 
 
+def test_corpus_search_matches_rank_images(clips):
+    """Multi-query search (one tcgen05 GEMM pass over the corpus + GPU top-k) == `rank_images` query by query
+    (src/clip.rs:136-170): same indices in the same order, same probabilities."""
+    from clip_embedder_rs_b200.corpus import EmbeddingCorpus, rank_corpus, search_corpus
+
+    for config in ("tiny_siglip", "tiny_clip"):  # sigmoid tail and softmax-over-corpus tail
+        clip, _ = clips(config)
+        size = clip.vision.config.model_cfg.vision_cfg.image_size
+        imgs = random_images(37, size, seed=78)
+        corpus = EmbeddingCorpus(clip.vision.session.embed_dim, capacity=40)
+        corpus.append(clip.vision.embed_images(imgs))
+        texts = random_texts(5, seed=9)
+        got = search_corpus(clip, corpus, texts, top_k=7)
+        for q, text in enumerate(texts):
+            want = clip.rank_images(imgs, text)[:7]
+            assert [i for i, _ in got[q]] == [i for i, _ in want], (config, q)
+            assert np.allclose([p for _, p in got[q]], [p for _, p in want], rtol=2e-4, atol=1e-7), (config, q)
+            assert [i for i, _ in rank_corpus(clip, corpus, text, top_k=7)] == [i for i, _ in want]
+        with pytest.raises(cb_error()):
+            corpus.search(np.zeros((1, corpus.dim), np.float32), 38, 1.0, 0.0, False)  # k > corpus size
+
+
+def cb_error():
+    import clip_embedder_rs_b200 as cb
+
+    return cb.ClipError
+
+
+def test_corpus_search_at_scale_against_float64():
+    """20 000 x 512 unit vectors, 130 queries (two GEMM row tiles), k = 100 with exact duplicates in the corpus: indices
+    equal to a float64 ranking wherever the float64 scores are not within fp32 noise of each other, ties resolved
+    towards the lower index, softmax probabilities normalised over the whole corpus."""
+    from clip_embedder_rs_b200.corpus import EmbeddingCorpus
+
+    rng = np.random.default_rng(123)
+    n, d, nq, k = 20000, 512, 130, 100
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+    rows[777] = rows[123]          # exact duplicates: the stable sort must keep 123 before 777
+    rows[15000] = rows[123]
+    queries = rng.standard_normal((nq, d)).astype(np.float32)
+    queries /= np.linalg.norm(queries, axis=1, keepdims=True)
+    queries[3] = rows[123]         # the duplicated row is this query's best match
+    corpus = EmbeddingCorpus(d, capacity=n)
+    for s in range(0, n, 7000):
+        corpus.append(rows[s:s + 7000])
+    scale, bias = 100.0, 0.0
+    idx, prob = corpus.search(queries, k, scale, bias, sigmoid=False)
+    logits = queries.astype(np.float64) @ rows.astype(np.float64).T * scale + bias
+    z = np.exp(logits - logits.max(axis=1, keepdims=True))
+    ref_prob = z / z.sum(axis=1, keepdims=True)
+    assert idx.shape == (nq, k) and list(idx[3, :3]) == [123, 777, 15000]
+    for q in range(nq):
+        order = np.lexsort((np.arange(n), -logits[q]))[:k]
+        same = idx[q] == order
+        if not same.all():  # positions may only differ where the float64 scores are closer than fp32 dot-product noise
+            bad = np.nonzero(~same)[0]
+            assert np.all(np.abs(logits[q, idx[q, bad]] - logits[q, order[bad]]) < 2e-4), (q, bad)
+        assert np.allclose(prob[q], ref_prob[q, idx[q]], rtol=2e-3, atol=1e-12), q
+        assert np.all(np.diff(prob[q]) <= 0)
+    # sigmoid tail and a k that needs two selection rounds per chunk list (k = 2048)
+    idx2, prob2 = corpus.search(queries[:2], 2048, 10.0, -1.0, sigmoid=True)
+    lg = queries[:2].astype(np.float64) @ rows.astype(np.float64).T * 10.0 - 1.0
+    for q in range(2):
+        order = np.lexsort((np.arange(n), -lg[q]))[:2048]
+        assert (idx2[q] == order).mean() > 0.99
+        assert np.allclose(prob2[q], 1.0 / (1.0 + np.exp(-lg[q, idx2[q]])), rtol=1e-4)
+
+
 def test_duplicate_handles_run_concurrently(clips):
     """SURVEY 8(b) threading row: distinct handles (`duplicate()`, vision.rs:87-91) may be used concurrently from
     different threads; each must give the same embeddings as a lone run."""

@@ -53,3 +53,27 @@ def test_weights_sum_and_precision():
     w16, p = RZ.normalise_i16(xw)
     assert 8 <= p <= 15 and np.abs(w16.sum(1) - (1 << p)).max() <= xw.shape[1]
     assert int(RZ._round_half_away(2.5)) == 3 and int(RZ._round_half_away(-2.5)) == -3
+
+
+@pytest.mark.parametrize("size", [224, 256, 384])
+@pytest.mark.parametrize("mode", ["shortest", "squash"])
+def test_reference_photos_against_pillow(size, mode):
+    """The photos the reference ships (assets/img, 1944x2592 ... 5312x2988 JPEGs; tests/integration_test.rs and the README
+    examples embed them): the oracle's bicubic resize is within 1 LSB of Pillow's on every one of them, for the centre
+    crop of `resize_mode: shortest` and for `squash`, at the three resolutions the reference's models use."""
+    from PIL import Image
+
+    from conftest import reference_photos
+
+    photos = reference_photos()
+    if not photos:
+        pytest.skip("reference photos not available (no /root/reference/assets/img and no tests/_ref_assets)")
+    for name, a in photos:
+        h, w = a.shape[:2]
+        mine = RZ.resize_rgb8(a, size, "bicubic", mode)
+        left, top, cw, ch = RZ.crop_box(w, h, size, mode)
+        box = (max(left, 0.0), max(top, 0.0), min(left + cw, w), min(top + ch, h))  # f64 rounding can leave -1e-13
+        pil = np.asarray(Image.fromarray(a).resize((size, size), Image.BICUBIC, box=box))
+        d = np.abs(mine.astype(int) - pil.astype(int))
+        assert d.max() <= 1, f"{name} {w}x{h} -> {size} {mode}: max diff {d.max()}"
+        assert (d > 0).mean() < 0.05, f"{name}: {(d > 0).mean():.3f} of the bytes differ"

@@ -66,3 +66,38 @@ def test_mixed_size_batch_embeddings(make_model):
     assert np.array_equal(pv, R.preprocess_batch(imgs, 64, pc.mean, pc.std, pc.interpolation, pc.resize_mode))
     labels = ["a photo of a cat", "a photo of a dog", "a photo of a beignet"]
     assert [l for l, _ in clip.classify(imgs[0], labels)] == [l for l, _ in o.classify(imgs[0], labels)]
+
+
+@pytest.mark.parametrize("size,patch", [(224, 32), (256, 32), (384, 32)])
+def test_reference_photos_bit_exact(model_root, size, patch):
+    """GPU resize == oracle, byte for byte, on the reference's own photos (assets/img: seven JPEGs between 2592x1456 and
+    5312x2988) for bicubic / shortest and bicubic / squash at 224, 256 and 384 px, singly (clipb200_resize_rgb8) and as
+    one mixed-size batch through the pipelined embed path (clipb200_vision_embed_rgb8_var)."""
+    import clip_embedder_rs_b200 as cb
+    import export_synthetic as ex
+    from conftest import reference_photos
+    from oracle import reference_forward as R
+    from oracle import resize as RZ
+
+    photos = reference_photos()
+    if not photos:
+        pytest.skip("reference photos not available (no /root/reference/assets/img and no tests/_ref_assets)")
+    spec = ex._clip(f"photo-{size}", size, patch, 128, 1, 2, 256, 64, 128, 1, 2, 256)
+    for mode in ("shortest", "squash"):
+        spec.resize_mode = mode
+        mdir = ex.write_model_dir(spec, os.path.join(model_root, f"photo_{size}_{mode}"), seed=0, towers=("vision",))
+        emb = cb.VisionEmbedder.from_local_dir(mdir).micro_batch(4).build()
+        want_px = []
+        for name, a in photos:
+            want = RZ.resize_rgb8(a, size, "bicubic", mode)
+            got = emb.resize(a)
+            assert np.array_equal(got, want), f"{name} -> {size} {mode}: {np.abs(got.astype(int) - want.astype(int)).max()} LSB off"
+            want_px.append(want)
+        # the batch path (groups of photos staged, uploaded and resized while the previous micro-batch runs) must see
+        # exactly the pixels of the single-image path: embeddings of the photos == embeddings of the resized photos
+        imgs = [a for _, a in photos]
+        got_e = emb.embed_images(imgs)
+        want_e = emb.embed_images(np.stack(want_px))
+        assert np.array_equal(got_e, want_e)
+        pc = emb.config.preprocess_cfg
+        assert np.array_equal(emb.preprocess_batch(imgs[:2]), R.preprocess_batch(imgs[:2], size, pc.mean, pc.std, "bicubic", mode))
