@@ -73,10 +73,16 @@ constexpr int THREADS = 32 * (NSW + 2);
 // to retire before storing P: the two barrier round trips that serialised every block of the single-S protocol
 // (s_full -> s_empty -> QK and p_full -> pv_done -> P store; with all arithmetic removed that skeleton alone took 82 % of
 // the kernel's run time) overlap with the arithmetic instead.
-template <int HD, int BKV, bool DB = false>
+// VT = V arrives TRANSPOSED ([B, H*hd, T], written by the qkv GEMM's epilogue): a V block is then a K-major operand
+// (rows = head-dim columns of O, 128-byte rows of 64 keys + an optional 64-byte-row part of 32 keys) and every 16-key
+// step of O += P V is ONE tcgen05.mma with N = HDP, instead of an N = 64 instruction plus an N = REMP instruction on
+// MN-major tiles.  The tensor pipe's front end costs ~94 cycles per TMEM-operand MMA whatever N is
+// (tests/native/mma_latency_test.cu), and those instructions were 72 of the 102 per 576-key tile.
+template <int HD, int BKV, bool DB = false, bool VT = false>
 struct Cfg {
   static_assert(HD >= 64 && HD % 8 == 0 && HD <= 128, "head dim");
   static_assert(BKV % 16 == 0 && BKV >= 32 && BKV <= 128, "kv block");
+  static_assert(!VT || BKV % 64 == 0 || BKV % 64 == 32, "transposed V: 64-key atoms plus at most one 32-key part");
   static constexpr int REM = HD - 64;                    // elements beyond the 64-wide main part
   static constexpr int REMP = (REM + 15) / 16 * 16;      // padded to the MMA K granularity
   static constexpr int REM_PLANES = REM / 8;             // chunk planes TMA fills
@@ -86,9 +92,16 @@ struct Cfg {
   static constexpr int Q_REM = REMP_PLANES * BQ * 16;
   static constexpr int KV_MAIN = BKV * 128;
   static constexpr int KV_REM = REMP_PLANES * BKV * 16;
-  static constexpr int KV_TILE = KV_MAIN + KV_REM;       // one of K or V
-  static constexpr int KV_STAGE = 2 * KV_TILE;
-  static constexpr int KV_TX = 2 * (KV_MAIN + REM_PLANES * BKV * 16);  // bytes TMA delivers per stage
+  static constexpr int KV_TILE = KV_MAIN + KV_REM;       // K (and V in its natural layout)
+  // transposed V block: V_ATOMS tiles of [HDP rows][64 keys] (128B swizzle) + one of [HDP rows][32 keys] (64B swizzle)
+  static constexpr int V_ATOMS = BKV / 64;
+  static constexpr int V_REM32 = BKV % 64;
+  static constexpr int VT_ATOM = HDP * 128;
+  static constexpr int VT_TILE = (V_ATOMS * VT_ATOM + (V_REM32 ? HDP * 64 : 0) + 1023) / 1024 * 1024;
+  static constexpr int V_TILE = VT ? VT_TILE : KV_TILE;
+  static constexpr int KV_STAGE = KV_TILE + V_TILE;
+  static constexpr int K_TX = KV_MAIN + REM_PLANES * BKV * 16;   // bytes TMA delivers per K block
+  static constexpr int V_TX = VT ? HD * BKV * 2 : K_TX;          // ... per V block
   static constexpr int Q_TX = Q_MAIN + REM_PLANES * BQ * 16;
   static constexpr int STAGES = (DB && HD < 96) ? 3 : 2;   // 3 where two CTAs still fit in one SM's shared memory
   static constexpr int OUT_ROW = HD * 2;                 // bytes
@@ -113,6 +126,7 @@ struct Cfg {
   static constexpr int TMEM_COLS = 256;
   static_assert(COL_O + HDP <= TMEM_COLS, "TMEM budget (2 CTAs per SM -> 256 columns each)");
   static_assert(KV_MAIN % 1024 == 0, "swizzle atom alignment");
+  static_assert(!VT || (KV_TILE % 1024 == 0 && VT_ATOM % 1024 == 0), "transposed V tiles start on swizzle-atom boundaries");
 };
 
 struct Params {
@@ -142,6 +156,16 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) 
   d |= static_cast<uint64_t>(1024 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// K-major, 64-byte swizzle: rows of 64 B = 32 elements along K, 8-row groups 512 B apart (SBO)
+__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;   // SWIZZLE_64B
   return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int b_mn_major) {
@@ -302,10 +326,10 @@ struct SmxCtx {
 
 // Softmax + epilogue of ONE work item (nb key/value blocks of one 128-query tile) for one softmax thread.
 // `g` is the tile's running block counter (parity of s_full / s_empty / p_full / pv_done).
-template <int HD, int BKV, bool CAUSAL, bool DB>
+template <int HD, int BKV, bool CAUSAL, bool DB, bool VT>
 __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, const CUtensorMap* tm_out, int qt, int h,
                                              int b, int nb, uint32_t& g, int quarter, int half, int lane) {
-  using C = Cfg<HD, BKV, DB>;
+  using C = Cfg<HD, BKV, DB, VT>;
   constexpr int CW = C::CW, OW = C::OW;
   const int row = quarter * 32 + lane;
   const int qrow = qt * BQ + row;
@@ -514,12 +538,13 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
   }
 }
 
-template <int HD, int BKV, bool CAUSAL, bool DB>
+template <int HD, int BKV, bool CAUSAL, bool DB, bool VT>
 __global__ void __launch_bounds__(THREADS, 2)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_constant__ CUtensorMap tm_q_rem,
                         const __grid_constant__ CUtensorMap tm_kv_main, const __grid_constant__ CUtensorMap tm_kv_rem,
+                        const __grid_constant__ CUtensorMap tm_vt_main, const __grid_constant__ CUtensorMap tm_vt_rem,
                         const __grid_constant__ CUtensorMap tm_out, Params p) {
-  using C = Cfg<HD, BKV, DB>;
+  using C = Cfg<HD, BKV, DB, VT>;
   constexpr int ST = C::STAGES;
   extern __shared__ uint8_t attn_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -559,11 +584,21 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
       }
     ptx::fence_proxy_async_smem();
   }
+  if (VT) {
+    // rows HD..HDP-1 of the transposed V tiles (the O columns that pad the head dim to the MMA's N granularity) are
+    // never written by TMA: zero the tiles once so the discarded accumulator columns stay finite
+    for (int st = 0; st < C::STAGES; ++st) {
+      uint4* tile = reinterpret_cast<uint4*>(s_kv + st * C::KV_STAGE_AL + C::KV_TILE);
+      for (int i = threadIdx.x; i < C::V_TILE / 16; i += THREADS) tile[i] = make_uint4(0, 0, 0, 0);
+    }
+    ptx::fence_proxy_async_smem();
+  }
   if (warp == WARP_TMA && lane == 0) {
     ptx::prefetch_tmap(&tm_q_main);
     ptx::prefetch_tmap(&tm_kv_main);
     ptx::prefetch_tmap(&tm_out);
     if (C::REM > 0) { ptx::prefetch_tmap(&tm_q_rem); ptx::prefetch_tmap(&tm_kv_rem); }
+    if (VT) { ptx::prefetch_tmap(&tm_vt_main); if (C::V_REM32) ptx::prefetch_tmap(&tm_vt_rem); }
     ptx::mbar_init(q_full, 1);
     ptx::mbar_init(q_empty, 1);
     for (int s = 0; s < ST; ++s) {
@@ -613,20 +648,35 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
           uint8_t* kt = s_kv + st * C::KV_STAGE_AL;
           uint8_t* vt = kt + C::KV_TILE;
           ATTN_TIMED_WAIT(1, &k_empty[st], par);
-          ptx::mbar_arrive_expect_tx(&k_full[st], C::KV_TX / 2);
+          ptx::mbar_arrive_expect_tx(&k_full[st], C::K_TX);
           tma_load_3d(&tm_kv_main, &k_full[st], kt, col_k, j * BKV, b);
           for (int pl = 0; pl < C::REM_PLANES; ++pl)
             tma_load_3d(&tm_kv_rem, &k_full[st], kt + C::KV_MAIN + pl * BKV * 16, col_k + 64 + 8 * pl, j * BKV, b);
           ATTN_TIMED_WAIT(2, &v_empty[st], par);
-          ptx::mbar_arrive_expect_tx(&v_full[st], C::KV_TX / 2);
-          tma_load_3d(&tm_kv_main, &v_full[st], vt, col_v, j * BKV, b);
-          for (int pl = 0; pl < C::REM_PLANES; ++pl)
-            tma_load_3d(&tm_kv_rem, &v_full[st], vt + C::KV_MAIN + pl * BKV * 16, col_v + 64 + 8 * pl, j * BKV, b);
+          ptx::mbar_arrive_expect_tx(&v_full[st], C::V_TX);
+          if (VT) {   // [B][H*hd][T]: rows h*HD .. +HD, keys j*BKV .. +BKV (keys beyond T are zero-filled)
+            for (int a = 0; a < C::V_ATOMS; ++a)
+              tma_load_3d(&tm_vt_main, &v_full[st], vt + a * C::VT_ATOM, j * BKV + a * 64, h * HD, b);
+            if (C::V_REM32)
+              tma_load_3d(&tm_vt_rem, &v_full[st], vt + C::V_ATOMS * C::VT_ATOM, j * BKV + C::V_ATOMS * 64, h * HD, b);
+          } else {
+            tma_load_3d(&tm_kv_main, &v_full[st], vt, col_v, j * BKV, b);
+            for (int pl = 0; pl < C::REM_PLANES; ++pl)
+              tma_load_3d(&tm_kv_rem, &v_full[st], vt + C::KV_MAIN + pl * BKV * 16, col_v + 64 + 8 * pl, j * BKV, b);
+          }
         }
       }
     }
   } else if (warp == WARP_MMA) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, uniform control flow)
+    // transposed V: descriptor of the 16-key step k of a block (k-steps 0..3 of each 64-key atom, then the 32-key part)
+    constexpr uint32_t idesc_pv_vt = make_idesc(BQ, C::HDP, 0);
+    auto vt_desc = [](uint32_t v_addr, int k) -> uint64_t {
+      const int a = k >> 2;
+      if (a < C::V_ATOMS) return ptx::make_kmajor_sw128_desc(v_addr + a * C::VT_ATOM) + static_cast<uint64_t>(2 * (k & 3));
+      return make_kmajor_sw64_desc(v_addr + C::V_ATOMS * C::VT_ATOM) + static_cast<uint64_t>(2 * (k - 4 * C::V_ATOMS));
+    };
+    (void)idesc_pv_vt; (void)vt_desc;
     if (DB) {
       constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, 0);
       constexpr uint32_t idesc_pv_main = make_idesc(BQ, 64, 1);
@@ -677,11 +727,15 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k) {
             const uint32_t acc = (j | k) != 0 ? 1u : 0u;
-            const uint64_t dv = make_mnmajor_sw128_desc(v_addr + k * 16 * 128);
-            ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), dv, idesc_pv_main, acc);
-            if (C::REMP > 0) {
-              const uint64_t dvr = make_nosw_desc(v_addr + C::KV_MAIN + k * 16 * 16, 128, BKV * 16);
-              ptx::umma_bf16_ts_w(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
+            if (VT) {
+              ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), vt_desc(v_addr, k), idesc_pv_vt, acc);
+            } else {
+              const uint64_t dv = make_mnmajor_sw128_desc(v_addr + k * 16 * 128);
+              ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), dv, idesc_pv_main, acc);
+              if (C::REMP > 0) {
+                const uint64_t dvr = make_nosw_desc(v_addr + C::KV_MAIN + k * 16 * 16, 128, BKV * 16);
+                ptx::umma_bf16_ts_w(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
+              }
             }
           }
           ptx::umma_commit_w(&v_empty[st]);
@@ -746,11 +800,15 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
 #pragma unroll
           for (int k = 0; k < ((CLIPB200_ATTN_DBG & 16) ? 0 : BKV / 16); ++k) {
             const uint32_t acc = (j | k) != 0 ? 1u : 0u;
-            const uint64_t dv = make_mnmajor_sw128_desc(v_addr + k * 16 * 128);
-            ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), dv, idesc_pv_main, acc);
-            if (C::REMP > 0 && !(CLIPB200_ATTN_DBG & 8)) {
-              const uint64_t dvr = make_nosw_desc(v_addr + C::KV_MAIN + k * 16 * 16, 128, BKV * 16);
-              ptx::umma_bf16_ts_w(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
+            if (VT) {
+              ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), vt_desc(v_addr, k), idesc_pv_vt, acc);
+            } else {
+              const uint64_t dv = make_mnmajor_sw128_desc(v_addr + k * 16 * 128);
+              ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), dv, idesc_pv_main, acc);
+              if (C::REMP > 0 && !(CLIPB200_ATTN_DBG & 8)) {
+                const uint64_t dvr = make_nosw_desc(v_addr + C::KV_MAIN + k * 16 * 16, 128, BKV * 16);
+                ptx::umma_bf16_ts_w(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
+              }
             }
           }
           ptx::umma_commit_w(&v_empty[st]);
@@ -782,7 +840,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
       const int bh = item / p.q_tiles;
       const int h = bh % p.H, b = bh / p.H;
       const int nb = item_blocks(qt);
-      softmax_item<HD, BKV, CAUSAL, DB>(ctx, p, &tm_out, qt, h, b, nb, g, quarter, half, lane);
+      softmax_item<HD, BKV, CAUSAL, DB, VT>(ctx, p, &tm_out, qt, h, b, nb, g, quarter, half, lane);
     }
     if (half == 0 && lane == 0) ptx::tma_store_wait<0>();
   }
@@ -808,17 +866,41 @@ inline bool make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t cols, uint6
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
+// 3-D tensor map over the transposed V tensor [B, rows = H*hd, T keys] bf16 with a padded key stride `ld` (multiple
+// of 8 elements): box = {box_keys, box_rows, 1}; 128-byte swizzle for 64-key boxes, 64-byte swizzle for 32-key boxes.
+// The key dimension is T, not ld: keys beyond T are out of bounds (zero-filled on load, dropped on store).
+inline bool make_tmap_vt(CUtensorMap* tm, const void* base, uint64_t T, uint64_t ld, uint64_t rows, uint64_t B,
+                         uint32_t box_keys, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[3] = {T, rows, B};
+  cuuint64_t strides[2] = {ld * 2, ld * 2 * rows};
+  cuuint32_t box[3] = {box_keys, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_keys == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+inline int attn_vt_ld(int T) { return (T + 7) & ~7; }   // key stride of the transposed V tensor
 
-template <int HD, int BKV, bool CAUSAL, bool DB>
-inline cudaError_t launch_t(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int num_sms,
-                            cudaStream_t st) {
-  using C = Cfg<HD, BKV, DB>;
-  CUtensorMap q_main, q_rem, kv_main, kv_rem, o_map;
+template <int HD, int BKV, bool CAUSAL, bool DB, bool VT>
+inline cudaError_t launch_t(const __nv_bfloat16* qkv, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int T, int H,
+                            int num_sms, cudaStream_t st) {
+  using C = Cfg<HD, BKV, DB, VT>;
+  CUtensorMap q_main, q_rem, kv_main, kv_rem, vt_main, vt_rem, o_map;
   const uint64_t cols = 3ull * H * HD;
   if (!make_tmap_3d(&q_main, qkv, cols, T, B, 64, BQ, true)) return cudaErrorUnknown;
   if (!make_tmap_3d(&kv_main, qkv, cols, T, B, 64, BKV, true)) return cudaErrorUnknown;
   if (!make_tmap_3d(&q_rem, qkv, cols, T, B, 8, BQ, false)) return cudaErrorUnknown;
   if (!make_tmap_3d(&kv_rem, qkv, cols, T, B, 8, BKV, false)) return cudaErrorUnknown;
+  vt_main = kv_main;
+  vt_rem = kv_rem;
+  if (VT) {
+    if (vt == nullptr) return cudaErrorInvalidValue;
+    if (!make_tmap_vt(&vt_main, vt, T, attn_vt_ld(T), static_cast<uint64_t>(H) * HD, B, 64, HD)) return cudaErrorUnknown;
+    if (!make_tmap_vt(&vt_rem, vt, T, attn_vt_ld(T), static_cast<uint64_t>(H) * HD, B, 32, HD)) return cudaErrorUnknown;
+  }
   if (!make_tmap_3d(&o_map, out, static_cast<uint64_t>(H) * HD, T, B, HD, 32, false)) return cudaErrorUnknown;
   Params p;
   p.T = T; p.H = H; p.B = B;
@@ -826,16 +908,17 @@ inline cudaError_t launch_t(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B,
   p.n_items = p.q_tiles * H * B;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   const int grid = p.n_items < 2 * num_sms ? p.n_items : 2 * num_sms;
-  attn_fwd_tcgen05_kernel<HD, BKV, CAUSAL, DB><<<grid, THREADS, C::SMEM_BYTES, st>>>(q_main, q_rem, kv_main, kv_rem, o_map, p);
+  attn_fwd_tcgen05_kernel<HD, BKV, CAUSAL, DB, VT><<<grid, THREADS, C::SMEM_BYTES, st>>>(q_main, q_rem, kv_main, kv_rem,
+                                                                                         vt_main, vt_rem, o_map, p);
   return cudaGetLastError();
 }
-template <int HD, int BKV, bool DB>
+template <int HD, int BKV, bool DB, bool VT = false>
 inline cudaError_t configure_t() {
-  cudaError_t e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<HD, BKV, false, DB>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HD, BKV, DB>::SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<HD, BKV, false, DB, VT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HD, BKV, DB, VT>::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<HD, BKV, true, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              Cfg<HD, BKV, DB>::SMEM_BYTES);
+  return cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<HD, BKV, true, DB, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              Cfg<HD, BKV, DB, VT>::SMEM_BYTES);
 }
 
 // Double-buffered S needs one softmax warp per row block (P aliases S); the SPLIT == 2 experiment keeps the single-S
@@ -850,6 +933,11 @@ inline cudaError_t attn_tcgen05_configure_device() {
   if ((e = attn::configure_t<72, 96, false>()) != cudaSuccess) return e;
   if ((e = attn::configure_t<80, 96, false>()) != cudaSuccess) return e;
   if ((e = attn::configure_t<96, 64, false>()) != cudaSuccess) return e;
+  // transposed-V variants (single S, 96-key blocks = one 64-key atom + one 32-key part per V block)
+  if ((e = attn::configure_t<64, 96, false, true>()) != cudaSuccess) return e;
+  if ((e = attn::configure_t<72, 96, false, true>()) != cudaSuccess) return e;
+  if ((e = attn::configure_t<80, 96, false, true>()) != cudaSuccess) return e;
+  if ((e = attn::configure_t<96, 64, false, true>()) != cudaSuccess) return e;
   if (attn::kDoubleS) {
     if ((e = attn::configure_t<64, 96, attn::kDoubleS>()) != cudaSuccess) return e;
     if ((e = attn::configure_t<72, 64, attn::kDoubleS>()) != cudaSuccess) return e;
@@ -868,8 +956,8 @@ inline cudaError_t attn_tcgen05(const __nv_bfloat16* qkv, __nv_bfloat16* out, in
   static const bool single_s = !attn::kDoubleS || getenv("CLIPB200_ATTN_SINGLE_S") != nullptr;
 #define CLIPB200_ATTN_CASE(HD_, BKV_, DB_)                                                             \
   if (hd == HD_)                                                                                       \
-    return causal ? attn::launch_t<HD_, BKV_, true, DB_>(qkv, out, B, T, H, num_sms, st)               \
-                  : attn::launch_t<HD_, BKV_, false, DB_>(qkv, out, B, T, H, num_sms, st);
+    return causal ? attn::launch_t<HD_, BKV_, true, DB_, false>(qkv, nullptr, out, B, T, H, num_sms, st) \
+                  : attn::launch_t<HD_, BKV_, false, DB_, false>(qkv, nullptr, out, B, T, H, num_sms, st);
   // Which protocol per head dim is a measurement (tests/native/attn_test.cu, B = 128 / 64, T = 576, profiles/r01g_*):
   //   hd 64: double-buffered S, 96-key blocks   616 TFLOP/s  (single S: 589)
   //   hd 72: single S, 96-key blocks            634          (double S needs 64-key blocks to fit 256 TMEM columns: 617)
@@ -890,6 +978,23 @@ inline cudaError_t attn_tcgen05(const __nv_bfloat16* qkv, __nv_bfloat16* out, in
   CLIPB200_ATTN_CASE(80, 96, false)
   CLIPB200_ATTN_CASE(96, 64, false)
 #undef CLIPB200_ATTN_CASE
+  return cudaErrorInvalidValue;
+}
+
+// Same, with V taken from the transposed tensor vt [B, H*hd, ld = attn_vt_ld(T)] (written by the qkv GEMM's epilogue,
+// gemm_sm100.cuh EPI_QKVT); the V third of `qkv` is not read.
+inline cudaError_t attn_tcgen05_vt(const __nv_bfloat16* qkv, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int T,
+                                   int H, int hd, bool causal, int num_sms, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+#define CLIPB200_ATTN_VT_CASE(HD_, BKV_)                                                                       \
+  if (hd == HD_)                                                                                               \
+    return causal ? attn::launch_t<HD_, BKV_, true, false, true>(qkv, vt, out, B, T, H, num_sms, st)           \
+                  : attn::launch_t<HD_, BKV_, false, false, true>(qkv, vt, out, B, T, H, num_sms, st);
+  CLIPB200_ATTN_VT_CASE(64, 96)
+  CLIPB200_ATTN_VT_CASE(72, 96)
+  CLIPB200_ATTN_VT_CASE(80, 96)
+  CLIPB200_ATTN_VT_CASE(96, 64)
+#undef CLIPB200_ATTN_VT_CASE
   return cudaErrorInvalidValue;
 }
 

@@ -394,6 +394,11 @@ Status Engine::AllocWorkspace() {
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&x_), rows * D_ * 4));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&h_), rows * D_ * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&qkv_), rows * 3 * D_ * 2));
+  // transposed V [mb][D][ld] for the single-instruction PV path (CLIPB200_ATTN_NO_VT=1 keeps V in qkv_: A/B runs)
+  attn_vt_ = !fastvit_ && attn_tcgen05_supported(hd_) && (2 * D_) % 32 == 0 &&
+             !(getenv("CLIPB200_ATTN_NO_VT") != nullptr && atoi(getenv("CLIPB200_ATTN_NO_VT")) != 0);
+  if (attn_vt_)
+    RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&vt_), static_cast<size_t>(mb_) * D_ * attn::attn_vt_ld(T_) * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&mlpbuf_), rows * mlp_ * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&pooled_), static_cast<size_t>(mb_) * D_ * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&proj_out_), static_cast<size_t>(mb_) * std::max(E_, D_) * 4));
@@ -638,11 +643,23 @@ Status Engine::Blocks(int rows, int n_seq, int T, bool causal) {
     GemmEpilogue ep;
     ep.out_bf16 = qkv_;
     ep.ldc = 3 * D_;
-    RET_IF_ERR(Gemm(h_, D_, b.qkv, rows, EPI_BF16, &ep));
+    // With the transposed-V attention kernel the qkv GEMM writes q | k as before and v straight into
+    // vt_[b][h*hd + d][t] (EPI_QKVT): V is then a K-major operand and O += P V is one tcgen05.mma per 16 keys.
+    const bool vt = attn_vt_ && vt_ != nullptr;
+    if (vt) {
+      ep.out_vt = vt_;
+      ep.vt_col0 = 2 * D_;
+      ep.vt_T = T;
+      ep.vt_ld = attn::attn_vt_ld(T);
+      ep.vt_B = n_seq;
+    }
+    RET_IF_ERR(Gemm(h_, D_, b.qkv, rows, vt ? EPI_QKVT : EPI_BF16, &ep));
     ProfBegin(PC_ATTN, compute_);
     // tcgen05/TMEM kernel for head dims >= 64; the mma.sync kernel remains for head dim 32 (FastViT-style heads)
-    e = attn_tcgen05_supported(hd_) ? attn_tcgen05(qkv_, h_, n_seq, T, H_, hd_, causal, num_sms_, compute_)
-                                    : launch_flash_attention(qkv_, h_, n_seq, T, H_, hd_, causal, compute_);
+    if (vt) e = attn_tcgen05_vt(qkv_, vt_, h_, n_seq, T, H_, hd_, causal, num_sms_, compute_);
+    else
+      e = attn_tcgen05_supported(hd_) ? attn_tcgen05(qkv_, h_, n_seq, T, H_, hd_, causal, num_sms_, compute_)
+                                      : launch_flash_attention(qkv_, h_, n_seq, T, H_, hd_, causal, compute_);
     ProfEnd(PC_ATTN, compute_);
     CUDA_RET(e, "attention");
     GemmEpilogue ep2;
@@ -1043,7 +1060,7 @@ Status Engine::GrowStage(ResizeStage* st, size_t src, size_t tmp, size_t arena_w
   return Status::OK();
 }
 
-// Copies a list of (dst, src, bytes) with up to 8 host threads: one core moves ~10 GB/s from pageable memory, a photo
+// Copies a list of (dst, src, bytes) with up to 16 host threads: one core moves ~10 GB/s from pageable memory, a photo
 // is tens of MB, and PCIe takes > 50 GB/s, so a single-threaded staging copy would be the bottleneck of the whole path.
 namespace {
 struct CopyPiece {
@@ -1060,7 +1077,7 @@ void parallel_copy(const std::vector<CopyPiece>& pieces) {
     for (size_t o = 0; o < p.bytes; o += kChunk) chunks.push_back({p.dst + o, p.src + o, std::min(kChunk, p.bytes - o)});
   }
   unsigned hw = std::thread::hardware_concurrency();
-  const size_t threads = std::min<size_t>({size_t(8), hw > 1 ? hw : 1, chunks.size()});
+  const size_t threads = std::min<size_t>({size_t(16), hw > 2 ? hw - 1 : 1, chunks.size()});
   if (total < (size_t(8) << 20) || threads <= 1) {
     for (const CopyPiece& c : chunks) memcpy(c.dst, c.src, c.bytes);
     return;
@@ -1222,15 +1239,18 @@ Status Engine::VisionEmbedRgb8Var(const uint8_t* const* imgs, const int32_t* wid
   cudaPointerAttributes attr;
   const bool out_pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
-  const int64_t steps = (batch + mb_ - 1) / mb_;
+  // Photos are tens of MB each: staging + PCIe of a micro-batch takes as long as its tower, so the micro-batch is kept
+  // small enough (<= 64 images) that even a call with a few dozen photos overlaps the two.
+  const int64_t mb = std::min<int64_t>(mb_, 64);
+  const int64_t steps = (batch + mb - 1) / mb;
   Status st = Status::OK();
   for (int64_t s = 0; s < steps && st.ok(); ++s) {
     const int slot = static_cast<int>(s & 1);
-    const int n = static_cast<int>(std::min<int64_t>(mb_, batch - s * mb_));
+    const int n = static_cast<int>(std::min<int64_t>(mb, batch - s * mb));
     if (s >= 2) CUDA_RET(cudaStreamWaitEvent(copy_in_, in_consumed_[slot], 0), "wait consumed");
     uint8_t* d_slot = static_cast<uint8_t*>(d_in_[slot]);
     for (int i = 0; i < n && st.ok();) {
-      const int64_t g = s * mb_ + i;
+      const int64_t g = s * mb + i;
       int consumed = 0;
       st = ResizeGroupToDevice(imgs + g, widths + g, heights + g, n - i, pp, d_slot + static_cast<size_t>(i) * px, &consumed);
       i += consumed;
@@ -1245,16 +1265,16 @@ Status Engine::VisionEmbedRgb8Var(const uint8_t* const* imgs, const int32_t* wid
     CUDA_RET(cudaEventRecord(out_ready_[slot], compute_), "record");
     CUDA_RET(cudaStreamWaitEvent(copy_out_, out_ready_[slot], 0), "wait output");
     ProfBegin(PC_D2H, copy_out_);
-    cudaError_t e = cudaMemcpyAsync(out_pinned ? out + static_cast<size_t>(s) * mb_ * E_ : h_out_[slot], d_out_[slot],
+    cudaError_t e = cudaMemcpyAsync(out_pinned ? out + static_cast<size_t>(s) * mb * E_ : h_out_[slot], d_out_[slot],
                                     static_cast<size_t>(n) * E_ * 4, cudaMemcpyDeviceToHost, copy_out_);
     ProfEnd(PC_D2H, copy_out_);
     CUDA_RET(e, "D2H copy");
     CUDA_RET(cudaEventRecord(out_copied_[slot], copy_out_), "record");
     if (!out_pinned && s >= 1) {  // drain the previous step's output while this one runs
       const int ps = static_cast<int>((s - 1) & 1);
-      const int pn = static_cast<int>(std::min<int64_t>(mb_, batch - (s - 1) * mb_));
+      const int pn = static_cast<int>(std::min<int64_t>(mb, batch - (s - 1) * mb));
       CUDA_RET(cudaEventSynchronize(out_copied_[ps]), "wait D2H");
-      memcpy(out + static_cast<size_t>(s - 1) * mb_ * E_, h_out_[ps], static_cast<size_t>(pn) * E_ * 4);
+      memcpy(out + static_cast<size_t>(s - 1) * mb * E_, h_out_[ps], static_cast<size_t>(pn) * E_ * 4);
     }
   }
   Status sync = Synchronize();
@@ -1262,8 +1282,8 @@ Status Engine::VisionEmbedRgb8Var(const uint8_t* const* imgs, const int32_t* wid
   RET_IF_ERR(sync);
   if (!out_pinned) {
     const int64_t s = steps - 1;
-    const int n = static_cast<int>(std::min<int64_t>(mb_, batch - s * mb_));
-    memcpy(out + static_cast<size_t>(s) * mb_ * E_, h_out_[s & 1], static_cast<size_t>(n) * E_ * 4);
+    const int n = static_cast<int>(std::min<int64_t>(mb, batch - s * mb));
+    memcpy(out + static_cast<size_t>(s) * mb * E_, h_out_[s & 1], static_cast<size_t>(n) * E_ * 4);
   }
   return Status::OK();
 }

@@ -219,7 +219,8 @@ class Engine {
 
   // workspace (device)
   __nv_bfloat16 *patches_ = nullptr, *h_ = nullptr, *qkv_ = nullptr, *mlpbuf_ = nullptr, *pooled_ = nullptr,
-                *yh_ = nullptr, *ymlp_ = nullptr;
+                *yh_ = nullptr, *ymlp_ = nullptr, *vt_ = nullptr;
+  bool attn_vt_ = false;
   float *x_ = nullptr, *y_ = nullptr, *proj_out_ = nullptr;
   int* row_map_ = nullptr;
   int* err_flag_ = nullptr;

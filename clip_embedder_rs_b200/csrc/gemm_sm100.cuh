@@ -26,7 +26,10 @@ enum ActKind : int { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_GELU_TANH = 2, ACT_GEL
 enum EpiMode : int {
   EPI_BF16 = 0,   // out_bf16[r,c] = act(acc + bias[c])
   EPI_RESID = 1,  // out_f32[r,c] += gamma[c] * (acc + bias[c])          (fp32 residual stream, in place)
-  EPI_F32 = 2     // out_f32[remap(r),c] = acc + bias[c] + pos[pos_row(r),c]
+  EPI_F32 = 2,    // out_f32[remap(r),c] = acc + bias[c] + pos[pos_row(r),c]
+  EPI_QKVT = 3    // EPI_BF16 for columns < vt_col0 (q | k); columns >= vt_col0 (v) are written TRANSPOSED into
+                  // out_vt[b][c - vt_col0][t] with r = b * vt_T + t: the layout in which the attention kernel takes V
+                  // as a K-major operand (one tcgen05.mma per 16 keys, attn_sm100.cuh)
 };
 
 struct GemmEpilogue {
@@ -39,6 +42,9 @@ struct GemmEpilogue {
   int act = ACT_NONE;
   // EPI_F32 row remap: out_row = (r / rows_in) * rows_out + (r % rows_in) + row_off (rows_in == 0: identity)
   int rows_in = 0, rows_out = 0, row_off = 0;
+  // EPI_QKVT: out_vt [vt_B][N - vt_col0][vt_ld] bf16, vt_T tokens per sequence (vt_ld >= vt_T, multiple of 8)
+  __nv_bfloat16* out_vt = nullptr;
+  int vt_col0 = 0, vt_T = 0, vt_ld = 0, vt_B = 0;
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -133,9 +139,11 @@ constexpr int GEMM_BK = 64;
 #endif
 template <int EPI>
 struct EpiTraits {
-  static constexpr int WARPS = EPI == 0 /* EPI_BF16 */ ? CLIPB200_GEMM_EPI_WARPS : (EPI == 1 ? CLIPB200_GEMM_RESID_WARPS : 8);
+  static constexpr bool BF16_OUT = EPI == 0 /* EPI_BF16 */ || EPI == 3 /* EPI_QKVT */;
+  static constexpr int WARPS = BF16_OUT ? CLIPB200_GEMM_EPI_WARPS : (EPI == 1 ? CLIPB200_GEMM_RESID_WARPS : 8);
   static constexpr int SLOTS = WARPS / 4;                 // warps per TMEM lane quarter
-  static constexpr bool NARROW = WARPS == 16 && EPI == 0;
+  static constexpr bool NARROW = WARPS == 16 && BF16_OUT;
+  static_assert(EPI != 3 || NARROW, "the transposing epilogue is written for the 16-warp bf16 layout");
   static constexpr int THREADS = 32 * (WARPS + 2);        // epilogue warps, then the TMA warp, then the MMA warp
   static constexpr int STAGE_BYTES = NARROW ? 32 * 64 : 32 * 128;  // per epilogue warp: 32 swizzled rows
 };
@@ -169,7 +177,7 @@ template <int BN, int EPI, int NCTA>
 __global__ void __launch_bounds__(EpiTraits<EPI>::THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                          const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_wt,
-                         int M, int N, int K, int n_tail, GemmEpilogue ep) {
+                         const __grid_constant__ CUtensorMap tmap_vt, int M, int N, int K, int n_tail, GemmEpilogue ep) {
   // n_tail = 128: the last column tile is only 128 wide (N = 1152 = 4 x 256 + 128, N = 3456 = 13 x 256 + 128): its W
   // box comes from `tmap_wt` and its MMAs use N = 128, so the tail costs half a tile instead of a padded full one.
   using Cfg = GemmCfg<BN, NCTA, EPI>;
@@ -206,6 +214,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_w);
     if (EPI != EPI_F32) ptx::prefetch_tmap(&tmap_c);
+    if (EPI == EPI_QKVT) ptx::prefetch_tmap(&tmap_vt);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -330,7 +339,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int row_base = m_blk * TILE_M + rank * GEMM_BM + quarter * 32;
       const uint32_t taddr_row = tmem_base + static_cast<uint32_t>(acc * 256) +
                                  (static_cast<uint32_t>(quarter * 32) << 16);
-      if (EPI == EPI_BF16 && ET::NARROW) {
+      if ((EPI == EPI_BF16 || EPI == EPI_QKVT) && ET::NARROW) {
         // 16 epilogue warps: 32-column chunks, 64-byte staging rows (SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3)
         const int sw64 = (lane >> 1) & 3;
 #pragma unroll 1
@@ -354,6 +363,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           if (lane == 0) ptx::tma_store_wait_read<0>();  // the previous store of this warp has left the staging tile
           __syncwarp();
+          if (EPI == EPI_QKVT && n0 >= ep.vt_col0) {
+            // V columns: the staging tile is written transposed, [32 columns][32 tokens] (64-byte rows, lane = token:
+            // every 2-byte store instruction covers 64 contiguous bytes, conflict-free), and stored into
+            // out_vt[b][column][t].  The 32 token rows of this warp may straddle sequences: one store per sequence,
+            // the tensor map's bounds (t in [0, T), b in [0, B)) clip what does not belong to it.
+            uint16_t* st16 = reinterpret_cast<uint16_t*>(stg);
+#pragma unroll
+            for (int c2 = 0; c2 < 16; ++c2) {
+              st16[(2 * c2) * 32 + lane] = static_cast<uint16_t>(pk[c2] & 0xFFFFu);
+              st16[(2 * c2 + 1) * 32 + lane] = static_cast<uint16_t>(pk[c2] >> 16);
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int T = ep.vt_T;
+              for (int b = row_base / T; b < ep.vt_B && b * T < row_base + 32; ++b)
+                ptx::tma_store_3d(&tmap_vt, stg, row_base - b * T, n0 - ep.vt_col0, b);
+              ptx::tma_store_commit();
+            }
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ sw64) << 4)) =
@@ -574,8 +604,8 @@ inline bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint6
 
 template <int BN, int EPI, int NCTA>
 inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc,
-                                 const CUtensorMap& twt, int n_tail, int M, int N, int K, const GemmEpilogue& ep,
-                                 int num_sms, cudaStream_t stream) {
+                                 const CUtensorMap& twt, const CUtensorMap& tvt, int n_tail, int M, int N, int K,
+                                 const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, NCTA, EPI>;
   const int tile_m = GEMM_BM * NCTA;
   const int tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
@@ -593,7 +623,7 @@ inline cudaError_t gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, NCTA>, ta, tw, tc, twt, M, N, K, n_tail, ep);
+  return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, NCTA>, ta, tw, tc, twt, tvt, M, N, K, n_tail, ep);
 }
 
 template <int BN, int EPI, int NCTA>
@@ -609,6 +639,8 @@ inline cudaError_t gemm_configure_device() {
   if ((e = gemm_configure_t<BN_, EPI_BF16, 1>()) != cudaSuccess) return e;     \
   if ((e = gemm_configure_t<BN_, EPI_RESID, 1>()) != cudaSuccess) return e;    \
   if ((e = gemm_configure_t<BN_, EPI_F32, 1>()) != cudaSuccess) return e;      \
+  if ((e = gemm_configure_t<BN_, EPI_QKVT, 1>()) != cudaSuccess) return e;     \
+  if ((e = gemm_configure_t<BN_, EPI_QKVT, 2>()) != cudaSuccess) return e;     \
   if ((e = gemm_configure_t<BN_, EPI_BF16, 2>()) != cudaSuccess) return e;     \
   if ((e = gemm_configure_t<BN_, EPI_RESID, 2>()) != cudaSuccess) return e;    \
   if ((e = gemm_configure_t<BN_, EPI_F32, 2>()) != cudaSuccess) return e;
@@ -662,8 +694,25 @@ inline cudaError_t gemm_bf16(const __nv_bfloat16* A, long long lda, const __nv_b
   const int n_tail = gemm_tail_cols(N, bn);
   CUtensorMap twt = tw;
   if (n_tail != 0 && !make_tmap_2d(&twt, W, N, K, ldw, n_tail / ncta, 2)) return cudaErrorUnknown;
-  if (epi_mode == EPI_BF16) {
+  CUtensorMap tvt = ta;  // only read in EPI_QKVT mode
+  if (epi_mode == EPI_BF16 || epi_mode == EPI_QKVT) {
     if (!make_tmap_2d(&tc, ep.out_bf16, M, N, ep.ldc, 32, 2, EpiTraits<EPI_BF16>::NARROW ? 64 : 128)) return cudaErrorUnknown;
+    if (epi_mode == EPI_QKVT) {
+      // columns [vt_col0, N) go to out_vt [B][N - vt_col0][ld] in 32-column x 32-token boxes (64-byte inner rows)
+      if (ep.out_vt == nullptr || ep.vt_T <= 0 || ep.vt_B <= 0 || (ep.vt_ld & 7) || ep.vt_ld < ep.vt_T ||
+          (ep.vt_col0 & 31) || ep.vt_col0 >= N)
+        return cudaErrorInvalidValue;
+      PFN_encodeTiled enc = get_encode_tiled();
+      if (enc == nullptr) return cudaErrorUnknown;
+      const cuuint64_t rows = static_cast<cuuint64_t>(N - ep.vt_col0);
+      cuuint64_t dims[3] = {static_cast<cuuint64_t>(ep.vt_T), rows, static_cast<cuuint64_t>(ep.vt_B)};
+      cuuint64_t strides[2] = {static_cast<cuuint64_t>(ep.vt_ld) * 2, static_cast<cuuint64_t>(ep.vt_ld) * 2 * rows};
+      cuuint32_t box[3] = {32, 32, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      if (enc(&tvt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ep.out_vt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorUnknown;
+    }
   } else if (epi_mode == EPI_RESID) {
     if (!make_tmap_2d(&tc, ep.out_f32, M, N, ep.ldc, 32, 4, EpiTraits<EPI_RESID>::NARROW ? 64 : 128)) return cudaErrorUnknown;
   } else {
@@ -671,14 +720,16 @@ inline cudaError_t gemm_bf16(const __nv_bfloat16* A, long long lda, const __nv_b
   }
 #define CLIPB200_GEMM_CASE(BN_)                                                                                  \
   if (bn == BN_ && ncta == 1) {                                                                                  \
-    if (epi_mode == EPI_BF16) return gemm_launch_t<BN_, EPI_BF16, 1>(ta, tw, tc, twt, n_tail, M, N, K, ep, num_sms, stream);   \
-    if (epi_mode == EPI_RESID) return gemm_launch_t<BN_, EPI_RESID, 1>(ta, tw, tc, twt, n_tail, M, N, K, ep, num_sms, stream); \
-    return gemm_launch_t<BN_, EPI_F32, 1>(ta, tw, tc, twt, n_tail, M, N, K, ep, num_sms, stream);                              \
+    if (epi_mode == EPI_BF16) return gemm_launch_t<BN_, EPI_BF16, 1>(ta, tw, tc, twt, tvt, n_tail, M, N, K, ep, num_sms, stream);   \
+    if (epi_mode == EPI_QKVT) return gemm_launch_t<BN_, EPI_QKVT, 1>(ta, tw, tc, twt, tvt, n_tail, M, N, K, ep, num_sms, stream);   \
+    if (epi_mode == EPI_RESID) return gemm_launch_t<BN_, EPI_RESID, 1>(ta, tw, tc, twt, tvt, n_tail, M, N, K, ep, num_sms, stream); \
+    return gemm_launch_t<BN_, EPI_F32, 1>(ta, tw, tc, twt, tvt, n_tail, M, N, K, ep, num_sms, stream);                              \
   }                                                                                                              \
   if (bn == BN_ && ncta == 2) {                                                                                  \
-    if (epi_mode == EPI_BF16) return gemm_launch_t<BN_, EPI_BF16, 2>(ta, tw, tc, twt, n_tail, M, N, K, ep, num_sms, stream);   \
-    if (epi_mode == EPI_RESID) return gemm_launch_t<BN_, EPI_RESID, 2>(ta, tw, tc, twt, n_tail, M, N, K, ep, num_sms, stream); \
-    return gemm_launch_t<BN_, EPI_F32, 2>(ta, tw, tc, twt, n_tail, M, N, K, ep, num_sms, stream);                              \
+    if (epi_mode == EPI_BF16) return gemm_launch_t<BN_, EPI_BF16, 2>(ta, tw, tc, twt, tvt, n_tail, M, N, K, ep, num_sms, stream);   \
+    if (epi_mode == EPI_QKVT) return gemm_launch_t<BN_, EPI_QKVT, 2>(ta, tw, tc, twt, tvt, n_tail, M, N, K, ep, num_sms, stream);   \
+    if (epi_mode == EPI_RESID) return gemm_launch_t<BN_, EPI_RESID, 2>(ta, tw, tc, twt, tvt, n_tail, M, N, K, ep, num_sms, stream); \
+    return gemm_launch_t<BN_, EPI_F32, 2>(ta, tw, tc, twt, tvt, n_tail, M, N, K, ep, num_sms, stream);                              \
   }
   CLIPB200_GEMM_CASE(256)
   CLIPB200_GEMM_CASE(192)

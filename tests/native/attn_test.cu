@@ -59,6 +59,17 @@ __global__ void ref_attn(const __nv_bfloat16* qkv, float* out, int B, int T, int
   for (int d = 0; d < hd; ++d) out[(long long)idx * hd + d] = acc[d] / l;
 }
 
+// vt[b][h*hd + d][t] = v[b][t][h*hd + d] (what the qkv GEMM's EPI_QKVT epilogue writes)
+__global__ void transpose_v(const __nv_bfloat16* qkv, __nv_bfloat16* vt, int B, int T, int H, int hd, int ld) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long D = (long long)H * hd;
+  if (idx >= (long long)B * T * D) return;
+  const int c = (int)(idx % D);
+  const long long bt = idx / D;
+  const int t = (int)(bt % T), b = (int)(bt / T);
+  vt[((long long)b * D + c) * ld + t] = qkv[bt * 3 * D + 2 * D + c];
+}
+
 static int run_case(int B, int T, int H, int hd, bool causal, bool time_it, int num_sms) {
   const size_t nq = (size_t)B * T * 3 * H * hd, no = (size_t)B * T * H * hd;
   __nv_bfloat16 *qkv, *o1, *o2;
@@ -68,8 +79,19 @@ static int run_case(int B, int T, int H, int hd, bool causal, bool time_it, int 
   fill_bf16<<<(unsigned)((nq + 255) / 256), 256>>>(qkv, nq, 7, 4.0f);
   CK(cudaMemset(o1, 0, no * 2));
   CK(cudaMemset(o2, 0x7f, no * 2));
+  // transposed V for the single-PV-instruction kernel; poisoned first so that unwritten padding shows up
+  const int ld = attn::attn_vt_ld(T);
+  const size_t nvt = (size_t)B * H * hd * ld;
+  __nv_bfloat16* vt;
+  CK(cudaMalloc(&vt, nvt * 2));
+  CK(cudaMemset(vt, 0x7f, nvt * 2));
+  transpose_v<<<(unsigned)(((size_t)B * T * H * hd + 255) / 256), 256>>>(qkv, vt, B, T, H, hd, ld);
+  static const bool use_vt = getenv("ATTN_NO_VT") == nullptr;
+  auto tc = [&](__nv_bfloat16* o) {
+    return use_vt ? attn_tcgen05_vt(qkv, vt, o, B, T, H, hd, causal, num_sms, 0) : attn_tcgen05(qkv, o, B, T, H, hd, causal, num_sms, 0);
+  };
   CK(launch_flash_attention(qkv, o1, B, T, H, hd, causal, 0));
-  CK(attn_tcgen05(qkv, o2, B, T, H, hd, causal, num_sms, 0));
+  CK(tc(o2));
   CK(cudaDeviceSynchronize());
   std::vector<__nv_bfloat16> h1(no), h2(no);
   CK(cudaMemcpy(h1.data(), o1, no * 2, cudaMemcpyDeviceToHost));
@@ -116,12 +138,12 @@ static int run_case(int B, int T, int H, int hd, bool causal, bool time_it, int 
     for (int w = 0; w < 2; ++w) {
       for (int i = 0; i < 3; ++i) {
         if (w == 0) CK(launch_flash_attention(qkv, o1, B, T, H, hd, causal, 0));
-        else CK(attn_tcgen05(qkv, o2, B, T, H, hd, causal, num_sms, 0));
+        else CK(tc(o2));
       }
       CK(cudaEventRecord(e0));
       for (int i = 0; i < 10; ++i) {
         if (w == 0) CK(launch_flash_attention(qkv, o1, B, T, H, hd, causal, 0));
-        else CK(attn_tcgen05(qkv, o2, B, T, H, hd, causal, num_sms, 0));
+        else CK(tc(o2));
       }
       CK(cudaEventRecord(e1));
       CK(cudaEventSynchronize(e1));
@@ -132,10 +154,10 @@ static int run_case(int B, int T, int H, int hd, bool causal, bool time_it, int 
   const double flops = 4.0 * B * H * (double)T * T * hd * (causal ? 0.5 : 1.0);
   printf("%s B=%d T=%d H=%d hd=%d causal=%d max|tc-mma|=%.4g max|tc-fp32|=%.4g nan=%lld bad=%lld", (bad || nan) ? "FAIL" : "ok  ",
          B, T, H, hd, causal ? 1 : 0, max_d, max_ref, nan, bad);
-  if (time_it) printf("  mma.sync %.3f ms (%.0f TF)  tcgen05 %.3f ms (%.0f TF)", ms1, flops / ms1 * 1e-9, ms2, flops / ms2 * 1e-9);
+  if (time_it) printf("  mma.sync %.3f ms (%.0f TF)  tcgen05%s %.3f ms (%.0f TF)", ms1, flops / ms1 * 1e-9, use_vt ? "+Vt" : "", ms2, flops / ms2 * 1e-9);
   printf("\n");
   fflush(stdout);
-  cudaFree(qkv); cudaFree(o1); cudaFree(o2); cudaFree(dq); cudaFree(dref);
+  cudaFree(qkv); cudaFree(o1); cudaFree(o2); cudaFree(dq); cudaFree(dref); cudaFree(vt);
   return (bad || nan) ? 1 : 0;
 }
 

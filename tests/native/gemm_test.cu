@@ -189,6 +189,73 @@ static int run_case(int M, int N, int K, int epi, int act, int force_bn, bool ti
   return bad ? 1 : 0;
 }
 
+// EPI_QKVT: the q | k columns must equal the plain bf16 epilogue's, the v columns must appear transposed in
+// vt[b][c][t] (ld = T rounded up to 8, padding untouched), bit for bit; optionally timed against the plain epilogue.
+static int run_qkvt_case(int B, int T, int D, int K, bool time_it, int num_sms, int ncta) {
+  const int M = B * T, N = 3 * D, ld = (T + 7) & ~7;
+  __nv_bfloat16 *A, *W, *C0, *C1, *Vt;
+  float* bias;
+  CK(cudaMalloc(&A, (size_t)M * K * 2));
+  CK(cudaMalloc(&W, (size_t)N * K * 2));
+  CK(cudaMalloc(&C0, (size_t)M * N * 2));
+  CK(cudaMalloc(&C1, (size_t)M * N * 2));
+  CK(cudaMalloc(&Vt, (size_t)B * D * ld * 2));
+  CK(cudaMalloc(&bias, (size_t)N * 4));
+  auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
+  fill_bf16<<<blocks((size_t)M * K), 256>>>(A, (size_t)M * K, 11, 2.0f);
+  fill_bf16<<<blocks((size_t)N * K), 256>>>(W, (size_t)N * K, 12, 0.25f);
+  fill_f32<<<blocks(N), 256>>>(bias, N, 13, 1.0f);
+  CK(cudaMemset(C0, 0, (size_t)M * N * 2));
+  CK(cudaMemset(C1, 0x11, (size_t)M * N * 2));
+  CK(cudaMemset(Vt, 0x22, (size_t)B * D * ld * 2));
+  GemmEpilogue e0, e1;
+  e0.bias = bias; e0.ldc = N; e0.out_bf16 = C0;
+  e1 = e0; e1.out_bf16 = C1; e1.out_vt = Vt; e1.vt_col0 = 2 * D; e1.vt_T = T; e1.vt_ld = ld; e1.vt_B = B;
+  CK(gemm_bf16(A, K, W, K, M, N, K, EPI_BF16, e0, num_sms, 0, 0, ncta));
+  CK(gemm_bf16(A, K, W, K, M, N, K, EPI_QKVT, e1, num_sms, 0, 0, ncta));
+  CK(cudaDeviceSynchronize());
+  std::vector<uint16_t> h0((size_t)M * N), h1((size_t)M * N), hv((size_t)B * D * ld);
+  CK(cudaMemcpy(h0.data(), C0, h0.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h1.data(), C1, h1.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hv.data(), Vt, hv.size() * 2, cudaMemcpyDeviceToHost));
+  long long bad = 0;
+  for (int r = 0; r < M && bad < 10; ++r) {
+    const int b = r / T, t = r % T;
+    for (int c = 0; c < 2 * D; ++c)
+      if (h0[(size_t)r * N + c] != h1[(size_t)r * N + c]) { if (bad < 5) printf("   q|k mismatch r=%d c=%d\n", r, c); ++bad; }
+    for (int c = 0; c < D; ++c)
+      if (hv[((size_t)b * D + c) * ld + t] != h0[(size_t)r * N + 2 * D + c]) {
+        if (bad < 5) printf("   vt mismatch b=%d c=%d t=%d: %04x vs %04x\n", b, c, t, hv[((size_t)b * D + c) * ld + t], h0[(size_t)r * N + 2 * D + c]);
+        ++bad;
+      }
+  }
+  for (int b = 0; b < B && bad < 10; ++b)   // padding keys [T, ld) must stay untouched
+    for (int c = 0; c < D; ++c)
+      for (int t = T; t < ld; ++t)
+        if (hv[((size_t)b * D + c) * ld + t] != 0x2222) ++bad;
+  double ms[2] = {0, 0};
+  if (time_it) {
+    cudaEvent_t a, b2;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b2));
+    for (int w = 0; w < 2; ++w) {
+      for (int i = 0; i < 13; ++i) {
+        if (i == 3) CK(cudaEventRecord(a));
+        CK(gemm_bf16(A, K, W, K, M, N, K, w == 0 ? EPI_BF16 : EPI_QKVT, w == 0 ? e0 : e1, num_sms, 0, 0, ncta));
+      }
+      CK(cudaEventRecord(b2));
+      CK(cudaEventSynchronize(b2));
+      float t; CK(cudaEventElapsedTime(&t, a, b2));
+      ms[w] = t / 10;
+    }
+  }
+  printf("%s qkvt B=%d T=%d D=%d K=%d ncta=%d bad=%lld", bad ? "FAIL" : "ok  ", B, T, D, K, ncta, bad);
+  if (time_it) printf("  bf16 %.3f ms (%.0f TF)  qkvt %.3f ms (%.0f TF)", ms[0], 2.0 * M * N * K / ms[0] * 1e-9, ms[1], 2.0 * M * N * K / ms[1] * 1e-9);
+  printf("\n");
+  fflush(stdout);
+  cudaFree(A); cudaFree(W); cudaFree(C0); cudaFree(C1); cudaFree(Vt); cudaFree(bias);
+  return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
   int dev = 0;
   CK(cudaSetDevice(dev));
@@ -220,6 +287,18 @@ int main(int argc, char** argv) {
   if (argc > 1 && atoi(argv[1]) == 4) {  // one short-K, epilogue-heavy launch for ncu (FastViT stage-1 fc1 + GELU)
     const int ncta = argc > 2 ? atoi(argv[2]) : 1;
     return run_case(1048576, 240, 80, EPI_BF16, ACT_GELU_ERF, 0, false, num_sms, ncta);
+  }
+  if (argc > 1 && atoi(argv[1]) == 7) {  // transposing qkv epilogue: correctness on awkward shapes, then the SO400M qkv GEMM timed
+    fails += run_qkvt_case(3, 50, 128, 128, false, num_sms, 1);     // T < 32: a 32-row group spans sequences
+    fails += run_qkvt_case(5, 17, 128, 64, false, num_sms, 1);      // ... three of them
+    fails += run_qkvt_case(4, 77, 512, 512, false, num_sms, 1);     // text tower, ld = 80
+    fails += run_qkvt_case(2, 576, 1152, 1152, false, num_sms, 1);
+    fails += run_qkvt_case(7, 576, 1152, 1152, false, num_sms, 2);  // CTA pairs, M tail
+    fails += run_qkvt_case(3, 730, 1280, 1280, false, num_sms, 2);  // ViT-H/14: ld = 736
+    fails += run_qkvt_case(256, 576, 1152, 1152, true, num_sms, 2);
+    fails += run_qkvt_case(128, 576, 1536, 1536, true, num_sms, 2);
+    printf("%s\n", fails ? "QKVT TEST FAILED" : "QKVT TEST PASSED");
+    return fails;
   }
   if (argc > 1 && atoi(argv[1]) == 6) {  // what does the fp32 reduce-add epilogue cost?  same shapes, bf16 store instead
     const int M = 256 * 576;
