@@ -28,6 +28,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "gemm_sm100.cuh"  // get_encode_tiled
 #include "ptx_sm100.cuh"
 
@@ -324,11 +326,63 @@ struct SmxCtx {
   bool timed;               // this warp feeds the CLIPB200_ATTN_TIMING counters
 };
 
+// CLIPB200_ATTN_DEFER_EPI: the epilogue of a work item (O / l -> bf16 -> smem -> TMA store) is not run when the item's
+// last P has been handed over, where the softmax warps would sit idle until the last PV retires (~1000 cycles of
+// tcgen05.mma execution + commit + barrier hand-off), but inside the NEXT item's first key block, after that block's
+// softmax arithmetic and right before its P store — the point where the protocol waits for that same PV anyway.  The next
+// item's first PV (which overwrites O) is only issued once that P has been stored, i.e. after O has been read.
+#ifndef CLIPB200_ATTN_DEFER_EPI
+#define CLIPB200_ATTN_DEFER_EPI 1
+#endif
+struct PendingEpilogue {
+  bool valid = false;
+  float l_run = 0.f;
+  int qt = 0, h = 0, b = 0;
+};
+
+// O / l -> bf16 -> this warp's staging tile -> TMA store.  The caller has waited for the item's last PV.
+template <int HD, int BKV, bool DB, bool VT>
+__device__ __forceinline__ void epilogue_item(const SmxCtx& cx, const CUtensorMap* tm_out, float l_run, int qt, int h, int b,
+                                              int quarter, int half, int lane) {
+  using C = Cfg<HD, BKV, DB, VT>;
+  constexpr int OW = C::OW;
+  const int row = quarter * 32 + lane;
+  ptx::tc_fence_after();
+  if (SPLIT == 2) cx.xch_sum[half * BQ + row] = l_run;
+  if (half == 0 && lane == 0) ptx::tma_store_wait_read<0>();  // previous item's store has left the staging tile
+  if (SPLIT == 2) pair_barrier(quarter); else __syncwarp();
+  const float l_tot = SPLIT == 2 ? l_run + cx.xch_sum[(half ^ 1) * BQ + row] : l_run;
+  const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+#pragma unroll
+  for (int c = 0; c < OW / 8; ++c) {
+    const int col = half * OW + c * 8;
+    if (col < HD) {
+      uint32_t r[8];
+      tmem_ld_32x32_x8(cx.t_o + static_cast<uint32_t>(c * 8), r);
+      ptx::tmem_ld_wait();
+      uint4 o;
+      o.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+      o.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+      o.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+      o.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+      *reinterpret_cast<uint4*>(cx.stg + lane * C::OUT_ROW + col * 2) = o;
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::fence_proxy_async_smem();
+  if (SPLIT == 2) pair_barrier(quarter); else __syncwarp();
+  if (half == 0 && lane == 0) {
+    tma_store_3d(tm_out, cx.stg, h * HD, qt * BQ + quarter * 32, b);
+    ptx::tma_store_commit();
+  }
+}
+
 // Softmax + epilogue of ONE work item (nb key/value blocks of one 128-query tile) for one softmax thread.
 // `g` is the tile's running block counter (parity of s_full / s_empty / p_full / pv_done).
 template <int HD, int BKV, bool CAUSAL, bool DB, bool VT>
 __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, const CUtensorMap* tm_out, int qt, int h,
-                                             int b, int nb, uint32_t& g, int quarter, int half, int lane) {
+                                             int b, int nb, uint32_t& g, int quarter, int half, int lane,
+                                             PendingEpilogue& pend) {
   using C = Cfg<HD, BKV, DB, VT>;
   constexpr int CW = C::CW, OW = C::OW;
   const int row = quarter * 32 + lane;
@@ -461,9 +515,14 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
     // the previous block's PV: buffer (g - 1) & 1, phase (g - 1) >> 1
     uint64_t* prev_done = DB ? &cx.pv_done[(g - 1) & 1] : cx.pv_done;
     const uint32_t prev_par = DB ? (((g - 1) >> 1) & 1) : ((g & 1) ^ 1);
-    if (!DB || rescale) {
+    const bool run_pending = CLIPB200_ATTN_DEFER_EPI && j == 0 && pend.valid;   // warp-uniform
+    if (!DB || rescale || run_pending) {
       if (cx.timed && lane == 0) { ATTN_TIMED_WAIT(9, prev_done, prev_par); } else { ptx::mbar_wait(prev_done, prev_par); }
       ptx::tc_fence_after();
+    }
+    if (run_pending) {   // the previous item's last PV has retired: read its O before this item's first PV overwrites it
+      epilogue_item<HD, BKV, DB, VT>(cx, tm_out, pend.l_run, pend.qt, pend.h, pend.b, quarter, half, lane);
+      pend.valid = false;
     }
 #pragma unroll
     for (int c = 0; c < CW / 32; ++c) {
@@ -502,40 +561,19 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
     ptx::tc_fence_before();
     if (CLIPB200_ATTN_ELECT_ARRIVE) { if (lane == 0) ptx::mbar_arrive(&cx.p_full[buf]); } else { ptx::mbar_arrive(&cx.p_full[buf]); }
   }
+  if (CLIPB200_ATTN_DEFER_EPI) {   // handed to the next item's first block (or to the kernel's tail)
+    pend.valid = true;
+    pend.l_run = l_run;
+    pend.qt = qt; pend.h = h; pend.b = b;
+    return;
+  }
   // epilogue: wait for the last PV, normalise, store this warp's slice of the O row
   {
     uint64_t* last_done = DB ? &cx.pv_done[(g - 1) & 1] : cx.pv_done;
     const uint32_t last_par = DB ? (((g - 1) >> 1) & 1) : ((g & 1) ^ 1);
     if (cx.timed && lane == 0) { ATTN_TIMED_WAIT(10, last_done, last_par); } else { ptx::mbar_wait(last_done, last_par); }
   }
-  ptx::tc_fence_after();
-  if (SPLIT == 2) cx.xch_sum[half * BQ + row] = l_run;
-  if (half == 0 && lane == 0) ptx::tma_store_wait_read<0>();  // previous item's store has left the staging tile
-  if (SPLIT == 2) pair_barrier(quarter); else __syncwarp();
-  const float l_tot = SPLIT == 2 ? l_run + cx.xch_sum[(half ^ 1) * BQ + row] : l_run;
-  const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
-#pragma unroll
-  for (int c = 0; c < OW / 8; ++c) {
-    const int col = half * OW + c * 8;
-    if (col < HD) {
-      uint32_t r[8];
-      tmem_ld_32x32_x8(cx.t_o + static_cast<uint32_t>(c * 8), r);
-      ptx::tmem_ld_wait();
-      uint4 o;
-      o.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
-      o.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
-      o.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
-      o.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
-      *reinterpret_cast<uint4*>(cx.stg + lane * C::OUT_ROW + col * 2) = o;
-    }
-  }
-  ptx::tc_fence_before();
-  ptx::fence_proxy_async_smem();
-  if (SPLIT == 2) pair_barrier(quarter); else __syncwarp();
-  if (half == 0 && lane == 0) {
-    tma_store_3d(tm_out, cx.stg, h * HD, qt * BQ + quarter * 32, b);
-    ptx::tma_store_commit();
-  }
+  epilogue_item<HD, BKV, DB, VT>(cx, tm_out, l_run, qt, h, b, quarter, half, lane);
 }
 
 template <int HD, int BKV, bool CAUSAL, bool DB, bool VT>
@@ -835,12 +873,19 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
     ctx.xch_sum = ctx.xch_max + 2 * 2 * BQ;                     // [half][row]
     ctx.timed = warp == 0;
     uint32_t g = 0;
+    PendingEpilogue pend;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int qt = item % p.q_tiles;
       const int bh = item / p.q_tiles;
       const int h = bh % p.H, b = bh / p.H;
       const int nb = item_blocks(qt);
-      softmax_item<HD, BKV, CAUSAL, DB, VT>(ctx, p, &tm_out, qt, h, b, nb, g, quarter, half, lane);
+      softmax_item<HD, BKV, CAUSAL, DB, VT>(ctx, p, &tm_out, qt, h, b, nb, g, quarter, half, lane, pend);
+    }
+    if (pend.valid) {   // the last item's epilogue has nobody to ride on
+      uint64_t* last_done = DB ? &pv_done[(g - 1) & 1] : pv_done;
+      const uint32_t last_par = DB ? (((g - 1) >> 1) & 1) : ((g & 1) ^ 1);
+      ptx::mbar_wait(last_done, last_par);
+      epilogue_item<HD, BKV, DB, VT>(ctx, &tm_out, pend.l_run, pend.qt, pend.h, pend.b, quarter, half, lane);
     }
     if (half == 0 && lane == 0) ptx::tma_store_wait<0>();
   }
@@ -888,20 +933,38 @@ template <int HD, int BKV, bool CAUSAL, bool DB, bool VT>
 inline cudaError_t launch_t(const __nv_bfloat16* qkv, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int T, int H,
                             int num_sms, cudaStream_t st) {
   using C = Cfg<HD, BKV, DB, VT>;
-  CUtensorMap q_main, q_rem, kv_main, kv_rem, vt_main, vt_rem, o_map;
-  const uint64_t cols = 3ull * H * HD;
-  if (!make_tmap_3d(&q_main, qkv, cols, T, B, 64, BQ, true)) return cudaErrorUnknown;
-  if (!make_tmap_3d(&kv_main, qkv, cols, T, B, 64, BKV, true)) return cudaErrorUnknown;
-  if (!make_tmap_3d(&q_rem, qkv, cols, T, B, 8, BQ, false)) return cudaErrorUnknown;
-  if (!make_tmap_3d(&kv_rem, qkv, cols, T, B, 8, BKV, false)) return cudaErrorUnknown;
-  vt_main = kv_main;
-  vt_rem = kv_rem;
-  if (VT) {
-    if (vt == nullptr) return cudaErrorInvalidValue;
-    if (!make_tmap_vt(&vt_main, vt, T, attn_vt_ld(T), static_cast<uint64_t>(H) * HD, B, 64, HD)) return cudaErrorUnknown;
-    if (!make_tmap_vt(&vt_rem, vt, T, attn_vt_ld(T), static_cast<uint64_t>(H) * HD, B, 32, HD)) return cudaErrorUnknown;
+  // the seven tensor maps of a launch depend on (buffers, B, T, H) only: encoded once per host thread and instantiation
+  struct Maps {
+    const void *qkv, *vt, *out;
+    int B, T, H;
+    CUtensorMap q_main, q_rem, kv_main, kv_rem, vt_main, vt_rem, o_map;
+  };
+  static thread_local std::vector<Maps> cache;
+  const Maps* m = nullptr;
+  for (const Maps& c : cache)
+    if (c.qkv == qkv && c.vt == vt && c.out == out && c.B == B && c.T == T && c.H == H) { m = &c; break; }
+  if (m == nullptr) {
+    Maps n;
+    n.qkv = qkv; n.vt = vt; n.out = out; n.B = B; n.T = T; n.H = H;
+    const uint64_t cols = 3ull * H * HD;
+    if (!make_tmap_3d(&n.q_main, qkv, cols, T, B, 64, BQ, true)) return cudaErrorUnknown;
+    if (!make_tmap_3d(&n.kv_main, qkv, cols, T, B, 64, BKV, true)) return cudaErrorUnknown;
+    if (!make_tmap_3d(&n.q_rem, qkv, cols, T, B, 8, BQ, false)) return cudaErrorUnknown;
+    if (!make_tmap_3d(&n.kv_rem, qkv, cols, T, B, 8, BKV, false)) return cudaErrorUnknown;
+    n.vt_main = n.kv_main;
+    n.vt_rem = n.kv_rem;
+    if (VT) {
+      if (vt == nullptr) return cudaErrorInvalidValue;
+      if (!make_tmap_vt(&n.vt_main, vt, T, attn_vt_ld(T), static_cast<uint64_t>(H) * HD, B, 64, HD)) return cudaErrorUnknown;
+      if (!make_tmap_vt(&n.vt_rem, vt, T, attn_vt_ld(T), static_cast<uint64_t>(H) * HD, B, 32, HD)) return cudaErrorUnknown;
+    }
+    if (!make_tmap_3d(&n.o_map, out, static_cast<uint64_t>(H) * HD, T, B, HD, 32, false)) return cudaErrorUnknown;
+    if (cache.size() >= 64) cache.clear();
+    cache.push_back(n);
+    m = &cache.back();
   }
-  if (!make_tmap_3d(&o_map, out, static_cast<uint64_t>(H) * HD, T, B, HD, 32, false)) return cudaErrorUnknown;
+  const CUtensorMap &q_main = m->q_main, &q_rem = m->q_rem, &kv_main = m->kv_main, &kv_rem = m->kv_rem,
+                    &vt_main = m->vt_main, &vt_rem = m->vt_rem, &o_map = m->o_map;
   Params p;
   p.T = T; p.H = H; p.B = B;
   p.q_tiles = (T + BQ - 1) / BQ;
@@ -938,6 +1001,12 @@ inline cudaError_t attn_tcgen05_configure_device() {
   if ((e = attn::configure_t<72, 96, false, true>()) != cudaSuccess) return e;
   if ((e = attn::configure_t<80, 96, false, true>()) != cudaSuccess) return e;
   if ((e = attn::configure_t<96, 64, false, true>()) != cudaSuccess) return e;
+  if (attn::kDoubleS) {
+    if ((e = attn::configure_t<64, 96, attn::kDoubleS, true>()) != cudaSuccess) return e;
+    if ((e = attn::configure_t<72, 64, attn::kDoubleS, true>()) != cudaSuccess) return e;
+    if ((e = attn::configure_t<80, 64, attn::kDoubleS, true>()) != cudaSuccess) return e;
+    if ((e = attn::configure_t<96, 64, attn::kDoubleS, true>()) != cudaSuccess) return e;
+  }
   if (attn::kDoubleS) {
     if ((e = attn::configure_t<64, 96, attn::kDoubleS>()) != cudaSuccess) return e;
     if ((e = attn::configure_t<72, 64, attn::kDoubleS>()) != cudaSuccess) return e;
@@ -986,14 +1055,22 @@ inline cudaError_t attn_tcgen05(const __nv_bfloat16* qkv, __nv_bfloat16* out, in
 inline cudaError_t attn_tcgen05_vt(const __nv_bfloat16* qkv, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int T,
                                    int H, int hd, bool causal, int num_sms, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-#define CLIPB200_ATTN_VT_CASE(HD_, BKV_)                                                                       \
+#define CLIPB200_ATTN_VT_CASE(HD_, BKV_, DB_)                                                                  \
   if (hd == HD_)                                                                                               \
-    return causal ? attn::launch_t<HD_, BKV_, true, false, true>(qkv, vt, out, B, T, H, num_sms, st)           \
-                  : attn::launch_t<HD_, BKV_, false, false, true>(qkv, vt, out, B, T, H, num_sms, st);
-  CLIPB200_ATTN_VT_CASE(64, 96)
-  CLIPB200_ATTN_VT_CASE(72, 96)
-  CLIPB200_ATTN_VT_CASE(80, 96)
-  CLIPB200_ATTN_VT_CASE(96, 64)
+    return causal ? attn::launch_t<HD_, BKV_, true, DB_, true>(qkv, vt, out, B, T, H, num_sms, st)             \
+                  : attn::launch_t<HD_, BKV_, false, DB_, true>(qkv, vt, out, B, T, H, num_sms, st);
+  // CLIPB200_ATTN_DOUBLE_S=1: the double-buffered-S protocol (see Cfg) on the transposed-V layout, for A/B runs
+  static const bool double_s = attn::kDoubleS && getenv("CLIPB200_ATTN_DOUBLE_S") != nullptr;
+  if (double_s) {
+    CLIPB200_ATTN_VT_CASE(64, 96, attn::kDoubleS)
+    CLIPB200_ATTN_VT_CASE(72, 64, attn::kDoubleS)
+    CLIPB200_ATTN_VT_CASE(80, 64, attn::kDoubleS)
+    CLIPB200_ATTN_VT_CASE(96, 64, attn::kDoubleS)
+  }
+  CLIPB200_ATTN_VT_CASE(64, 96, false)
+  CLIPB200_ATTN_VT_CASE(72, 96, false)
+  CLIPB200_ATTN_VT_CASE(80, 96, false)
+  CLIPB200_ATTN_VT_CASE(96, 64, false)
 #undef CLIPB200_ATTN_VT_CASE
   return cudaErrorInvalidValue;
 }

@@ -394,9 +394,11 @@ Status Engine::AllocWorkspace() {
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&x_), rows * D_ * 4));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&h_), rows * D_ * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&qkv_), rows * 3 * D_ * 2));
-  // transposed V [mb][D][ld] for the single-instruction PV path (CLIPB200_ATTN_NO_VT=1 keeps V in qkv_: A/B runs)
-  attn_vt_ = !fastvit_ && attn_tcgen05_supported(hd_) && (2 * D_) % 32 == 0 &&
-             !(getenv("CLIPB200_ATTN_NO_VT") != nullptr && atoi(getenv("CLIPB200_ATTN_NO_VT")) != 0);
+  // Transposed V [mb][D][ld] for the single-instruction PV path.  Opt-in (CLIPB200_ATTN_VT=1): measured on B200
+  // (profiles/r02b_*), it makes the attention kernel 2.6 % faster and the qkv GEMM's epilogue as much slower, so the
+  // step time does not move; needs T % 32 == 0 (see gemm_sm100.cuh EPI_QKVT).
+  attn_vt_ = !fastvit_ && attn_tcgen05_supported(hd_) && (2 * D_) % 32 == 0 && T_ % 32 == 0 &&
+             getenv("CLIPB200_ATTN_VT") != nullptr && atoi(getenv("CLIPB200_ATTN_VT")) != 0;
   if (attn_vt_)
     RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&vt_), static_cast<size_t>(mb_) * D_ * attn::attn_vt_ld(T_) * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&mlpbuf_), rows * mlp_ * 2));

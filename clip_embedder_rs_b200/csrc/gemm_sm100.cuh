@@ -17,6 +17,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <unordered_map>
+
 #include "ptx_sm100.cuh"
 #include "tensormap.h"
 
@@ -29,7 +31,7 @@ enum EpiMode : int {
   EPI_F32 = 2,    // out_f32[remap(r),c] = acc + bias[c] + pos[pos_row(r),c]
   EPI_QKVT = 3    // EPI_BF16 for columns < vt_col0 (q | k); columns >= vt_col0 (v) are written TRANSPOSED into
                   // out_vt[b][c - vt_col0][t] with r = b * vt_T + t: the layout in which the attention kernel takes V
-                  // as a K-major operand (one tcgen05.mma per 16 keys, attn_sm100.cuh)
+                  // as a K-major operand (one tcgen05.mma per 16 keys, attn_sm100.cuh).  Needs vt_T % 32 == 0.
 };
 
 struct GemmEpilogue {
@@ -366,8 +368,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (EPI == EPI_QKVT && n0 >= ep.vt_col0) {
             // V columns: the staging tile is written transposed, [32 columns][32 tokens] (64-byte rows, lane = token:
             // every 2-byte store instruction covers 64 contiguous bytes, conflict-free), and stored into
-            // out_vt[b][column][t].  The 32 token rows of this warp may straddle sequences: one store per sequence,
-            // the tensor map's bounds (t in [0, T), b in [0, B)) clip what does not belong to it.
+            // out_vt[b][column][t] by one TMA store.  (A token group that straddled two sequences would need a store
+            // with a negative start coordinate for the second one; the hardware rejects that as an illegal
+            // instruction — measured, r02b — so this mode requires T % 32 == 0.)
             uint16_t* st16 = reinterpret_cast<uint16_t*>(stg);
 #pragma unroll
             for (int c2 = 0; c2 < 16; ++c2) {
@@ -377,9 +380,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              const int T = ep.vt_T;
-              for (int b = row_base / T; b < ep.vt_B && b * T < row_base + 32; ++b)
-                ptx::tma_store_3d(&tmap_vt, stg, row_base - b * T, n0 - ep.vt_col0, b);
+              // vt_T is a multiple of 32 (checked by the launcher), so the 32 token rows of this warp belong to one
+              // sequence; rows beyond M land at b >= vt_B and are dropped by the tensor map's bounds
+              const int b = row_base / ep.vt_T;
+              ptx::tma_store_3d(&tmap_vt, stg, row_base - b * ep.vt_T, n0 - ep.vt_col0, b);
               ptx::tma_store_commit();
             }
             continue;
@@ -587,8 +591,46 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 // ------------------------------------------------------------------------------------------------
 // Row-major [rows, cols] tensor (cols contiguous, leading dimension ld elements), box = [box_rows, 128 bytes of
 // columns], 128-byte swizzle.  elem_bytes 2 = bf16 (64-column box), 4 = fp32 (32-column box).
+inline bool make_tmap_2d_uncached(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                                  uint32_t box_rows, int elem_bytes, int inner_bytes);
+// Encoding a tensor map is a driver call; the engine launches the same few hundred (pointer, shape) combinations every
+// step (452 GEMM launches x 3-4 maps for one SO400M micro-batch), so the encoded maps are kept per host thread.
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows;
+  int elem_bytes, inner_bytes;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           elem_bytes == o.elem_bytes && inner_bytes == o.inner_bytes;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.cols * 0xBF58476D1CE4E5B9ull + (h << 6) + (h >> 2));
+    h ^= (k.ld * 0x94D049BB133111EBull + (h << 6) + (h >> 2));
+    h ^= ((static_cast<uint64_t>(k.box_rows) << 16 | static_cast<uint64_t>(k.elem_bytes) << 8 | static_cast<uint64_t>(k.inner_bytes)) + (h << 6) + (h >> 2));
+    return static_cast<size_t>(h);
+  }
+};
 inline bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                          uint32_t box_rows, int elem_bytes, int inner_bytes = 128) {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  const TmapKey key{base, rows, cols, ld, box_rows, elem_bytes, inner_bytes};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *tm = it->second;
+    return true;
+  }
+  if (!make_tmap_2d_uncached(tm, base, rows, cols, ld, box_rows, elem_bytes, inner_bytes)) return false;
+  if (cache.size() >= 4096) cache.clear();  // bounded: shapes change with the micro-batch tail, pointers with the engine
+  cache.emplace(key, *tm);
+  return true;
+}
+inline bool make_tmap_2d_uncached(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                                  uint32_t box_rows, int elem_bytes, int inner_bytes) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (enc == nullptr) return false;
   cuuint64_t dims[2] = {cols, rows};
@@ -699,7 +741,7 @@ inline cudaError_t gemm_bf16(const __nv_bfloat16* A, long long lda, const __nv_b
     if (!make_tmap_2d(&tc, ep.out_bf16, M, N, ep.ldc, 32, 2, EpiTraits<EPI_BF16>::NARROW ? 64 : 128)) return cudaErrorUnknown;
     if (epi_mode == EPI_QKVT) {
       // columns [vt_col0, N) go to out_vt [B][N - vt_col0][ld] in 32-column x 32-token boxes (64-byte inner rows)
-      if (ep.out_vt == nullptr || ep.vt_T <= 0 || ep.vt_B <= 0 || (ep.vt_ld & 7) || ep.vt_ld < ep.vt_T ||
+      if (ep.out_vt == nullptr || ep.vt_T <= 0 || (ep.vt_T & 31) || ep.vt_B <= 0 || (ep.vt_ld & 7) || ep.vt_ld < ep.vt_T ||
           (ep.vt_col0 & 31) || ep.vt_col0 >= N)
         return cudaErrorInvalidValue;
       PFN_encodeTiled enc = get_encode_tiled();
