@@ -715,147 +715,99 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
       return make_kmajor_sw64_desc(v_addr + C::V_ATOMS * C::VT_ATOM) + static_cast<uint64_t>(2 * (k - 4 * C::V_ATOMS));
     };
     (void)idesc_pv_vt; (void)vt_desc;
-    if (DB) {
-      constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, 0);
-      constexpr uint32_t idesc_pv_main = make_idesc(BQ, 64, 1);
-      constexpr uint32_t idesc_pv_rem = make_idesc(BQ, C::REMP > 0 ? C::REMP : 16, 1);
-      const uint32_t t_o = tmem_base + C::COL_O;
-      const uint32_t q_addr = ptx::smem_u32(s_q);
-      uint32_t g = 0, it = 0;
-      // S(gg) = Q K(gg)^T into S buffer gg & 1.  No wait on the softmax warps: the buffer's previous contents (P of block
-      // gg - 2) were consumed by PV(gg - 2), which this warp issued earlier and the tensor pipe executes first.
-      auto issue_qk = [&](uint32_t gg) {
-        const int st = gg % ST;
-        const int buf = gg & 1;
-        const uint32_t k_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL);
-        const uint32_t t_s = tmem_base + C::COL_S + static_cast<uint32_t>(buf * BKV);
-        ATTN_TIMED_WAIT(3, &k_full[st], (gg / ST) & 1);
-        ptx::tc_fence_after();
-        const uint64_t dq = ptx::make_kmajor_sw128_desc(q_addr);
-        const uint64_t dk = ptx::make_kmajor_sw128_desc(k_addr);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          ptx::umma_bf16_ss_w(t_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_qk,
-                              k != 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < C::REMP / 16; ++k) {
-          const uint64_t dqr = make_nosw_desc(q_addr + C::Q_MAIN + k * 2 * BQ * 16, BQ * 16, 128);
-          const uint64_t dkr = make_nosw_desc(k_addr + C::KV_MAIN + k * 2 * BKV * 16, BKV * 16, 128);
-          ptx::umma_bf16_ss_w(t_s, dqr, dkr, idesc_qk, 1u);
-        }
-        ptx::umma_commit_w(&k_empty[st]);
-        ptx::umma_commit_w(&s_full[buf]);
-      };
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        const int qt = item % p.q_tiles;
-        const int nb = item_blocks(qt);
-        ATTN_TIMED_WAIT(5, q_full, it & 1);
-        ptx::tc_fence_after();
-        issue_qk(g);
-        if (nb > 1) issue_qk(g + 1);
-        if (nb <= 2) ptx::umma_commit_w(q_empty);        // every QK^T of this item is issued: Q is free when they retire
-        for (int j = 0; j < nb; ++j, ++g) {
-          const int st = g % ST;
-          const int buf = g & 1;
-          const uint32_t v_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL + C::KV_TILE);
-          const uint32_t t_p = tmem_base + C::COL_S + static_cast<uint32_t>(buf * BKV);   // P(j) in place over S(j)
-          ATTN_TIMED_WAIT(6, &v_full[st], (g / ST) & 1);
-          ATTN_TIMED_WAIT(7, &p_full[buf], (g >> 1) & 1);
-          ptx::tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
-            const uint32_t acc = (j | k) != 0 ? 1u : 0u;
-            if (VT) {
-              ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), vt_desc(v_addr, k), idesc_pv_vt, acc);
-            } else {
-              const uint64_t dv = make_mnmajor_sw128_desc(v_addr + k * 16 * 128);
-              ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), dv, idesc_pv_main, acc);
-              if (C::REMP > 0) {
-                const uint64_t dvr = make_nosw_desc(v_addr + C::KV_MAIN + k * 16 * 16, 128, BKV * 16);
-                ptx::umma_bf16_ts_w(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
-              }
-            }
-          }
-          ptx::umma_commit_w(&v_empty[st]);
-          ptx::umma_commit_w(&pv_done[buf]);
-          if (j + 2 < nb) {
-            issue_qk(g + 2);                               // reuses S buffer `buf` behind PV(j)
-            if (j + 3 == nb) ptx::umma_commit_w(q_empty);
-          }
-        }
+    // One flat software pipeline over every key block this CTA will ever process: the QK^T of a block is issued a fixed
+    // distance ahead of its PV (1 block with a single S tile, 2 with two), ACROSS work-item boundaries.  Q is single-
+    // buffered, so the first QK^T of the next item waits for its Q tile, which the producer loads as soon as the current
+    // item's last QK^T has retired (q_empty is committed right behind that last QK^T).  Without the look-ahead the first
+    // S of every item was only requested after the previous item's last PV had been issued, and the softmax warps sat
+    // idle for a PV + QK^T + commit round trip (~1100 cycles of a ~17 000-cycle item at T = 576).
+    constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, 0);
+    constexpr uint32_t idesc_pv_main = make_idesc(BQ, 64, 1);
+    constexpr uint32_t idesc_pv_rem = make_idesc(BQ, C::REMP > 0 ? C::REMP : 16, 1);
+    (void)idesc_pv_main; (void)idesc_pv_rem;
+    const uint32_t t_o = tmem_base + C::COL_O;
+    const uint32_t q_addr = ptx::smem_u32(s_q);
+    struct Cursor {   // (item, block-in-item) in processing order
+      int item, j, nb;
+      uint32_t it;
+    };
+    auto cursor_valid = [&](const Cursor& c) { return c.item < p.n_items; };
+    auto cursor_begin = [&]() {
+      Cursor c;
+      c.item = blockIdx.x; c.j = 0; c.it = 0;
+      c.nb = c.item < p.n_items ? item_blocks(c.item % p.q_tiles) : 0;
+      return c;
+    };
+    auto cursor_next = [&](Cursor& c) {
+      if (++c.j < c.nb) return;
+      c.item += gridDim.x; c.j = 0; ++c.it;
+      c.nb = c.item < p.n_items ? item_blocks(c.item % p.q_tiles) : 0;
+    };
+    Cursor cq = cursor_begin(), cp = cq;
+    uint32_t gq = 0, gp = 0;   // running block counters of the QK^T and PV streams
+    // S(gq) = Q K(gq)^T.  single S: waits until the softmax warps have read S(gq - 1); double S: no wait, the buffer's
+    // previous contents (P of block gq - 2) were consumed by PV(gq - 2), issued earlier on the same in-order pipe.
+    auto issue_next_qk = [&]() {
+      if (!cursor_valid(cq)) return;
+      if (cq.j == 0) {   // first block of an item: its Q tile must have landed
+        ATTN_TIMED_WAIT(5, q_full, cq.it & 1);
       }
-    } else {
-      constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, 0);
-      constexpr uint32_t idesc_pv_main = make_idesc(BQ, 64, 1);
-      constexpr uint32_t idesc_pv_rem = make_idesc(BQ, C::REMP > 0 ? C::REMP : 16, 1);
-      const uint32_t t_s = tmem_base + C::COL_S, t_p = tmem_base + C::COL_P, t_o = tmem_base + C::COL_O;
-      const uint32_t q_addr = ptx::smem_u32(s_q);
-      uint32_t g = 0, it = 0;
-      auto issue_qk = [&](uint32_t gg) {
-        const int st = gg & 1;
-        const uint32_t k_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL);
-        ATTN_TIMED_WAIT(3, &k_full[st], (gg >> 1) & 1);
-        ATTN_TIMED_WAIT(4, s_empty, (gg & 1) ^ 1);
-        ptx::tc_fence_after();
-#ifdef CLIPB200_ATTN_TIMING
-        const long long tq0 = clock64();
-#endif
-        const uint64_t dq = ptx::make_kmajor_sw128_desc(q_addr);
-        const uint64_t dk = ptx::make_kmajor_sw128_desc(k_addr);
+      const int st = DB ? static_cast<int>(gq % ST) : static_cast<int>(gq & 1);
+      const int buf = DB ? static_cast<int>(gq & 1) : 0;
+      const uint32_t k_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL);
+      const uint32_t t_s = tmem_base + C::COL_S + static_cast<uint32_t>(buf * BKV);
+      ATTN_TIMED_WAIT(3, &k_full[st], DB ? ((gq / ST) & 1) : ((gq >> 1) & 1));
+      if (!DB) { ATTN_TIMED_WAIT(4, s_empty, (gq & 1) ^ 1); }
+      ptx::tc_fence_after();
+      const uint64_t dq = ptx::make_kmajor_sw128_desc(q_addr);
+      const uint64_t dk = ptx::make_kmajor_sw128_desc(k_addr);
 #pragma unroll
-        for (int k = 0; k < ((CLIPB200_ATTN_DBG & 32) ? 0 : 4); ++k)
-          ptx::umma_bf16_ss_w(t_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_qk,
+      for (int k = 0; k < ((CLIPB200_ATTN_DBG & 32) ? 0 : 4); ++k)
+        ptx::umma_bf16_ss_w(t_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_qk,
                             k != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < ((CLIPB200_ATTN_DBG & (8 | 32)) ? 0 : C::REMP / 16); ++k) {
-          const uint64_t dqr = make_nosw_desc(q_addr + C::Q_MAIN + k * 2 * BQ * 16, BQ * 16, 128);
-          const uint64_t dkr = make_nosw_desc(k_addr + C::KV_MAIN + k * 2 * BKV * 16, BKV * 16, 128);
-          ptx::umma_bf16_ss_w(t_s, dqr, dkr, idesc_qk, 1u);
-        }
-        ptx::umma_commit_w(&k_empty[st]);
-        ptx::umma_commit_w(s_full);
-#ifdef CLIPB200_ATTN_TIMING
-        if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_attn_wait[11], (unsigned long long)(clock64() - tq0));
-#endif
-      };
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        const int qt = item % p.q_tiles;
-        const int nb = item_blocks(qt);
-        ATTN_TIMED_WAIT(5, q_full, it & 1);
-        ptx::tc_fence_after();
-        issue_qk(g);
-        for (int j = 0; j < nb; ++j, ++g) {
-          if (j + 1 < nb) issue_qk(g + 1);             // S(j+1) overlaps softmax(j)
-          else ptx::umma_commit_w(q_empty);              // all QK^T of this item are issued: Q tile is free when they retire
-          const int st = g & 1;
-          const uint32_t v_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL + C::KV_TILE);
-          ATTN_TIMED_WAIT(6, &v_full[st], (g >> 1) & 1);
-          ATTN_TIMED_WAIT(7, p_full, g & 1);
-          ptx::tc_fence_after();
-#ifdef CLIPB200_ATTN_TIMING
-          const long long tp0 = clock64();
-#endif
+      for (int k = 0; k < ((CLIPB200_ATTN_DBG & (8 | 32)) ? 0 : C::REMP / 16); ++k) {
+        const uint64_t dqr = make_nosw_desc(q_addr + C::Q_MAIN + k * 2 * BQ * 16, BQ * 16, 128);
+        const uint64_t dkr = make_nosw_desc(k_addr + C::KV_MAIN + k * 2 * BKV * 16, BKV * 16, 128);
+        ptx::umma_bf16_ss_w(t_s, dqr, dkr, idesc_qk, 1u);
+      }
+      ptx::umma_commit_w(&k_empty[st]);
+      ptx::umma_commit_w(&s_full[buf]);
+      if (cq.j == cq.nb - 1) ptx::umma_commit_w(q_empty);   // every QK^T of this item is issued: Q is free when they retire
+      ++gq;
+      cursor_next(cq);
+    };
+    issue_next_qk();
+    if (DB) issue_next_qk();
+    while (cursor_valid(cp)) {
+      if (!DB) issue_next_qk();   // S(gp + 1) overlaps softmax(gp)
+      const int st = DB ? static_cast<int>(gp % ST) : static_cast<int>(gp & 1);
+      const int buf = DB ? static_cast<int>(gp & 1) : 0;
+      const uint32_t v_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL + C::KV_TILE);
+      // P(gp): in place over S(gp) with two S tiles, in its own columns with one
+      const uint32_t t_p = DB ? tmem_base + C::COL_S + static_cast<uint32_t>(buf * BKV) : tmem_base + C::COL_P;
+      ATTN_TIMED_WAIT(6, &v_full[st], DB ? ((gp / ST) & 1) : ((gp >> 1) & 1));
+      ATTN_TIMED_WAIT(7, &p_full[buf], DB ? ((gp >> 1) & 1) : (gp & 1));
+      ptx::tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < ((CLIPB200_ATTN_DBG & 16) ? 0 : BKV / 16); ++k) {
-            const uint32_t acc = (j | k) != 0 ? 1u : 0u;
-            if (VT) {
-              ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), vt_desc(v_addr, k), idesc_pv_vt, acc);
-            } else {
-              const uint64_t dv = make_mnmajor_sw128_desc(v_addr + k * 16 * 128);
-              ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), dv, idesc_pv_main, acc);
-              if (C::REMP > 0 && !(CLIPB200_ATTN_DBG & 8)) {
-                const uint64_t dvr = make_nosw_desc(v_addr + C::KV_MAIN + k * 16 * 16, 128, BKV * 16);
-                ptx::umma_bf16_ts_w(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
-              }
-            }
+      for (int k = 0; k < ((CLIPB200_ATTN_DBG & 16) ? 0 : BKV / 16); ++k) {
+        const uint32_t acc = (cp.j | k) != 0 ? 1u : 0u;
+        if (VT) {
+          ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), vt_desc(v_addr, k), idesc_pv_vt, acc);
+        } else {
+          const uint64_t dv = make_mnmajor_sw128_desc(v_addr + k * 16 * 128);
+          ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), dv, idesc_pv_main, acc);
+          if (C::REMP > 0 && !(CLIPB200_ATTN_DBG & 8)) {
+            const uint64_t dvr = make_nosw_desc(v_addr + C::KV_MAIN + k * 16 * 16, 128, BKV * 16);
+            ptx::umma_bf16_ts_w(t_o + 64, t_p + static_cast<uint32_t>(k * 8), dvr, idesc_pv_rem, acc);
           }
-          ptx::umma_commit_w(&v_empty[st]);
-          ptx::umma_commit_w(pv_done);
-#ifdef CLIPB200_ATTN_TIMING
-          if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_attn_wait[12], (unsigned long long)(clock64() - tp0));
-#endif
         }
       }
+      ptx::umma_commit_w(&v_empty[st]);
+      ptx::umma_commit_w(&pv_done[buf]);
+      ++gp;
+      cursor_next(cp);
+      if (DB) issue_next_qk();    // reuses the S buffer PV(gp - 1) has just been queued to consume
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue (warps 0..NSW-1)
@@ -1016,6 +968,9 @@ inline cudaError_t attn_tcgen05_configure_device() {
   return cudaSuccess;
 }
 inline bool attn_tcgen05_supported(int hd) { return hd == 64 || hd == 72 || hd == 80 || hd == 96; }
+// Head dims / sequence lengths for which the transposed-V path (attn_tcgen05_vt + the qkv GEMM's EPI_QKVT epilogue) is
+// the faster one: the epilogue needs T % 32 == 0, and at head dim 64 the natural-V kernel stays ahead.
+inline bool attn_vt_preferred(int hd, int T) { return (hd == 72 || hd == 80 || hd == 96) && T % 32 == 0; }
 
 // qkv: [B*T, 3*H*hd] bf16, out: [B*T, H*hd] bf16
 inline cudaError_t attn_tcgen05(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, bool causal,
@@ -1059,12 +1014,19 @@ inline cudaError_t attn_tcgen05_vt(const __nv_bfloat16* qkv, const __nv_bfloat16
   if (hd == HD_)                                                                                               \
     return causal ? attn::launch_t<HD_, BKV_, true, DB_, true>(qkv, vt, out, B, T, H, num_sms, st)             \
                   : attn::launch_t<HD_, BKV_, false, DB_, true>(qkv, vt, out, B, T, H, num_sms, st);
-  // CLIPB200_ATTN_DOUBLE_S=1: the double-buffered-S protocol (see Cfg) on the transposed-V layout, for A/B runs
-  static const bool double_s = attn::kDoubleS && getenv("CLIPB200_ATTN_DOUBLE_S") != nullptr;
-  if (double_s) {
+  // Protocol per head dim by measurement (tests/native/attn_test.bin, B = 128 / 64, T = 576, B200 at 1.965 GHz, r02c):
+  //   hd 72: single S 662 TFLOP/s (double S 648)      hd 80: single S 713 (double S 703)
+  //   hd 96: double S 740 (single S 712)              hd 64: 628 / 643 — slower than the natural-V kernel (648), which
+  //                                                    the engine therefore keeps for that head dim
+  // CLIPB200_ATTN_DOUBLE_S=1 / CLIPB200_ATTN_SINGLE_S=1 force one protocol for every head dim (A/B runs).
+  static const bool force_double = attn::kDoubleS && getenv("CLIPB200_ATTN_DOUBLE_S") != nullptr;
+  static const bool force_single = !attn::kDoubleS || getenv("CLIPB200_ATTN_SINGLE_S") != nullptr;
+  if (force_double) {
     CLIPB200_ATTN_VT_CASE(64, 96, attn::kDoubleS)
     CLIPB200_ATTN_VT_CASE(72, 64, attn::kDoubleS)
     CLIPB200_ATTN_VT_CASE(80, 64, attn::kDoubleS)
+  }
+  if (!force_single) {
     CLIPB200_ATTN_VT_CASE(96, 64, attn::kDoubleS)
   }
   CLIPB200_ATTN_VT_CASE(64, 96, false)

@@ -394,11 +394,15 @@ Status Engine::AllocWorkspace() {
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&x_), rows * D_ * 4));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&h_), rows * D_ * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&qkv_), rows * 3 * D_ * 2));
-  // Transposed V [mb][D][ld] for the single-instruction PV path.  Opt-in (CLIPB200_ATTN_VT=1): measured on B200
-  // (profiles/r02b_*), it makes the attention kernel 2.6 % faster and the qkv GEMM's epilogue as much slower, so the
-  // step time does not move; needs T % 32 == 0 (see gemm_sm100.cuh EPI_QKVT).
-  attn_vt_ = !fastvit_ && attn_tcgen05_supported(hd_) && (2 * D_) % 32 == 0 && T_ % 32 == 0 &&
-             getenv("CLIPB200_ATTN_VT") != nullptr && atoi(getenv("CLIPB200_ATTN_VT")) != 0;
+  // Transposed V [mb][D][ld]: the qkv GEMM's epilogue writes V as [b][h*hd + d][t] and O += P V becomes one tcgen05.mma
+  // per 16 keys.  Used where it measures faster (attn_vt_preferred: head dims 72 / 80 / 96 with T % 32 == 0, i.e. the
+  // SigLIP2 towers at 576 tokens; +3...7 % on the attention kernel, nothing on the GEMM, profiles/r02c_*).
+  // CLIPB200_ATTN_VT=0 / 1 forces it off / on (wherever T % 32 == 0) for A/B runs.
+  {
+    const char* env = getenv("CLIPB200_ATTN_VT");
+    const bool possible = !fastvit_ && attn_tcgen05_supported(hd_) && (2 * D_) % 32 == 0 && T_ % 32 == 0;
+    attn_vt_ = possible && (env != nullptr ? atoi(env) != 0 : attn_vt_preferred(hd_, T_));
+  }
   if (attn_vt_)
     RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&vt_), static_cast<size_t>(mb_) * D_ * attn::attn_vt_ld(T_) * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&mlpbuf_), rows * mlp_ * 2));
