@@ -969,8 +969,10 @@ inline cudaError_t attn_tcgen05_configure_device() {
 }
 inline bool attn_tcgen05_supported(int hd) { return hd == 64 || hd == 72 || hd == 80 || hd == 96; }
 // Head dims / sequence lengths for which the transposed-V path (attn_tcgen05_vt + the qkv GEMM's EPI_QKVT epilogue) is
-// the faster one: the epilogue needs T % 32 == 0, and at head dim 64 the natural-V kernel stays ahead.
-inline bool attn_vt_preferred(int hd, int T) { return (hd == 72 || hd == 80 || hd == 96) && T % 32 == 0; }
+// the faster one (tests/native/attn_test.bin at T = 576, final kernels, profiles/r02d_attn_*.log):
+//   hd 96: 755 vs 700 TFLOP/s   hd 72: 674 vs 676   hd 80: 735 vs 737   hd 64: 651 vs 673
+// i.e. only where the natural layout needs two remainder planes per V block; the epilogue also needs T % 32 == 0.
+inline bool attn_vt_preferred(int hd, int T) { return hd == 96 && T % 32 == 0; }
 
 // qkv: [B*T, 3*H*hd] bf16, out: [B*T, H*hd] bf16
 inline cudaError_t attn_tcgen05(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, bool causal,
@@ -1014,10 +1016,9 @@ inline cudaError_t attn_tcgen05_vt(const __nv_bfloat16* qkv, const __nv_bfloat16
   if (hd == HD_)                                                                                               \
     return causal ? attn::launch_t<HD_, BKV_, true, DB_, true>(qkv, vt, out, B, T, H, num_sms, st)             \
                   : attn::launch_t<HD_, BKV_, false, DB_, true>(qkv, vt, out, B, T, H, num_sms, st);
-  // Protocol per head dim by measurement (tests/native/attn_test.bin, B = 128 / 64, T = 576, B200 at 1.965 GHz, r02c):
-  //   hd 72: single S 662 TFLOP/s (double S 648)      hd 80: single S 713 (double S 703)
-  //   hd 96: double S 740 (single S 712)              hd 64: 628 / 643 — slower than the natural-V kernel (648), which
-  //                                                    the engine therefore keeps for that head dim
+  // Protocol per head dim by measurement (tests/native/attn_test.bin, B = 128 / 64, T = 576, B200 at 1.965 GHz; r02c,
+  // before the cross-item look-ahead): hd 72: single S 662 TFLOP/s (double S 648), hd 80: single S 713 (double S 703),
+  // hd 96: double S 740 (single S 712), hd 64: 628 / 643.
   // CLIPB200_ATTN_DOUBLE_S=1 / CLIPB200_ATTN_SINGLE_S=1 force one protocol for every head dim (A/B runs).
   static const bool force_double = attn::kDoubleS && getenv("CLIPB200_ATTN_DOUBLE_S") != nullptr;
   static const bool force_single = !attn::kDoubleS || getenv("CLIPB200_ATTN_SINGLE_S") != nullptr;

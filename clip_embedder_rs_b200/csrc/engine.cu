@@ -395,8 +395,9 @@ Status Engine::AllocWorkspace() {
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&h_), rows * D_ * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&qkv_), rows * 3 * D_ * 2));
   // Transposed V [mb][D][ld]: the qkv GEMM's epilogue writes V as [b][h*hd + d][t] and O += P V becomes one tcgen05.mma
-  // per 16 keys.  Used where it measures faster (attn_vt_preferred: head dims 72 / 80 / 96 with T % 32 == 0, i.e. the
-  // SigLIP2 towers at 576 tokens; +3...7 % on the attention kernel, nothing on the GEMM, profiles/r02c_*).
+  // per 16 keys.  Used where it measures faster (attn_vt_preferred: head dim 96 with T % 32 == 0, the giant-opt
+  // SigLIP2 tower: +8 % on the attention kernel, nothing on the GEMM; at head dims 64 / 72 / 80 the natural layout is
+  // as fast or faster once the item-boundary bubbles are gone, profiles/r02d_*).
   // CLIPB200_ATTN_VT=0 / 1 forces it off / on (wherever T % 32 == 0) for A/B runs.
   {
     const char* env = getenv("CLIPB200_ATTN_VT");
