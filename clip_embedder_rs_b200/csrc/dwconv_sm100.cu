@@ -33,6 +33,24 @@ __device__ __forceinline__ void tma_load_4d(const void* tmap, uint64_t* bar, voi
       : "memory");
 }
 
+// CLIPB200_DWCONV_PACKED=0 at compile time keeps the scalar-FFMA 7x7 path (A/B builds)
+#ifndef CLIPB200_DWCONV_PACKED
+#define CLIPB200_DWCONV_PACKED 1
+#endif
+constexpr bool kDwPacked = CLIPB200_DWCONV_PACKED != 0;
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 
@@ -62,36 +80,93 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __rest
   ptx::mbar_wait(&bar, 0);
 
   const int r0 = warp * 2;  // this warp's two output rows inside the tile
-  float acc0[DW_TW], acc1[DW_TW];
+  if constexpr (K == 7 && kDwPacked) {
+    // 7x7: 49 FMAs per output made the kernel FFMA-issue bound (81 % of the 64 FMA/clk/SM three-register FFMA rate,
+    // profiles/r01f).  Packed f32x2 FMAs (FFMA2) do two outputs per issue slot: accumulators are pairs of neighbouring
+    // output pixels (x, x+1); the input pair (x+kx, x+kx+1) comes from one of two register copies of the staged row —
+    // `ev` holds the pairs that start at an even column, `od` those that start at an odd one — so every FFMA2 operand is
+    // an aligned register pair and no per-FMA shuffling is needed.  Costs twice the LDS (still under the FFMA2 time).
+    uint64_t acc0[DW_TW / 2], acc1[DW_TW / 2];
 #pragma unroll
-  for (int x = 0; x < DW_TW; ++x) acc0[x] = acc1[x] = bv;
+    for (int x = 0; x < DW_TW / 2; ++x) acc0[x] = acc1[x] = pack_f32x2(bv, bv);
 #pragma unroll
-  for (int iy = 0; iy < K + 1; ++iy) {  // staged rows r0 .. r0+K feed output rows r0 (taps ky = iy) and r0+1 (ky = iy-1)
-    float rv[IW];
-    const float* src = tile + ((r0 + iy) * IW) * DW_CI + lane;
+    for (int iy = 0; iy < K + 1; ++iy) {
+      const float* src = tile + ((r0 + iy) * IW) * DW_CI + lane;
+      uint64_t ev[IW / 2], od[IW / 2];   // IW = 22: ev[i] = (row[2i], row[2i+1]), od[i] = (row[2i+1], row[2i+2])
 #pragma unroll
-    for (int i = 0; i < IW; ++i) rv[i] = src[i * DW_CI];
-    if (iy < K) {
+      for (int i = 0; i < IW / 2; ++i) {
+        ev[i] = pack_f32x2(src[(2 * i) * DW_CI], src[(2 * i + 1) * DW_CI]);
+        od[i] = pack_f32x2(src[(2 * i + 1) * DW_CI], (2 * i + 2 < IW) ? src[(2 * i + 2) * DW_CI] : 0.f);
+      }
+      if (iy < K) {
 #pragma unroll
-      for (int x = 0; x < DW_TW; ++x)
+        for (int kx = 0; kx < K; ++kx) {
+          const uint64_t ww = pack_f32x2(wk[iy * K + kx], wk[iy * K + kx]);
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx) acc0[x] = fmaf(rv[x + kx], wk[iy * K + kx], acc0[x]);
+          for (int x = 0; x < DW_TW / 2; ++x)   // outputs (2x, 2x+1) read columns (2x+kx, 2x+kx+1)
+            acc0[x] = fma_f32x2((kx & 1) ? od[x + kx / 2] : ev[x + kx / 2], ww, acc0[x]);
+        }
+      }
+      if (iy > 0) {
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const uint64_t ww = pack_f32x2(wk[(iy - 1) * K + kx], wk[(iy - 1) * K + kx]);
+#pragma unroll
+          for (int x = 0; x < DW_TW / 2; ++x)
+            acc1[x] = fma_f32x2((kx & 1) ? od[x + kx / 2] : ev[x + kx / 2], ww, acc1[x]);
+        }
+      }
     }
-    if (iy > 0) {
+    if (!c_ok) return;
+    const int oy = ty0 + r0;
+    Tout* o0 = out + ((static_cast<long long>(b) * H + oy) * W + tx0) * C + c;
 #pragma unroll
-      for (int x = 0; x < DW_TW; ++x)
-#pragma unroll
-        for (int kx = 0; kx < K; ++kx) acc1[x] = fmaf(rv[x + kx], wk[(iy - 1) * K + kx], acc1[x]);
+    for (int x = 0; x < DW_TW / 2; ++x) {
+      float a0, a1, b0, b1;
+      unpack_f32x2(acc0[x], a0, a1);
+      unpack_f32x2(acc1[x], b0, b1);
+      if (tx0 + 2 * x < W) {
+        if (oy < H) store_out(o0 + static_cast<long long>(2 * x) * C, a0);
+        if (oy + 1 < H) store_out(o0 + (static_cast<long long>(W) + 2 * x) * C, b0);
+      }
+      if (tx0 + 2 * x + 1 < W) {
+        if (oy < H) store_out(o0 + static_cast<long long>(2 * x + 1) * C, a1);
+        if (oy + 1 < H) store_out(o0 + (static_cast<long long>(W) + 2 * x + 1) * C, b1);
+      }
     }
-  }
-  if (!c_ok) return;
-  const int oy = ty0 + r0;
-  Tout* o0 = out + ((static_cast<long long>(b) * H + oy) * W + tx0) * C + c;
-#pragma unroll
-  for (int x = 0; x < DW_TW; ++x) {
-    if (tx0 + x < W) {
-      if (oy < H) store_out(o0 + static_cast<long long>(x) * C, acc0[x]);
-      if (oy + 1 < H) store_out(o0 + (static_cast<long long>(W) + x) * C, acc1[x]);
+    return;
+  } else {
+    float acc0[DW_TW], acc1[DW_TW];
+  #pragma unroll
+    for (int x = 0; x < DW_TW; ++x) acc0[x] = acc1[x] = bv;
+  #pragma unroll
+    for (int iy = 0; iy < K + 1; ++iy) {  // staged rows r0 .. r0+K feed output rows r0 (taps ky = iy) and r0+1 (ky = iy-1)
+      float rv[IW];
+      const float* src = tile + ((r0 + iy) * IW) * DW_CI + lane;
+  #pragma unroll
+      for (int i = 0; i < IW; ++i) rv[i] = src[i * DW_CI];
+      if (iy < K) {
+  #pragma unroll
+        for (int x = 0; x < DW_TW; ++x)
+  #pragma unroll
+          for (int kx = 0; kx < K; ++kx) acc0[x] = fmaf(rv[x + kx], wk[iy * K + kx], acc0[x]);
+      }
+      if (iy > 0) {
+  #pragma unroll
+        for (int x = 0; x < DW_TW; ++x)
+  #pragma unroll
+          for (int kx = 0; kx < K; ++kx) acc1[x] = fmaf(rv[x + kx], wk[(iy - 1) * K + kx], acc1[x]);
+      }
+    }
+    if (!c_ok) return;
+    const int oy = ty0 + r0;
+    Tout* o0 = out + ((static_cast<long long>(b) * H + oy) * W + tx0) * C + c;
+  #pragma unroll
+    for (int x = 0; x < DW_TW; ++x) {
+      if (tx0 + x < W) {
+        if (oy < H) store_out(o0 + static_cast<long long>(x) * C, acc0[x]);
+        if (oy + 1 < H) store_out(o0 + (static_cast<long long>(W) + x) * C, acc1[x]);
+      }
     }
   }
 }
