@@ -33,20 +33,22 @@ __device__ __forceinline__ void tma_load_4d(const void* tmap, uint64_t* bar, voi
       : "memory");
 }
 
-// CLIPB200_DWCONV_PACKED=0 at compile time keeps the scalar-FFMA 7x7 path (A/B builds)
+// CLIPB200_DWCONV_PACKED=1 at compile time selects the packed-f32x2 7x7 path below.  Measured on B200 (MobileCLIP2-S2,
+// 256 images, profiles/r02a_bench.json vs r02g_bench.json): depthwise class 8.62 ms scalar vs 8.76 ms packed — FFMA2 with
+// three 64-bit register operands does not issue faster than two FFMAs here, so the scalar path stays the default.
 #ifndef CLIPB200_DWCONV_PACKED
-#define CLIPB200_DWCONV_PACKED 1
+#define CLIPB200_DWCONV_PACKED 0
 #endif
 constexpr bool kDwPacked = CLIPB200_DWCONV_PACKED != 0;
-__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+[[maybe_unused]] __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
   return r;
 }
-__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+[[maybe_unused]] __device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
-__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+[[maybe_unused]] __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;

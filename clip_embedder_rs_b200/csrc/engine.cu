@@ -389,11 +389,48 @@ Status Engine::LoadText(const OnnxModel& m) {
   return Status::OK();
 }
 
-Status Engine::AllocWorkspace() {
+// Activation buffers of ONE compute lane, allocated into the members Forward* use (SaveLane / BindLane move them).
+Status Engine::AllocActivations() {
   const size_t rows = fastvit_ ? 1 : static_cast<size_t>(mb_) * T_;  // FastViT sizes its own buffers below
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&x_), rows * D_ * 4));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&h_), rows * D_ * 2));
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&qkv_), rows * 3 * D_ * 2));
+  if (attn_vt_)
+    RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&vt_), static_cast<size_t>(mb_) * D_ * attn::attn_vt_ld(T_) * 2));
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&mlpbuf_), rows * mlp_ * 2));
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&pooled_), static_cast<size_t>(mb_) * D_ * 2));
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&proj_out_), static_cast<size_t>(mb_) * std::max(E_, D_) * 4));
+  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&row_map_), static_cast<size_t>(mb_) * 4));
+  if (kind == CLIPB200_KIND_VISION && !fastvit_) {
+    RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&patches_), static_cast<size_t>(mb_) * Tp_ * Kp_ * 2));
+    if (pool_map_) {
+      RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&y_), static_cast<size_t>(mb_) * D_ * 4));
+      RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&yh_), static_cast<size_t>(mb_) * D_ * 2));
+      RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&ymlp_), static_cast<size_t>(mb_) * mlp_ * 2));
+    }
+  }
+  if (fastvit_) RET_IF_ERR(AllocFastVitWorkspace());
+  return Status::OK();
+}
+
+void Engine::SaveLane(int k) {
+  Lane& l = lanes_[k];
+  l.patches = patches_; l.h = h_; l.qkv = qkv_; l.mlpbuf = mlpbuf_; l.pooled = pooled_; l.yh = yh_; l.ymlp = ymlp_;
+  l.vt = vt_; l.fv_stem_out = fv_stem_out_; l.x = x_; l.y = y_; l.proj_out = proj_out_; l.fv_xa = fv_xa_; l.fv_xb = fv_xb_;
+  l.fv_tmp = fv_tmp_; l.fv_s = fv_s_; l.fv_gate = fv_gate_; l.row_map = row_map_;
+  l.stream = compute_;
+}
+void Engine::BindLane(int k) {
+  if (k >= n_lanes_) k = 0;
+  const Lane& l = lanes_[k];
+  patches_ = l.patches; h_ = l.h; qkv_ = l.qkv; mlpbuf_ = l.mlpbuf; pooled_ = l.pooled; yh_ = l.yh; ymlp_ = l.ymlp;
+  vt_ = l.vt; fv_stem_out_ = l.fv_stem_out; x_ = l.x; y_ = l.y; proj_out_ = l.proj_out; fv_xa_ = l.fv_xa; fv_xb_ = l.fv_xb;
+  fv_tmp_ = l.fv_tmp; fv_s_ = l.fv_s; fv_gate_ = l.fv_gate; row_map_ = l.row_map;
+  compute_ = l.stream;
+  lane_ = k;
+}
+
+Status Engine::AllocWorkspace() {
   // Transposed V [mb][D][ld]: the qkv GEMM's epilogue writes V as [b][h*hd + d][t] and O += P V becomes one tcgen05.mma
   // per 16 keys.  Used where it measures faster (attn_vt_preferred: head dim 96 with T % 32 == 0, the giant-opt
   // SigLIP2 tower: +8 % on the attention kernel, nothing on the GEMM; at head dims 64 / 72 / 80 the natural layout is
@@ -404,27 +441,21 @@ Status Engine::AllocWorkspace() {
     const bool possible = !fastvit_ && attn_tcgen05_supported(hd_) && (2 * D_) % 32 == 0 && T_ % 32 == 0;
     attn_vt_ = possible && (env != nullptr ? atoi(env) != 0 : attn_vt_preferred(hd_, T_));
   }
-  if (attn_vt_)
-    RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&vt_), static_cast<size_t>(mb_) * D_ * attn::attn_vt_ld(T_) * 2));
-  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&mlpbuf_), rows * mlp_ * 2));
-  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&pooled_), static_cast<size_t>(mb_) * D_ * 2));
-  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&proj_out_), static_cast<size_t>(mb_) * std::max(E_, D_) * 4));
-  RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&row_map_), static_cast<size_t>(mb_) * 4));
+  // CLIPB200_LANES=1 keeps one compute stream (A/B runs); the second lane costs one more activation workspace
+  n_lanes_ = 2;
+  if (const char* env = getenv("CLIPB200_LANES")) n_lanes_ = atoi(env) >= 2 ? 2 : 1;
+  for (int k = 0; k < n_lanes_; ++k) {
+    compute_ = lanes_[k].stream;   // created in Init
+    RET_IF_ERR(AllocActivations());
+    SaveLane(k);
+  }
+  BindLane(0);
+  CUDA_RET(cudaEventCreateWithFlags(&lane_fork_, cudaEventDisableTiming), "event");
+  CUDA_RET(cudaEventCreateWithFlags(&lane_join_, cudaEventDisableTiming), "event");
   RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&err_flag_), 4));
   CUDA_RET(cudaMemset(err_flag_, 0, 4), "memset");
-  if (kind == CLIPB200_KIND_VISION && fastvit_) {
-    in_slot_bytes_ = static_cast<size_t>(mb_) * S_ * S_ * 3;
-  } else if (kind == CLIPB200_KIND_VISION) {
-    RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&patches_), static_cast<size_t>(mb_) * Tp_ * Kp_ * 2));
-    if (pool_map_) {
-      RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&y_), static_cast<size_t>(mb_) * D_ * 4));
-      RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&yh_), static_cast<size_t>(mb_) * D_ * 2));
-      RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&ymlp_), static_cast<size_t>(mb_) * mlp_ * 2));
-    }
-    in_slot_bytes_ = static_cast<size_t>(mb_) * S_ * S_ * 3;
-  } else {
-    in_slot_bytes_ = static_cast<size_t>(mb_) * T_ * 8;
-  }
+  if (kind == CLIPB200_KIND_VISION) in_slot_bytes_ = static_cast<size_t>(mb_) * S_ * S_ * 3;
+  else in_slot_bytes_ = static_cast<size_t>(mb_) * T_ * 8;
   for (int i = 0; i < 2; ++i) {
     RET_IF_ERR(DevAlloc(&d_in_[i], in_slot_bytes_));
     RET_IF_ERR(DevAlloc(reinterpret_cast<void**>(&d_out_[i]), static_cast<size_t>(mb_) * E_ * 4));
@@ -437,7 +468,6 @@ Status Engine::AllocWorkspace() {
     CUDA_RET(cudaEventCreateWithFlags(&out_copied_[i], cudaEventDisableTiming), "event");
   }
   for (int i = 0; i < 16; ++i) CUDA_RET(cudaEventCreate(&user_events_[i]), "event");
-  if (fastvit_) RET_IF_ERR(AllocFastVitWorkspace());
   return Status::OK();
 }
 
@@ -492,7 +522,8 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
   CUDA_RET(flash_attention_configure_device(), "configure attention kernels");
   CUDA_RET(attn_tcgen05_configure_device(), "configure tcgen05 attention kernels");
   CUDA_RET(dwconv_tma_configure_device(), "configure depthwise-conv kernels");
-  CUDA_RET(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking), "stream");
+  for (int k = 0; k < 2; ++k) CUDA_RET(cudaStreamCreateWithFlags(&lanes_[k].stream, cudaStreamNonBlocking), "stream");
+  compute_ = lanes_[0].stream;
   CUDA_RET(cudaStreamCreateWithFlags(&copy_in_, cudaStreamNonBlocking), "stream");
   CUDA_RET(cudaStreamCreateWithFlags(&copy_out_, cudaStreamNonBlocking), "stream");
 
@@ -553,7 +584,9 @@ Engine::~Engine() {
     if (rs.d_jobs) cudaFree(rs.d_jobs);
     if (rs.free_ev) cudaEventDestroy(rs.free_ev);
   }
-  if (compute_) cudaStreamDestroy(compute_);
+  for (int k = 0; k < 2; ++k) if (lanes_[k].stream) cudaStreamDestroy(lanes_[k].stream);
+  if (lane_fork_) cudaEventDestroy(lane_fork_);
+  if (lane_join_) cudaEventDestroy(lane_join_);
   if (copy_in_) cudaStreamDestroy(copy_in_);
   if (copy_out_) cudaStreamDestroy(copy_out_);
 }
@@ -618,7 +651,7 @@ Status Engine::ElapsedMs(int a, int b, double* ms) {
 Status Engine::Synchronize() {
   CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
   CUDA_RET(cudaStreamSynchronize(copy_in_), "sync");
-  CUDA_RET(cudaStreamSynchronize(compute_), "sync");
+  for (int k = 0; k < n_lanes_; ++k) CUDA_RET(cudaStreamSynchronize(lanes_[k].stream), "sync");
   CUDA_RET(cudaStreamSynchronize(copy_out_), "sync");
   return Status::OK();
 }
@@ -825,6 +858,7 @@ Status Engine::ForwardText(int n, const int64_t* d_ids, float* d_out) {
 // is ~90 kernels of a few microseconds each), so their kernel sequence is captured once into a CUDA graph per
 // (mode, n, slot) and replayed; tensor maps are by-value kernel parameters, so the captured launches are complete.
 Status Engine::ForwardSlot(int mode, int n, int slot) {
+  BindLane(slot);   // slot s & 1 <-> compute lane s & 1: the caller's event waits / records below use `compute_` too
   auto fwd = [&]() -> Status {
     if (mode == 0) return ForwardVision(n, static_cast<const uint8_t*>(d_in_[slot]), nullptr, d_out_[slot]);
     if (mode == 1) return ForwardVision(n, nullptr, d_in_f32_[slot], d_out_[slot]);
@@ -865,15 +899,30 @@ Status Engine::RunPipelined(const InT* in, int64_t batch, size_t in_elems_per_it
   const size_t item_bytes = in_elems_per_item * sizeof(InT);
   const int64_t steps = (batch + mb_ - 1) / mb_;
   if (device_buffers) {
-    for (int64_t s = 0; s < steps; ++s) {
+    // micro-batches alternate between the compute lanes; lane 1 starts behind whatever the caller queued on lane 0
+    // (its events, earlier calls) and lane 0 ends behind lane 1, so the call stays "asynchronous on ONE stream" for
+    // the caller's event records
+    BindLane(0);
+    if (n_lanes_ > 1 && steps > 1) {
+      CUDA_RET(cudaEventRecord(lane_fork_, lanes_[0].stream), "record");
+      CUDA_RET(cudaStreamWaitEvent(lanes_[1].stream, lane_fork_, 0), "fork lane");
+    }
+    Status st = Status::OK();
+    for (int64_t s = 0; s < steps && st.ok(); ++s) {
       const int n = static_cast<int>(std::min<int64_t>(mb_, batch - s * mb_));
       const InT* src = in + static_cast<size_t>(s) * mb_ * in_elems_per_item;
       float* dst = out + static_cast<size_t>(s) * mb_ * E_;
-      if (mode == 0) RET_IF_ERR(ForwardVision(n, reinterpret_cast<const uint8_t*>(src), nullptr, dst));
-      else if (mode == 1) RET_IF_ERR(ForwardVision(n, nullptr, reinterpret_cast<const float*>(src), dst));
-      else RET_IF_ERR(ForwardText(n, reinterpret_cast<const int64_t*>(src), dst));
+      BindLane(static_cast<int>(s & 1));
+      if (mode == 0) st = ForwardVision(n, reinterpret_cast<const uint8_t*>(src), nullptr, dst);
+      else if (mode == 1) st = ForwardVision(n, nullptr, reinterpret_cast<const float*>(src), dst);
+      else st = ForwardText(n, reinterpret_cast<const int64_t*>(src), dst);
     }
-    return Status::OK();  // asynchronous on the compute stream; caller synchronises / records events
+    if (n_lanes_ > 1 && steps > 1) {
+      cudaEventRecord(lane_join_, lanes_[1].stream);
+      cudaStreamWaitEvent(lanes_[0].stream, lane_join_, 0);
+    }
+    BindLane(0);
+    return st;  // asynchronous on compute lane 0; caller synchronises / records events
   }
   // host buffers: pinned staging unless the caller's memory is already pinned
   cudaPointerAttributes attr;
@@ -903,6 +952,7 @@ Status Engine::RunPipelined(const InT* in, int64_t batch, size_t in_elems_per_it
     ProfEnd(PC_H2D, copy_in_);
     CUDA_RET(e, "H2D copy");
     CUDA_RET(cudaEventRecord(in_ready_[slot], copy_in_), "record");
+    BindLane(slot);
     CUDA_RET(cudaStreamWaitEvent(compute_, in_ready_[slot], 0), "wait input");
     if (s >= 2) CUDA_RET(cudaStreamWaitEvent(compute_, out_copied_[slot], 0), "wait output slot");
     st = ForwardSlot(mode, n, slot);
@@ -925,6 +975,7 @@ Status Engine::RunPipelined(const InT* in, int64_t batch, size_t in_elems_per_it
       memcpy(out + static_cast<size_t>(s - 1) * mb_ * E_, h_out_[ps], static_cast<size_t>(pn) * E_ * 4);
     }
   }
+  BindLane(0);
   Status sync = Synchronize();
   if (!st.ok()) return st;
   RET_IF_ERR(sync);
@@ -1264,6 +1315,7 @@ Status Engine::VisionEmbedRgb8Var(const uint8_t* const* imgs, const int32_t* wid
     }
     if (!st.ok()) break;
     CUDA_RET(cudaEventRecord(in_ready_[slot], copy_in_), "record");
+    BindLane(slot);
     CUDA_RET(cudaStreamWaitEvent(compute_, in_ready_[slot], 0), "wait input");
     if (s >= 2) CUDA_RET(cudaStreamWaitEvent(compute_, out_copied_[slot], 0), "wait output slot");
     st = ForwardSlot(0, n, slot);
@@ -1284,6 +1336,7 @@ Status Engine::VisionEmbedRgb8Var(const uint8_t* const* imgs, const int32_t* wid
       memcpy(out + static_cast<size_t>(s - 1) * mb * E_, h_out_[ps], static_cast<size_t>(pn) * E_ * 4);
     }
   }
+  BindLane(0);
   Status sync = Synchronize();
   if (!st.ok()) return st;
   RET_IF_ERR(sync);

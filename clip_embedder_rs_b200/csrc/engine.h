@@ -234,6 +234,24 @@ class Engine {
   size_t in_slot_bytes_ = 0;
   std::vector<void*> dev_allocs_;
 
+  // Two compute lanes (round 2): consecutive micro-batches alternate between two compute streams, each with its own
+  // activation workspace, so the HBM-bound kernels of one micro-batch (LayerNorm, preprocessing, pooling) and the tail
+  // waves of its GEMMs run under the tensor-bound GEMMs of the other.  `compute_` and the workspace pointers above are
+  // the CURRENT lane's (BindLane); lane 0 is also the stream of the public event / synchronise / flush entry points.
+  struct Lane {
+    __nv_bfloat16 *patches = nullptr, *h = nullptr, *qkv = nullptr, *mlpbuf = nullptr, *pooled = nullptr, *yh = nullptr,
+                  *ymlp = nullptr, *vt = nullptr, *fv_stem_out = nullptr;
+    float *x = nullptr, *y = nullptr, *proj_out = nullptr, *fv_xa = nullptr, *fv_xb = nullptr, *fv_tmp = nullptr,
+          *fv_s = nullptr, *fv_gate = nullptr;
+    int* row_map = nullptr;
+    cudaStream_t stream = nullptr;
+  };
+  Lane lanes_[2];
+  int n_lanes_ = 1, lane_ = 0;
+  cudaEvent_t lane_fork_ = nullptr, lane_join_ = nullptr;
+  void SaveLane(int k);
+  void BindLane(int k);
+  Status AllocActivations();
   cudaStream_t compute_ = nullptr, copy_in_ = nullptr, copy_out_ = nullptr;
   cudaEvent_t in_ready_[2] = {nullptr, nullptr}, in_consumed_[2] = {nullptr, nullptr},
               out_ready_[2] = {nullptr, nullptr}, out_copied_[2] = {nullptr, nullptr};

@@ -68,6 +68,37 @@ def test_onnx_inspect_and_loader_errors(make_model, tmp_path):
     assert "outside" in _native.last_error()
 
 
+def test_external_data_must_stay_inside_the_model_directory(tmp_path):
+    """An untrusted .onnx must not be able to map files outside its own directory through an external-data `location`
+    (absolute path, or `..` components): onnxruntime refuses those, so does the loader — before opening anything."""
+    import onnx_proto as op
+    from clip_embedder_rs_b200 import _native, error
+    from clip_embedder_rs_b200.onnx import inspect_onnx
+
+    secret = tmp_path / "secret.bin"
+    secret.write_bytes(np.arange(64, dtype=np.float32).tobytes())
+    mdir = tmp_path / "model"
+    mdir.mkdir()
+    (mdir / "inside.bin").write_bytes(np.arange(64, dtype=np.float32).tobytes())
+    (mdir / "sub").mkdir()
+    (mdir / "sub" / "deep.bin").write_bytes(np.arange(64, dtype=np.float32).tobytes())
+
+    def model_with(location: str) -> str:
+        g = op.f_str(2, "g") + op.f_bytes(5, op.tensor_proto("w", dims=(8, 8), data_type=op.FLOAT, external=(location, 0, 256)))
+        g += op.f_bytes(11, op.value_info("pixel_values", op.FLOAT, ("b", 3, 8, 8)))
+        m = op.f_varint(1, 8) + op.f_bytes(7, g) + op.f_bytes(8, op.f_str(1, "") + op.f_varint(2, 18))
+        path = mdir / "visual.onnx"
+        path.write_bytes(m)
+        return str(path)
+
+    for ok in ("inside.bin", "./inside.bin", "sub/deep.bin", "sub/../inside.bin"):
+        assert inspect_onnx(model_with(ok))["num_initializers"] == 1, ok
+    for bad in ("../secret.bin", str(secret), "sub/../../secret.bin", "..", "/etc/passwd", "..\\secret.bin"):
+        with pytest.raises(error.Ort) as ei:
+            inspect_onnx(model_with(bad))
+        assert ei.value.code == _native.ERR_PARSE and "escapes the model directory" in str(ei.value), (bad, str(ei.value))
+
+
 def test_onnx_writer_reader_roundtrip(tmp_path):
     import onnx_proto as op
 

@@ -187,8 +187,8 @@ def test_third_party_export_hf_clip_vision(hf_clip_vision):
 
 
 def test_unrecognised_graph_is_reported_not_guessed(tmp_path):
-    """A graph that is not one of the supported tower layouts must be declined with a reason (the engine then falls
-    back to binding by parameter names and reports both failures)."""
+    """A graph that is not one of the supported tower layouts must be declined with a reason; the engine refuses such a
+    file (tests/test_real_export_gpu.py::test_declined_graph_is_refused_not_guessed) instead of binding it by name."""
 
     class Odd(torch.nn.Module):
         def __init__(self):

@@ -112,3 +112,66 @@ def test_engine_matches_opencv_dnn_on_the_same_file(tmp_path, config):
     cos = cosine_rows(out, want)
     print(f"\n[{config} vs OpenCV DNN] cos >= {cos.min():.6f} max abs {np.abs(out - want).max():.2e}")
     assert cos.min() >= COS_BAR
+
+
+def test_declined_graph_is_refused_not_guessed(make_real_model, tmp_path):
+    """A file that carries an executable graph is bound from that graph or not at all.  Here the graph is a real CLIP
+    vision export whose GELU was swapped for a Relu: every parameter keeps its open_clip name, so a name-bound loader
+    would accept it and silently compute QuickGELU where onnxruntime computes what the graph says.  The engine must
+    refuse it with CLIPB200_ERR_UNSUPPORTED and the recogniser's reason; a graph that declares an attention_mask input is
+    refused the same way."""
+    import shutil
+
+    import clip_embedder_rs_b200 as cb
+    import onnx_proto as op
+    from clip_embedder_rs_b200 import _native
+    from clip_embedder_rs_b200.onnx import OnnxSession, inspect_onnx
+
+    src = make_real_model("tiny_clip", anonymize=False)
+    dst = tmp_path / "model"
+    shutil.copytree(src, dst)
+
+    def rewrite(path, node_fn=None, extra_input=None):
+        buf = memoryview(open(path, "rb").read())
+        out = bytearray()
+        for f, w, val in op._fields(buf):
+            if f != 7:
+                out += op.f_bytes(f, bytes(val)) if w == 2 else op.f_varint(f, val)
+                continue
+            g = bytearray()
+            for gf, gw, gval in op._fields(val):
+                if gf == 1 and node_fn is not None:
+                    g += op.f_bytes(1, node_fn(gval))
+                elif gw == 2:
+                    g += op.f_bytes(gf, bytes(gval))
+                else:
+                    g += op.f_varint(gf, gval)
+            if extra_input is not None:
+                g += op.f_bytes(11, extra_input)
+            out += op.f_bytes(7, bytes(g))
+        open(path, "wb").write(out)
+
+    def sigmoid_to_relu(node):  # QuickGELU is x * sigmoid(1.702 x): turn its Sigmoid into a Relu
+        nb = bytearray()
+        for nf, nw, nval in op._fields(node):
+            if nf == 4 and bytes(nval) == b"Sigmoid":
+                nb += op.f_str(4, "Relu")
+            elif nw == 2:
+                nb += op.f_bytes(nf, bytes(nval))
+            else:
+                nb += op.f_varint(nf, nval)
+        return bytes(nb)
+
+    vis = str(dst / "visual.onnx")
+    rewrite(vis, node_fn=sigmoid_to_relu)
+    j = inspect_onnx(vis)
+    assert j["graph"]["attempted"] and not j["graph"]["recognized"]
+    with pytest.raises(cb.ClipError) as ei:
+        OnnxSession(vis)
+    assert ei.value.code == _native.ERR_UNSUPPORTED and "graph recogniser" in str(ei.value)
+
+    txt = str(dst / "text.onnx")
+    rewrite(txt, extra_input=op.value_info("attention_mask", op.INT64, ("batch_size", 77)))
+    with pytest.raises(cb.ClipError) as ei:
+        OnnxSession(txt)
+    assert ei.value.code == _native.ERR_UNSUPPORTED and "attention_mask" in str(ei.value)
