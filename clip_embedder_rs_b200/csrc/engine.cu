@@ -441,8 +441,11 @@ Status Engine::AllocWorkspace() {
     const bool possible = !fastvit_ && attn_tcgen05_supported(hd_) && (2 * D_) % 32 == 0 && T_ % 32 == 0;
     attn_vt_ = possible && (env != nullptr ? atoi(env) != 0 : attn_vt_preferred(hd_, T_));
   }
-  // CLIPB200_LANES=1 keeps one compute stream (A/B runs); the second lane costs one more activation workspace
-  n_lanes_ = 2;
+  // CLIPB200_LANES=2 turns the second compute lane on (it costs one more activation workspace).  Off by default:
+  // measured on B200 (profiles/r02h_*), two lanes overlap the HBM-bound kernels of one micro-batch with the GEMMs of the
+  // other as intended, but the step is energy-bound under the 1 kW cap — the overlapped step draws more power, the clock
+  // drops from 1.327 to 1.29 GHz and the throughput does not move (SO400M 1 938 -> 1 921 img/s, DFN5B text +1.4 %).
+  n_lanes_ = 1;
   if (const char* env = getenv("CLIPB200_LANES")) n_lanes_ = atoi(env) >= 2 ? 2 : 1;
   for (int k = 0; k < n_lanes_; ++k) {
     compute_ = lanes_[k].stream;   // created in Init
@@ -498,6 +501,13 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
   input_names = m.inputs;
   // Real exports (torch.onnx.export graphs) are bound from the graph structure; initializer-only files and graphs
   // the recogniser does not know (FastViT) fall through to binding by open_clip / timm parameter names.
+  // src/text.rs:156-161 feeds an attention_mask when the graph declares one.  pull_onnx.py's TextWrapper never does;
+  // a graph that does uses the mask in a way only its nodes define, so it is refused instead of being ignored.
+  for (const std::string& n : m.inputs)
+    if (n == "attention_mask")
+      return Status::Err(CLIPB200_ERR_UNSUPPORTED,
+                         onnx_path + ": the graph declares an attention_mask input; this engine only runs text towers "
+                                     "whose padding is handled inside the graph (pull_onnx.py:61-68)");
   // A file with an executable graph is bound ONLY from that graph: guessing hyper-parameters (activation, eps, heads,
   // causal mask, pooling) from parameter names would load such a file and return silently wrong embeddings where
   // onnxruntime executes what the graph says.  The one family bound by name is the re-parameterised FastViT trunk
@@ -508,13 +518,6 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
       return Status::Err(CLIPB200_ERR_UNSUPPORTED, onnx_path + ": " + graph_err);
     graph_note_ = graph_err;
   }
-  // src/text.rs:156-161 feeds an attention_mask when the graph declares one.  pull_onnx.py's TextWrapper never does;
-  // a graph that does uses the mask in a way only its nodes define, so it is refused instead of being ignored.
-  for (const std::string& n : m.inputs)
-    if (n == "attention_mask")
-      return Status::Err(CLIPB200_ERR_UNSUPPORTED,
-                         onnx_path + ": the graph declares an attention_mask input; this engine only runs text towers "
-                                     "whose padding is handled inside the graph (pull_onnx.py:61-68)");
   if (get_encode_tiled() == nullptr)  // resolved here so that it never happens inside a graph capture
     return Status::Err(CLIPB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
   if (const char* env = getenv("CLIPB200_NO_GRAPHS")) if (atoi(env) != 0) graph_max_n_ = 0;

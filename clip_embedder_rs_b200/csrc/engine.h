@@ -234,10 +234,12 @@ class Engine {
   size_t in_slot_bytes_ = 0;
   std::vector<void*> dev_allocs_;
 
-  // Two compute lanes (round 2): consecutive micro-batches alternate between two compute streams, each with its own
-  // activation workspace, so the HBM-bound kernels of one micro-batch (LayerNorm, preprocessing, pooling) and the tail
-  // waves of its GEMMs run under the tensor-bound GEMMs of the other.  `compute_` and the workspace pointers above are
-  // the CURRENT lane's (BindLane); lane 0 is also the stream of the public event / synchronise / flush entry points.
+  // Compute lanes (round 2, opt-in with CLIPB200_LANES=2): consecutive micro-batches alternate between two compute
+  // streams, each with its own activation workspace, so the HBM-bound kernels of one micro-batch (LayerNorm,
+  // preprocessing, pooling) and the tail waves of its GEMMs run under the tensor-bound GEMMs of the other.  Measured
+  // neutral under the power cap (engine.cu, AllocWorkspace), so one lane is the default.  `compute_` and the workspace
+  // pointers above are the CURRENT lane's (BindLane); lane 0 is also the stream of the public event / synchronise /
+  // flush entry points.
   struct Lane {
     __nv_bfloat16 *patches = nullptr, *h = nullptr, *qkv = nullptr, *mlpbuf = nullptr, *pooled = nullptr, *yh = nullptr,
                   *ymlp = nullptr, *vt = nullptr, *fv_stem_out = nullptr;
