@@ -387,6 +387,7 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
   constexpr int CW = C::CW, OW = C::OW;
   const int row = quarter * 32 + lane;
   const int qrow = qt * BQ + row;
+  const bool idle_rows = SPLIT == 1 && qt * BQ + quarter * 32 >= p.T;   // warp-uniform
   float m_run = -INFINITY, l_run = 0.f;
   for (int j = 0; j < nb; ++j, ++g) {
     // DB: block g lives in S buffer g & 1; every per-buffer barrier completes one phase per two blocks
@@ -396,6 +397,30 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
     const uint32_t t_p = DB ? t_s : cx.t_p;
     if (cx.timed && lane == 0) { ATTN_TIMED_WAIT(8, &cx.s_full[buf], par); } else { ptx::mbar_wait(&cx.s_full[buf], par); }
     ptx::tc_fence_after();
+    if (idle_rows) {
+      // All 32 query rows of this warp lie beyond T (the lower half of the last tile when T % 128 <= 64, e.g. rows
+      // 576..639 of a 576-token image): keep the hand-off protocol in step and do none of the arithmetic.  What the
+      // PV then reads from this warp's P rows is whatever an earlier item left there; those O rows are never stored
+      // (the output tensor map ends at T).  Frees a tenth of the softmax issue slots / MUFU time at T = 576.
+      ptx::tc_fence_before();
+      if (!DB) {
+        if (CLIPB200_ATTN_ELECT_ARRIVE) { if (lane == 0) ptx::mbar_arrive(cx.s_empty); } else { ptx::mbar_arrive(cx.s_empty); }
+      }
+      uint64_t* prev_done_i = DB ? &cx.pv_done[(g - 1) & 1] : cx.pv_done;
+      const uint32_t prev_par_i = DB ? (((g - 1) >> 1) & 1) : ((g & 1) ^ 1);
+      const bool run_pending_i = CLIPB200_ATTN_DEFER_EPI && j == 0 && pend.valid;
+      if (!DB || run_pending_i) {
+        ptx::mbar_wait(prev_done_i, prev_par_i);
+        ptx::tc_fence_after();
+      }
+      if (run_pending_i) {
+        epilogue_item<HD, BKV, DB, VT>(cx, tm_out, pend.l_run, pend.qt, pend.h, pend.b, quarter, half, lane);
+        pend.valid = false;
+      }
+      ptx::tc_fence_before();
+      if (CLIPB200_ATTN_ELECT_ARRIVE) { if (lane == 0) ptx::mbar_arrive(&cx.p_full[buf]); } else { ptx::mbar_arrive(&cx.p_full[buf]); }
+      continue;
+    }
     float sv[CW];
     float mx_pipe[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // LDPIPE: maxima of the chunks already read
     if (CLIPB200_ATTN_LDPIPE && CW % 32 == 0 && !(CLIPB200_ATTN_DBG & 2)) {
@@ -560,6 +585,10 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
     tmem_st_wait();
     ptx::tc_fence_before();
     if (CLIPB200_ATTN_ELECT_ARRIVE) { if (lane == 0) ptx::mbar_arrive(&cx.p_full[buf]); } else { ptx::mbar_arrive(&cx.p_full[buf]); }
+  }
+  if (idle_rows) {   // nothing of this warp's O rows is ever stored
+    pend.valid = false;
+    return;
   }
   if (CLIPB200_ATTN_DEFER_EPI) {   // handed to the next item's first block (or to the kernel's tail)
     pend.valid = true;

@@ -499,8 +499,6 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
     return Status::Err(io ? CLIPB200_ERR_IO : CLIPB200_ERR_PARSE, err);
   }
   input_names = m.inputs;
-  // Real exports (torch.onnx.export graphs) are bound from the graph structure; initializer-only files and graphs
-  // the recogniser does not know (FastViT) fall through to binding by open_clip / timm parameter names.
   // src/text.rs:156-161 feeds an attention_mask when the graph declares one.  pull_onnx.py's TextWrapper never does;
   // a graph that does uses the mask in a way only its nodes define, so it is refused instead of being ignored.
   for (const std::string& n : m.inputs)
