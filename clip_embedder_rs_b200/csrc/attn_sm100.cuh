@@ -278,6 +278,34 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 #ifndef CLIPB200_ATTN_MAXTREE
 #define CLIPB200_ATTN_MAXTREE 1
 #endif
+// CLIPB200_ATTN_PEXP: how P = exp2(s * scale - m) is produced where the head dim leaves a spare O column (hd 72 -> 80):
+//   0  fp32 exp2 per element (MUFU, a quarter on the FMA-pipe polynomial), packed to bf16, row sum by FADD2
+//   1  one packed `ex2.approx.f16x2` per PAIR of scores; P goes to the tensor core as fp16 (A operand fp16, V bf16)
+//   2  one packed `ex2.approx.ftz.bf16x2` per pair; P stays bf16 (the exponent's argument is rounded to bf16 first)
+// With 1 / 2 the row sum l is not accumulated by the softmax warps at all: the first padding column of V (column HD of
+// the zero plane) is set to 1.0, so O[:, HD] = sum_k P[:, k] comes out of the PV product in fp32, consistent with the
+// P the tensor core actually multiplied.  Per score pair that is FFMA2 + CVT + MUFU (3 instructions, half the MUFU
+// work) against FFMA2 + 2 MUFU + FADD2 + F2FP (5) or the 14-instruction polynomial pair.
+#ifndef CLIPB200_ATTN_PEXP
+#define CLIPB200_ATTN_PEXP 0
+#endif
+template <int HD, int BKV, bool DB, bool VT>
+struct PExp {
+  // needs the natural V layout's padding plane (columns HD .. HDP-1) and one softmax warp per row
+  static constexpr bool kOn = CLIPB200_ATTN_PEXP != 0 && !VT && SPLIT == 1 && ((HD - 64) % 16) != 0 && HD > 64;
+};
+__device__ __forceinline__ uint32_t exp2_pair_f16(float lo, float hi) {
+  uint32_t h, r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h));
+  return r;
+}
+__device__ __forceinline__ uint32_t exp2_pair_bf16(float lo, float hi) {
+  uint32_t h, r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(r) : "r"(h));
+  return r;
+}
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -334,6 +362,15 @@ struct SmxCtx {
 #ifndef CLIPB200_ATTN_DEFER_EPI
 #define CLIPB200_ATTN_DEFER_EPI 1
 #endif
+// A/B switches for same-box measurements of the two other item-boundary changes (defaults = shipped behaviour):
+// CLIPB200_ATTN_LOOKAHEAD=0: the first QK^T of an item is only issued after the previous item's last PV (single-S path);
+// CLIPB200_ATTN_IDLE_SKIP=0: warps whose 32 query rows all lie beyond T run the full softmax on them anyway.
+#ifndef CLIPB200_ATTN_LOOKAHEAD
+#define CLIPB200_ATTN_LOOKAHEAD 1
+#endif
+#ifndef CLIPB200_ATTN_IDLE_SKIP
+#define CLIPB200_ATTN_IDLE_SKIP 1
+#endif
 struct PendingEpilogue {
   bool valid = false;
   float l_run = 0.f;
@@ -351,7 +388,13 @@ __device__ __forceinline__ void epilogue_item(const SmxCtx& cx, const CUtensorMa
   if (SPLIT == 2) cx.xch_sum[half * BQ + row] = l_run;
   if (half == 0 && lane == 0) ptx::tma_store_wait_read<0>();  // previous item's store has left the staging tile
   if (SPLIT == 2) pair_barrier(quarter); else __syncwarp();
-  const float l_tot = SPLIT == 2 ? l_run + cx.xch_sum[(half ^ 1) * BQ + row] : l_run;
+  float l_tot = SPLIT == 2 ? l_run + cx.xch_sum[(half ^ 1) * BQ + row] : l_run;
+  if (PExp<HD, BKV, DB, VT>::kOn) {   // the row sum came out of the PV product: O[:, HD] (ones column of V)
+    uint32_t r[8];
+    tmem_ld_32x32_x8(cx.t_o + static_cast<uint32_t>(HD), r);
+    ptx::tmem_ld_wait();
+    l_tot = __uint_as_float(r[0]);
+  }
   const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
 #pragma unroll
   for (int c = 0; c < OW / 8; ++c) {
@@ -387,7 +430,7 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
   constexpr int CW = C::CW, OW = C::OW;
   const int row = quarter * 32 + lane;
   const int qrow = qt * BQ + row;
-  const bool idle_rows = SPLIT == 1 && qt * BQ + quarter * 32 >= p.T;   // warp-uniform
+  const bool idle_rows = CLIPB200_ATTN_IDLE_SKIP && SPLIT == 1 && qt * BQ + quarter * 32 >= p.T;   // warp-uniform
   float m_run = -INFINITY, l_run = 0.f;
   for (int j = 0; j < nb; ++j, ++g) {
     // DB: block g lives in S buffer g & 1; every per-buffer barrier completes one phase per two blocks
@@ -511,6 +554,12 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
       // exp2(s * scale - m): one FFMA + one MUFU per element, or (POLY_NUM of every POLY_DEN pairs) the packed
       // FMA-pipe polynomial
       float p0, p1;
+      if (PExp<HD, BKV, DB, VT>::kOn) {
+        float a0, a1;
+        unpack2(fma2(pack2(sv[2 * e], sv[2 * e + 1]), scale2, negm2), a0, a1);
+        pk[e] = CLIPB200_ATTN_PEXP == 1 ? exp2_pair_f16(a0, a1) : exp2_pair_bf16(a0, a1);
+        continue;
+      }
       if (CLIPB200_ATTN_POLY_NUM > 0 && (e % CLIPB200_ATTN_POLY_DEN) >= CLIPB200_ATTN_POLY_DEN - CLIPB200_ATTN_POLY_NUM) {
         exp2_poly_pair(fma2(pack2(sv[2 * e], sv[2 * e + 1]), scale2, negm2), p0, p1);
       } else if (CLIPB200_ATTN_PACKED) {
@@ -649,6 +698,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
         for (int i = threadIdx.x; i < (C::REMP_PLANES - C::REM_PLANES) * BKV; i += THREADS)
           reinterpret_cast<uint4*>(tile + C::KV_MAIN + C::REM_PLANES * BKV * 16)[i] = make_uint4(0, 0, 0, 0);
       }
+    if (PExp<HD, BKV, DB, VT>::kOn) {
+      __syncthreads();   // the zeroing above is complete
+      for (int st = 0; st < C::STAGES; ++st) {
+        uint8_t* vpad = s_kv + st * C::KV_STAGE_AL + C::KV_TILE + C::KV_MAIN + C::REM_PLANES * BKV * 16;
+        for (int i = threadIdx.x; i < BKV; i += THREADS) *reinterpret_cast<uint16_t*>(vpad + i * 16) = 0x3F80;  // bf16 1.0
+      }
+    }
     ptx::fence_proxy_async_smem();
   }
   if (VT) {
@@ -751,8 +807,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
     // S of every item was only requested after the previous item's last PV had been issued, and the softmax warps sat
     // idle for a PV + QK^T + commit round trip (~1100 cycles of a ~17 000-cycle item at T = 576).
     constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, 0);
-    constexpr uint32_t idesc_pv_main = make_idesc(BQ, 64, 1);
-    constexpr uint32_t idesc_pv_rem = make_idesc(BQ, C::REMP > 0 ? C::REMP : 16, 1);
+    // with CLIPB200_ATTN_PEXP == 1 the A operand (P) is fp16: clear the A-format field (bit 7: 1 = bf16, 0 = fp16)
+    constexpr uint32_t a_fmt_mask = (PExp<HD, BKV, DB, VT>::kOn && CLIPB200_ATTN_PEXP == 1) ? ~(1u << 7) : ~0u;
+    constexpr uint32_t idesc_pv_main = make_idesc(BQ, 64, 1) & a_fmt_mask;
+    constexpr uint32_t idesc_pv_rem = make_idesc(BQ, C::REMP > 0 ? C::REMP : 16, 1) & a_fmt_mask;
     (void)idesc_pv_main; (void)idesc_pv_rem;
     const uint32_t t_o = tmem_base + C::COL_O;
     const uint32_t q_addr = ptx::smem_u32(s_q);
@@ -809,7 +867,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
     issue_next_qk();
     if (DB) issue_next_qk();
     while (cursor_valid(cp)) {
-      if (!DB) issue_next_qk();   // S(gp + 1) overlaps softmax(gp)
+      // S(gp + 1) overlaps softmax(gp); without the look-ahead a block that starts a new item waits for this PV
+      if (!DB && gq == gp + 1 && (CLIPB200_ATTN_LOOKAHEAD || cq.j != 0)) issue_next_qk();
       const int st = DB ? static_cast<int>(gp % ST) : static_cast<int>(gp & 1);
       const int buf = DB ? static_cast<int>(gp & 1) : 0;
       const uint32_t v_addr = ptx::smem_u32(s_kv + st * C::KV_STAGE_AL + C::KV_TILE);
@@ -837,6 +896,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
       ++gp;
       cursor_next(cp);
       if (DB) issue_next_qk();    // reuses the S buffer PV(gp - 1) has just been queued to consume
+      else if (gq == gp) issue_next_qk();   // CLIPB200_ATTN_LOOKAHEAD == 0: first QK^T of the next item, behind the last PV
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue (warps 0..NSW-1)
