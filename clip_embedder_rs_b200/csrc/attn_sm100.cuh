@@ -278,14 +278,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 #ifndef CLIPB200_ATTN_MAXTREE
 #define CLIPB200_ATTN_MAXTREE 1
 #endif
-// CLIPB200_ATTN_PEXP: how P = exp2(s * scale - m) is produced where the head dim leaves a spare O column (hd 72 -> 80):
-//   0  fp32 exp2 per element (MUFU, a quarter on the FMA-pipe polynomial), packed to bf16, row sum by FADD2
-//   1  one packed `ex2.approx.f16x2` per PAIR of scores; P goes to the tensor core as fp16 (A operand fp16, V bf16)
-//   2  one packed `ex2.approx.ftz.bf16x2` per pair; P stays bf16 (the exponent's argument is rounded to bf16 first)
-// With 1 / 2 the row sum l is not accumulated by the softmax warps at all: the first padding column of V (column HD of
-// the zero plane) is set to 1.0, so O[:, HD] = sum_k P[:, k] comes out of the PV product in fp32, consistent with the
-// P the tensor core actually multiplied.  Per score pair that is FFMA2 + CVT + MUFU (3 instructions, half the MUFU
-// work) against FFMA2 + 2 MUFU + FADD2 + F2FP (5) or the 14-instruction polynomial pair.
+// CLIPB200_ATTN_PEXP=2 (experiment, off): where the head dim leaves a spare O column (hd 72 -> 80), P = exp2(s * scale - m)
+// is produced by one packed `ex2.approx.ftz.bf16x2` per PAIR of scores (argument rounded to bf16 first) and the row sum l
+// is not accumulated by the softmax warps at all: the first padding column of V (column HD of the zero plane) is set
+// to 1.0, so O[:, HD] = sum_k P[:, k] comes out of the PV product in fp32.  Per score pair that is FFMA2 + CVT + 2 MUFU
+// (the packed ex2 still issues one MUFU per half) against FFMA2 + 2 MUFU + FADD2 + F2FP or the 14-instruction polynomial
+// pair: 35 % fewer instructions, but every exponential is back on the MUFU.  Measured on one box (profiles/r02j_*):
+// correct on every case (max |error| vs fp32 0.0063 instead of 0.0038), 0.312 ms against 0.304 ms at T = 576 and 1.018
+// against 0.985 ms at T = 2304 — slower: the MUFU rate, not the instruction count, is what the polynomial quarter buys
+// back.  (The fp16 twin, P as fp16 with V in bf16, is rejected by the hardware: a tcgen05.mma.kind::f16 whose A and B
+// formats differ raises "illegal instruction".)
 #ifndef CLIPB200_ATTN_PEXP
 #define CLIPB200_ATTN_PEXP 0
 #endif
@@ -294,12 +296,6 @@ struct PExp {
   // needs the natural V layout's padding plane (columns HD .. HDP-1) and one softmax warp per row
   static constexpr bool kOn = CLIPB200_ATTN_PEXP != 0 && !VT && SPLIT == 1 && ((HD - 64) % 16) != 0 && HD > 64;
 };
-__device__ __forceinline__ uint32_t exp2_pair_f16(float lo, float hi) {
-  uint32_t h, r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h));
-  return r;
-}
 __device__ __forceinline__ uint32_t exp2_pair_bf16(float lo, float hi) {
   uint32_t h, r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
@@ -557,7 +553,7 @@ __device__ __forceinline__ void softmax_item(const SmxCtx& cx, const Params& p, 
       if (PExp<HD, BKV, DB, VT>::kOn) {
         float a0, a1;
         unpack2(fma2(pack2(sv[2 * e], sv[2 * e + 1]), scale2, negm2), a0, a1);
-        pk[e] = CLIPB200_ATTN_PEXP == 1 ? exp2_pair_f16(a0, a1) : exp2_pair_bf16(a0, a1);
+        pk[e] = exp2_pair_bf16(a0, a1);
         continue;
       }
       if (CLIPB200_ATTN_POLY_NUM > 0 && (e % CLIPB200_ATTN_POLY_DEN) >= CLIPB200_ATTN_POLY_DEN - CLIPB200_ATTN_POLY_NUM) {
@@ -807,10 +803,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __g
     // S of every item was only requested after the previous item's last PV had been issued, and the softmax warps sat
     // idle for a PV + QK^T + commit round trip (~1100 cycles of a ~17 000-cycle item at T = 576).
     constexpr uint32_t idesc_qk = make_idesc(BQ, BKV, 0);
-    // with CLIPB200_ATTN_PEXP == 1 the A operand (P) is fp16: clear the A-format field (bit 7: 1 = bf16, 0 = fp16)
-    constexpr uint32_t a_fmt_mask = (PExp<HD, BKV, DB, VT>::kOn && CLIPB200_ATTN_PEXP == 1) ? ~(1u << 7) : ~0u;
-    constexpr uint32_t idesc_pv_main = make_idesc(BQ, 64, 1) & a_fmt_mask;
-    constexpr uint32_t idesc_pv_rem = make_idesc(BQ, C::REMP > 0 ? C::REMP : 16, 1) & a_fmt_mask;
+    constexpr uint32_t idesc_pv_main = make_idesc(BQ, 64, 1);
+    constexpr uint32_t idesc_pv_rem = make_idesc(BQ, C::REMP > 0 ? C::REMP : 16, 1);
     (void)idesc_pv_main; (void)idesc_pv_rem;
     const uint32_t t_o = tmem_base + C::COL_O;
     const uint32_t q_addr = ptx::smem_u32(s_q);
