@@ -171,6 +171,7 @@ class Engine {
                              const clipb200_preproc* pp, uint8_t* d_dst, int* consumed);
   Status GrowStage(ResizeStage* st, size_t src, size_t tmp, size_t arena_words, size_t jobs);
   bool fastvit_ = false;
+  bool fused_mlp_ = true;   // fc1 -> GELU -> fc2 of the FastViT ConvMlp in one kernel (CLIPB200_FUSED_MLP=0: two GEMM launches)
   ConvW fv_stem0_, fv_stem1_, fv_final_;
   LinearW fv_stem2_;
   SeW fv_final_se_;

@@ -11,6 +11,7 @@
 #include "attn_sm100.cuh"
 #include "conv_kernels.cuh"
 #include "engine.h"
+#include "fused_mlp_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "kernels.cuh"
 
@@ -70,6 +71,8 @@ Status Engine::UploadSe(const OnnxModel& m, const std::string& name, int C, SeW*
 
 Status Engine::LoadFastVit(const OnnxModel& m) {
   fastvit_ = true;
+  if (const char* env = getenv("CLIPB200_FUSED_MLP")) fused_mlp_ = atoi(env) != 0;
+  CUDA_RET(fused_mlp_configure_device(), "configure fused ConvMlp kernels");
   family_ = "fastvit";
   const std::string pre = "model.visual.trunk";
   const OnnxTensor* s0 = m.find(pre + ".stem.0.reparam_conv.weight");
@@ -231,6 +234,14 @@ Status Engine::FvMlp(const FvBlock& b, float* cur, int n, int Hh, int C, const f
   const int rows = n * Hh * Hh;
   cudaError_t e = DwConv(cur, false, n, Hh, Hh, C, 7, 1, 1, b.mlp_dw.w, b.mlp_dw.b, false, h_, true);
   CUDA_RET(e, "depthwise 7x7");
+  if (fused_mlp_ && fused_mlp_supported(C, b.fc1.N) && b.fc1.ldk == C && b.fc2.ldk == b.fc1.N) {
+    // fc1 -> GELU -> fc2 -> layer scale -> residual in one kernel: the 3C-wide hidden activation stays on the SM
+    ProfBegin(PC_GEMM, compute_);
+    e = fused_mlp(h_, C, b.fc1.w, b.fc1.ldk, b.fc1.b, b.fc2.w, b.fc2.ldk, b.fc2.b, gamma, cur, C, rows, C, b.fc1.N, compute_);
+    ProfEnd(PC_GEMM, compute_);
+    if (profile_) prof_acc_.gemm_flops += 4.0 * rows * static_cast<double>(C) * b.fc1.N;
+    return Check(e, "fused ConvMlp");
+  }
   GemmEpilogue e1;
   e1.out_bf16 = mlpbuf_;
   e1.ldc = b.fc1.N;

@@ -1,0 +1,330 @@
+// Fused ConvMlp tail of the FastViT / MobileCLIP2 blocks for sm_100a:
+//
+//     x[r, :] += gamma ⊙ ( W2 · gelu( W1 · a[r, :] + b1 ) + b2 )          a = dw7x7(x) (bf16, from dwconv_sm100.cu)
+//
+// i.e. the two 1x1 convolutions of timm's ConvMlp with the GELU between them, the layer scale and the residual add
+// (reference: the Conv -> Erf-GELU -> Conv -> Mul -> Add nodes onnxruntime executes for every re-parameterised RepMixer /
+// attention block, pull_onnx.py:110-116).  As two GEMM launches the 3C-wide hidden activation crosses HBM twice (6C
+// bytes written by fc1, 6C read by fc2 per pixel, C = 80 ... 320), which bounds fc1 at 60 ... 240 FLOP/B — 390 ... 1560
+// TFLOP/s at the copy peak — and is why the 1x1-conv GEMM class sat at 404 TFLOP/s.  Here the hidden
+// activation never leaves the SM:
+//
+//   per CTA: one tile of 128 pixels.  A [128 x C] is loaded once (TMA, 128B swizzle, K-major).  The hidden dimension is
+//   walked in chunks of 64 columns:
+//       MMA warp   S_b[128 x 64]  = A · W1[chunk]^T          tcgen05.mma, accumulator in TMEM buffer b (2 buffers)
+//       4 warps    h = gelu(S_b + b1) -> bf16 -> shared memory tile H_b [128 x 64] written in the 128B-swizzled K-major
+//                  layout the tensor core reads (2 buffers)
+//       MMA warp   O[128 x C]    += H_b · W2[:, chunk]^T      accumulator in TMEM (C columns)
+//   W1 / W2 chunks stream through TMA rings; chunk i's GELU overlaps chunk i+1's first GEMM and chunk i-1's second.
+//   Epilogue: O -> (+ b2) * gamma -> staging -> TMA reduce-add into the fp32 residual stream (as the GEMM's EPI_RESID).
+//
+// HBM traffic per pixel: 2C (a) + 8C (x read-modify-write) instead of 2C + 6C + 6C + 8C.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_sm100.cuh"
+#include "ptx_sm100.cuh"
+
+namespace clipb200 {
+namespace fmlp {
+
+constexpr int BM = 128;        // pixels per CTA
+constexpr int HC = 64;         // hidden columns per chunk (one 128B-swizzle atom of K for the second GEMM)
+constexpr int THREADS = 192;   // warps 0..3 epilogue, 4 TMA, 5 MMA
+constexpr int WARP_TMA = 4, WARP_MMA = 5;
+
+template <int C>
+struct Cfg {
+  static_assert(C % 16 == 0 && C >= 16 && C <= 320, "channel count");
+  static constexpr int KB = (C + 63) / 64;                 // 64-column k-blocks of A / W1
+  static constexpr int KSTEPS1 = C / 16;                   // UMMA k-steps of the first GEMM
+  static constexpr int A_BYTES = KB * BM * 128;            // [KB][128 rows][128 B]
+  static constexpr int W1_BYTES = KB * HC * 128;           // [KB][64 rows][128 B]
+  static constexpr int W2_ROWS = (C + 7) / 8 * 8;
+  static constexpr int W2_BYTES = (W2_ROWS * 128 + 1023) / 1024 * 1024;  // [C rows][128 B]
+  static constexpr int H_BYTES = BM * 128;                 // [128 rows][64 bf16]
+  static constexpr int WST = C > 192 ? 1 : 2;              // W ring depth (shared-memory budget)
+  static constexpr int STG_BYTES = 4 * 32 * 128;           // 4 epilogue warps x [32 rows][32 fp32]
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_W1 = OFF_A + A_BYTES;
+  static constexpr int OFF_W2 = OFF_W1 + WST * W1_BYTES;
+  static constexpr int OFF_H = OFF_W2 + WST * W2_BYTES;
+  static constexpr int OFF_STG = OFF_H + 2 * H_BYTES;
+  static constexpr int OFF_BAR = OFF_STG + STG_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int COL_O = 0;                          // O accumulator: C columns
+  static constexpr int COL_S = (C + 31) / 32 * 32;         // two hidden buffers of HC columns
+  static constexpr int TMEM_NEED = COL_S + 2 * HC;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+  static constexpr int N2 = C > 256 ? C / 2 : C;           // second GEMM: N per instruction (<= 256)
+  static constexpr int N2_PARTS = C > 256 ? 2 : 1;
+  static_assert(N2 % 16 == 0, "UMMA N granularity");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+};
+
+struct Params {
+  int M, C, Hd;          // rows (pixels), channels, hidden width (fc1.N)
+  const float* b1;       // [Hd]
+  const float* b2;       // [C]
+  const float* gamma;    // [C] or null
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return gelu_erf_fast(x); }
+
+template <int C>
+__global__ void __launch_bounds__(THREADS, 2)
+fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w1,
+                 const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_x, Params p) {
+  using K = Cfg<C>;
+  extern __shared__ uint8_t fmlp_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fmlp_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_a = smem + K::OFF_A;
+  uint8_t* s_w1 = smem + K::OFF_W1;
+  uint8_t* s_w2 = smem + K::OFF_W2;
+  uint8_t* s_h = smem + K::OFF_H;
+  uint8_t* s_stg = smem + K::OFF_STG;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::OFF_BAR);
+  uint64_t* a_full = bars + 0;
+  uint64_t* w1_full = bars + 1;    // [2]
+  uint64_t* w1_empty = bars + 3;   // [2]
+  uint64_t* w2_full = bars + 5;    // [2]
+  uint64_t* w2_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;     // [2]  MMA -> epilogue: hidden accumulator b complete
+  uint64_t* s_empty = bars + 11;   // [2]  epilogue -> MMA: accumulator b read out
+  uint64_t* h_full = bars + 13;    // [2]  epilogue -> MMA: H_b written
+  uint64_t* h_empty = bars + 15;   // [2]  MMA -> epilogue: second GEMM of H_b retired
+  uint64_t* o_full = bars + 17;
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * BM;
+  const int n_chunks = (p.Hd + HC - 1) / HC;
+
+  if (warp == WARP_TMA && lane == 0) {
+    ptx::prefetch_tmap(&tm_a);
+    ptx::prefetch_tmap(&tm_w1);
+    ptx::prefetch_tmap(&tm_w2);
+    ptx::prefetch_tmap(&tm_x);
+    ptx::mbar_init(a_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&w1_full[i], 1);
+      ptx::mbar_init(&w1_empty[i], 1);
+      ptx::mbar_init(&w2_full[i], 1);
+      ptx::mbar_init(&w2_empty[i], 1);
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&s_empty[i], 128);
+      ptx::mbar_init(&h_full[i], 128);
+      ptx::mbar_init(&h_empty[i], 1);
+    }
+    ptx::mbar_init(o_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == WARP_MMA) ptx::tmem_alloc<K::TMEM_COLS>(tmem_base_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);
+
+  if (warp == WARP_TMA) {
+    if (lane == 0) {
+      // A tile: KB boxes of 64 columns x 128 rows (columns >= C and rows >= M are zero-filled)
+      ptx::mbar_arrive_expect_tx(a_full, K::KB * BM * 128);
+      for (int kb = 0; kb < K::KB; ++kb) ptx::tma_load_2d(&tm_a, a_full, s_a + kb * BM * 128, kb * 64, row0);
+      for (int i = 0; i < n_chunks; ++i) {
+        const int st = i % K::WST;
+        const uint32_t par = ((i / K::WST) & 1) ^ 1;
+        ptx::mbar_wait(&w1_empty[st], par);
+        ptx::mbar_arrive_expect_tx(&w1_full[st], K::KB * HC * 128);
+        for (int kb = 0; kb < K::KB; ++kb)   // W1 rows [i*64, +64) (hidden units), columns kb*64.. (input channels)
+          ptx::tma_load_2d(&tm_w1, &w1_full[st], s_w1 + st * K::W1_BYTES + kb * HC * 128, kb * 64, i * HC);
+        ptx::mbar_wait(&w2_empty[st], par);
+        ptx::mbar_arrive_expect_tx(&w2_full[st], K::N2_PARTS * K::N2 * 128);
+        for (int part = 0; part < K::N2_PARTS; ++part)   // W2 rows = output channels, columns [i*64, +64) of the hidden dim
+          ptx::tma_load_2d(&tm_w2, &w2_full[st], s_w2 + st * K::W2_BYTES + part * K::N2 * 128, i * HC, part * K::N2);
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    constexpr uint32_t idesc1 = ptx::make_idesc_bf16_f32(BM, HC);
+    constexpr uint32_t idesc2 = ptx::make_idesc_bf16_f32(BM, K::N2);
+    const uint32_t a_addr = ptx::smem_u32(s_a);
+    ptx::mbar_wait(a_full, 0);
+    // chunk i's first GEMM is issued before chunk i-1's second one, so the GELU of chunk i-1 overlaps it
+    auto gemm1 = [&](int i) {
+      const int st = i % K::WST, b = i & 1;
+      ptx::mbar_wait(&w1_full[st], (i / K::WST) & 1);
+      ptx::mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t w_addr = ptx::smem_u32(s_w1 + st * K::W1_BYTES);
+      const uint32_t t_s = tmem_base + K::COL_S + static_cast<uint32_t>(b * HC);
+#pragma unroll
+      for (int k = 0; k < K::KSTEPS1; ++k) {
+        const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr + (k >> 2) * BM * 128) + static_cast<uint64_t>(2 * (k & 3));
+        const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr + (k >> 2) * HC * 128) + static_cast<uint64_t>(2 * (k & 3));
+        ptx::umma_bf16_ss_w(t_s, da, dw, idesc1, k != 0 ? 1u : 0u);
+      }
+      ptx::umma_commit_w(&w1_empty[st]);
+      ptx::umma_commit_w(&s_full[b]);
+    };
+    auto gemm2 = [&](int i) {
+      const int st = i % K::WST, b = i & 1;
+      ptx::mbar_wait(&w2_full[st], (i / K::WST) & 1);
+      ptx::mbar_wait(&h_full[b], (i >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t h_addr = ptx::smem_u32(s_h + b * K::H_BYTES);
+      const uint32_t w_addr = ptx::smem_u32(s_w2 + st * K::W2_BYTES);
+#pragma unroll
+      for (int part = 0; part < K::N2_PARTS; ++part) {
+#pragma unroll
+        for (int k = 0; k < HC / 16; ++k) {
+          const uint64_t dh = ptx::make_kmajor_sw128_desc(h_addr) + static_cast<uint64_t>(2 * k);
+          const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr + part * K::N2 * 128) + static_cast<uint64_t>(2 * k);
+          ptx::umma_bf16_ss_w(tmem_base + K::COL_O + static_cast<uint32_t>(part * K::N2), dh, dw, idesc2, (i | k) != 0 ? 1u : 0u);
+        }
+      }
+      ptx::umma_commit_w(&w2_empty[st]);
+      ptx::umma_commit_w(&h_empty[b]);
+    };
+    gemm1(0);
+    for (int i = 0; i < n_chunks; ++i) {
+      if (i + 1 < n_chunks) gemm1(i + 1);
+      gemm2(i);
+    }
+    ptx::umma_commit_w(o_full);
+  } else {
+    // ------------------------------------------------------------ epilogue warps: GELU between the GEMMs, final store
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;                       // this thread's pixel row inside the tile
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const int sw = row & 7;                                    // 128B-swizzle phase of this row
+    for (int i = 0; i < n_chunks; ++i) {
+      const int b = i & 1;
+      ptx::mbar_wait(&s_full[b], (i >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_S + static_cast<uint32_t>(b * HC), r0);
+      ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_S + static_cast<uint32_t>(b * HC + 32), r1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&s_empty[b]);
+      const int h0 = i * HC;
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int c0 = h0 + 2 * j, c1 = h0 + 32 + 2 * j;
+        const bool hb = p.b1 != nullptr;
+        const float ba = hb && c0 < p.Hd ? __ldg(p.b1 + c0) : 0.f, bb = hb && c0 + 1 < p.Hd ? __ldg(p.b1 + c0 + 1) : 0.f;
+        const float bc = hb && c1 < p.Hd ? __ldg(p.b1 + c1) : 0.f, bd = hb && c1 + 1 < p.Hd ? __ldg(p.b1 + c1 + 1) : 0.f;
+        __nv_bfloat162 lo = __floats2bfloat162_rn(gelu_erf(__uint_as_float(r0[2 * j]) + ba), gelu_erf(__uint_as_float(r0[2 * j + 1]) + bb));
+        __nv_bfloat162 hi = __floats2bfloat162_rn(gelu_erf(__uint_as_float(r1[2 * j]) + bc), gelu_erf(__uint_as_float(r1[2 * j + 1]) + bd));
+        pk[j] = *reinterpret_cast<uint32_t*>(&lo);
+        pk[16 + j] = *reinterpret_cast<uint32_t*>(&hi);
+      }
+      ptx::mbar_wait(&h_empty[b], ((i >> 1) & 1) ^ 1);         // the second GEMM of chunk i-2 has finished reading H_b
+      uint8_t* hrow = s_h + b * K::H_BYTES + row * 128;        // 64 bf16 = 8 chunks of 16 B, chunk c at (c ^ sw)
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(hrow + ((c ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&h_full[b]);
+    }
+    // final: O -> (+ b2) * gamma -> staging tile [32 rows][32 fp32] (128B swizzle) -> TMA reduce-add into x
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    uint8_t* stg = s_stg + quarter * (32 * 128);
+    const int swl = lane & 7;
+#pragma unroll 1
+    for (int c = 0; c < (C + 31) / 32; ++c) {
+      const int n0 = c * 32;
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_O + static_cast<uint32_t>(n0), r);
+      ptx::tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = n0 + j;
+        const float bj = (p.b2 != nullptr && col < C) ? __ldg(p.b2 + col) : 0.f;
+        const float gj = (p.gamma != nullptr && col < C) ? __ldg(p.gamma + col) : 1.f;
+        v[j] = (__uint_as_float(r[j]) + bj) * gj;
+      }
+      if (lane == 0) ptx::tma_store_wait_read<0>();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ swl) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_reduce_add_2d(&tm_x, stg, n0, row0 + quarter * 32);   // columns >= C and rows >= M are clipped
+        ptx::tma_store_commit();
+      }
+    }
+    if (lane == 0) ptx::tma_store_wait<0>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<K::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int C>
+inline cudaError_t configure_t() {
+  return cudaFuncSetAttribute(fused_mlp_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<C>::SMEM_BYTES);
+}
+
+template <int C>
+inline cudaError_t launch_t(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w1, long long ldw1,
+                            const __nv_bfloat16* w2, long long ldw2, float* x, long long ldx, const Params& p,
+                            cudaStream_t st) {
+  using K = Cfg<C>;
+  CUtensorMap ta, tw1, tw2, tx;
+  if (!make_tmap_2d(&ta, a, p.M, C, lda, BM, 2)) return cudaErrorUnknown;
+  if (!make_tmap_2d(&tw1, w1, p.Hd, C, ldw1, HC, 2)) return cudaErrorUnknown;
+  if (!make_tmap_2d(&tw2, w2, C, p.Hd, ldw2, K::N2, 2)) return cudaErrorUnknown;
+  if (!make_tmap_2d(&tx, x, p.M, C, ldx, 32, 4)) return cudaErrorUnknown;
+  const int grid = (p.M + BM - 1) / BM;
+  fused_mlp_kernel<C><<<grid, THREADS, K::SMEM_BYTES, st>>>(ta, tw1, tw2, tx, p);
+  return cudaGetLastError();
+}
+
+}  // namespace fmlp
+
+inline bool fused_mlp_supported(int C, int Hd) {
+  return (C == 80 || C == 96 || C == 128 || C == 160 || C == 192 || C == 256 || C == 320) && Hd % 8 == 0 && Hd >= 64;
+}
+inline cudaError_t fused_mlp_configure_device() {
+  cudaError_t e;
+  if ((e = fmlp::configure_t<80>()) != cudaSuccess) return e;
+  if ((e = fmlp::configure_t<96>()) != cudaSuccess) return e;
+  if ((e = fmlp::configure_t<128>()) != cudaSuccess) return e;
+  if ((e = fmlp::configure_t<160>()) != cudaSuccess) return e;
+  if ((e = fmlp::configure_t<192>()) != cudaSuccess) return e;
+  if ((e = fmlp::configure_t<256>()) != cudaSuccess) return e;
+  return fmlp::configure_t<320>();
+}
+// a [M, C] bf16, w1 [Hd, C] bf16, w2 [C, Hd] bf16 (both torch Linear / 1x1-conv layout, K contiguous), x [M, C] fp32 in place
+inline cudaError_t fused_mlp(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w1, long long ldw1, const float* b1,
+                             const __nv_bfloat16* w2, long long ldw2, const float* b2, const float* gamma, float* x,
+                             long long ldx, int M, int C, int Hd, cudaStream_t st) {
+  if (M <= 0) return cudaSuccess;
+  if (!fused_mlp_supported(C, Hd) || (lda & 7) || (ldw1 & 7) || (ldw2 & 7) || (ldx & 3)) return cudaErrorInvalidValue;
+  fmlp::Params p;
+  p.M = M; p.C = C; p.Hd = Hd; p.b1 = b1; p.b2 = b2; p.gamma = gamma;
+#define CLIPB200_FMLP_CASE(C_) \
+  if (C == C_) return fmlp::launch_t<C_>(a, lda, w1, ldw1, w2, ldw2, x, ldx, p, st);
+  CLIPB200_FMLP_CASE(80)
+  CLIPB200_FMLP_CASE(96)
+  CLIPB200_FMLP_CASE(128)
+  CLIPB200_FMLP_CASE(160)
+  CLIPB200_FMLP_CASE(192)
+  CLIPB200_FMLP_CASE(256)
+  CLIPB200_FMLP_CASE(320)
+#undef CLIPB200_FMLP_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace clipb200

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../clip_embedder_rs_b200/csrc/gemm_sm100.cuh"
+#include "../../clip_embedder_rs_b200/csrc/fused_mlp_sm100.cuh"
 
 using namespace clipb200;
 
@@ -256,6 +257,85 @@ static int run_qkvt_case(int B, int T, int D, int K, bool time_it, int num_sms, 
   return bad ? 1 : 0;
 }
 
+// Fused ConvMlp tail (fused_mlp_sm100.cuh) against the two-launch path it replaces: fc1 + GELU as a bf16-store GEMM,
+// fc2 + layer scale + residual as the fp32 reduce-add GEMM.  Both round the hidden activation to bf16 once, so the results
+// differ only by fp32 summation order.
+static int run_fused_mlp_case(int M, int C, int Hd, bool time_it, int num_sms) {
+  __nv_bfloat16 *A, *W1, *W2, *Hbuf;
+  float *b1, *b2, *gamma, *x0, *xa, *xb;
+  CK(cudaMalloc(&A, (size_t)M * C * 2));
+  CK(cudaMalloc(&W1, (size_t)Hd * C * 2));
+  CK(cudaMalloc(&W2, (size_t)C * Hd * 2));
+  CK(cudaMalloc(&Hbuf, (size_t)M * Hd * 2));
+  CK(cudaMalloc(&b1, (size_t)Hd * 4));
+  CK(cudaMalloc(&b2, (size_t)C * 4));
+  CK(cudaMalloc(&gamma, (size_t)C * 4));
+  CK(cudaMalloc(&x0, (size_t)M * C * 4));
+  CK(cudaMalloc(&xa, (size_t)M * C * 4));
+  CK(cudaMalloc(&xb, (size_t)M * C * 4));
+  auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
+  fill_bf16<<<blocks((size_t)M * C), 256>>>(A, (size_t)M * C, 21, 2.0f);
+  fill_bf16<<<blocks((size_t)Hd * C), 256>>>(W1, (size_t)Hd * C, 22, 0.5f);
+  fill_bf16<<<blocks((size_t)C * Hd), 256>>>(W2, (size_t)C * Hd, 23, 0.25f);
+  fill_f32<<<blocks(Hd), 256>>>(b1, Hd, 24, 1.0f);
+  fill_f32<<<blocks(C), 256>>>(b2, C, 25, 1.0f);
+  fill_f32<<<blocks(C), 256>>>(gamma, C, 26, 2.0f);
+  fill_f32<<<blocks((size_t)M * C), 256>>>(x0, (size_t)M * C, 27, 1.0f);
+  CK(cudaMemcpy(xa, x0, (size_t)M * C * 4, cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(xb, x0, (size_t)M * C * 4, cudaMemcpyDeviceToDevice));
+  auto unfused = [&](float* x) {
+    GemmEpilogue e1;
+    e1.bias = b1; e1.act = ACT_GELU_ERF; e1.ldc = Hd; e1.out_bf16 = Hbuf;
+    CK(gemm_bf16(A, C, W1, C, M, Hd, C, EPI_BF16, e1, num_sms, 0));
+    GemmEpilogue e2;
+    e2.bias = b2; e2.gamma = gamma; e2.ldc = C; e2.out_f32 = x;
+    CK(gemm_bf16(Hbuf, Hd, W2, Hd, M, C, Hd, EPI_RESID, e2, num_sms, 0));
+  };
+  auto fused = [&](float* x) { CK(fused_mlp(A, C, W1, C, b1, W2, Hd, b2, gamma, x, C, M, C, Hd, 0)); };
+  unfused(xa);
+  fused(xb);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> ha((size_t)M * C), hb((size_t)M * C), h0((size_t)M * C);
+  CK(cudaMemcpy(ha.data(), xa, ha.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hb.data(), xb, hb.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h0.data(), x0, h0.size() * 4, cudaMemcpyDeviceToHost));
+  double max_abs = 0, max_mag = 0;
+  long long bad = 0, unchanged = 0;
+  for (size_t i = 0; i < ha.size(); ++i) {
+    const double d = fabs((double)ha[i] - hb[i]);
+    max_abs = d > max_abs ? d : max_abs;
+    max_mag = fabs(ha[i] - h0[i]) > max_mag ? fabs(ha[i] - h0[i]) : max_mag;
+    if (!(hb[i] == hb[i]) || d > 2e-2 + 2e-3 * fabs(ha[i] - h0[i])) {
+      if (bad < 5) printf("   mismatch row %zu col %zu: two launches %f fused %f (x0 %f)\n", i / C, i % C, ha[i], hb[i], h0[i]);
+      ++bad;
+    }
+    if (hb[i] == h0[i]) ++unchanged;
+  }
+  if (unchanged > (long long)ha.size() / 100) { printf("   %lld outputs untouched by the fused kernel\n", unchanged); ++bad; }
+  double ms[2] = {0, 0};
+  if (time_it) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int w = 0; w < 2; ++w) {
+      for (int i = 0; i < 13; ++i) {
+        if (i == 3) CK(cudaEventRecord(e0));
+        if (w == 0) unfused(xa); else fused(xb);
+      }
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float t; CK(cudaEventElapsedTime(&t, e0, e1));
+      ms[w] = t / 10;
+    }
+  }
+  const double flops = 4.0 * M * (double)C * Hd;
+  printf("%s fused_mlp M=%d C=%d Hd=%d max|diff|=%.4g (update magnitude up to %.3g) bad=%lld", bad ? "FAIL" : "ok  ", M, C, Hd, max_abs, max_mag, bad);
+  if (time_it) printf("  two launches %.1f us (%.0f TF)  fused %.1f us (%.0f TF)", ms[0] * 1e3, flops / ms[0] * 1e-9, ms[1] * 1e3, flops / ms[1] * 1e-9);
+  printf("\n");
+  fflush(stdout);
+  cudaFree(A); cudaFree(W1); cudaFree(W2); cudaFree(Hbuf); cudaFree(b1); cudaFree(b2); cudaFree(gamma); cudaFree(x0); cudaFree(xa); cudaFree(xb);
+  return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
   int dev = 0;
   CK(cudaSetDevice(dev));
@@ -287,6 +367,20 @@ int main(int argc, char** argv) {
   if (argc > 1 && atoi(argv[1]) == 4) {  // one short-K, epilogue-heavy launch for ncu (FastViT stage-1 fc1 + GELU)
     const int ncta = argc > 2 ? atoi(argv[2]) : 1;
     return run_case(1048576, 240, 80, EPI_BF16, ACT_GELU_ERF, 0, false, num_sms, ncta);
+  }
+  if (argc > 1 && atoi(argv[1]) == 8) {  // fused ConvMlp tail: small shapes with every tail, then the MobileCLIP2-S2 stage shapes timed
+    CK(fused_mlp_configure_device());
+    fails += run_fused_mlp_case(128, 80, 64, false, num_sms);        // one tile, one chunk
+    fails += run_fused_mlp_case(128, 80, 240, false, num_sms);       // hidden tail (240 = 3 x 64 + 48)
+    fails += run_fused_mlp_case(300, 160, 480, false, num_sms);      // row tail
+    fails += run_fused_mlp_case(1000, 320, 960, false, num_sms);     // C > 256: two N halves, single-stage W ring
+    fails += run_fused_mlp_case(777, 96, 384, false, num_sms);
+    fails += run_fused_mlp_case(520, 256, 1024, false, num_sms);
+    fails += run_fused_mlp_case(1048576, 80, 240, true, num_sms);    // S2 stage 1, 256 images
+    fails += run_fused_mlp_case(262144, 160, 480, true, num_sms);    // stage 2
+    fails += run_fused_mlp_case(65536, 320, 960, true, num_sms);     // stage 3
+    printf("%s\n", fails ? "FUSED MLP TEST FAILED" : "FUSED MLP TEST PASSED");
+    return fails;
   }
   if (argc > 1 && atoi(argv[1]) == 7) {  // transposing qkv epilogue: correctness on awkward shapes, then the SO400M qkv GEMM timed
     fails += run_qkvt_case(3, 32, 128, 128, false, num_sms, 1);     // one 32-token group per sequence, M tail (96 rows)
