@@ -33,8 +33,10 @@ namespace fmlp {
 
 constexpr int BM = 128;        // pixels per CTA
 constexpr int HC = 64;         // hidden columns per chunk (one 128B-swizzle atom of K for the second GEMM)
-constexpr int THREADS = 192;   // warps 0..3 epilogue, 4 TMA, 5 MMA
-constexpr int WARP_TMA = 4, WARP_MMA = 5;
+constexpr int EPI_WARPS = 8;   // two per TMEM lane quarter, 32 of a chunk's 64 hidden columns each: the GELU between the
+                               // GEMMs is ~14 instructions per hidden element and is what a chunk waits for
+constexpr int THREADS = 32 * (EPI_WARPS + 2);   // warps 0..7 epilogue, 8 TMA, 9 MMA
+constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
 
 template <int C>
 struct Cfg {
@@ -46,14 +48,19 @@ struct Cfg {
   static constexpr int W2_ROWS = (C + 7) / 8 * 8;
   static constexpr int W2_BYTES = (W2_ROWS * 128 + 1023) / 1024 * 1024;  // [C rows][128 B]
   static constexpr int H_BYTES = BM * 128;                 // [128 rows][64 bf16]
-  static constexpr int WST = C > 192 ? 1 : 2;              // W ring depth (shared-memory budget)
-  static constexpr int STG_BYTES = 4 * 32 * 128;           // 4 epilogue warps x [32 rows][32 fp32]
+  // Two CTAs per SM where the tiles are small enough (C <= 96: 90 KB with a single-stage W ring), so that one CTA's
+  // prologue / final epilogue overlaps the other's chunks; otherwise one CTA with a two-stage W ring, or (C > 192) one
+  // stage again for the shared-memory budget.
+  static constexpr int CTAS_PER_SM = C <= 96 ? 2 : 1;
+  static constexpr int WST = (C <= 96 || C > 192) ? 1 : 2;
+  static constexpr int STG_BYTES = EPI_WARPS * 32 * 128;   // 8 epilogue warps x [32 rows][32 fp32]; aliases the H buffers
   static constexpr int OFF_A = 0;
   static constexpr int OFF_W1 = OFF_A + A_BYTES;
   static constexpr int OFF_W2 = OFF_W1 + WST * W1_BYTES;
   static constexpr int OFF_H = OFF_W2 + WST * W2_BYTES;
-  static constexpr int OFF_STG = OFF_H + 2 * H_BYTES;
-  static constexpr int OFF_BAR = OFF_STG + STG_BYTES;
+  static constexpr int OFF_STG = OFF_H;                    // the final epilogue runs after the last second GEMM retired
+  static_assert(STG_BYTES <= 2 * H_BYTES, "staging aliases the two H buffers");
+  static constexpr int OFF_BAR = OFF_H + 2 * H_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int COL_O = 0;                          // O accumulator: C columns
   static constexpr int COL_S = (C + 31) / 32 * 32;         // two hidden buffers of HC columns
@@ -62,7 +69,8 @@ struct Cfg {
   static constexpr int N2 = C > 256 ? C / 2 : C;           // second GEMM: N per instruction (<= 256)
   static constexpr int N2_PARTS = C > 256 ? 2 : 1;
   static_assert(N2 % 16 == 0, "UMMA N granularity");
-  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+  static_assert(SMEM_BYTES * CTAS_PER_SM <= 227 * 1024, "shared memory");
+  static_assert(TMEM_COLS * CTAS_PER_SM <= 512, "tensor memory");
 };
 
 struct Params {
@@ -75,7 +83,7 @@ struct Params {
 __device__ __forceinline__ float gelu_erf(float x) { return gelu_erf_fast(x); }
 
 template <int C>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, Cfg<C>::CTAS_PER_SM)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w1,
                  const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_x, Params p) {
   using K = Cfg<C>;
@@ -115,12 +123,32 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       ptx::mbar_init(&w2_full[i], 1);
       ptx::mbar_init(&w2_empty[i], 1);
       ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&s_empty[i], 128);
-      ptx::mbar_init(&h_full[i], 128);
+      ptx::mbar_init(&s_empty[i], 32 * EPI_WARPS);
+      ptx::mbar_init(&h_full[i], 32 * EPI_WARPS);
       ptx::mbar_init(&h_empty[i], 1);
     }
     ptx::mbar_init(o_full, 1);
     ptx::fence_mbar_init();
+  }
+  // W1 / W2 chunk i into ring stage i % WST (called by the one producer thread)
+  auto load_chunk = [&](int i) {
+    const int st = i % K::WST;
+    const uint32_t par = ((i / K::WST) & 1) ^ 1;
+    ptx::mbar_wait(&w1_empty[st], par);
+    ptx::mbar_arrive_expect_tx(&w1_full[st], K::KB * HC * 128);
+    for (int kb = 0; kb < K::KB; ++kb)   // W1 rows [i*64, +64) (hidden units), columns kb*64.. (input channels)
+      ptx::tma_load_2d(&tm_w1, &w1_full[st], s_w1 + st * K::W1_BYTES + kb * HC * 128, kb * 64, i * HC);
+    ptx::mbar_wait(&w2_empty[st], par);
+    ptx::mbar_arrive_expect_tx(&w2_full[st], K::N2_PARTS * K::N2 * 128);
+    for (int part = 0; part < K::N2_PARTS; ++part)   // W2 rows = output channels, columns [i*64, +64) of the hidden dim
+      ptx::tma_load_2d(&tm_w2, &w2_full[st], s_w2 + st * K::W2_BYTES + part * K::N2 * 128, i * HC, part * K::N2);
+  };
+  if (warp == WARP_TMA && lane == 0) {
+    // the producer initialised the barriers itself: the A tile and the first W chunk are requested before the CTA-wide
+    // sync below, so their latency overlaps the TMEM allocation
+    ptx::mbar_arrive_expect_tx(a_full, K::KB * BM * 128);
+    for (int kb = 0; kb < K::KB; ++kb) ptx::tma_load_2d(&tm_a, a_full, s_a + kb * BM * 128, kb * 64, row0);
+    load_chunk(0);
   }
   if (warp == WARP_MMA) ptx::tmem_alloc<K::TMEM_COLS>(tmem_base_ptr);
   ptx::tc_fence_before();
@@ -129,23 +157,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);
 
   if (warp == WARP_TMA) {
-    if (lane == 0) {
-      // A tile: KB boxes of 64 columns x 128 rows (columns >= C and rows >= M are zero-filled)
-      ptx::mbar_arrive_expect_tx(a_full, K::KB * BM * 128);
-      for (int kb = 0; kb < K::KB; ++kb) ptx::tma_load_2d(&tm_a, a_full, s_a + kb * BM * 128, kb * 64, row0);
-      for (int i = 0; i < n_chunks; ++i) {
-        const int st = i % K::WST;
-        const uint32_t par = ((i / K::WST) & 1) ^ 1;
-        ptx::mbar_wait(&w1_empty[st], par);
-        ptx::mbar_arrive_expect_tx(&w1_full[st], K::KB * HC * 128);
-        for (int kb = 0; kb < K::KB; ++kb)   // W1 rows [i*64, +64) (hidden units), columns kb*64.. (input channels)
-          ptx::tma_load_2d(&tm_w1, &w1_full[st], s_w1 + st * K::W1_BYTES + kb * HC * 128, kb * 64, i * HC);
-        ptx::mbar_wait(&w2_empty[st], par);
-        ptx::mbar_arrive_expect_tx(&w2_full[st], K::N2_PARTS * K::N2 * 128);
-        for (int part = 0; part < K::N2_PARTS; ++part)   // W2 rows = output channels, columns [i*64, +64) of the hidden dim
-          ptx::tma_load_2d(&tm_w2, &w2_full[st], s_w2 + st * K::W2_BYTES + part * K::N2 * 128, i * HC, part * K::N2);
-      }
-    }
+    if (lane == 0)
+      for (int i = 1; i < n_chunks; ++i) load_chunk(i);
   } else if (warp == WARP_MMA) {
     constexpr uint32_t idesc1 = ptx::make_idesc_bf16_f32(BM, HC);
     constexpr uint32_t idesc2 = ptx::make_idesc_bf16_f32(BM, K::N2);
@@ -195,65 +208,73 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     ptx::umma_commit_w(o_full);
   } else {
     // ------------------------------------------------------------ epilogue warps: GELU between the GEMMs, final store
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;                              // TMEM lane quarter
+    const int half = warp >> 2;                                // which 32 of a chunk's 64 hidden columns
     const int row = quarter * 32 + lane;                       // this thread's pixel row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const int sw = row & 7;                                    // 128B-swizzle phase of this row
+    const bool has_b1 = p.b1 != nullptr;
     for (int i = 0; i < n_chunks; ++i) {
       const int b = i & 1;
       ptx::mbar_wait(&s_full[b], (i >> 1) & 1);
       ptx::tc_fence_after();
-      uint32_t r0[32], r1[32];
-      ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_S + static_cast<uint32_t>(b * HC), r0);
-      ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_S + static_cast<uint32_t>(b * HC + 32), r1);
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_S + static_cast<uint32_t>(b * HC + half * 32), r);
+      const int h0 = i * HC + half * 32;
+      float4 bv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_b1 && h0 + 4 * j < p.Hd) bv[j] = __ldg(reinterpret_cast<const float4*>(p.b1 + h0) + j);   // Hd % 8 == 0
+      }
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&s_empty[b]);
-      const int h0 = i * HC;
-      uint32_t pk[32];
+      uint32_t pk[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int c0 = h0 + 2 * j, c1 = h0 + 32 + 2 * j;
-        const bool hb = p.b1 != nullptr;
-        const float ba = hb && c0 < p.Hd ? __ldg(p.b1 + c0) : 0.f, bb = hb && c0 + 1 < p.Hd ? __ldg(p.b1 + c0 + 1) : 0.f;
-        const float bc = hb && c1 < p.Hd ? __ldg(p.b1 + c1) : 0.f, bd = hb && c1 + 1 < p.Hd ? __ldg(p.b1 + c1 + 1) : 0.f;
-        __nv_bfloat162 lo = __floats2bfloat162_rn(gelu_erf(__uint_as_float(r0[2 * j]) + ba), gelu_erf(__uint_as_float(r0[2 * j + 1]) + bb));
-        __nv_bfloat162 hi = __floats2bfloat162_rn(gelu_erf(__uint_as_float(r1[2 * j]) + bc), gelu_erf(__uint_as_float(r1[2 * j + 1]) + bd));
-        pk[j] = *reinterpret_cast<uint32_t*>(&lo);
-        pk[16 + j] = *reinterpret_cast<uint32_t*>(&hi);
+      for (int j = 0; j < 8; ++j) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(gelu_erf(__uint_as_float(r[4 * j]) + bv[j].x), gelu_erf(__uint_as_float(r[4 * j + 1]) + bv[j].y));
+        __nv_bfloat162 hi = __floats2bfloat162_rn(gelu_erf(__uint_as_float(r[4 * j + 2]) + bv[j].z), gelu_erf(__uint_as_float(r[4 * j + 3]) + bv[j].w));
+        pk[2 * j] = *reinterpret_cast<uint32_t*>(&lo);
+        pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
       }
       ptx::mbar_wait(&h_empty[b], ((i >> 1) & 1) ^ 1);         // the second GEMM of chunk i-2 has finished reading H_b
-      uint8_t* hrow = s_h + b * K::H_BYTES + row * 128;        // 64 bf16 = 8 chunks of 16 B, chunk c at (c ^ sw)
+      uint8_t* hrow = s_h + b * K::H_BYTES + row * 128;        // 64 bf16 = 8 chunks of 16 B, chunk c stored at (c ^ sw)
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(hrow + ((c ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(hrow + (((half * 4 + c) ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&h_full[b]);
     }
-    // final: O -> (+ b2) * gamma -> staging tile [32 rows][32 fp32] (128B swizzle) -> TMA reduce-add into x
+    // final: O -> (+ b2) * gamma -> staging tile [32 rows][32 fp32] (128B swizzle) -> TMA reduce-add into x.  The staging
+    // tiles alias the H buffers: o_full completes only after the last second GEMM has finished reading them.
     ptx::mbar_wait(o_full, 0);
     ptx::tc_fence_after();
-    uint8_t* stg = s_stg + quarter * (32 * 128);
+    uint8_t* stg = s_stg + warp * (32 * 128);
     const int swl = lane & 7;
 #pragma unroll 1
-    for (int c = 0; c < (C + 31) / 32; ++c) {
+    for (int c = half; c < (C + 31) / 32; c += 2) {
       const int n0 = c * 32;
       uint32_t r[32];
       ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_O + static_cast<uint32_t>(n0), r);
-      ptx::tmem_ld_wait();
-      float v[32];
+      float4 b4[8], g4[8];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = n0 + j;
-        const float bj = (p.b2 != nullptr && col < C) ? __ldg(p.b2 + col) : 0.f;
-        const float gj = (p.gamma != nullptr && col < C) ? __ldg(p.gamma + col) : 1.f;
-        v[j] = (__uint_as_float(r[j]) + bj) * gj;
+      for (int j = 0; j < 8; ++j) {
+        b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g4[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (n0 + 4 * j < C) {   // C % 16 == 0
+          if (p.b2 != nullptr) b4[j] = __ldg(reinterpret_cast<const float4*>(p.b2 + n0) + j);
+          if (p.gamma != nullptr) g4[j] = __ldg(reinterpret_cast<const float4*>(p.gamma + n0) + j);
+        }
       }
+      ptx::tmem_ld_wait();
       if (lane == 0) ptx::tma_store_wait_read<0>();
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ swl) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ swl) << 4)) =
+            make_float4((__uint_as_float(r[4 * j]) + b4[j].x) * g4[j].x, (__uint_as_float(r[4 * j + 1]) + b4[j].y) * g4[j].y,
+                        (__uint_as_float(r[4 * j + 2]) + b4[j].z) * g4[j].z, (__uint_as_float(r[4 * j + 3]) + b4[j].w) * g4[j].w);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
