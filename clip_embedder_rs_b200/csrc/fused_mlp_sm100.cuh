@@ -44,32 +44,35 @@ struct Cfg {
   static constexpr int KB = (C + 63) / 64;                 // 64-column k-blocks of A / W1
   static constexpr int KSTEPS1 = C / 16;                   // UMMA k-steps of the first GEMM
   static constexpr int A_BYTES = KB * BM * 128;            // [KB][128 rows][128 B]
-  static constexpr int W1_BYTES = KB * HC * 128;           // [KB][64 rows][128 B]
-  static constexpr int W2_ROWS = (C + 7) / 8 * 8;
-  static constexpr int W2_BYTES = (W2_ROWS * 128 + 1023) / 1024 * 1024;  // [C rows][128 B]
+  // W1 streams in tiles of [64 hidden rows][64 input channels] (one per k-block of a chunk), W2 in tiles of
+  // [N2 output channels][64 hidden columns] (one or two per chunk), each through its own ring, in the order the MMA warp
+  // consumes them: the rings hold about two chunks' worth, so a chunk's weights arrive while the previous one computes.
+  static constexpr int N2 = C > 256 ? C / 2 : C;           // second GEMM: N per instruction (<= 256)
+  static constexpr int N2_PARTS = C > 256 ? 2 : 1;
+  static constexpr int W1_TILE = HC * 128;                 // 8 KB
+  static constexpr int W2_TILE = ((N2 + 7) / 8 * 8 * 128 + 1023) / 1024 * 1024;
   static constexpr int H_BYTES = BM * 128;                 // [128 rows][64 bf16]
-  // Two CTAs per SM where the tiles are small enough (C <= 96: 90 KB with a single-stage W ring), so that one CTA's
-  // prologue / final epilogue overlaps the other's chunks; otherwise one CTA with a two-stage W ring, or (C > 192) one
-  // stage again for the shared-memory budget.
+  // Two CTAs per SM where the tiles are small enough (C <= 96), so that one CTA's prologue / final epilogue overlaps
+  // the other's chunks; otherwise one CTA.
   static constexpr int CTAS_PER_SM = C <= 96 ? 2 : 1;
-  static constexpr int WST = (C <= 96 || C > 192) ? 1 : 2;
+  static constexpr int NS1 = C <= 80 ? KB + 1 : (C <= 96 ? KB : (C > 256 ? 4 : 2 * KB));   // W1 ring stages (smem budget)
+  static constexpr int NS2 = C > 256 ? 4 : 2;                             // W2 ring stages (>= 2 chunks' worth)
   static constexpr int STG_BYTES = EPI_WARPS * 32 * 128;   // 8 epilogue warps x [32 rows][32 fp32]; aliases the H buffers
   static constexpr int OFF_A = 0;
   static constexpr int OFF_W1 = OFF_A + A_BYTES;
-  static constexpr int OFF_W2 = OFF_W1 + WST * W1_BYTES;
-  static constexpr int OFF_H = OFF_W2 + WST * W2_BYTES;
+  static constexpr int OFF_W2 = OFF_W1 + NS1 * W1_TILE;
+  static constexpr int OFF_H = OFF_W2 + NS2 * W2_TILE;
   static constexpr int OFF_STG = OFF_H;                    // the final epilogue runs after the last second GEMM retired
   static_assert(STG_BYTES <= 2 * H_BYTES, "staging aliases the two H buffers");
   static constexpr int OFF_BAR = OFF_H + 2 * H_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
   static constexpr int COL_O = 0;                          // O accumulator: C columns
   static constexpr int COL_S = (C + 31) / 32 * 32;         // two hidden buffers of HC columns
   static constexpr int TMEM_NEED = COL_S + 2 * HC;
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
-  static constexpr int N2 = C > 256 ? C / 2 : C;           // second GEMM: N per instruction (<= 256)
-  static constexpr int N2_PARTS = C > 256 ? 2 : 1;
   static_assert(N2 % 16 == 0, "UMMA N granularity");
-  static_assert(SMEM_BYTES * CTAS_PER_SM <= 227 * 1024, "shared memory");
+  static_assert(NS1 <= 8 && NS2 <= 4, "barrier carve");
+  static_assert((SMEM_BYTES + 2048) * CTAS_PER_SM <= 228 * 1024, "shared memory (static + reserved included)");
   static_assert(TMEM_COLS * CTAS_PER_SM <= 512, "tensor memory");
 };
 
@@ -96,16 +99,16 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint8_t* s_stg = smem + K::OFF_STG;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::OFF_BAR);
   uint64_t* a_full = bars + 0;
-  uint64_t* w1_full = bars + 1;    // [2]
-  uint64_t* w1_empty = bars + 3;   // [2]
-  uint64_t* w2_full = bars + 5;    // [2]
-  uint64_t* w2_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;     // [2]  MMA -> epilogue: hidden accumulator b complete
-  uint64_t* s_empty = bars + 11;   // [2]  epilogue -> MMA: accumulator b read out
-  uint64_t* h_full = bars + 13;    // [2]  epilogue -> MMA: H_b written
-  uint64_t* h_empty = bars + 15;   // [2]  MMA -> epilogue: second GEMM of H_b retired
-  uint64_t* o_full = bars + 17;
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* w1_full = bars + 1;    // [NS1 <= 8]
+  uint64_t* w1_empty = bars + 9;   // [NS1]
+  uint64_t* w2_full = bars + 17;   // [NS2 <= 4]
+  uint64_t* w2_empty = bars + 21;  // [NS2]
+  uint64_t* s_full = bars + 25;    // [2]  MMA -> epilogue: hidden accumulator b complete
+  uint64_t* s_empty = bars + 27;   // [2]  epilogue -> MMA: accumulator b read out
+  uint64_t* h_full = bars + 29;    // [2]  epilogue -> MMA: H_b written
+  uint64_t* h_empty = bars + 31;   // [2]  MMA -> epilogue: second GEMM of H_b retired
+  uint64_t* o_full = bars + 33;
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 34);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * BM;
@@ -117,11 +120,15 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     ptx::prefetch_tmap(&tm_w2);
     ptx::prefetch_tmap(&tm_x);
     ptx::mbar_init(a_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < K::NS1; ++i) {
       ptx::mbar_init(&w1_full[i], 1);
       ptx::mbar_init(&w1_empty[i], 1);
+    }
+    for (int i = 0; i < K::NS2; ++i) {
       ptx::mbar_init(&w2_full[i], 1);
       ptx::mbar_init(&w2_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&s_full[i], 1);
       ptx::mbar_init(&s_empty[i], 32 * EPI_WARPS);
       ptx::mbar_init(&h_full[i], 32 * EPI_WARPS);
@@ -130,18 +137,20 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     ptx::mbar_init(o_full, 1);
     ptx::fence_mbar_init();
   }
-  // W1 / W2 chunk i into ring stage i % WST (called by the one producer thread)
+  // W1 / W2 tiles of chunk i into their rings (called by the one producer thread)
   auto load_chunk = [&](int i) {
-    const int st = i % K::WST;
-    const uint32_t par = ((i / K::WST) & 1) ^ 1;
-    ptx::mbar_wait(&w1_empty[st], par);
-    ptx::mbar_arrive_expect_tx(&w1_full[st], K::KB * HC * 128);
-    for (int kb = 0; kb < K::KB; ++kb)   // W1 rows [i*64, +64) (hidden units), columns kb*64.. (input channels)
-      ptx::tma_load_2d(&tm_w1, &w1_full[st], s_w1 + st * K::W1_BYTES + kb * HC * 128, kb * 64, i * HC);
-    ptx::mbar_wait(&w2_empty[st], par);
-    ptx::mbar_arrive_expect_tx(&w2_full[st], K::N2_PARTS * K::N2 * 128);
-    for (int part = 0; part < K::N2_PARTS; ++part)   // W2 rows = output channels, columns [i*64, +64) of the hidden dim
-      ptx::tma_load_2d(&tm_w2, &w2_full[st], s_w2 + st * K::W2_BYTES + part * K::N2 * 128, i * HC, part * K::N2);
+    for (int kb = 0; kb < K::KB; ++kb) {   // W1 rows [i*64, +64) (hidden units), columns kb*64.. (input channels)
+      const int t = i * K::KB + kb, st = t % K::NS1;
+      ptx::mbar_wait(&w1_empty[st], ((t / K::NS1) & 1) ^ 1);
+      ptx::mbar_arrive_expect_tx(&w1_full[st], K::W1_TILE);
+      ptx::tma_load_2d(&tm_w1, &w1_full[st], s_w1 + st * K::W1_TILE, kb * 64, i * HC);
+    }
+    for (int part = 0; part < K::N2_PARTS; ++part) {   // W2 rows = output channels, columns [i*64, +64) of the hidden dim
+      const int t = i * K::N2_PARTS + part, st = t % K::NS2;
+      ptx::mbar_wait(&w2_empty[st], ((t / K::NS2) & 1) ^ 1);
+      ptx::mbar_arrive_expect_tx(&w2_full[st], K::N2 * 128);
+      ptx::tma_load_2d(&tm_w2, &w2_full[st], s_w2 + st * K::W2_TILE, i * HC, part * K::N2);
+    }
   };
   if (warp == WARP_TMA && lane == 0) {
     // the producer initialised the barriers itself: the A tile and the first W chunk are requested before the CTA-wide
@@ -166,38 +175,45 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     ptx::mbar_wait(a_full, 0);
     // chunk i's first GEMM is issued before chunk i-1's second one, so the GELU of chunk i-1 overlaps it
     auto gemm1 = [&](int i) {
-      const int st = i % K::WST, b = i & 1;
-      ptx::mbar_wait(&w1_full[st], (i / K::WST) & 1);
-      ptx::mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t w_addr = ptx::smem_u32(s_w1 + st * K::W1_BYTES);
+      const int b = i & 1;
       const uint32_t t_s = tmem_base + K::COL_S + static_cast<uint32_t>(b * HC);
+      ptx::mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
 #pragma unroll
-      for (int k = 0; k < K::KSTEPS1; ++k) {
-        const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr + (k >> 2) * BM * 128) + static_cast<uint64_t>(2 * (k & 3));
-        const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr + (k >> 2) * HC * 128) + static_cast<uint64_t>(2 * (k & 3));
-        ptx::umma_bf16_ss_w(t_s, da, dw, idesc1, k != 0 ? 1u : 0u);
+      for (int kb = 0; kb < K::KB; ++kb) {
+        const int t = i * K::KB + kb, st = t % K::NS1;
+        ptx::mbar_wait(&w1_full[st], (t / K::NS1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t w_addr = ptx::smem_u32(s_w1 + st * K::W1_TILE);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (kb * 4 + k < K::KSTEPS1) {
+            const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr + kb * BM * 128) + static_cast<uint64_t>(2 * k);
+            const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr) + static_cast<uint64_t>(2 * k);
+            ptx::umma_bf16_ss_w(t_s, da, dw, idesc1, (kb | k) != 0 ? 1u : 0u);
+          }
+        }
+        ptx::umma_commit_w(&w1_empty[st]);
       }
-      ptx::umma_commit_w(&w1_empty[st]);
       ptx::umma_commit_w(&s_full[b]);
     };
     auto gemm2 = [&](int i) {
-      const int st = i % K::WST, b = i & 1;
-      ptx::mbar_wait(&w2_full[st], (i / K::WST) & 1);
+      const int b = i & 1;
       ptx::mbar_wait(&h_full[b], (i >> 1) & 1);
-      ptx::tc_fence_after();
       const uint32_t h_addr = ptx::smem_u32(s_h + b * K::H_BYTES);
-      const uint32_t w_addr = ptx::smem_u32(s_w2 + st * K::W2_BYTES);
 #pragma unroll
       for (int part = 0; part < K::N2_PARTS; ++part) {
+        const int t = i * K::N2_PARTS + part, st = t % K::NS2;
+        ptx::mbar_wait(&w2_full[st], (t / K::NS2) & 1);
+        ptx::tc_fence_after();
+        const uint32_t w_addr = ptx::smem_u32(s_w2 + st * K::W2_TILE);
 #pragma unroll
         for (int k = 0; k < HC / 16; ++k) {
           const uint64_t dh = ptx::make_kmajor_sw128_desc(h_addr) + static_cast<uint64_t>(2 * k);
-          const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr + part * K::N2 * 128) + static_cast<uint64_t>(2 * k);
+          const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr) + static_cast<uint64_t>(2 * k);
           ptx::umma_bf16_ss_w(tmem_base + K::COL_O + static_cast<uint32_t>(part * K::N2), dh, dw, idesc2, (i | k) != 0 ? 1u : 0u);
         }
+        ptx::umma_commit_w(&w2_empty[st]);
       }
-      ptx::umma_commit_w(&w2_empty[st]);
       ptx::umma_commit_w(&h_empty[b]);
     };
     gemm1(0);
@@ -305,7 +321,7 @@ inline cudaError_t launch_t(const __nv_bfloat16* a, long long lda, const __nv_bf
   CUtensorMap ta, tw1, tw2, tx;
   if (!make_tmap_2d(&ta, a, p.M, C, lda, BM, 2)) return cudaErrorUnknown;
   if (!make_tmap_2d(&tw1, w1, p.Hd, C, ldw1, HC, 2)) return cudaErrorUnknown;
-  if (!make_tmap_2d(&tw2, w2, C, p.Hd, ldw2, K::N2, 2)) return cudaErrorUnknown;
+  if (!make_tmap_2d(&tw2, w2, C, p.Hd, ldw2, K::N2, 2)) return cudaErrorUnknown;   // box = [N2 output channels][64 hidden]
   if (!make_tmap_2d(&tx, x, p.M, C, ldx, 32, 4)) return cudaErrorUnknown;
   const int grid = (p.M + BM - 1) / BM;
   fused_mlp_kernel<C><<<grid, THREADS, K::SMEM_BYTES, st>>>(ta, tw1, tw2, tx, p);
