@@ -157,7 +157,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // sync below, so their latency overlaps the TMEM allocation
     ptx::mbar_arrive_expect_tx(a_full, K::KB * BM * 128);
     for (int kb = 0; kb < K::KB; ++kb) ptx::tma_load_2d(&tm_a, a_full, s_a + kb * BM * 128, kb * 64, row0);
-    load_chunk(0);
+    if (K::KB <= K::NS1) load_chunk(0);   // (a chunk with more k-blocks than ring stages needs the MMA warp running)
   }
   if (warp == WARP_MMA) ptx::tmem_alloc<K::TMEM_COLS>(tmem_base_ptr);
   ptx::tc_fence_before();
@@ -167,7 +167,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   if (warp == WARP_TMA) {
     if (lane == 0)
-      for (int i = 1; i < n_chunks; ++i) load_chunk(i);
+      for (int i = (K::KB <= K::NS1 ? 1 : 0); i < n_chunks; ++i) load_chunk(i);
   } else if (warp == WARP_MMA) {
     constexpr uint32_t idesc1 = ptx::make_idesc_bf16_f32(BM, HC);
     constexpr uint32_t idesc2 = ptx::make_idesc_bf16_f32(BM, K::N2);
