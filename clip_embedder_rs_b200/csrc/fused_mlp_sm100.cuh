@@ -173,7 +173,6 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     constexpr uint32_t idesc2 = ptx::make_idesc_bf16_f32(BM, K::N2);
     const uint32_t a_addr = ptx::smem_u32(s_a);
     ptx::mbar_wait(a_full, 0);
-    // chunk i's first GEMM is issued before chunk i-1's second one, so the GELU of chunk i-1 overlaps it
     auto gemm1 = [&](int i) {
       const int b = i & 1;
       const uint32_t t_s = tmem_base + K::COL_S + static_cast<uint32_t>(b * HC);
@@ -216,9 +215,14 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
       ptx::umma_commit_w(&h_empty[b]);
     };
+    // The first GEMM runs TWO chunks ahead of the second: S buffer (i + 2) & 1 is free as soon as the epilogue warps have
+    // LOADED S(i) (the start of chunk i's GELU), whereas the second GEMM of chunk i needs that GELU finished.  Issued in
+    // this order the tensor pipe computes S(i + 2) while GELU(i) runs, so the epilogue warps (the busiest resource: ~14
+    // instructions per hidden element) always find their next accumulator ready.
     gemm1(0);
+    if (n_chunks > 1) gemm1(1);
     for (int i = 0; i < n_chunks; ++i) {
-      if (i + 1 < n_chunks) gemm1(i + 1);
+      if (i + 2 < n_chunks) gemm1(i + 2);
       gemm2(i);
     }
     ptx::umma_commit_w(o_full);

@@ -16,7 +16,4 @@ for f in sorted(glob.glob("gpurun_out/r2m_mc_*.json")):
     d=json.loads(open(f).read().strip().splitlines()[0]); r=d["roofline"]
     print(f, round(d["value"],1), "e2e", round(d["e2e"]["value"],1), {k:round(v,2) for k,v in r["kernel_ms_per_step"].items() if v>0}, "gemm TF", round(r["achieved"]))
 PY
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_mlp -s 21 -c 1 -f -o gpurun_out/r02m_fmlp_c160 tests/native/gemm_test.bin 8 > gpurun_out/r2m_ncu1.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_mlp -s 35 -c 1 -f -o gpurun_out/r02m_fmlp_c320 tests/native/gemm_test.bin 8 > gpurun_out/r2m_ncu2.log 2>&1
-  tail -2 gpurun_out/r2m_ncu2.log
 fi
