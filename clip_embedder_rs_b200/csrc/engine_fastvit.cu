@@ -237,7 +237,7 @@ Status Engine::FvMlp(const FvBlock& b, float* cur, int n, int Hh, int C, const f
   if (fused_mlp_ && fused_mlp_supported(C, b.fc1.N) && b.fc1.ldk == C && b.fc2.ldk == b.fc1.N) {
     // fc1 -> GELU -> fc2 -> layer scale -> residual in one kernel: the 3C-wide hidden activation stays on the SM
     ProfBegin(PC_GEMM, compute_);
-    e = fused_mlp(h_, C, b.fc1.w, b.fc1.ldk, b.fc1.b, b.fc2.w, b.fc2.ldk, b.fc2.b, gamma, cur, C, rows, C, b.fc1.N, compute_);
+    e = fused_mlp(h_, C, b.fc1.w, b.fc1.ldk, b.fc1.b, b.fc2.w, b.fc2.ldk, b.fc2.b, gamma, cur, C, rows, C, b.fc1.N, num_sms_, compute_);
     ProfEnd(PC_GEMM, compute_);
     if (profile_) prof_acc_.gemm_flops += 4.0 * rows * static_cast<double>(C) * b.fc1.N;
     return Check(e, "fused ConvMlp");

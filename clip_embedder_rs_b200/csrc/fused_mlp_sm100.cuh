@@ -9,7 +9,7 @@
 // TFLOP/s at the copy peak — and is why the 1x1-conv GEMM class sat at 404 TFLOP/s.  Here the hidden
 // activation never leaves the SM:
 //
-//   per CTA: one tile of 128 pixels.  A [128 x C] is loaded once (TMA, 128B swizzle, K-major).  The hidden dimension is
+//   persistent CTAs, one tile of 128 pixels at a time.  A [128 x C] is loaded once (TMA, 128B swizzle, K-major).  The hidden dimension is
 //   walked in chunks of 64 columns:
 //       MMA warp   S_b[128 x 64]  = A · W1[chunk]^T          tcgen05.mma, accumulator in TMEM buffer b (2 buffers)
 //       4 warps    h = gelu(S_b + b1) -> bf16 -> shared memory tile H_b [128 x 64] written in the 128B-swizzled K-major
@@ -107,12 +107,14 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint64_t* s_empty = bars + 27;   // [2]  epilogue -> MMA: accumulator b read out
   uint64_t* h_full = bars + 29;    // [2]  epilogue -> MMA: H_b written
   uint64_t* h_empty = bars + 31;   // [2]  MMA -> epilogue: second GEMM of H_b retired
-  uint64_t* o_full = bars + 33;
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 34);
+  uint64_t* o_full = bars + 33;    //      MMA -> epilogue: O of this tile complete
+  uint64_t* o_empty = bars + 34;   //      epilogue -> MMA: O read out, the next tile may overwrite it
+  uint64_t* a_empty = bars + 35;   //      MMA -> producer: every first GEMM of this tile retired, A may be reloaded
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 36);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * BM;
   const int n_chunks = (p.Hd + HC - 1) / HC;
+  const int n_tiles = (p.M + BM - 1) / BM;
 
   if (warp == WARP_TMA && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
@@ -120,6 +122,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     ptx::prefetch_tmap(&tm_w2);
     ptx::prefetch_tmap(&tm_x);
     ptx::mbar_init(a_full, 1);
+    ptx::mbar_init(a_empty, 1);
     for (int i = 0; i < K::NS1; ++i) {
       ptx::mbar_init(&w1_full[i], 1);
       ptx::mbar_init(&w1_empty[i], 1);
@@ -135,29 +138,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       ptx::mbar_init(&h_empty[i], 1);
     }
     ptx::mbar_init(o_full, 1);
+    ptx::mbar_init(o_empty, 32 * EPI_WARPS);
     ptx::fence_mbar_init();
-  }
-  // W1 / W2 tiles of chunk i into their rings (called by the one producer thread)
-  auto load_chunk = [&](int i) {
-    for (int kb = 0; kb < K::KB; ++kb) {   // W1 rows [i*64, +64) (hidden units), columns kb*64.. (input channels)
-      const int t = i * K::KB + kb, st = t % K::NS1;
-      ptx::mbar_wait(&w1_empty[st], ((t / K::NS1) & 1) ^ 1);
-      ptx::mbar_arrive_expect_tx(&w1_full[st], K::W1_TILE);
-      ptx::tma_load_2d(&tm_w1, &w1_full[st], s_w1 + st * K::W1_TILE, kb * 64, i * HC);
-    }
-    for (int part = 0; part < K::N2_PARTS; ++part) {   // W2 rows = output channels, columns [i*64, +64) of the hidden dim
-      const int t = i * K::N2_PARTS + part, st = t % K::NS2;
-      ptx::mbar_wait(&w2_empty[st], ((t / K::NS2) & 1) ^ 1);
-      ptx::mbar_arrive_expect_tx(&w2_full[st], K::N2 * 128);
-      ptx::tma_load_2d(&tm_w2, &w2_full[st], s_w2 + st * K::W2_TILE, i * HC, part * K::N2);
-    }
-  };
-  if (warp == WARP_TMA && lane == 0) {
-    // the producer initialised the barriers itself: the A tile and the first W chunk are requested before the CTA-wide
-    // sync below, so their latency overlaps the TMEM allocation
-    ptx::mbar_arrive_expect_tx(a_full, K::KB * BM * 128);
-    for (int kb = 0; kb < K::KB; ++kb) ptx::tma_load_2d(&tm_a, a_full, s_a + kb * BM * 128, kb * 64, row0);
-    if (K::KB <= K::NS1) load_chunk(0);   // (a chunk with more k-blocks than ring stages needs the MMA warp running)
   }
   if (warp == WARP_MMA) ptx::tmem_alloc<K::TMEM_COLS>(tmem_base_ptr);
   ptx::tc_fence_before();
@@ -165,67 +147,96 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);
 
+  // Persistent CTAs: tile = blockIdx.x, += gridDim.x.  All ring / buffer counters run across tiles, so the producer
+  // fetches the next tile's A and first weight tiles, and the MMA warp issues the next tile's first GEMMs, while the
+  // epilogue warps are still storing the current tile's output.
   if (warp == WARP_TMA) {
-    if (lane == 0)
-      for (int i = (K::KB <= K::NS1 ? 1 : 0); i < n_chunks; ++i) load_chunk(i);
+    if (lane == 0) {
+      uint32_t t1 = 0, t2 = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        ptx::mbar_wait(a_empty, (it & 1) ^ 1);
+        // A tile: KB boxes of 64 columns x 128 rows (columns >= C and rows >= M are zero-filled)
+        ptx::mbar_arrive_expect_tx(a_full, K::KB * BM * 128);
+        for (int kb = 0; kb < K::KB; ++kb) ptx::tma_load_2d(&tm_a, a_full, s_a + kb * BM * 128, kb * 64, tile * BM);
+        for (int i = 0; i < n_chunks; ++i) {
+          for (int kb = 0; kb < K::KB; ++kb, ++t1) {   // W1 rows [i*64, +64) (hidden units), columns kb*64.. (input channels)
+            const int st = t1 % K::NS1;
+            ptx::mbar_wait(&w1_empty[st], ((t1 / K::NS1) & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(&w1_full[st], K::W1_TILE);
+            ptx::tma_load_2d(&tm_w1, &w1_full[st], s_w1 + st * K::W1_TILE, kb * 64, i * HC);
+          }
+          for (int part = 0; part < K::N2_PARTS; ++part, ++t2) {   // W2 rows = output channels, columns [i*64, +64) of the hidden dim
+            const int st = t2 % K::NS2;
+            ptx::mbar_wait(&w2_empty[st], ((t2 / K::NS2) & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(&w2_full[st], K::N2 * 128);
+            ptx::tma_load_2d(&tm_w2, &w2_full[st], s_w2 + st * K::W2_TILE, i * HC, part * K::N2);
+          }
+        }
+      }
+    }
   } else if (warp == WARP_MMA) {
     constexpr uint32_t idesc1 = ptx::make_idesc_bf16_f32(BM, HC);
     constexpr uint32_t idesc2 = ptx::make_idesc_bf16_f32(BM, K::N2);
     const uint32_t a_addr = ptx::smem_u32(s_a);
-    ptx::mbar_wait(a_full, 0);
-    auto gemm1 = [&](int i) {
-      const int b = i & 1;
-      const uint32_t t_s = tmem_base + K::COL_S + static_cast<uint32_t>(b * HC);
-      ptx::mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
+    uint32_t t1 = 0, t2 = 0;      // running W1 / W2 ring tile counters
+    uint32_t g1 = 0, g2 = 0;      // running chunk counters of the first / second GEMM (S and H buffer = counter & 1)
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      ptx::mbar_wait(a_full, it & 1);
+      auto gemm1 = [&](bool last_of_tile) {
+        const int b = g1 & 1;
+        const uint32_t t_s = tmem_base + K::COL_S + static_cast<uint32_t>(b * HC);
+        ptx::mbar_wait(&s_empty[b], ((g1 >> 1) & 1) ^ 1);
 #pragma unroll
-      for (int kb = 0; kb < K::KB; ++kb) {
-        const int t = i * K::KB + kb, st = t % K::NS1;
-        ptx::mbar_wait(&w1_full[st], (t / K::NS1) & 1);
-        ptx::tc_fence_after();
-        const uint32_t w_addr = ptx::smem_u32(s_w1 + st * K::W1_TILE);
+        for (int kb = 0; kb < K::KB; ++kb, ++t1) {
+          const int st = t1 % K::NS1;
+          ptx::mbar_wait(&w1_full[st], (t1 / K::NS1) & 1);
+          ptx::tc_fence_after();
+          const uint32_t w_addr = ptx::smem_u32(s_w1 + st * K::W1_TILE);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (kb * 4 + k < K::KSTEPS1) {
-            const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr + kb * BM * 128) + static_cast<uint64_t>(2 * k);
-            const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr) + static_cast<uint64_t>(2 * k);
-            ptx::umma_bf16_ss_w(t_s, da, dw, idesc1, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            if (kb * 4 + k < K::KSTEPS1) {
+              const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr + kb * BM * 128) + static_cast<uint64_t>(2 * k);
+              const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr) + static_cast<uint64_t>(2 * k);
+              ptx::umma_bf16_ss_w(t_s, da, dw, idesc1, (kb | k) != 0 ? 1u : 0u);
+            }
           }
+          ptx::umma_commit_w(&w1_empty[st]);
         }
-        ptx::umma_commit_w(&w1_empty[st]);
-      }
-      ptx::umma_commit_w(&s_full[b]);
-    };
-    auto gemm2 = [&](int i) {
-      const int b = i & 1;
-      ptx::mbar_wait(&h_full[b], (i >> 1) & 1);
-      const uint32_t h_addr = ptx::smem_u32(s_h + b * K::H_BYTES);
+        ptx::umma_commit_w(&s_full[b]);
+        if (last_of_tile) ptx::umma_commit_w(a_empty);   // every read of this tile's A has been issued
+        ++g1;
+      };
+      auto gemm2 = [&](int i) {
+        const int b = g2 & 1;
+        ptx::mbar_wait(&h_full[b], (g2 >> 1) & 1);
+        if (i == 0) ptx::mbar_wait(o_empty, (it & 1) ^ 1);   // the previous tile's O has been read out
+        const uint32_t h_addr = ptx::smem_u32(s_h + b * K::H_BYTES);
 #pragma unroll
-      for (int part = 0; part < K::N2_PARTS; ++part) {
-        const int t = i * K::N2_PARTS + part, st = t % K::NS2;
-        ptx::mbar_wait(&w2_full[st], (t / K::NS2) & 1);
-        ptx::tc_fence_after();
-        const uint32_t w_addr = ptx::smem_u32(s_w2 + st * K::W2_TILE);
+        for (int part = 0; part < K::N2_PARTS; ++part, ++t2) {
+          const int st = t2 % K::NS2;
+          ptx::mbar_wait(&w2_full[st], (t2 / K::NS2) & 1);
+          ptx::tc_fence_after();
+          const uint32_t w_addr = ptx::smem_u32(s_w2 + st * K::W2_TILE);
 #pragma unroll
-        for (int k = 0; k < HC / 16; ++k) {
-          const uint64_t dh = ptx::make_kmajor_sw128_desc(h_addr) + static_cast<uint64_t>(2 * k);
-          const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr) + static_cast<uint64_t>(2 * k);
-          ptx::umma_bf16_ss_w(tmem_base + K::COL_O + static_cast<uint32_t>(part * K::N2), dh, dw, idesc2, (i | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < HC / 16; ++k) {
+            const uint64_t dh = ptx::make_kmajor_sw128_desc(h_addr) + static_cast<uint64_t>(2 * k);
+            const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr) + static_cast<uint64_t>(2 * k);
+            ptx::umma_bf16_ss_w(tmem_base + K::COL_O + static_cast<uint32_t>(part * K::N2), dh, dw, idesc2, (i | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit_w(&w2_empty[st]);
         }
-        ptx::umma_commit_w(&w2_empty[st]);
+        ptx::umma_commit_w(&h_empty[b]);
+        ++g2;
+      };
+      // the first GEMM runs one chunk ahead of the second, so chunk i's GELU overlaps S(i + 1)
+      gemm1(n_chunks == 1);
+      for (int i = 0; i < n_chunks; ++i) {
+        if (i + 1 < n_chunks) gemm1(i + 2 == n_chunks);
+        gemm2(i);
       }
-      ptx::umma_commit_w(&h_empty[b]);
-    };
-    // The first GEMM runs TWO chunks ahead of the second: S buffer (i + 2) & 1 is free as soon as the epilogue warps have
-    // LOADED S(i) (the start of chunk i's GELU), whereas the second GEMM of chunk i needs that GELU finished.  Issued in
-    // this order the tensor pipe computes S(i + 2) while GELU(i) runs, so the epilogue warps (the busiest resource: ~14
-    // instructions per hidden element) always find their next accumulator ready.
-    gemm1(0);
-    if (n_chunks > 1) gemm1(1);
-    for (int i = 0; i < n_chunks; ++i) {
-      if (i + 2 < n_chunks) gemm1(i + 2);
-      gemm2(i);
+      ptx::umma_commit_w(o_full);
     }
-    ptx::umma_commit_w(o_full);
   } else {
     // ------------------------------------------------------------ epilogue warps: GELU between the GEMMs, final store
     const int quarter = warp & 3;                              // TMEM lane quarter
@@ -234,72 +245,90 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const int sw = row & 7;                                    // 128B-swizzle phase of this row
     const bool has_b1 = p.b1 != nullptr;
-    for (int i = 0; i < n_chunks; ++i) {
-      const int b = i & 1;
-      ptx::mbar_wait(&s_full[b], (i >> 1) & 1);
-      ptx::tc_fence_after();
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_S + static_cast<uint32_t>(b * HC + half * 32), r);
-      const int h0 = i * HC + half * 32;
-      float4 bv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_b1 && h0 + 4 * j < p.Hd) bv[j] = __ldg(reinterpret_cast<const float4*>(p.b1 + h0) + j);   // Hd % 8 == 0
-      }
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&s_empty[b]);
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(gelu_erf(__uint_as_float(r[4 * j]) + bv[j].x), gelu_erf(__uint_as_float(r[4 * j + 1]) + bv[j].y));
-        __nv_bfloat162 hi = __floats2bfloat162_rn(gelu_erf(__uint_as_float(r[4 * j + 2]) + bv[j].z), gelu_erf(__uint_as_float(r[4 * j + 3]) + bv[j].w));
-        pk[2 * j] = *reinterpret_cast<uint32_t*>(&lo);
-        pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
-      }
-      ptx::mbar_wait(&h_empty[b], ((i >> 1) & 1) ^ 1);         // the second GEMM of chunk i-2 has finished reading H_b
-      uint8_t* hrow = s_h + b * K::H_BYTES + row * 128;        // 64 bf16 = 8 chunks of 16 B, chunk c stored at (c ^ sw)
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(hrow + (((half * 4 + c) ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&h_full[b]);
-    }
-    // final: O -> (+ b2) * gamma -> staging tile [32 rows][32 fp32] (128B swizzle) -> TMA reduce-add into x.  The staging
-    // tiles alias the H buffers: o_full completes only after the last second GEMM has finished reading them.
-    ptx::mbar_wait(o_full, 0);
-    ptx::tc_fence_after();
     uint8_t* stg = s_stg + warp * (32 * 128);
     const int swl = lane & 7;
-#pragma unroll 1
-    for (int c = half; c < (C + 31) / 32; c += 2) {
-      const int n0 = c * 32;
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_O + static_cast<uint32_t>(n0), r);
-      float4 b4[8], g4[8];
+    uint32_t g = 0, it = 0;                                    // running chunk / tile counters
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      if (it > 0) {
+        // the staging tiles of the previous tile's output alias the H buffers: every TMA read of them must be over, for
+        // both warps of this lane quarter (they write interleaved 16-byte chunks of the same H rows)
+        if (lane == 0) ptx::tma_store_wait_read<0>();
+        asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+      }
+      for (int i = 0; i < n_chunks; ++i, ++g) {
+        const int b = g & 1;
+        ptx::mbar_wait(&s_full[b], (g >> 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_S + static_cast<uint32_t>(b * HC + half * 32), r);
+        const int h0 = i * HC + half * 32;
+        float4 bv[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        g4[j] = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (n0 + 4 * j < C) {   // C % 16 == 0
-          if (p.b2 != nullptr) b4[j] = __ldg(reinterpret_cast<const float4*>(p.b2 + n0) + j);
-          if (p.gamma != nullptr) g4[j] = __ldg(reinterpret_cast<const float4*>(p.gamma + n0) + j);
+        for (int j = 0; j < 8; ++j) {
+          bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_b1 && h0 + 4 * j < p.Hd) bv[j] = __ldg(reinterpret_cast<const float4*>(p.b1 + h0) + j);   // Hd % 8 == 0
+        }
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&s_empty[b]);
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(gelu_erf(__uint_as_float(r[4 * j]) + bv[j].x), gelu_erf(__uint_as_float(r[4 * j + 1]) + bv[j].y));
+          __nv_bfloat162 hi = __floats2bfloat162_rn(gelu_erf(__uint_as_float(r[4 * j + 2]) + bv[j].z), gelu_erf(__uint_as_float(r[4 * j + 3]) + bv[j].w));
+          pk[2 * j] = *reinterpret_cast<uint32_t*>(&lo);
+          pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
+        }
+        ptx::mbar_wait(&h_empty[b], ((g >> 1) & 1) ^ 1);       // the second GEMM of the chunk two back has finished reading H_b
+        uint8_t* hrow = s_h + b * K::H_BYTES + row * 128;      // 64 bf16 = 8 chunks of 16 B, chunk c stored at (c ^ sw)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(hrow + (((half * 4 + c) ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&h_full[b]);
+      }
+      // final: O -> (+ b2) * gamma -> staging tile [32 rows][32 fp32] (128B swizzle) -> TMA reduce-add into x.  The staging
+      // tiles alias the H buffers: o_full completes only after the last second GEMM has finished reading them.
+      ptx::mbar_wait(o_full, it & 1);
+      ptx::tc_fence_after();
+      constexpr int NCC = (C + 31) / 32;                        // 32-column chunks of O; this warp takes c = half, half + 2, ...
+#pragma unroll 1
+      for (int c = half; c < NCC; c += 2) {
+        const int n0 = c * 32;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_O + static_cast<uint32_t>(n0), r);
+        float4 b4[8], g4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          g4[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (n0 + 4 * j < C) {   // C % 16 == 0
+            if (p.b2 != nullptr) b4[j] = __ldg(reinterpret_cast<const float4*>(p.b2 + n0) + j);
+            if (p.gamma != nullptr) g4[j] = __ldg(reinterpret_cast<const float4*>(p.gamma + n0) + j);
+          }
+        }
+        ptx::tmem_ld_wait();
+        if (c + 2 >= NCC) {   // this warp's last read of O: the next tile's second GEMM may overwrite it
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(o_empty);
+        }
+        if (lane == 0) ptx::tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ swl) << 4)) =
+              make_float4((__uint_as_float(r[4 * j]) + b4[j].x) * g4[j].x, (__uint_as_float(r[4 * j + 1]) + b4[j].y) * g4[j].y,
+                          (__uint_as_float(r[4 * j + 2]) + b4[j].z) * g4[j].z, (__uint_as_float(r[4 * j + 3]) + b4[j].w) * g4[j].w);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_reduce_add_2d(&tm_x, stg, n0, tile * BM + quarter * 32);   // columns >= C and rows >= M are clipped
+          ptx::tma_store_commit();
         }
       }
-      ptx::tmem_ld_wait();
-      if (lane == 0) ptx::tma_store_wait_read<0>();
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ swl) << 4)) =
-            make_float4((__uint_as_float(r[4 * j]) + b4[j].x) * g4[j].x, (__uint_as_float(r[4 * j + 1]) + b4[j].y) * g4[j].y,
-                        (__uint_as_float(r[4 * j + 2]) + b4[j].z) * g4[j].z, (__uint_as_float(r[4 * j + 3]) + b4[j].w) * g4[j].w);
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        ptx::tma_reduce_add_2d(&tm_x, stg, n0, row0 + quarter * 32);   // columns >= C and rows >= M are clipped
-        ptx::tma_store_commit();
+      if (half >= NCC) {   // (only when C <= 32: a warp without a column chunk still has to release O)
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(o_empty);
       }
     }
     if (lane == 0) ptx::tma_store_wait<0>();
@@ -320,14 +349,15 @@ inline cudaError_t configure_t() {
 template <int C>
 inline cudaError_t launch_t(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w1, long long ldw1,
                             const __nv_bfloat16* w2, long long ldw2, float* x, long long ldx, const Params& p,
-                            cudaStream_t st) {
+                            int num_sms, cudaStream_t st) {
   using K = Cfg<C>;
   CUtensorMap ta, tw1, tw2, tx;
   if (!make_tmap_2d(&ta, a, p.M, C, lda, BM, 2)) return cudaErrorUnknown;
   if (!make_tmap_2d(&tw1, w1, p.Hd, C, ldw1, HC, 2)) return cudaErrorUnknown;
   if (!make_tmap_2d(&tw2, w2, C, p.Hd, ldw2, K::N2, 2)) return cudaErrorUnknown;   // box = [N2 output channels][64 hidden]
   if (!make_tmap_2d(&tx, x, p.M, C, ldx, 32, 4)) return cudaErrorUnknown;
-  const int grid = (p.M + BM - 1) / BM;
+  const int tiles = (p.M + BM - 1) / BM, slots = num_sms * K::CTAS_PER_SM;
+  const int grid = tiles < slots ? tiles : slots;   // persistent: every CTA walks tiles blockIdx.x, += gridDim.x
   fused_mlp_kernel<C><<<grid, THREADS, K::SMEM_BYTES, st>>>(ta, tw1, tw2, tx, p);
   return cudaGetLastError();
 }
@@ -350,13 +380,13 @@ inline cudaError_t fused_mlp_configure_device() {
 // a [M, C] bf16, w1 [Hd, C] bf16, w2 [C, Hd] bf16 (both torch Linear / 1x1-conv layout, K contiguous), x [M, C] fp32 in place
 inline cudaError_t fused_mlp(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w1, long long ldw1, const float* b1,
                              const __nv_bfloat16* w2, long long ldw2, const float* b2, const float* gamma, float* x,
-                             long long ldx, int M, int C, int Hd, cudaStream_t st) {
+                             long long ldx, int M, int C, int Hd, int num_sms, cudaStream_t st) {
   if (M <= 0) return cudaSuccess;
   if (!fused_mlp_supported(C, Hd) || (lda & 7) || (ldw1 & 7) || (ldw2 & 7) || (ldx & 3)) return cudaErrorInvalidValue;
   fmlp::Params p;
   p.M = M; p.C = C; p.Hd = Hd; p.b1 = b1; p.b2 = b2; p.gamma = gamma;
 #define CLIPB200_FMLP_CASE(C_) \
-  if (C == C_) return fmlp::launch_t<C_>(a, lda, w1, ldw1, w2, ldw2, x, ldx, p, st);
+  if (C == C_) return fmlp::launch_t<C_>(a, lda, w1, ldw1, w2, ldw2, x, ldx, p, num_sms, st);
   CLIPB200_FMLP_CASE(80)
   CLIPB200_FMLP_CASE(96)
   CLIPB200_FMLP_CASE(128)

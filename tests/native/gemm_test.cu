@@ -291,7 +291,7 @@ static int run_fused_mlp_case(int M, int C, int Hd, bool time_it, int num_sms) {
     e2.bias = b2; e2.gamma = gamma; e2.ldc = C; e2.out_f32 = x;
     CK(gemm_bf16(Hbuf, Hd, W2, Hd, M, C, Hd, EPI_RESID, e2, num_sms, 0));
   };
-  auto fused = [&](float* x) { CK(fused_mlp(A, C, W1, C, b1, W2, Hd, b2, gamma, x, C, M, C, Hd, 0)); };
+  auto fused = [&](float* x) { CK(fused_mlp(A, C, W1, C, b1, W2, Hd, b2, gamma, x, C, M, C, Hd, num_sms, 0)); };
   unfused(xa);
   fused(xb);
   CK(cudaDeviceSynchronize());
