@@ -33,10 +33,9 @@ namespace fmlp {
 
 constexpr int BM = 128;        // pixels per CTA
 constexpr int HC = 64;         // hidden columns per chunk (one 128B-swizzle atom of K for the second GEMM)
-constexpr int EPI_WARPS = 8;   // two per TMEM lane quarter, 32 of a chunk's 64 hidden columns each: the GELU between the
-                               // GEMMs is ~14 instructions per hidden element and is what a chunk waits for
-constexpr int THREADS = 32 * (EPI_WARPS + 2);   // warps 0..7 epilogue, 8 TMA, 9 MMA
-constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
+// Epilogue warps: SLOTS per TMEM lane quarter, each taking 64 / SLOTS of a chunk's hidden columns.  The GELU between the
+// GEMMs (~9 instructions and 2 MUFU ops per hidden element) is what a chunk waits for, so the SM wants 16 of them:
+// 8 per CTA where two CTAs share an SM (C <= 96), 16 where one CTA has it alone.  Then the TMA warp, then the MMA warp.
 
 template <int C>
 struct Cfg {
@@ -55,9 +54,16 @@ struct Cfg {
   // Two CTAs per SM where the tiles are small enough (C <= 96), so that one CTA's prologue / final epilogue overlaps
   // the other's chunks; otherwise one CTA.
   static constexpr int CTAS_PER_SM = C <= 96 ? 2 : 1;
+  static constexpr int EPI_WARPS = CTAS_PER_SM == 2 ? 8 : 16;
+  static constexpr int SLOTS = EPI_WARPS / 4;              // warps per lane quarter
+  static constexpr int CPW = HC / SLOTS;                   // hidden columns per warp and chunk (32 | 16)
+  static constexpr int OCW = CPW;                          // output columns per final-epilogue chunk (fp32: 128 B | 64 B rows)
+  static constexpr int THREADS = 32 * (EPI_WARPS + 2);
+  static constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
   static constexpr int NS1 = C <= 80 ? KB + 1 : (C <= 96 ? KB : (C > 256 ? 4 : 2 * KB));   // W1 ring stages (smem budget)
   static constexpr int NS2 = C > 256 ? 4 : 2;                             // W2 ring stages (>= 2 chunks' worth)
-  static constexpr int STG_BYTES = EPI_WARPS * 32 * 128;   // 8 epilogue warps x [32 rows][32 fp32]; aliases the H buffers
+  static constexpr int STG_WARP = 32 * OCW * 4;            // per epilogue warp: [32 rows][OCW fp32]
+  static constexpr int STG_BYTES = EPI_WARPS * STG_WARP;   // aliases the H buffers
   static constexpr int OFF_A = 0;
   static constexpr int OFF_W1 = OFF_A + A_BYTES;
   static constexpr int OFF_W2 = OFF_W1 + NS1 * W1_TILE;
@@ -85,11 +91,65 @@ struct Params {
 
 __device__ __forceinline__ float gelu_erf(float x) { return gelu_erf_fast(x); }
 
+// gelu_erf_fast (gemm_sm100.cuh: x * Phi(x), Phi from Abramowitz-Stegun 7.1.26, |error| <= 4.3e-7) for TWO values at
+// once in packed f32x2 arithmetic: the polynomial, the scalings and the final x * Phi are one FFMA2 / FMUL2 per pair
+// instead of one instruction per element; the two MUFU ops per element (rcp, ex2) remain.  ~9 instead of ~14
+// instructions per element — the GELU between the two GEMMs is what the fused kernel's epilogue warps spend their time on.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_splat(float v) { return f2_pack(v, v); }
+// returns bf16x2 {gelu(x0 + b0), gelu(x1 + b1)}
+__device__ __forceinline__ uint32_t gelu_erf_pair_bf16(float x0, float x1, float b0, float b1) {
+  const uint64_t x = f2_pack(x0 + b0, x1 + b1);
+  float xa, xb;
+  f2_unpack(x, xa, xb);
+  const uint64_t ax = f2_pack(fabsf(xa), fabsf(xb));
+  float d0, d1, s0, s1;
+  f2_unpack(f2_fma(ax, f2_splat(0.23164189f), f2_splat(1.0f)), d0, d1);          // 1 + p |x| / sqrt 2 folded: p' = 0.3275911 / sqrt 2
+  f2_unpack(f2_mul(f2_mul(x, x), f2_splat(-0.72134752f)), s0, s1);              // -x^2 / 2 * log2(e)
+  float t0, t1, e0, e1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1));
+  const uint64_t t = f2_pack(t0, t1), e = f2_pack(e0, e1);
+  uint64_t q = f2_fma(t, f2_splat(0.5307027145f), f2_splat(-0.7265760135f));
+  q = f2_fma(t, q, f2_splat(0.7107068705f));
+  q = f2_fma(t, q, f2_splat(-0.142248368f));
+  q = f2_fma(t, q, f2_splat(0.127414796f));
+  const uint64_t h = f2_mul(f2_mul(q, t), e);                                    // h = Phi(-|x|)
+  // Phi(x) = x < 0 ? h : 1 - h = 0.5 + copysign(0.5 - h, x);   gelu = x * Phi = 0.5 x + x * copysign(0.5 - h, x)
+  float c0, c1;
+  f2_unpack(f2_fma(h, f2_splat(-1.0f), f2_splat(0.5f)), c0, c1);
+  const uint64_t cs = f2_pack(copysignf(c0, xa), copysignf(c1, xb));
+  float g0, g1;
+  f2_unpack(f2_fma(x, cs, f2_mul(x, f2_splat(0.5f))), g0, g1);
+  __nv_bfloat162 r = __floats2bfloat162_rn(g0, g1);
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
 template <int C>
-__global__ void __launch_bounds__(THREADS, Cfg<C>::CTAS_PER_SM)
+__global__ void __launch_bounds__(Cfg<C>::THREADS, Cfg<C>::CTAS_PER_SM)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w1,
                  const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_x, Params p) {
   using K = Cfg<C>;
+  constexpr int EPI_WARPS = K::EPI_WARPS, WARP_TMA = K::WARP_TMA, WARP_MMA = K::WARP_MMA;
   extern __shared__ uint8_t fmlp_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fmlp_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_a = smem + K::OFF_A;
@@ -240,66 +300,67 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   } else {
     // ------------------------------------------------------------ epilogue warps: GELU between the GEMMs, final store
     const int quarter = warp & 3;                              // TMEM lane quarter
-    const int half = warp >> 2;                                // which 32 of a chunk's 64 hidden columns
+    const int slot = warp >> 2;                                // which CPW of a chunk's 64 hidden columns
     const int row = quarter * 32 + lane;                       // this thread's pixel row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const int sw = row & 7;                                    // 128B-swizzle phase of this row
     const bool has_b1 = p.b1 != nullptr;
-    uint8_t* stg = s_stg + warp * (32 * 128);
-    const int swl = lane & 7;
+    constexpr int CPW = K::CPW, OCW = K::OCW;
+    uint8_t* stg = s_stg + warp * K::STG_WARP;
     uint32_t g = 0, it = 0;                                    // running chunk / tile counters
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       if (it > 0) {
         // the staging tiles of the previous tile's output alias the H buffers: every TMA read of them must be over, for
-        // both warps of this lane quarter (they write interleaved 16-byte chunks of the same H rows)
+        // all warps of this lane quarter (they write interleaved 16-byte chunks of the same H rows)
         if (lane == 0) ptx::tma_store_wait_read<0>();
-        asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(quarter + 1), "n"(32 * K::SLOTS) : "memory");
       }
       for (int i = 0; i < n_chunks; ++i, ++g) {
         const int b = g & 1;
         ptx::mbar_wait(&s_full[b], (g >> 1) & 1);
         ptx::tc_fence_after();
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_S + static_cast<uint32_t>(b * HC + half * 32), r);
-        const int h0 = i * HC + half * 32;
-        float4 bv[8];
+        uint32_t r[CPW];
+        if (CPW == 32) ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_S + static_cast<uint32_t>(b * HC + slot * CPW), *reinterpret_cast<uint32_t(*)[32]>(r));
+        else ptx::tmem_ld_32x32_x16(tmem_base + lane_base + K::COL_S + static_cast<uint32_t>(b * HC + slot * CPW), *reinterpret_cast<uint32_t(*)[16]>(r));
+        const int h0 = i * HC + slot * CPW;
+        float4 bv[CPW / 4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < CPW / 4; ++j) {
           bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (has_b1 && h0 + 4 * j < p.Hd) bv[j] = __ldg(reinterpret_cast<const float4*>(p.b1 + h0) + j);   // Hd % 8 == 0
         }
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&s_empty[b]);
-        uint32_t pk[16];
+        uint32_t pk[CPW / 2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(gelu_erf(__uint_as_float(r[4 * j]) + bv[j].x), gelu_erf(__uint_as_float(r[4 * j + 1]) + bv[j].y));
-          __nv_bfloat162 hi = __floats2bfloat162_rn(gelu_erf(__uint_as_float(r[4 * j + 2]) + bv[j].z), gelu_erf(__uint_as_float(r[4 * j + 3]) + bv[j].w));
-          pk[2 * j] = *reinterpret_cast<uint32_t*>(&lo);
-          pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
+        for (int j = 0; j < CPW / 4; ++j) {
+          pk[2 * j] = gelu_erf_pair_bf16(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), bv[j].x, bv[j].y);
+          pk[2 * j + 1] = gelu_erf_pair_bf16(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]), bv[j].z, bv[j].w);
         }
         ptx::mbar_wait(&h_empty[b], ((g >> 1) & 1) ^ 1);       // the second GEMM of the chunk two back has finished reading H_b
         uint8_t* hrow = s_h + b * K::H_BYTES + row * 128;      // 64 bf16 = 8 chunks of 16 B, chunk c stored at (c ^ sw)
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<uint4*>(hrow + (((half * 4 + c) ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        for (int c = 0; c < CPW / 8; ++c)
+          *reinterpret_cast<uint4*>(hrow + (((slot * (CPW / 8) + c) ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&h_full[b]);
       }
-      // final: O -> (+ b2) * gamma -> staging tile [32 rows][32 fp32] (128B swizzle) -> TMA reduce-add into x.  The staging
+      // final: O -> (+ b2) * gamma -> staging tile [32 rows][OCW fp32] (swizzled) -> TMA reduce-add into x.  The staging
       // tiles alias the H buffers: o_full completes only after the last second GEMM has finished reading them.
       ptx::mbar_wait(o_full, it & 1);
       ptx::tc_fence_after();
-      constexpr int NCC = (C + 31) / 32;                        // 32-column chunks of O; this warp takes c = half, half + 2, ...
+      constexpr int NCC = (C + OCW - 1) / OCW;                  // OCW-column chunks of O; this warp takes c = slot, slot + SLOTS, ...
+      bool released = false;
 #pragma unroll 1
-      for (int c = half; c < NCC; c += 2) {
-        const int n0 = c * 32;
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_O + static_cast<uint32_t>(n0), r);
-        float4 b4[8], g4[8];
+      for (int c = slot; c < NCC; c += K::SLOTS) {
+        const int n0 = c * OCW;
+        uint32_t r[OCW];
+        if (OCW == 32) ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_O + static_cast<uint32_t>(n0), *reinterpret_cast<uint32_t(*)[32]>(r));
+        else ptx::tmem_ld_32x32_x16(tmem_base + lane_base + K::COL_O + static_cast<uint32_t>(n0), *reinterpret_cast<uint32_t(*)[16]>(r));
+        float4 b4[OCW / 4], g4[OCW / 4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < OCW / 4; ++j) {
           b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           g4[j] = make_float4(1.f, 1.f, 1.f, 1.f);
           if (n0 + 4 * j < C) {   // C % 16 == 0
@@ -308,15 +369,18 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
         }
         ptx::tmem_ld_wait();
-        if (c + 2 >= NCC) {   // this warp's last read of O: the next tile's second GEMM may overwrite it
+        if (c + K::SLOTS >= NCC) {   // this warp's last read of O: the next tile's second GEMM may overwrite it
           ptx::tc_fence_before();
           ptx::mbar_arrive(o_empty);
+          released = true;
         }
         if (lane == 0) ptx::tma_store_wait_read<0>();
         __syncwarp();
+        // staging rows are 128 B (OCW = 32, 128B swizzle: chunk ^= row & 7) or 64 B (OCW = 16, 64B swizzle: chunk ^= (row >> 1) & 3)
+        const int swz = OCW == 32 ? (lane & 7) : ((lane >> 1) & 3);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ swl) << 4)) =
+        for (int j = 0; j < OCW / 4; ++j)
+          *reinterpret_cast<float4*>(stg + lane * (OCW * 4) + ((j ^ swz) << 4)) =
               make_float4((__uint_as_float(r[4 * j]) + b4[j].x) * g4[j].x, (__uint_as_float(r[4 * j + 1]) + b4[j].y) * g4[j].y,
                           (__uint_as_float(r[4 * j + 2]) + b4[j].z) * g4[j].z, (__uint_as_float(r[4 * j + 3]) + b4[j].w) * g4[j].w);
         ptx::fence_proxy_async_smem();
@@ -326,7 +390,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           ptx::tma_store_commit();
         }
       }
-      if (half >= NCC) {   // (only when C <= 32: a warp without a column chunk still has to release O)
+      if (!released) {   // a warp without a column chunk of its own (NCC < SLOTS) still has to release O
         ptx::tc_fence_before();
         ptx::mbar_arrive(o_empty);
       }
@@ -355,10 +419,10 @@ inline cudaError_t launch_t(const __nv_bfloat16* a, long long lda, const __nv_bf
   if (!make_tmap_2d(&ta, a, p.M, C, lda, BM, 2)) return cudaErrorUnknown;
   if (!make_tmap_2d(&tw1, w1, p.Hd, C, ldw1, HC, 2)) return cudaErrorUnknown;
   if (!make_tmap_2d(&tw2, w2, C, p.Hd, ldw2, K::N2, 2)) return cudaErrorUnknown;   // box = [N2 output channels][64 hidden]
-  if (!make_tmap_2d(&tx, x, p.M, C, ldx, 32, 4)) return cudaErrorUnknown;
+  if (!make_tmap_2d(&tx, x, p.M, C, ldx, 32, 4, K::OCW * 4)) return cudaErrorUnknown;   // box = [32 rows][OCW fp32]
   const int tiles = (p.M + BM - 1) / BM, slots = num_sms * K::CTAS_PER_SM;
   const int grid = tiles < slots ? tiles : slots;   // persistent: every CTA walks tiles blockIdx.x, += gridDim.x
-  fused_mlp_kernel<C><<<grid, THREADS, K::SMEM_BYTES, st>>>(ta, tw1, tw2, tx, p);
+  fused_mlp_kernel<C><<<grid, K::THREADS, K::SMEM_BYTES, st>>>(ta, tw1, tw2, tx, p);
   return cudaGetLastError();
 }
 
