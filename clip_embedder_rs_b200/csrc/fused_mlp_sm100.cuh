@@ -306,7 +306,11 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int sw = row & 7;                                    // 128B-swizzle phase of this row
     const bool has_b1 = p.b1 != nullptr;
     constexpr int CPW = K::CPW, OCW = K::OCW;
-    uint8_t* stg = s_stg + warp * K::STG_WARP;
+    // Staging tile of this warp, carved out of the H rows of ITS OWN lane quarter (4 KB per quarter in each of the two H
+    // buffers = 8 KB for the quarter's SLOTS warps): the only warps that write those H rows are the quarter's own, and
+    // they synchronise on the named barrier below before the next tile's first H write.
+    uint8_t* stg = s_stg + ((slot * K::STG_WARP) / 4096) * K::H_BYTES + quarter * 4096 + (slot * K::STG_WARP) % 4096;
+    static_assert(K::SLOTS * K::STG_WARP == 8192, "staging carve");
     uint32_t g = 0, it = 0;                                    // running chunk / tile counters
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       if (it > 0) {
