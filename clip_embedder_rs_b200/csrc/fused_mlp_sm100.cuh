@@ -31,6 +31,25 @@
 namespace clipb200 {
 namespace fmlp {
 
+// Build-time A/B switches; the defaults are what shipped, the alternatives were measured on one box and lost
+// (profiles/r02p_fused_mlp_ab.md):
+//   CLIPB200_FMLP_GROUPS      1: all 16 epilogue warps work on every hidden chunk;  2: two groups of 8 take alternate
+//                                chunks (one S / H buffer each) so that one group's GELU overlaps the other's TMEM load,
+//                                shared-memory store, proxy fence and barrier round trip (C = 160: 162 -> 179 us)
+//   CLIPB200_FMLP_DIRECT_RED  0: staging tile + TMA reduce-add into x;  1: red.global.add.v4.f32 straight from the
+//                                registers, every thread owning 64 contiguous bytes of its pixel row (C = 80: 271 -> 302 us)
+//   CLIPB200_FMLP_POLL        0: the MMA warp issues S(i + 1) then O += H(i) in a fixed interleaving;  1: it polls both
+//                                streams and issues whichever is ready, S up to two chunks ahead (C = 320: 118 -> 136 us)
+#ifndef CLIPB200_FMLP_GROUPS
+#define CLIPB200_FMLP_GROUPS 1
+#endif
+#ifndef CLIPB200_FMLP_DIRECT_RED
+#define CLIPB200_FMLP_DIRECT_RED 0
+#endif
+#ifndef CLIPB200_FMLP_POLL
+#define CLIPB200_FMLP_POLL 0
+#endif
+
 constexpr int BM = 128;        // pixels per CTA
 constexpr int HC = 64;         // hidden columns per chunk (one 128B-swizzle atom of K for the second GEMM)
 // Epilogue warps: SLOTS per TMEM lane quarter, each taking 64 / SLOTS of a chunk's hidden columns.  The GELU between the
@@ -56,12 +75,17 @@ struct Cfg {
   static constexpr int CTAS_PER_SM = C <= 96 ? 2 : 1;
   static constexpr int EPI_WARPS = CTAS_PER_SM == 2 ? 8 : 16;
   static constexpr int SLOTS = EPI_WARPS / 4;              // warps per lane quarter
-  static constexpr int CPW = HC / SLOTS;                   // hidden columns per warp and chunk (32 | 16)
-  static constexpr int OCW = CPW;                          // output columns per final-epilogue chunk (fp32: 128 B | 64 B rows)
+  static constexpr int GROUPS = (EPI_WARPS == 16 && CLIPB200_FMLP_GROUPS == 2) ? 2 : 1;   // warp groups on alternate chunks
+  static constexpr int CSLOTS = SLOTS / GROUPS;            // warps per lane quarter working on one chunk
+  static constexpr int CPW = HC / CSLOTS;                  // hidden columns per warp and chunk (32 | 16)
+  static constexpr bool DIRECT = CLIPB200_FMLP_DIRECT_RED != 0;
+  static constexpr int OCW = DIRECT ? 16 : HC / SLOTS;     // output columns per final-epilogue chunk (staging: 128 B | 64 B rows)
   static constexpr int THREADS = 32 * (EPI_WARPS + 2);
   static constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
-  static constexpr int NS1 = C <= 80 ? KB + 1 : (C <= 96 ? KB : (C > 256 ? 4 : 2 * KB));   // W1 ring stages (smem budget)
-  static constexpr int NS2 = C > 256 ? 4 : 2;                             // W2 ring stages (>= 2 chunks' worth)
+  // ring depths: what the shared memory allows; at C = 320 the weight stream is the limiter whatever the split (a CTA
+  // re-reads 1.2 MB of W1 / W2 per tile: 6.5 TB/s of L2 -> SM traffic over the 148 SMs), and 4 + 4 measured best
+  static constexpr int NS1 = C <= 80 ? KB + 1 : (C <= 96 ? KB : (C > 256 ? 4 : (3 * KB < 8 ? 3 * KB : 8)));   // W1 ring stages
+  static constexpr int NS2 = C <= 96 ? 2 : (C > 256 ? 4 : (C > 192 ? 2 : 3));                                 // W2 ring stages
   static constexpr int STG_WARP = 32 * OCW * 4;            // per epilogue warp: [32 rows][OCW fp32]
   static constexpr int STG_BYTES = EPI_WARPS * STG_WARP;   // aliases the H buffers
   static constexpr int OFF_A = 0;
@@ -87,13 +111,28 @@ struct Params {
   const float* b1;       // [Hd]
   const float* b2;       // [C]
   const float* gamma;    // [C] or null
+  float* x;              // [M, ldx] fp32 residual stream (direct reduce mode)
+  long long ldx;
+#ifdef CLIPB200_FMLP_TIMING
+  unsigned long long* dbg;   // 32 counters written by CTA 0 (tests/native/gemm_test.cu prints them)
+#endif
 };
+#ifdef CLIPB200_FMLP_TIMING
+// Where-does-the-time-go build (-DCLIPB200_FMLP_TIMING): CTA 0's first epilogue warp and its MMA warp accumulate clock64
+// deltas around every wait and every phase; never compiled into the library.
+inline unsigned long long*& timing_buffer() { static unsigned long long* p = nullptr; return p; }
+#define FMLP_T(var) const long long var = clock64()
+#define FMLP_ACC(i, a, b) tacc[i] += (b) - (a)
+#else
+#define FMLP_T(var)
+#define FMLP_ACC(i, a, b)
+#endif
 
 __device__ __forceinline__ float gelu_erf(float x) { return gelu_erf_fast(x); }
 
 // gelu_erf_fast (gemm_sm100.cuh: x * Phi(x), Phi from Abramowitz-Stegun 7.1.26, |error| <= 4.3e-7) for TWO values at
 // once in packed f32x2 arithmetic: the polynomial, the scalings and the final x * Phi are one FFMA2 / FMUL2 per pair
-// instead of one instruction per element; the two MUFU ops per element (rcp, ex2) remain.  ~9 instead of ~14
+// instead of one instruction per element; the two MUFU ops per element (rcp, ex2) remain.  ~8 instead of ~14
 // instructions per element — the GELU between the two GEMMs is what the fused kernel's epilogue warps spend their time on.
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
   uint64_t r;
@@ -116,13 +155,16 @@ __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
 __device__ __forceinline__ uint64_t f2_splat(float v) { return f2_pack(v, v); }
 // returns bf16x2 {gelu(x0 + b0), gelu(x1 + b1)}
 __device__ __forceinline__ uint32_t gelu_erf_pair_bf16(float x0, float x1, float b0, float b1) {
-  const uint64_t x = f2_pack(x0 + b0, x1 + b1);
-  float xa, xb;
-  f2_unpack(x, xa, xb);
-  const uint64_t ax = f2_pack(fabsf(xa), fabsf(xb));
+#if defined(CLIPB200_FMLP_EXPERIMENT) && CLIPB200_FMLP_EXPERIMENT == 1   // timing aid: how much of the kernel is the GELU?  (wrong results)
+  __nv_bfloat162 r0 = __floats2bfloat162_rn(x0 + b0, x1 + b1);
+  return *reinterpret_cast<uint32_t*>(&r0);
+#endif
+  // gelu(x) = x * Phi(x) = relu(x) - |x| * Phi(-|x|): no sign select, and h = Phi(-|x|) is what the formula yields
+  const float xa = x0 + b0, xb = x1 + b1;
+  const uint64_t nax = f2_pack(-fabsf(xa), -fabsf(xb));
   float d0, d1, s0, s1;
-  f2_unpack(f2_fma(ax, f2_splat(0.23164189f), f2_splat(1.0f)), d0, d1);          // 1 + p |x| / sqrt 2 folded: p' = 0.3275911 / sqrt 2
-  f2_unpack(f2_mul(f2_mul(x, x), f2_splat(-0.72134752f)), s0, s1);              // -x^2 / 2 * log2(e)
+  f2_unpack(f2_fma(nax, f2_splat(-0.23164189f), f2_splat(1.0f)), d0, d1);        // 1 + p |x| / sqrt 2 folded: p' = 0.3275911 / sqrt 2
+  f2_unpack(f2_mul(f2_mul(nax, nax), f2_splat(-0.72134752f)), s0, s1);          // -x^2 / 2 * log2(e)
   float t0, t1, e0, e1;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
@@ -134,12 +176,8 @@ __device__ __forceinline__ uint32_t gelu_erf_pair_bf16(float x0, float x1, float
   q = f2_fma(t, q, f2_splat(-0.142248368f));
   q = f2_fma(t, q, f2_splat(0.127414796f));
   const uint64_t h = f2_mul(f2_mul(q, t), e);                                    // h = Phi(-|x|)
-  // Phi(x) = x < 0 ? h : 1 - h = 0.5 + copysign(0.5 - h, x);   gelu = x * Phi = 0.5 x + x * copysign(0.5 - h, x)
-  float c0, c1;
-  f2_unpack(f2_fma(h, f2_splat(-1.0f), f2_splat(0.5f)), c0, c1);
-  const uint64_t cs = f2_pack(copysignf(c0, xa), copysignf(c1, xb));
   float g0, g1;
-  f2_unpack(f2_fma(x, cs, f2_mul(x, f2_splat(0.5f))), g0, g1);
+  f2_unpack(f2_fma(nax, h, f2_pack(fmaxf(xa, 0.f), fmaxf(xb, 0.f))), g0, g1);
   __nv_bfloat162 r = __floats2bfloat162_rn(g0, g1);
   return *reinterpret_cast<uint32_t*>(&r);
 }
@@ -193,8 +231,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&s_empty[i], 32 * EPI_WARPS);
-      ptx::mbar_init(&h_full[i], 32 * EPI_WARPS);
+      ptx::mbar_init(&s_empty[i], 32 * EPI_WARPS / K::GROUPS);
+      ptx::mbar_init(&h_full[i], 32 * EPI_WARPS / K::GROUPS);
       ptx::mbar_init(&h_empty[i], 1);
     }
     ptx::mbar_init(o_full, 1);
@@ -239,68 +277,139 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     constexpr uint32_t idesc2 = ptx::make_idesc_bf16_f32(BM, K::N2);
     const uint32_t a_addr = ptx::smem_u32(s_a);
     uint32_t t1 = 0, t2 = 0;      // running W1 / W2 ring tile counters
-    uint32_t g1 = 0, g2 = 0;      // running chunk counters of the first / second GEMM (S and H buffer = counter & 1)
-    uint32_t it = 0;
+#ifdef CLIPB200_FMLP_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long m_begin = clock64();
+#endif
+    // S(g) = A · W1[chunk]^T into TMEM buffer g & 1 (every wait but the weight ring's is done by the caller)
+    auto gemm1 = [&](uint32_t g, bool last_of_tile) {
+      const int b = g & 1;
+      const uint32_t t_s = tmem_base + K::COL_S + static_cast<uint32_t>(b * HC);
+#pragma unroll
+      for (int kb = 0; kb < K::KB; ++kb, ++t1) {
+        const int st = t1 % K::NS1;
+        FMLP_T(mw0);
+        ptx::mbar_wait(&w1_full[st], (t1 / K::NS1) & 1);
+        FMLP_T(mw1);
+        FMLP_ACC(2, mw0, mw1);
+        ptx::tc_fence_after();
+        const uint32_t w_addr = ptx::smem_u32(s_w1 + st * K::W1_TILE);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (kb * 4 + k < K::KSTEPS1) {
+            const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr + kb * BM * 128) + static_cast<uint64_t>(2 * k);
+            const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr) + static_cast<uint64_t>(2 * k);
+            ptx::umma_bf16_ss_w(t_s, da, dw, idesc1, (kb | k) != 0 ? 1u : 0u);
+          }
+        }
+        ptx::umma_commit_w(&w1_empty[st]);
+      }
+      ptx::umma_commit_w(&s_full[b]);
+      if (last_of_tile) ptx::umma_commit_w(a_empty);   // every read of this tile's A has been issued
+    };
+    // O (+)= H(g) · W2[:, chunk]^T; i = chunk index inside the tile (0 starts a new accumulation)
+    auto gemm2 = [&](uint32_t g, int i) {
+      const int b = g & 1;
+      const uint32_t h_addr = ptx::smem_u32(s_h + b * K::H_BYTES);
+#pragma unroll
+      for (int part = 0; part < K::N2_PARTS; ++part, ++t2) {
+        const int st = t2 % K::NS2;
+        FMLP_T(mv0);
+        ptx::mbar_wait(&w2_full[st], (t2 / K::NS2) & 1);
+        FMLP_T(mv1);
+        FMLP_ACC(5, mv0, mv1);
+        ptx::tc_fence_after();
+        const uint32_t w_addr = ptx::smem_u32(s_w2 + st * K::W2_TILE);
+#pragma unroll
+        for (int k = 0; k < HC / 16; ++k) {
+          const uint64_t dh = ptx::make_kmajor_sw128_desc(h_addr) + static_cast<uint64_t>(2 * k);
+          const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr) + static_cast<uint64_t>(2 * k);
+          ptx::umma_bf16_ss_w(tmem_base + K::COL_O + static_cast<uint32_t>(part * K::N2), dh, dw, idesc2, (i | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit_w(&w2_empty[st]);
+      }
+      ptx::umma_commit_w(&h_empty[b]);
+    };
+#if CLIPB200_FMLP_POLL
+    // Two instruction streams over this CTA's chunks (running index g across its tiles), issued as their inputs become
+    // ready rather than in a fixed interleaving: the first GEMM of chunk g needs S buffer g & 1 read out (chunk g - 2,
+    // early in that chunk's GELU) and, at a tile's first chunk, the A tile; the second GEMM of chunk g needs H(g) written
+    // and, at a tile's first chunk, the previous tile's O read out.  The older stream goes first when both are ready.
+    // S(g + 2) is therefore under way while chunk g's GELU still runs, which is what lets two warp groups on alternate
+    // chunks (CLIPB200_FMLP_GROUPS) both find their next S waiting.  The weight rings are consumed in this order too;
+    // the producer's order (W1(c), W2(c), W1(c + 1), ...) cannot deadlock it while the W2 ring holds two chunks.
+    // g1 - g2 <= 2 keeps that true with two warp groups as well (their S buffers free up early).
+    static_assert(K::NS2 >= 2 * K::N2_PARTS, "W2 ring: two chunks' worth");
+    const uint32_t my_tiles = (static_cast<uint32_t>(n_tiles) - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const uint32_t total = my_tiles * static_cast<uint32_t>(n_chunks);
+    uint32_t g1 = 0, g2 = 0, it1 = 0, it2 = 0;
+    int c1 = 0, c2 = 0;           // chunk index inside the tile of each stream
+    while (g2 < total) {
+      bool did = false;
+      if (g2 < g1 && ptx::mbar_test_wait(&h_full[g2 & 1], (g2 >> 1) & 1) &&
+          (c2 != 0 || ptx::mbar_test_wait(o_empty, (it2 & 1) ^ 1))) {
+        ptx::tc_fence_after();
+        gemm2(g2, c2);
+        if (++c2 == n_chunks) {
+          ptx::umma_commit_w(o_full);
+          c2 = 0;
+          ++it2;
+        }
+        ++g2;
+        did = true;
+      }
+      if (g1 < total && g1 - g2 <= 2 && ptx::mbar_test_wait(&s_empty[g1 & 1], ((g1 >> 1) & 1) ^ 1) &&
+          (c1 != 0 || ptx::mbar_test_wait(a_full, it1 & 1))) {
+        ptx::tc_fence_after();
+        gemm1(g1, c1 + 1 == n_chunks);
+        if (++c1 == n_chunks) {
+          c1 = 0;
+          ++it1;
+        }
+        ++g1;
+        did = true;
+      }
+      if (!did) {   // sleep on the older stream's barrier for a moment instead of burning the epilogue warps' issue slots
+        FMLP_T(mi0);
+        if (g2 < g1) ptx::mbar_try_wait_hint(&h_full[g2 & 1], (g2 >> 1) & 1, 100u);
+        else if (g1 < total) ptx::mbar_try_wait_hint(&s_empty[g1 & 1], ((g1 >> 1) & 1) ^ 1, 100u);
+        FMLP_T(mi1);
+        FMLP_ACC(3, mi0, mi1);
+      }
+    }
+#else
+    uint32_t g1 = 0, g2 = 0, it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       ptx::mbar_wait(a_full, it & 1);
-      auto gemm1 = [&](bool last_of_tile) {
-        const int b = g1 & 1;
-        const uint32_t t_s = tmem_base + K::COL_S + static_cast<uint32_t>(b * HC);
-        ptx::mbar_wait(&s_empty[b], ((g1 >> 1) & 1) ^ 1);
-#pragma unroll
-        for (int kb = 0; kb < K::KB; ++kb, ++t1) {
-          const int st = t1 % K::NS1;
-          ptx::mbar_wait(&w1_full[st], (t1 / K::NS1) & 1);
-          ptx::tc_fence_after();
-          const uint32_t w_addr = ptx::smem_u32(s_w1 + st * K::W1_TILE);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (kb * 4 + k < K::KSTEPS1) {
-              const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr + kb * BM * 128) + static_cast<uint64_t>(2 * k);
-              const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr) + static_cast<uint64_t>(2 * k);
-              ptx::umma_bf16_ss_w(t_s, da, dw, idesc1, (kb | k) != 0 ? 1u : 0u);
-            }
-          }
-          ptx::umma_commit_w(&w1_empty[st]);
-        }
-        ptx::umma_commit_w(&s_full[b]);
-        if (last_of_tile) ptx::umma_commit_w(a_empty);   // every read of this tile's A has been issued
+      // fixed order: the first GEMM runs one chunk ahead of the second, so chunk i's GELU overlaps S(i + 1)
+      auto first = [&](bool last_of_tile) {
+        ptx::mbar_wait(&s_empty[g1 & 1], ((g1 >> 1) & 1) ^ 1);
+        gemm1(g1, last_of_tile);
         ++g1;
       };
-      auto gemm2 = [&](int i) {
-        const int b = g2 & 1;
-        ptx::mbar_wait(&h_full[b], (g2 >> 1) & 1);
-        if (i == 0) ptx::mbar_wait(o_empty, (it & 1) ^ 1);   // the previous tile's O has been read out
-        const uint32_t h_addr = ptx::smem_u32(s_h + b * K::H_BYTES);
-#pragma unroll
-        for (int part = 0; part < K::N2_PARTS; ++part, ++t2) {
-          const int st = t2 % K::NS2;
-          ptx::mbar_wait(&w2_full[st], (t2 / K::NS2) & 1);
-          ptx::tc_fence_after();
-          const uint32_t w_addr = ptx::smem_u32(s_w2 + st * K::W2_TILE);
-#pragma unroll
-          for (int k = 0; k < HC / 16; ++k) {
-            const uint64_t dh = ptx::make_kmajor_sw128_desc(h_addr) + static_cast<uint64_t>(2 * k);
-            const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr) + static_cast<uint64_t>(2 * k);
-            ptx::umma_bf16_ss_w(tmem_base + K::COL_O + static_cast<uint32_t>(part * K::N2), dh, dw, idesc2, (i | k) != 0 ? 1u : 0u);
-          }
-          ptx::umma_commit_w(&w2_empty[st]);
-        }
-        ptx::umma_commit_w(&h_empty[b]);
-        ++g2;
-      };
-      // the first GEMM runs one chunk ahead of the second, so chunk i's GELU overlaps S(i + 1)
-      gemm1(n_chunks == 1);
+      first(n_chunks == 1);
       for (int i = 0; i < n_chunks; ++i) {
-        if (i + 1 < n_chunks) gemm1(i + 2 == n_chunks);
-        gemm2(i);
+        if (i + 1 < n_chunks) first(i + 2 == n_chunks);
+        ptx::mbar_wait(&h_full[g2 & 1], (g2 >> 1) & 1);
+        if (i == 0) ptx::mbar_wait(o_empty, (it & 1) ^ 1);   // the previous tile's O has been read out
+        gemm2(g2, i);
+        ++g2;
       }
       ptx::umma_commit_w(o_full);
     }
+#endif
+#ifdef CLIPB200_FMLP_TIMING
+    if (blockIdx.x == 0 && lane == 0 && p.dbg != nullptr) {
+      for (int i = 0; i < 8; ++i) p.dbg[16 + i] = static_cast<unsigned long long>(tacc[i]);
+      p.dbg[24] = static_cast<unsigned long long>(clock64() - m_begin);
+    }
+#endif
   } else {
     // ------------------------------------------------------------ epilogue warps: GELU between the GEMMs, final store
     const int quarter = warp & 3;                              // TMEM lane quarter
-    const int slot = warp >> 2;                                // which CPW of a chunk's 64 hidden columns
+    const int slot = warp >> 2;                                // final epilogue: which output column chunks
+    const int group = K::GROUPS == 2 ? slot / K::CSLOTS : 0;   // which chunks (running index parity) this warp works on
+    const int cslot = slot % K::CSLOTS;                        // which CPW of a chunk's 64 hidden columns
     const int row = quarter * 32 + lane;                       // this thread's pixel row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const int sw = row & 7;                                    // 128B-swizzle phase of this row
@@ -310,23 +419,35 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // buffers = 8 KB for the quarter's SLOTS warps): the only warps that write those H rows are the quarter's own, and
     // they synchronise on the named barrier below before the next tile's first H write.
     uint8_t* stg = s_stg + ((slot * K::STG_WARP) / 4096) * K::H_BYTES + quarter * 4096 + (slot * K::STG_WARP) % 4096;
-    static_assert(K::SLOTS * K::STG_WARP == 8192, "staging carve");
+    static_assert(K::DIRECT || K::SLOTS * K::STG_WARP == 8192, "staging carve");
+    (void)stg;
     uint32_t g = 0, it = 0;                                    // running chunk / tile counters
+#ifdef CLIPB200_FMLP_TIMING
+    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long e_begin = clock64();
+#endif
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      if (it > 0) {
+      FMLP_T(eb0);
+      if (!K::DIRECT && it > 0) {
         // the staging tiles of the previous tile's output alias the H buffers: every TMA read of them must be over, for
         // all warps of this lane quarter (they write interleaved 16-byte chunks of the same H rows)
         if (lane == 0) ptx::tma_store_wait_read<0>();
         asm volatile("bar.sync %0, %1;" ::"r"(quarter + 1), "n"(32 * K::SLOTS) : "memory");
       }
+      FMLP_T(eb1);
+      FMLP_ACC(7, eb0, eb1);
       for (int i = 0; i < n_chunks; ++i, ++g) {
         const int b = g & 1;
+        if (K::GROUPS == 2 && b != group) continue;            // the other group's chunk (it owns S_b and H_b)
+        FMLP_T(e0);
         ptx::mbar_wait(&s_full[b], (g >> 1) & 1);
+        FMLP_T(e1);
+        FMLP_ACC(0, e0, e1);
         ptx::tc_fence_after();
         uint32_t r[CPW];
-        if (CPW == 32) ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_S + static_cast<uint32_t>(b * HC + slot * CPW), *reinterpret_cast<uint32_t(*)[32]>(r));
-        else ptx::tmem_ld_32x32_x16(tmem_base + lane_base + K::COL_S + static_cast<uint32_t>(b * HC + slot * CPW), *reinterpret_cast<uint32_t(*)[16]>(r));
-        const int h0 = i * HC + slot * CPW;
+        if (CPW == 32) ptx::tmem_ld_32x32(tmem_base + lane_base + K::COL_S + static_cast<uint32_t>(b * HC + cslot * CPW), *reinterpret_cast<uint32_t(*)[32]>(r));
+        else ptx::tmem_ld_32x32_x16(tmem_base + lane_base + K::COL_S + static_cast<uint32_t>(b * HC + cslot * CPW), *reinterpret_cast<uint32_t(*)[16]>(r));
+        const int h0 = i * HC + cslot * CPW;
         float4 bv[CPW / 4];
 #pragma unroll
         for (int j = 0; j < CPW / 4; ++j) {
@@ -334,6 +455,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (has_b1 && h0 + 4 * j < p.Hd) bv[j] = __ldg(reinterpret_cast<const float4*>(p.b1 + h0) + j);   // Hd % 8 == 0
         }
         ptx::tmem_ld_wait();
+        FMLP_T(e2);
+        FMLP_ACC(1, e1, e2);
         ptx::tc_fence_before();
         ptx::mbar_arrive(&s_empty[b]);
         uint32_t pk[CPW / 2];
@@ -342,17 +465,29 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           pk[2 * j] = gelu_erf_pair_bf16(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), bv[j].x, bv[j].y);
           pk[2 * j + 1] = gelu_erf_pair_bf16(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]), bv[j].z, bv[j].w);
         }
+#ifdef CLIPB200_FMLP_TIMING
+        asm volatile("" ::"r"(pk[0]), "r"(pk[CPW / 2 - 1]) : "memory");   // the packed values exist before the clock is read
+#endif
+        FMLP_T(e3);
+        FMLP_ACC(2, e2, e3);
         ptx::mbar_wait(&h_empty[b], ((g >> 1) & 1) ^ 1);       // the second GEMM of the chunk two back has finished reading H_b
+        FMLP_T(e4);
+        FMLP_ACC(3, e3, e4);
         uint8_t* hrow = s_h + b * K::H_BYTES + row * 128;      // 64 bf16 = 8 chunks of 16 B, chunk c stored at (c ^ sw)
 #pragma unroll
         for (int c = 0; c < CPW / 8; ++c)
-          *reinterpret_cast<uint4*>(hrow + (((slot * (CPW / 8) + c) ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          *reinterpret_cast<uint4*>(hrow + (((cslot * (CPW / 8) + c) ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&h_full[b]);
+        FMLP_T(e5);
+        FMLP_ACC(4, e4, e5);
       }
+      FMLP_T(f0);
       // final: O -> (+ b2) * gamma -> staging tile [32 rows][OCW fp32] (swizzled) -> TMA reduce-add into x.  The staging
       // tiles alias the H buffers: o_full completes only after the last second GEMM has finished reading them.
       ptx::mbar_wait(o_full, it & 1);
+      FMLP_T(f1);
+      FMLP_ACC(5, f0, f1);
       ptx::tc_fence_after();
       constexpr int NCC = (C + OCW - 1) / OCW;                  // OCW-column chunks of O; this warp takes c = slot, slot + SLOTS, ...
       bool released = false;
@@ -378,28 +513,52 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           ptx::mbar_arrive(o_empty);
           released = true;
         }
-        if (lane == 0) ptx::tma_store_wait_read<0>();
-        __syncwarp();
-        // staging rows are 128 B (OCW = 32, 128B swizzle: chunk ^= row & 7) or 64 B (OCW = 16, 64B swizzle: chunk ^= (row >> 1) & 3)
-        const int swz = OCW == 32 ? (lane & 7) : ((lane >> 1) & 3);
+        if (K::DIRECT) {
+          // this thread's 16 consecutive fp32 of its pixel row: four 16-byte reductions, resolved in L2 like the TMA form
+          const long long grow = static_cast<long long>(tile) * BM + row;
+          if (grow < p.M) {
+            float* xr = p.x + grow * p.ldx + n0;
 #pragma unroll
-        for (int j = 0; j < OCW / 4; ++j)
-          *reinterpret_cast<float4*>(stg + lane * (OCW * 4) + ((j ^ swz) << 4)) =
-              make_float4((__uint_as_float(r[4 * j]) + b4[j].x) * g4[j].x, (__uint_as_float(r[4 * j + 1]) + b4[j].y) * g4[j].y,
-                          (__uint_as_float(r[4 * j + 2]) + b4[j].z) * g4[j].z, (__uint_as_float(r[4 * j + 3]) + b4[j].w) * g4[j].w);
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          ptx::tma_reduce_add_2d(&tm_x, stg, n0, tile * BM + quarter * 32);   // columns >= C and rows >= M are clipped
-          ptx::tma_store_commit();
+            for (int j = 0; j < OCW / 4; ++j)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(xr + 4 * j),
+                           "f"((__uint_as_float(r[4 * j]) + b4[j].x) * g4[j].x), "f"((__uint_as_float(r[4 * j + 1]) + b4[j].y) * g4[j].y),
+                           "f"((__uint_as_float(r[4 * j + 2]) + b4[j].z) * g4[j].z), "f"((__uint_as_float(r[4 * j + 3]) + b4[j].w) * g4[j].w)
+                           : "memory");
+          }
+        } else {
+          if (lane == 0) ptx::tma_store_wait_read<0>();
+          __syncwarp();
+          // staging rows are 128 B (OCW = 32, 128B swizzle: chunk ^= row & 7) or 64 B (OCW = 16, 64B swizzle: chunk ^= (row >> 1) & 3)
+          const int swz = OCW == 32 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+          for (int j = 0; j < OCW / 4; ++j)
+            *reinterpret_cast<float4*>(stg + lane * (OCW * 4) + ((j ^ swz) << 4)) =
+                make_float4((__uint_as_float(r[4 * j]) + b4[j].x) * g4[j].x, (__uint_as_float(r[4 * j + 1]) + b4[j].y) * g4[j].y,
+                            (__uint_as_float(r[4 * j + 2]) + b4[j].z) * g4[j].z, (__uint_as_float(r[4 * j + 3]) + b4[j].w) * g4[j].w);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_reduce_add_2d(&tm_x, stg, n0, tile * BM + quarter * 32);   // columns >= C and rows >= M are clipped
+            ptx::tma_store_commit();
+          }
         }
       }
       if (!released) {   // a warp without a column chunk of its own (NCC < SLOTS) still has to release O
         ptx::tc_fence_before();
         ptx::mbar_arrive(o_empty);
       }
+      FMLP_T(f2);
+      FMLP_ACC(6, f1, f2);
     }
-    if (lane == 0) ptx::tma_store_wait<0>();
+#ifdef CLIPB200_FMLP_TIMING
+    if (blockIdx.x == 0 && warp == 0 && lane == 0 && p.dbg != nullptr) {
+      for (int i = 0; i < 8; ++i) p.dbg[i] = static_cast<unsigned long long>(tacc[i]);
+      p.dbg[8] = static_cast<unsigned long long>(clock64() - e_begin);
+      p.dbg[9] = it;
+      p.dbg[10] = g;
+    }
+#endif
+    if (!K::DIRECT && lane == 0) ptx::tma_store_wait<0>();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -452,7 +611,10 @@ inline cudaError_t fused_mlp(const __nv_bfloat16* a, long long lda, const __nv_b
   if (M <= 0) return cudaSuccess;
   if (!fused_mlp_supported(C, Hd) || (lda & 7) || (ldw1 & 7) || (ldw2 & 7) || (ldx & 3)) return cudaErrorInvalidValue;
   fmlp::Params p;
-  p.M = M; p.C = C; p.Hd = Hd; p.b1 = b1; p.b2 = b2; p.gamma = gamma;
+  p.M = M; p.C = C; p.Hd = Hd; p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.x = x; p.ldx = ldx;
+#ifdef CLIPB200_FMLP_TIMING
+  p.dbg = fmlp::timing_buffer();
+#endif
 #define CLIPB200_FMLP_CASE(C_) \
   if (C == C_) return fmlp::launch_t<C_>(a, lda, w1, ldw1, w2, ldw2, x, ldx, p, num_sms, st);
   CLIPB200_FMLP_CASE(80)

@@ -327,6 +327,26 @@ static int run_fused_mlp_case(int M, int C, int Hd, bool time_it, int num_sms) {
       ms[w] = t / 10;
     }
   }
+#ifdef CLIPB200_FMLP_TIMING
+  if (time_it) {
+    unsigned long long* dbg;
+    CK(cudaMalloc(&dbg, 32 * 8));
+    CK(cudaMemset(dbg, 0, 32 * 8));
+    clipb200::fmlp::timing_buffer() = dbg;
+    fused(xb);
+    CK(cudaDeviceSynchronize());
+    clipb200::fmlp::timing_buffer() = nullptr;
+    unsigned long long h[32];
+    CK(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    const double tiles = (double)h[9], chunks = (double)h[10];
+    printf("   CTA 0, %.0f tiles, %.0f chunks; epilogue warp 0, clocks per chunk: wait S %.0f | tmem ld %.0f | GELU %.0f | wait H free %.0f | st + fence + arrive %.0f"
+           "   per tile: wait O %.0f | final epilogue %.0f | tile-start barrier %.0f | total %.0f\n",
+           tiles, chunks, h[0] / chunks, h[1] / chunks, h[2] / chunks, h[3] / chunks, h[4] / chunks, h[5] / tiles, h[6] / tiles, h[7] / tiles, h[8] / tiles);
+    printf("   MMA warp, clocks per tile: wait A %.0f | wait S free %.0f | wait W1 %.0f | wait H %.0f | wait O free %.0f | wait W2 %.0f | total %.0f\n",
+           h[16] / tiles, h[17] / tiles, h[18] / tiles, h[19] / tiles, h[20] / tiles, h[21] / tiles, h[24] / tiles);
+    cudaFree(dbg);
+  }
+#endif
   const double flops = 4.0 * M * (double)C * Hd;
   printf("%s fused_mlp M=%d C=%d Hd=%d max|diff|=%.4g (update magnitude up to %.3g) bad=%lld", bad ? "FAIL" : "ok  ", M, C, Hd, max_abs, max_mag, bad);
   if (time_it) printf("  two launches %.1f us (%.0f TF)  fused %.1f us (%.0f TF)", ms[0] * 1e3, flops / ms[0] * 1e-9, ms[1] * 1e3, flops / ms[1] * 1e-9);
