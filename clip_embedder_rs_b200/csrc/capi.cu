@@ -104,6 +104,11 @@ int clipb200_onnx_inspect(const char* onnx_path, char* json_out, size_t capacity
   std::string graph_err;
   const bool graph_tried = clipb200::graph_needs_recognition(m);
   const bool graph_ok = graph_tried && clipb200::recognize_graph(&m, &graph_err, &bindings);
+  // ... and for the one family bound by name, the FastViT trunk: its attention Linears come out of the graph
+  bool fastvit_ok = false;
+  std::string fastvit_err;
+  if (graph_tried && !graph_ok && m.has("model.visual.trunk.stem.0.reparam_conv.weight"))
+    fastvit_ok = clipb200::bind_fastvit_graph(&m, &fastvit_err);
   std::string j = "{\"inputs\": [";
   for (size_t i = 0; i < m.inputs.size(); ++i) j += std::string(i ? ", " : "") + "\"" + esc(m.inputs[i]) + "\"";
   j += "], \"outputs\": [";
@@ -117,7 +122,8 @@ int clipb200_onnx_inspect(const char* onnx_path, char* json_out, size_t capacity
     first = false;
   }
   j += "}, \"graph\": {\"attempted\": " + std::string(graph_tried ? "true" : "false") + ", \"recognized\": " +
-       std::string(graph_ok ? "true" : "false") + ", \"error\": \"" + esc(graph_err) + "\", \"bindings\": [";
+       std::string(graph_ok ? "true" : "false") + ", \"fastvit_by_name\": " + std::string(fastvit_ok ? "true" : "false") +
+       ", \"error\": \"" + esc(graph_err + (fastvit_err.empty() ? "" : "; " + fastvit_err)) + "\", \"bindings\": [";
   for (size_t i = 0; i < bindings.size(); ++i)
     j += std::string(i ? ", " : "") + "{\"name\": \"" + esc(bindings[i].canonical) + "\", \"source\": \"" +
          esc(bindings[i].source) + "\", \"transposed\": " + (bindings[i].transposed ? "true" : "false") + "}";
@@ -143,6 +149,8 @@ int clipb200_onnx_read_tensor(const char* onnx_path, const char* name, float* ou
   }
   if (clipb200::graph_needs_recognition(m) && !clipb200::recognize_graph(&m, &err, nullptr)) {
     // not fatal: the tensor may still be present under its exported name
+    std::string fv_err;
+    if (m.has("model.visual.trunk.stem.0.reparam_conv.weight") && !clipb200::bind_fastvit_graph(&m, &fv_err)) err += "; " + fv_err;
   }
   const clipb200::OnnxTensor* t = m.find(name);
   if (t == nullptr) return fail(CLIPB200_ERR_UNSUPPORTED, std::string("tensor '") + name + "' not found" + (err.empty() ? "" : "; " + err));

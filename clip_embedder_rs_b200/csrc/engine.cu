@@ -113,6 +113,13 @@ Status Engine::HostF32(const OnnxModel& m, const std::string& name, int64_t expe
     return Status::Err(CLIPB200_ERR_UNSUPPORTED,
                        "initializer '" + name + "' has data_type " + std::to_string(t->data_type) + " (need f32/f16/bf16)");
   }
+  if (t->transposed && t->dims.size() == 2) {   // canonical [r, c] alias whose bytes are [c, r] (onnx_graph.cc): hand out [r, c]
+    const int64_t r = t->dims[0], c = t->dims[1];
+    std::vector<float> tmp(out->size());
+    for (int64_t i = 0; i < r; ++i)
+      for (int64_t j = 0; j < c; ++j) tmp[static_cast<size_t>(i * c + j)] = (*out)[static_cast<size_t>(j * r + i)];
+    out->swap(tmp);
+  }
   return Status::OK();
 }
 
@@ -515,6 +522,8 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
     if (!m.has("model.visual.trunk.stem.0.reparam_conv.weight"))
       return Status::Err(CLIPB200_ERR_UNSUPPORTED, onnx_path + ": " + graph_err);
     graph_note_ = graph_err;
+    std::string fv_err;   // a real FastViT export: the attention blocks' Linear weights come out of the graph
+    if (!bind_fastvit_graph(&m, &fv_err)) return Status::Err(CLIPB200_ERR_UNSUPPORTED, onnx_path + ": " + fv_err);
   }
   if (get_encode_tiled() == nullptr)  // resolved here so that it never happens inside a graph capture
     return Status::Err(CLIPB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");

@@ -94,8 +94,12 @@ Status Engine::LoadFastVit(const OnnxModel& m) {
   }
   if (dims.empty() || dims.size() != depths.size() || dims[0] != d0)
     return Status::Err(CLIPB200_ERR_UNSUPPORTED, "cannot determine FastViT stage layout");
+  // image size: metadata, else the declared input shape [batch, 3, S, S] of a real export, else MobileCLIP2's 256
   const std::string isz = m.meta("clipb200.image_size");
   S_ = isz.empty() ? 256 : atoi(isz.c_str());
+  if (isz.empty() && m.input_infos.size() == 1 && m.input_infos[0].dims.size() == 4 && m.input_infos[0].dims[2] > 0 &&
+      m.input_infos[0].dims[2] == m.input_infos[0].dims[3])
+    S_ = static_cast<int>(m.input_infos[0].dims[2]);
   image_size = S_;
   if (S_ % 32 != 0) return Status::Err(CLIPB200_ERR_UNSUPPORTED, "FastViT image size must be a multiple of 32");
   act_ = ACT_GELU_ERF;

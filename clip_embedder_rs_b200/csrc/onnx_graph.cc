@@ -1816,6 +1816,99 @@ struct Recognizer {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// Re-parameterised FastViT trunks (MobileCLIP2): the conv graph is not parsed by the recogniser above, and it does not
+// have to be: `torch.onnx.export` keeps every Conv / BatchNorm / bias / layer-scale / head parameter under its module
+// name, so those bind by name.  What it does NOT keep are the two `nn.Linear` weights of every attention block: a Linear
+// applied to [B, N, C] tokens becomes `MatMul(x, W^T)` with the pre-transposed constant renamed `onnx::MatMul_<n>`.
+// They are found from the named tensors next to them, following the graph's edges:
+//   qkv :  BatchNormalization(scale = "<block>.norm.weight") -> {Reshape | Flatten | Transpose | ...} -> MatMul(B = const [C, 3C])
+//   proj:  Add(_, "<block>.token_mixer.proj.bias") <- MatMul(B = const [C, C])
+// and registered under timm's names as transposed aliases of the same bytes.
+bool bind_fastvit_graph(OnnxModel* m, std::string* err) {
+  if (m->nodes.empty()) return true;   // initializer-only file: every name is already there
+  std::map<std::string, std::vector<int>> consumers;
+  std::map<std::string, int> producer;
+  for (size_t i = 0; i < m->nodes.size(); ++i) {
+    for (const std::string& in : m->nodes[i].inputs) consumers[in].push_back(static_cast<int>(i));
+    for (const std::string& out : m->nodes[i].outputs) producer[out] = static_cast<int>(i);
+  }
+  auto const_b = [&](const OnnxNode& n, int64_t rows, int64_t cols) -> const OnnxTensor* {
+    if (n.op_type != "MatMul" || n.inputs.size() != 2) return nullptr;
+    const OnnxTensor* t = m->find(n.inputs[1]);
+    if (t == nullptr || t->dims.size() != 2 || t->dims[0] != rows || t->dims[1] != cols || !is_float_dt(t->data_type)) return nullptr;
+    return t;
+  };
+  auto alias = [&](const std::string& name, const OnnxTensor& src, int64_t rows, int64_t cols) {
+    OnnxTensor t;
+    t.name = name;
+    t.dims = {rows, cols};
+    t.data_type = src.data_type;
+    t.data = src.data;
+    t.nbytes = src.nbytes;
+    t.owned = src.owned;
+    if (!t.owned.empty()) t.data = nullptr;
+    t.transposed = true;   // bytes are [cols, rows]
+    m->initializers[name] = std::move(t);
+    OnnxTensor& ref = m->initializers[name];
+    if (!ref.owned.empty()) ref.data = ref.owned.data();
+  };
+  int bound = 0;
+  for (const OnnxNode& bn : m->nodes) {
+    if (bn.op_type != "BatchNormalization" || bn.inputs.size() < 5) continue;
+    const std::string& scale = bn.inputs[1];
+    const std::string suffix = ".norm.weight";
+    if (scale.size() <= suffix.size() || scale.compare(scale.size() - suffix.size(), suffix.size(), suffix) != 0) continue;
+    const std::string block = scale.substr(0, scale.size() - suffix.size());
+    if (m->has(block + ".token_mixer.qkv.weight")) continue;   // the exporter kept the names (or an earlier pass bound them)
+    const OnnxTensor* sc = m->find(scale);
+    if (sc == nullptr || sc->dims.size() != 1) continue;
+    const int64_t C = sc->dims[0];
+    // qkv: breadth-first from the BatchNorm output through shape-only operators
+    const OnnxTensor* wq = nullptr;
+    std::vector<std::string> frontier = {bn.outputs[0]};
+    for (int depth = 0; depth < 6 && wq == nullptr && !frontier.empty(); ++depth) {
+      std::vector<std::string> next;
+      for (const std::string& tname : frontier) {
+        for (int ci : consumers[tname]) {
+          const OnnxNode& n = m->nodes[static_cast<size_t>(ci)];
+          if (n.inputs[0] != tname) continue;   // only along the data input
+          if ((wq = const_b(n, C, 3 * C)) != nullptr) break;
+          if (n.op_type == "Reshape" || n.op_type == "Flatten" || n.op_type == "Transpose" || n.op_type == "Identity" ||
+              n.op_type == "Squeeze" || n.op_type == "Unsqueeze")
+            next.push_back(n.outputs[0]);
+        }
+        if (wq != nullptr) break;
+      }
+      frontier.swap(next);
+    }
+    if (wq == nullptr) {
+      *err = "FastViT attention block '" + block + "': no MatMul with a constant [C, 3C] operand follows its BatchNormalization";
+      return false;
+    }
+    // proj: the MatMul feeding the Add that carries the named bias
+    const OnnxTensor* wp = nullptr;
+    const std::string pbias = block + ".token_mixer.proj.bias";
+    for (int ci : consumers[pbias]) {
+      const OnnxNode& add = m->nodes[static_cast<size_t>(ci)];
+      if (add.op_type != "Add" || add.inputs.size() != 2) continue;
+      const std::string& other = add.inputs[0] == pbias ? add.inputs[1] : add.inputs[0];
+      auto it = producer.find(other);
+      if (it != producer.end()) wp = const_b(m->nodes[static_cast<size_t>(it->second)], C, C);
+      if (wp != nullptr) break;
+    }
+    if (wp == nullptr) {
+      *err = "FastViT attention block '" + block + "': no MatMul with a constant [C, C] operand feeds the Add of '" + pbias + "'";
+      return false;
+    }
+    alias(block + ".token_mixer.qkv.weight", *wq, 3 * C, C);
+    alias(block + ".token_mixer.proj.weight", *wp, C, C);
+    ++bound;
+  }
+  if (bound > 0) m->metadata["clipb200.fastvit_graph_linears"] = std::to_string(2 * bound);
+  return true;
+}
+
 bool graph_needs_recognition(const OnnxModel& m) {
   if (!m.meta("clipb200.family").empty()) return false;
   for (const OnnxNode& n : m.nodes)

@@ -40,6 +40,11 @@ bool graph_needs_recognition(const OnnxModel& m);
 // On failure returns false with a reason in `err`; `m` is left untouched.
 bool recognize_graph(OnnxModel* m, std::string* err, std::vector<GraphBinding>* bindings_or_null);
 
+// Re-parameterised FastViT trunk exported as a real graph: registers the attention blocks' two Linear weights (renamed
+// and pre-transposed by the exporter) under timm's names by following the graph from the named tensors beside them.
+// No-op for initializer-only files.  Returns false with a reason when an attention block cannot be resolved.
+bool bind_fastvit_graph(OnnxModel* m, std::string* err);
+
 // fp32 copy of an initializer in its canonical layout (undoes `OnnxTensor::transposed`); f32 / f16 / bf16 sources.
 bool tensor_to_f32(const OnnxTensor& t, std::vector<float>* out);
 

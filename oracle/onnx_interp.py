@@ -313,6 +313,9 @@ def run(graph: Graph, feeds: Dict[str, np.ndarray], dtype=torch.float32) -> List
             axis = a.get("axis", -1)
             shape = x[0].shape[axis:] if axis < 0 else x[0].shape[axis:]
             y = F.layer_norm(x[0], tuple(shape), x[1], x[2] if len(x) > 2 else None, a.get("epsilon", 1e-5))
+        elif op == "BatchNormalization":   # inference form: (x - mean) / sqrt(var + eps) * scale + bias, per channel
+            sh = (1, -1) + (1,) * (x[0].dim() - 2)
+            y = (x[0] - x[3].reshape(sh)) / torch.sqrt(x[4].reshape(sh) + a.get("epsilon", 1e-5)) * x[1].reshape(sh) + x[2].reshape(sh)
         elif op == "GlobalAveragePool":
             y = x[0].mean(dim=(2, 3), keepdim=True)
         elif op in ("ReduceMean", "ReduceSum", "ReduceL2", "ReduceMax"):

@@ -192,6 +192,8 @@ int main(int argc, char** argv) {
   run(128, 576, 14, 80, false, true);  // 14: two real remainder planes
   run(32, 2304, 16, 72, false, true);  // 15: 24 key blocks per item (per-block vs per-item cost, with 16)
   run(256, 288, 16, 72, false, true);  // 16: 3 key blocks per item
+  run(2048, 77, 16, 64, true, true);   // 17: DFN5B text micro-batch: one causal key block per item
+  run(2048, 77, 8, 64, true, true);    // 18: ViT-B/32 text width
 #ifdef CLIPB200_ATTN_TIMING
   {
     unsigned long long h[16];

@@ -180,6 +180,45 @@ def test_c2_mobileclip2_s2(make_big):
     assert np.abs(whole - got_v).max() < 2e-3
 
 
+def test_c2_mobileclip2_s2_real_export_full_size(make_real_model, tmp_path):
+    """BASELINE config C2 as the reference would receive it: the full-size MobileCLIP2-S2 FastViT trunk as a
+    `torch.onnx.export` graph (Conv / BatchNormalization / SE / Erf-GELU nodes, attention Linears renamed by the exporter,
+    no metadata).  The engine binds it by parameter name plus graph edges (`bind_fastvit_graph`); two independent
+    executors of the same file are the reference: the oracle's ONNX interpreter and, with the batch baked in, OpenCV's
+    DNN module (its own convolution kernels)."""
+    import clip_embedder_rs_b200 as cb
+    from oracle import onnx_interp as oi
+    from oracle import reference_forward as R
+
+    mdir = make_real_model("mobileclip2_s2", towers=("vision",))
+    vis = cb.VisionEmbedder.from_local_dir(mdir).build()
+    assert vis.session.image_size == 256 and vis.session.embed_dim == 512
+    imgs = random_images(4, 256, seed=6)
+    pc = vis.config.preprocess_cfg
+    pv = R.preprocess_batch(list(imgs), 256, pc.mean, pc.std)
+    want = oi.OnnxSession(os.path.join(mdir, "visual.onnx")).run({"pixel_values": pv})
+    got = vis.embed_images(imgs)
+    cos = cosine_rows(got, want)
+    print(f"\n[C2 real export] cos >= {cos.min():.6f} max_abs {np.abs(got - want).max():.2e}")
+    assert got.shape == (4, 512) and cos.min() >= COS_BAR
+    cv2 = pytest.importorskip("cv2")
+    import export_synthetic as ex
+    import torch
+    import torch_export as te
+
+    model = te.build_model(ex.CONFIGS["mobileclip2_s2"], 0, towers=("vision",))
+    path = str(tmp_path / "s2_static.onnx")
+    te.export_tower(te.VisualWrapper(model), torch.from_numpy(pv[:2]), path, "pixel_values", "image_embeddings",
+                    dynamic_batch=False, external_data=False)
+    net = cv2.dnn.readNetFromONNX(path)
+    net.setInput(pv[:2], "pixel_values")
+    got_cv = net.forward()
+    print(f"[C2 real export] OpenCV DNN vs interpreter {np.abs(got_cv - want[:2]).max():.2e}, engine vs OpenCV cos >= "
+          f"{cosine_rows(got[:2], got_cv).min():.6f}")
+    assert np.abs(got_cv - want[:2]).max() < 1e-4
+    assert cosine_rows(got[:2], got_cv).min() >= COS_BAR
+
+
 def test_c3_so400m_real_export_full_size(make_real_model):
     """BASELINE config C3 as the reference would receive it: a full-size `torch.onnx.export` graph (27 x 1152, MAP head,
     1.7 GB of external fp32 weights), every initializer anonymised.  The engine binds it from graph structure; the

@@ -260,3 +260,68 @@ def test_opencv_dnn_runs_the_same_file(tmp_path, make_model, config, tower):
     assert j["graph"]["recognized"], j["graph"]["error"]
     spec = ex.CONFIGS[config]
     assert int(j["metadata"]["clipb200.heads"]) == (spec.vision.heads if tower == "vision" else spec.text.heads)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Re-parameterised FastViT (MobileCLIP2) as a REAL exported graph: Conv / BatchNormalization / Sigmoid / Relu / Erf nodes.
+# Until round 2 the FastViT restatement of the oracle had no independent implementation beside it; now the same seeded
+# weights go through (1) the timm-shaped nn.Module of tools/torch_export.py, (2) the file torch.onnx.export writes,
+# executed by the oracle's ONNX interpreter and (3) by OpenCV's DNN module, and (4) the functional oracle.
+FASTVIT_CASES = ["tiny_mobileclip", "tiny_mobileclip5"]   # 4 stages / attention in the last; 5 stages / attention in the last two
+
+
+@pytest.mark.parametrize("config", FASTVIT_CASES)
+def test_fastvit_real_graph_matches_module_interpreter_and_functional_oracle(make_real_model, make_model, config):
+    spec = ex.CONFIGS[config]
+    real = make_real_model(config, towers=("vision",))
+    synth = make_model(config)
+    model = te.build_model(spec, 0, towers=("vision",))
+    s = spec.vision.image_size
+    x = np.random.default_rng(0).random((3, 3, s, s)).astype(np.float32)
+    with torch.no_grad():
+        want = te.VisualWrapper(model)(torch.from_numpy(x)).numpy()
+    sess = oi.OnnxSession(os.path.join(real, "visual.onnx"))
+    assert sess.input_names == ["pixel_values"]
+    got = sess.run({"pixel_values": x})
+    assert np.abs(got - want).max() < 2e-6
+    assert np.abs(sess.run({"pixel_values": x[:1]}) - want[:1]).max() < 2e-6     # dynamic batch axis
+    fv = R.vision_forward(R.Tower(os.path.join(synth, "visual.onnx")), x)
+    assert np.abs(fv - got).max() < 1e-5, "the functional FastViT restatement and the executed graph disagree"
+    # embeddings of different images must differ (a collapsed random network would make every comparison vacuous)
+    assert (got[0] @ got[1]) < 0.999
+
+
+@pytest.mark.parametrize("config", FASTVIT_CASES)
+def test_fastvit_real_graph_binds_by_name_plus_graph(make_real_model, config):
+    """`torch.onnx.export` keeps every FastViT parameter under its module name except the attention blocks' two Linear
+    weights (pre-transposed and renamed `onnx::MatMul_<n>`); `bind_fastvit_graph` (csrc/onnx_graph.cc) finds those from
+    the named BatchNorm scale / proj bias next to them.  Every tensor the engine loads must come back exactly."""
+    spec = ex.CONFIGS[config]
+    path = os.path.join(make_real_model(config, towers=("vision",)), "visual.onnx")
+    j = inspect_onnx(path)
+    assert j["graph"]["attempted"] and not j["graph"]["recognized"] and j["graph"]["fastvit_by_name"], j["graph"]
+    n_attn = sum(spec.vision.depths[len(spec.vision.dims) - spec.vision.attn_stages:])
+    assert int(j["metadata"]["clipb200.fastvit_graph_linears"]) == 2 * n_attn
+    w = {}
+    ex.gen_vision(spec, 0, lambda n, a: w.__setitem__(n, np.array(a)))
+    renamed = [k for k in w if k.endswith("token_mixer.qkv.weight") or k.endswith("token_mixer.proj.weight")]
+    assert len(renamed) == 2 * n_attn
+    for k, v in w.items():
+        got = read_onnx_tensor(path, k)
+        assert got.shape == v.shape and np.array_equal(got, v.astype(np.float32)), k
+
+
+def test_opencv_dnn_runs_the_fastvit_graph(tmp_path, make_model):
+    cv2 = pytest.importorskip("cv2")
+    config = "tiny_mobileclip"
+    path, in_name, feed, want = _export_static(tmp_path, config, "vision")
+    net = cv2.dnn.readNetFromONNX(path)
+    net.setInput(feed, in_name)
+    got_cv = net.forward()
+    got_interp = oi.OnnxSession(path).run({in_name: feed})
+    got_oracle = R.vision_forward(R.Tower(os.path.join(make_model(config), "visual.onnx")), feed)
+    assert got_cv.shape == want.shape
+    assert np.abs(got_cv - want).max() < 5e-6
+    assert np.abs(got_cv - got_interp).max() < 5e-6
+    assert np.abs(got_cv - got_oracle).max() < 1e-5
+    assert inspect_onnx(path)["graph"]["fastvit_by_name"]

@@ -175,3 +175,29 @@ def test_declined_graph_is_refused_not_guessed(make_real_model, tmp_path):
     with pytest.raises(cb.ClipError) as ei:
         OnnxSession(txt)
     assert ei.value.code == _native.ERR_UNSUPPORTED and "attention_mask" in str(ei.value)
+
+
+@pytest.mark.parametrize("config", ["tiny_mobileclip", "tiny_mobileclip5"])
+def test_fastvit_real_export(make_real_model, make_model, config):
+    """A re-parameterised FastViT trunk exported as a real graph (Conv / BatchNormalization / ... nodes, the attention
+    Linears renamed by the exporter, no `clipb200.*` metadata, image size only in the input's declared shape): the engine
+    must agree with the ONNX interpreter executing the same file, and bit-for-bit with itself loaded from the
+    initializer-only file of the same weights."""
+    import clip_embedder_rs_b200 as cb
+    from oracle import onnx_interp as oi
+    from oracle import reference_forward as R
+
+    mdir = make_real_model(config, towers=("vision",))
+    vis = cb.VisionEmbedder.from_local_dir(mdir).build()
+    size = vis.config.model_cfg.vision_cfg.image_size
+    assert vis.session.image_size == size
+    pc = vis.config.preprocess_cfg
+    imgs = random_images(5, size, seed=41)
+    pv = R.preprocess_batch(list(imgs), size, pc.mean, pc.std)
+    want = oi.OnnxSession(os.path.join(mdir, "visual.onnx")).run({"pixel_values": pv})
+    got = vis.embed_images(imgs)
+    c = cosine_rows(got, want)
+    print(f"\n[{config} real graph] vision cos >= {c.min():.6f} (max abs {np.abs(got - want).max():.2e})")
+    assert c.min() >= COS_BAR
+    same = cb.VisionEmbedder.from_local_dir(make_model(config)).build().embed_images(imgs)
+    assert np.array_equal(got, same)

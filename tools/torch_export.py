@@ -7,7 +7,9 @@ that are laid out like the classes `open_clip.create_model_and_transforms` build
   * `ClipVisionTower` / `ClipTextTower`  — open_clip `VisionTransformer` / `CLIP.encode_text` / `TextTransformer`:
     `nn.MultiheadAttention` residual blocks, class token, `ln_pre` / `ln_post`, `x @ proj`, EOT-argmax or last pooling;
   * `TimmVisionTower`  — timm `VisionTransformer` trunk with fused-qkv `Attention` (scaled_dot_product_attention) and
-    the `AttentionPoolLatent` MAP head.
+    the `AttentionPoolLatent` MAP head;
+  * `FastVitVisionTower`  — timm `FastVit` (MobileCLIP2's fastvit_mci2 / mci3 / mci4) as `reparameterize_model` leaves
+    it: one `reparam_conv` per block branch set, ConvMlp, RepCPE + BatchNorm + attention blocks in the last stage(s).
 
 They are wrapped exactly like `pull_onnx.py:53-68` (`self.model = ...`, `encode_image(x, normalize=True)`), exported
 with `opset_version=18, do_constant_folding=True, dynamic_axes={name: {0: "batch_size"}}` and dummy batch 2
@@ -262,6 +264,175 @@ class TimmVisionTower(nn.Module):
         return self.trunk(x)
 
 
+# ----------------------------------------------------------------------------- timm FastViT (MobileCLIP2), re-parameterised
+class _SqueezeExcite(nn.Module):  # timm SqueezeExcite with 1x1 convs: fc1 -> ReLU -> fc2 -> sigmoid gate
+    def __init__(self, ch: int, rd: int):
+        super().__init__()
+        self.fc1 = nn.Conv2d(ch, rd, 1)
+        self.fc2 = nn.Conv2d(rd, ch, 1)
+
+    def forward(self, x):
+        s = x.mean((2, 3), keepdim=True)
+        return x * torch.sigmoid(self.fc2(F.relu(self.fc1(s))))
+
+
+class _RepConv(nn.Module):
+    """timm `MobileOneBlock` / `ReparamLargeKernelConv` / `RepCPE` / `RepMixer` after `reparameterize_model`
+    (pull_onnx.py:110-116): every branch and BatchNorm folded into one `reparam_conv`, then the optional SE and GELU."""
+
+    def __init__(self, cin, cout, k, stride=1, groups=1, se_rd: int = 0, act: bool = True):
+        super().__init__()
+        self.reparam_conv = nn.Conv2d(cin, cout, k, stride, k // 2, groups=groups)
+        if se_rd:
+            self.se = _SqueezeExcite(cout, se_rd)
+        self.has_se, self.has_act = bool(se_rd), act
+
+    def forward(self, x):
+        x = self.reparam_conv(x)
+        if self.has_se:
+            x = self.se(x)
+        return F.gelu(x) if self.has_act else x
+
+
+class _ConvNorm(nn.Module):  # timm ConvNormAct of ConvMlp with the BatchNorm folded: `.conv`
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 7, 1, 3, groups=c)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class _ConvMlp(nn.Module):
+    def __init__(self, c, hidden):
+        super().__init__()
+        self.conv = _ConvNorm(c)
+        self.fc1 = nn.Conv2d(c, hidden, 1)
+        self.fc2 = nn.Conv2d(hidden, c, 1)
+
+    def forward(self, x):
+        return self.fc2(F.gelu(self.fc1(self.conv(x))))
+
+
+class _LayerScale2d(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(c, 1, 1))
+
+    def forward(self, x):
+        return x * self.gamma
+
+
+class _RepMixerBlock(nn.Module):
+    def __init__(self, c, hidden):
+        super().__init__()
+        self.token_mixer = _RepConv(c, c, 3, groups=c, act=False)
+        self.mlp = _ConvMlp(c, hidden)
+        self.layer_scale = _LayerScale2d(c)
+
+    def forward(self, x):
+        x = self.token_mixer(x)
+        return x + self.layer_scale(self.mlp(x))
+
+
+class _FastVitAttention(nn.Module):  # timm fastvit.Attention: tokens = flattened pixels, head dim 32, no qkv bias
+    def __init__(self, c):
+        super().__init__()
+        self.heads = c // 32
+        self.qkv = nn.Linear(c, 3 * c, bias=False)
+        self.proj = nn.Linear(c, c)
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        t = x.flatten(2).transpose(-2, -1)
+        qkv = self.qkv(t).reshape(B, H * W, 3, self.heads, 32).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv[0], qkv[1], qkv[2]
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, H * W, C)
+        return self.proj(o).transpose(-2, -1).reshape(B, C, H, W)
+
+
+class _AttentionBlock(nn.Module):
+    def __init__(self, c, hidden):
+        super().__init__()
+        self.norm = nn.BatchNorm2d(c)
+        self.token_mixer = _FastVitAttention(c)
+        self.layer_scale_1 = _LayerScale2d(c)
+        self.mlp = _ConvMlp(c, hidden)
+        self.layer_scale_2 = _LayerScale2d(c)
+
+    def forward(self, x):
+        x = x + self.layer_scale_1(self.token_mixer(self.norm(x)))
+        return x + self.layer_scale_2(self.mlp(x))
+
+
+class _PatchEmbed(nn.Module):  # stage downsampling: 7x7 s2 depthwise (+ SE) -> GELU -> 1x1 -> GELU
+    def __init__(self, cin, cout, se_rd):
+        super().__init__()
+        self.proj = nn.Sequential(_RepConv(cin, cout, 7, 2, groups=cin, se_rd=se_rd), _RepConv(cout, cout, 1))
+
+    def forward(self, x):
+        return self.proj(x)
+
+
+class _FastVitStage(nn.Module):
+    def __init__(self, cin, c, depth, hidden, down_se_rd, attention: bool):
+        super().__init__()
+        if cin != c:
+            self.downsample = _PatchEmbed(cin, c, down_se_rd)
+        if attention:
+            self.pos_emb = _RepConv(c, c, 7, groups=c, act=False)   # RepCPE, identity branch folded in
+        self.has_down, self.has_cpe = cin != c, attention
+        self.blocks = nn.Sequential(*[(_AttentionBlock if attention else _RepMixerBlock)(c, hidden) for _ in range(depth)])
+
+    def forward(self, x):
+        if self.has_down:
+            x = self.downsample(x)
+        if self.has_cpe:
+            x = self.pos_emb(x)
+        return self.blocks(x)
+
+
+class _FastVitHead(nn.Module):  # timm ClassifierHead: global average pool + fc
+    def __init__(self, cin, embed):
+        super().__init__()
+        self.fc = nn.Linear(cin, embed)
+
+    def forward(self, x):
+        return self.fc(x.mean((2, 3)))
+
+
+class FastVitTrunk(nn.Module):
+    """timm `FastVit` (fastvit_mci2 / mci3 / mci4) in its re-parameterised inference form; parameter names as timm's."""
+
+    def __init__(self, v: ex.VisionSpec, embed_dim: int, shapes: Dict[str, tuple]):
+        super().__init__()
+        pre = "model.visual.trunk"
+        d0 = v.dims[0]
+        self.stem = nn.Sequential(_RepConv(3, d0, 3, 2), _RepConv(d0, d0, 3, 2, groups=d0), _RepConv(d0, d0, 1))
+        stages, prev = [], d0
+        n = len(v.dims)
+        for i, (c, depth) in enumerate(zip(v.dims, v.depths)):
+            se_key = f"{pre}.stages.{i}.downsample.proj.0.se.fc1.weight"
+            se_rd = shapes[se_key][0] if se_key in shapes else 0
+            stages.append(_FastVitStage(prev, c, depth, v.mlp_ratio * c, se_rd, attention=i >= n - v.attn_stages))
+            prev = c
+        self.stages = nn.Sequential(*stages)
+        self.final_conv = _RepConv(prev, 2 * prev, 3, groups=prev, se_rd=shapes[f"{pre}.final_conv.se.fc1.weight"][0])
+        self.head = _FastVitHead(2 * prev, embed_dim)
+
+    def forward(self, x):
+        return self.head(self.final_conv(self.stages(self.stem(x))))
+
+
+class FastVitVisionTower(nn.Module):
+    def __init__(self, v: ex.VisionSpec, embed_dim: int, shapes):
+        super().__init__()
+        self.trunk = FastVitTrunk(v, embed_dim, shapes)
+
+    def forward(self, x):
+        return self.trunk(x)
+
+
 # ----------------------------------------------------------------------------- CLIP containers + export wrappers
 class ClipModel(nn.Module):
     """`open_clip.CLIP`: `.visual`, text parameters on the model itself."""
@@ -285,10 +456,11 @@ class ClipModel(nn.Module):
 class CustomTextClipModel(nn.Module):
     """`open_clip.CustomTextCLIP`: `.visual` (TimmModel) and `.text` (TextTransformer)."""
 
-    def __init__(self, spec: ex.ModelSpec, towers):
+    def __init__(self, spec: ex.ModelSpec, towers, shapes=None):
         super().__init__()
         if "vision" in towers:
-            self.visual = TimmVisionTower(spec.vision)
+            self.visual = (FastVitVisionTower(spec.vision, spec.embed_dim, shapes) if spec.vision.family == "fastvit"
+                           else TimmVisionTower(spec.vision))
         if "text" in towers:
             self.text = TextTower(spec.text, spec.embed_dim)
 
@@ -320,18 +492,18 @@ class TextWrapper(nn.Module):  # pull_onnx.py:62-68
 
 
 def build_model(spec: ex.ModelSpec, seed: int = 0, towers=("vision", "text")) -> nn.Module:
-    if spec.vision.family == "fastvit":
-        raise ValueError("FastViT graphs are not exported by this tool (initializer-only files cover them)")
     clip_style = spec.text.family == "clip"
-    model = ClipModel(spec, towers) if clip_style else CustomTextClipModel(spec, towers)
     weights: Dict[str, np.ndarray] = {}
     if "vision" in towers:
         ex.gen_vision(spec, seed, lambda n, a: weights.__setitem__(n, a))
     if "text" in towers:
         ex.gen_text(spec, seed, lambda n, a: weights.__setitem__(n, a))
+    shapes = {k: tuple(np.shape(v)) for k, v in weights.items()}
+    model = ClipModel(spec, towers) if clip_style else CustomTextClipModel(spec, towers, shapes)
     sd = {k[len("model."):]: torch.from_numpy(np.array(v)) for k, v in weights.items()}
     missing, unexpected = model.load_state_dict(sd, strict=False)
     assert not unexpected, unexpected
+    missing = [k for k in missing if not k.endswith("num_batches_tracked")]   # BatchNorm bookkeeping, not a weight
     assert not missing, missing
     return model.eval()
 
@@ -401,6 +573,8 @@ def export_tower(module: nn.Module, dummy: torch.Tensor, path: str, in_name: str
     `dynamic_axes`); `external_data=False` keeps the exporter's file as it is, weights inline — the form OpenCV's DNN
     importer (an independent ONNX runtime, used as a cross-check in the tests) can read."""
     _patch_exporter()
+    module.eval()   # a fresh wrapper is in training mode; the exporter restores that mode afterwards, recursively, which
+                    # would leave the wrapped model's BatchNorm layers (FastViT) using batch statistics in eager runs
     kw = dict(dynamic_axes={in_name: {0: "batch_size"}, out_name: {0: "batch_size"}}) if dynamic_batch else {}
     with tempfile.TemporaryDirectory() as tmp, warnings.catch_warnings():
         warnings.simplefilter("ignore")
