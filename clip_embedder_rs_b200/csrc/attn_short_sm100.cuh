@@ -1,0 +1,310 @@
+// Attention for SHORT sequences on sm_100a: T <= 80 tokens, head dim 64 — the CLIP text towers (context 77: ViT-B/32,
+// DFN5B ViT-H/14, MobileCLIP2), whose attention is one key block per (batch, head).
+//
+// Why a second kernel.  attn_sm100.cuh is built around long sequences: two CTAs per SM, each owning 256 TMEM columns and
+// ~110 KB of shared memory for deep K/V rings and an online softmax across key blocks.  At T = 77 an item is ONE block:
+// nothing to pipeline inside it, and its cost is the serial chain (load -> QK^T -> softmax -> PV -> epilogue) of a
+// softmax warp that issues ~1100 instructions at the IPC two resident warps per scheduler allow.  Measured
+// (tests/native/attn_test.bin 17: B = 2048, H = 16, causal): 0.345 ms per launch = 5 900 clocks per item and CTA, the
+// softmax warps busy 95 % of the time (profiles/r02q_attn_t77_timing.log) — 11 % of the DFN5B text step for 1.2 % of
+// its FLOPs.  The cure is occupancy, not a faster chain:
+//
+//   * one item needs S [128 x 80] fp32 = 80 TMEM columns; P (bf16, 40 columns) overwrites S in place once a thread has
+//     read its row, and O [128 x 64] is accumulated in columns 64..127 — overlapping S's tail, which is dead by the time
+//     the PV product is issued.  128 columns per CTA instead of 256  ->  FOUR CTAs per SM;
+//   * shared memory: Q, K, V single-buffered (16 + 10 + 10 KB) + a 16 KB output staging tile = 53 KB per CTA; the next
+//     item's loads are issued as soon as the PV product has retired, under the epilogue;
+//   * the softmax reads S twice in 16-column chunks (row maximum, then exponentials) instead of holding the whole row:
+//     <= 80 registers per thread, which four CTAs of 192 threads need;
+//   * causal towers skip the 16-key chunks that are masked for every row of a warp (rows 0..31 never look past key 31).
+//
+// Same numerics as the long-sequence kernel: bf16 operands, fp32 scores / sums / accumulators, P rounded to bf16.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "attn_sm100.cuh"
+#include "ptx_sm100.cuh"
+
+namespace clipb200 {
+namespace attn_short {
+
+constexpr int HD = 64;          // head dim: one 128-byte swizzle atom per row
+constexpr int BKV = 80;         // keys per item (>= T)
+constexpr int BQ = 128;         // MMA M; rows >= T are never stored
+constexpr int THREADS = 192;    // 4 softmax warps + TMA warp + MMA warp
+constexpr int CTAS_PER_SM = 4;
+constexpr int WARP_TMA = 4, WARP_MMA = 5;
+constexpr int Q_BYTES = BQ * 128;      // the TMA box fills the first 80 rows; the MMA reads 128 (rows 80.. are garbage in, garbage out)
+constexpr int KV_BYTES = BKV * 128;
+constexpr int OUT_WARP = 32 * 128;
+constexpr int OFF_Q = 0, OFF_K = OFF_Q + Q_BYTES, OFF_V = OFF_K + KV_BYTES, OFF_OUT = OFF_V + KV_BYTES;
+constexpr int OFF_BAR = OFF_OUT + 4 * OUT_WARP;
+constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+constexpr int TX_BYTES = 3 * KV_BYTES;   // three boxes of [80 rows][64 bf16]; out-of-range rows arrive as zeros and count
+constexpr int TMEM_COLS = 128;
+constexpr int COL_S = 0, COL_P = 0, COL_O = 64;
+static_assert((SMEM_BYTES + 1024) * CTAS_PER_SM <= 227 * 1024, "shared memory");
+static_assert(TMEM_COLS * CTAS_PER_SM <= 512, "tensor memory");
+static_assert(COL_P + BKV / 2 <= COL_O, "P must not reach into O");
+
+struct Params {
+  int T, H, B, n_items;
+  float scale_log2e;
+};
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
+attn_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, Params p) {
+  extern __shared__ uint8_t attn_short_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_short_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem + OFF_Q;
+  uint8_t* s_k = smem + OFF_K;
+  uint8_t* s_v = smem + OFF_V;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* full = bars + 0;      // producer -> MMA: Q, K, V of the item have landed
+  uint64_t* s_full = bars + 1;    // MMA -> softmax: S complete
+  uint64_t* p_full = bars + 2;    // softmax -> MMA: P written (and S read) by every active thread
+  uint64_t* o_full = bars + 3;    // MMA -> softmax, producer: PV retired (O complete; Q / K / V may be overwritten)
+  uint64_t* o_empty = bars + 4;   // softmax -> MMA: O read out, the next S may overwrite the columns
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int active_warps = (p.T + 31) / 32;   // softmax warps that own at least one real query row (T = 77: three)
+
+  if (warp == WARP_TMA && lane == 0) {
+    ptx::prefetch_tmap(&tm_qkv);
+    ptx::prefetch_tmap(&tm_out);
+    ptx::mbar_init(full, 1);
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(p_full, 32 * active_warps);
+    ptx::mbar_init(o_full, 1);
+    ptx::mbar_init(o_empty, 32 * active_warps);
+    ptx::fence_mbar_init();
+  }
+  if (warp == WARP_MMA) ptx::tmem_alloc<TMEM_COLS>(tmem_base_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);
+
+  if (warp == WARP_TMA) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int h = item % p.H, b = item / p.H;
+        if (it > 0) ptx::mbar_wait(o_full, (it - 1) & 1);   // the previous item's MMAs have finished reading Q, K and V
+        ptx::mbar_arrive_expect_tx(full, TX_BYTES);
+        attn::tma_load_3d(&tm_qkv, full, s_q, h * HD, 0, b);
+        attn::tma_load_3d(&tm_qkv, full, s_k, (p.H + h) * HD, 0, b);
+        attn::tma_load_3d(&tm_qkv, full, s_v, (2 * p.H + h) * HD, 0, b);
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    constexpr uint32_t idesc_qk = attn::make_idesc(BQ, BKV, 0);
+    constexpr uint32_t idesc_pv = attn::make_idesc(BQ, HD, 1);   // V: keys along K, head dim contiguous (MN-major)
+    const uint32_t q_addr = ptx::smem_u32(s_q), k_addr = ptx::smem_u32(s_k), v_addr = ptx::smem_u32(s_v);
+    const uint32_t t_s = tmem_base + COL_S, t_p = tmem_base + COL_P, t_o = tmem_base + COL_O;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      ptx::mbar_wait(full, it & 1);
+      if (it > 0) ptx::mbar_wait(o_empty, (it - 1) & 1);   // S overlaps the previous item's O
+      ptx::tc_fence_after();
+      const uint64_t dq = ptx::make_kmajor_sw128_desc(q_addr), dk = ptx::make_kmajor_sw128_desc(k_addr);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k)
+        ptx::umma_bf16_ss_w(t_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_qk, k != 0 ? 1u : 0u);
+      ptx::umma_commit_w(s_full);
+      ptx::mbar_wait(p_full, it & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < BKV / 16; ++k)
+        ptx::umma_bf16_ts_w(t_o, t_p + static_cast<uint32_t>(k * 8), attn::make_mnmajor_sw128_desc(v_addr + k * 16 * 128), idesc_pv,
+                            k != 0 ? 1u : 0u);
+      ptx::umma_commit_w(o_full);
+    }
+  } else if (warp < active_warps) {
+    // ------------------------------------------------------------------ softmax + epilogue: one query row per thread
+    const int quarter = warp;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + COL_S, t_p = tmem_base + lane_base + COL_P, t_o = tmem_base + lane_base + COL_O;
+    uint8_t* stg = smem + OFF_OUT + quarter * OUT_WARP;
+    // keys this row may look at: 0 .. kmax; chunks of 16 keys beyond the warp's largest kmax are skipped altogether,
+    // chunks that end at or below the warp's smallest kmax need no per-element mask
+    const int kmax = CAUSAL ? (row < p.T - 1 ? row : p.T - 1) : p.T - 1;
+    const int warp_kmax = CAUSAL ? (quarter * 32 + 31 < p.T - 1 ? quarter * 32 + 31 : p.T - 1) : p.T - 1;
+    const int warp_kmin = CAUSAL ? quarter * 32 : p.T - 1;   // smallest kmax among this warp's real rows
+    const int n_chunks = warp_kmax / 16 + 1;
+    const uint64_t scale2 = attn::pack2(p.scale_log2e, p.scale_log2e);
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      const int h = item % p.H, b = item / p.H;
+      ptx::mbar_wait(s_full, it & 1);
+      ptx::tc_fence_after();
+      // pass 1: row maximum of the raw scores over the visible keys
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; ++c) {
+        uint32_t r[16];
+        attn::tmem_ld_32x32_x16(t_s + static_cast<uint32_t>(c * 16), r);
+        ptx::tmem_ld_wait();
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (c * 16 + 15 <= warp_kmin) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(r[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], c * 16 + e <= kmax ? __uint_as_float(r[e]) : -INFINITY);
+        }
+        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      }
+      const float m = mx * p.scale_log2e;   // key 0 is visible to every row, so the maximum is finite for real rows
+      const uint64_t negm2 = attn::pack2(-m, -m);
+      // pass 2: P = exp2(s * scale - m) -> bf16, written over S chunk by chunk (P chunk c lands in columns 8c .. 8c+7,
+      // i.e. inside S chunks <= c, which this thread has already consumed)
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BKV / 16; ++c) {
+        uint32_t pk[8];
+        if (c < n_chunks) {
+          uint32_t r[16];
+          attn::tmem_ld_32x32_x16(t_s + static_cast<uint32_t>(c * 16), r);
+          ptx::tmem_ld_wait();
+          const bool interior = c * 16 + 15 <= warp_kmin;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float p0, p1;
+            const uint64_t a = attn::fma2(attn::pack2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), scale2, negm2);
+            if ((e & 3) == 3) {   // a quarter of the exponentials on the FMA pipe (the MUFU is the shared resource of 16 warps)
+              attn::exp2_poly_pair(a, p0, p1);
+            } else {
+              float a0, a1;
+              attn::unpack2(a, a0, a1);
+              p0 = attn::ex2(a0);
+              p1 = attn::ex2(a1);
+            }
+            if (!interior) {
+              if (c * 16 + 2 * e > kmax) p0 = 0.f;
+              if (c * 16 + 2 * e + 1 > kmax) p1 = 0.f;
+            }
+            l0 += p0;
+            l1 += p1;
+            pk[e] = attn::pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pk[e] = 0u;   // masked for the whole warp: P = 0 (the PV product reads all 80 keys)
+        }
+        attn::tmem_st_32x32_x8(t_p + static_cast<uint32_t>(c * 8), pk);
+      }
+      attn::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(p_full);
+      // epilogue: O / l -> bf16 -> staging tile (128-byte rows, 16-byte chunks XOR-swizzled like the output map) -> TMA store
+      const float l = l0 + l1;
+      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      ptx::mbar_wait(o_full, it & 1);
+      ptx::tc_fence_after();
+      if (lane == 0) ptx::tma_store_wait_read<0>();   // the previous item's store has left the staging tile
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < HD / 16; ++c) {
+        uint32_t r[16];
+        attn::tmem_ld_32x32_x16(t_o + static_cast<uint32_t>(c * 16), r);
+        ptx::tmem_ld_wait();
+        uint4 o0, o1;
+        o0.x = attn::pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+        o0.y = attn::pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+        o0.z = attn::pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+        o0.w = attn::pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+        o1.x = attn::pack_bf16(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
+        o1.y = attn::pack_bf16(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
+        o1.z = attn::pack_bf16(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
+        o1.w = attn::pack_bf16(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
+        *reinterpret_cast<uint4*>(stg + lane * 128 + (((2 * c) ^ (lane & 7)) << 4)) = o0;
+        *reinterpret_cast<uint4*>(stg + lane * 128 + (((2 * c + 1) ^ (lane & 7)) << 4)) = o1;
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(o_empty);   // O is in registers / shared memory: the next item's S may overwrite it
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        attn::tma_store_3d(&tm_out, stg, h * HD, quarter * 32, b);   // rows >= T are clipped by the tensor map
+        ptx::tma_store_commit();
+      }
+    }
+    if (lane == 0) ptx::tma_store_wait<0>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+inline cudaError_t configure() {
+  cudaError_t e = cudaFuncSetAttribute(attn_short_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(attn_short_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+}
+
+inline cudaError_t launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, bool causal, int num_sms,
+                          cudaStream_t st) {
+  struct Maps {
+    const void *qkv, *out;
+    int B, T, H;
+    CUtensorMap in, o;
+  };
+  static thread_local std::vector<Maps> cache;
+  const Maps* m = nullptr;
+  for (const Maps& c : cache)
+    if (c.qkv == qkv && c.out == out && c.B == B && c.T == T && c.H == H) { m = &c; break; }
+  if (m == nullptr) {
+    Maps n;
+    n.qkv = qkv; n.out = out; n.B = B; n.T = T; n.H = H;
+    if (!attn::make_tmap_3d(&n.in, qkv, 3ull * H * HD, T, B, 64, BKV, true)) return cudaErrorUnknown;
+    if (!attn::make_tmap_3d(&n.o, out, static_cast<uint64_t>(H) * HD, T, B, HD, 32, true)) return cudaErrorUnknown;
+    if (cache.size() >= 64) cache.clear();
+    cache.push_back(n);
+    m = &cache.back();
+  }
+  Params p;
+  p.T = T; p.H = H; p.B = B;
+  p.n_items = B * H;
+  p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  const int slots = CTAS_PER_SM * num_sms;
+  const int grid = p.n_items < slots ? p.n_items : slots;
+  if (causal) attn_short_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(m->in, m->o, p);
+  else attn_short_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(m->in, m->o, p);
+  return cudaGetLastError();
+}
+
+}  // namespace attn_short
+
+inline bool attn_short_supported(int hd, int T) { return hd == attn_short::HD && T >= 1 && T <= attn_short::BKV; }
+
+inline cudaError_t attn_configure_all() {
+  cudaError_t e = attn_tcgen05_configure_device();
+  if (e != cudaSuccess) return e;
+  return attn_short::configure();
+}
+// Natural-layout attention with the kernel picked by shape: the short-sequence kernel where it applies
+// (CLIPB200_ATTN_SHORT=0 forces the long-sequence kernel everywhere, for A/B runs), else attn_tcgen05.
+inline cudaError_t attn_auto(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, bool causal,
+                             int num_sms, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  static const bool short_on = [] {
+    const char* env = getenv("CLIPB200_ATTN_SHORT");
+    return env == nullptr || atoi(env) != 0;
+  }();
+  if (short_on && attn_short_supported(hd, T)) return attn_short::launch(qkv, out, B, T, H, causal, num_sms, st);
+  return attn_tcgen05(qkv, out, B, T, H, hd, causal, num_sms, st);
+}
+
+}  // namespace clipb200

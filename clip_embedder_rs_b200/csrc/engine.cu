@@ -9,6 +9,7 @@
 #include <thread>
 
 #include "attn_sm100.cuh"
+#include "attn_short_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "conv_kernels.cuh"
 #include "kernels.cuh"
@@ -530,7 +531,7 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
   if (const char* env = getenv("CLIPB200_NO_GRAPHS")) if (atoi(env) != 0) graph_max_n_ = 0;
   CUDA_RET(gemm_configure_device(), "configure GEMM kernels");
   CUDA_RET(flash_attention_configure_device(), "configure attention kernels");
-  CUDA_RET(attn_tcgen05_configure_device(), "configure tcgen05 attention kernels");
+  CUDA_RET(attn_configure_all(), "configure tcgen05 attention kernels");
   CUDA_RET(dwconv_tma_configure_device(), "configure depthwise-conv kernels");
   for (int k = 0; k < 2; ++k) CUDA_RET(cudaStreamCreateWithFlags(&lanes_[k].stream, cudaStreamNonBlocking), "stream");
   compute_ = lanes_[0].stream;
@@ -708,7 +709,7 @@ Status Engine::Blocks(int rows, int n_seq, int T, bool causal) {
     // tcgen05/TMEM kernel for head dims >= 64; the mma.sync kernel remains for head dim 32 (FastViT-style heads)
     if (vt) e = attn_tcgen05_vt(qkv_, vt_, h_, n_seq, T, H_, hd_, causal, num_sms_, compute_);
     else
-      e = attn_tcgen05_supported(hd_) ? attn_tcgen05(qkv_, h_, n_seq, T, H_, hd_, causal, num_sms_, compute_)
+      e = attn_tcgen05_supported(hd_) ? attn_auto(qkv_, h_, n_seq, T, H_, hd_, causal, num_sms_, compute_)
                                       : launch_flash_attention(qkv_, h_, n_seq, T, H_, hd_, causal, compute_);
     ProfEnd(PC_ATTN, compute_);
     CUDA_RET(e, "attention");

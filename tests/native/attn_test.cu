@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../clip_embedder_rs_b200/csrc/attn_sm100.cuh"
+#include "../../clip_embedder_rs_b200/csrc/attn_short_sm100.cuh"
 #include "../../clip_embedder_rs_b200/csrc/kernels.cuh"
 
 using namespace clipb200;
@@ -88,7 +89,7 @@ static int run_case(int B, int T, int H, int hd, bool causal, bool time_it, int 
   transpose_v<<<(unsigned)(((size_t)B * T * H * hd + 255) / 256), 256>>>(qkv, vt, B, T, H, hd, ld);
   static const bool use_vt = getenv("ATTN_NO_VT") == nullptr;
   auto tc = [&](__nv_bfloat16* o) {
-    return use_vt ? attn_tcgen05_vt(qkv, vt, o, B, T, H, hd, causal, num_sms, 0) : attn_tcgen05(qkv, o, B, T, H, hd, causal, num_sms, 0);
+    return use_vt ? attn_tcgen05_vt(qkv, vt, o, B, T, H, hd, causal, num_sms, 0) : attn_auto(qkv, o, B, T, H, hd, causal, num_sms, 0);
   };
   CK(launch_flash_attention(qkv, o1, B, T, H, hd, causal, 0));
   CK(tc(o2));
@@ -167,7 +168,7 @@ int main(int argc, char** argv) {
   CK(cudaGetDeviceProperties(&prop, 0));
   const int num_sms = getenv("ATTN_HALF_GRID") ? prop.multiProcessorCount / 2 : prop.multiProcessorCount;
   CK(flash_attention_configure_device());
-  CK(attn_tcgen05_configure_device());
+  CK(attn_configure_all());
   int fails = 0;
   const int only = argc > 1 ? atoi(argv[1]) : -1;
   int idx = 0;
