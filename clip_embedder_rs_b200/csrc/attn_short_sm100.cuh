@@ -13,10 +13,11 @@
 //     read its row, and O [128 x 64] is accumulated in columns 64..127 — overlapping S's tail, which is dead by the time
 //     the PV product is issued.  128 columns per CTA instead of 256  ->  FOUR CTAs per SM;
 //   * shared memory: Q, K, V single-buffered (16 + 10 + 10 KB) + a 16 KB output staging tile = 53 KB per CTA; the next
-//     item's loads are issued as soon as the PV product has retired, under the epilogue;
-//   * the softmax reads S twice in 16-column chunks (row maximum, then exponentials) instead of holding the whole row:
-//     <= 80 registers per thread, which four CTAs of 192 threads need;
-//   * causal towers skip the 16-key chunks that are masked for every row of a warp (rows 0..31 never look past key 31).
+//     item's Q and K are requested as soon as this item's QK^T has retired and its V as soon as the PV product has, so
+//     they arrive under the softmax / epilogue;
+//   * the softmax reads S twice in 32-column blocks (row maximum, then exponentials) instead of holding the whole row:
+//     <= 85 registers per thread, which four CTAs of 192 threads need;
+//   * causal towers skip the key blocks that are masked for every row of a warp (rows 0..31 never look past key 31).
 //
 // Same numerics as the long-sequence kernel: bf16 operands, fp32 scores / sums / accumulators, P rounded to bf16.
 #pragma once
@@ -45,7 +46,7 @@ constexpr int OUT_WARP = 32 * 128;
 constexpr int OFF_Q = 0, OFF_K = OFF_Q + Q_BYTES, OFF_V = OFF_K + KV_BYTES, OFF_OUT = OFF_V + KV_BYTES;
 constexpr int OFF_BAR = OFF_OUT + 4 * OUT_WARP;
 constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
-constexpr int TX_BYTES = 3 * KV_BYTES;   // three boxes of [80 rows][64 bf16]; out-of-range rows arrive as zeros and count
+// every TMA box is [80 rows][64 bf16]; out-of-range rows arrive as zeros and count toward the transaction bytes
 constexpr int TMEM_COLS = 128;
 constexpr int COL_S = 0, COL_P = 0, COL_O = 64;
 static_assert((SMEM_BYTES + 1024) * CTAS_PER_SM <= 227 * 1024, "shared memory");
@@ -57,6 +58,65 @@ struct Params {
   float scale_log2e;
 };
 
+template <int N>
+__device__ __forceinline__ void ld_cols(uint32_t taddr, uint32_t (&r)[N]) {
+  static_assert(N == 32 || N == 16, "chunk width");
+  if constexpr (N == 32) ptx::tmem_ld_32x32(taddr, r);
+  else attn::tmem_ld_32x32_x16(taddr, r);
+}
+// max of this thread's scores in columns [taddr, taddr + N) = keys [k0, k0 + N); keys > kmax are masked
+template <int N>
+__device__ __forceinline__ float chunk_max(uint32_t taddr, int k0, int kmax, bool interior) {
+  uint32_t r[N];
+  ld_cols<N>(taddr, r);
+  ptx::tmem_ld_wait();
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  if (interior) {
+#pragma unroll
+    for (int e = 0; e < N; ++e) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(r[e]));
+  } else {
+#pragma unroll
+    for (int e = 0; e < N; ++e) m4[e & 3] = fmaxf(m4[e & 3], k0 + e <= kmax ? __uint_as_float(r[e]) : -INFINITY);
+  }
+  return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+}
+// P = exp2(s * scale - m) for keys [k0, k0 + N) as packed bf16 into N / 2 columns at t_p; `live` false: zeros
+template <int N>
+__device__ __forceinline__ void chunk_exp(uint32_t t_s, uint32_t t_p, int k0, int kmax, bool interior, bool live,
+                                          uint64_t scale2, uint64_t negm2, float& l0, float& l1) {
+  uint32_t pk[N / 2];
+  if (live) {   // warp-uniform
+    uint32_t r[N];
+    ld_cols<N>(t_s, r);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < N / 2; ++e) {
+      float p0, p1;
+      const uint64_t a = attn::fma2(attn::pack2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), scale2, negm2);
+      if ((e & 3) == 3) {   // a quarter of the exponentials on the FMA pipe (the MUFU is shared by 16 resident warps)
+        attn::exp2_poly_pair(a, p0, p1);
+      } else {
+        float a0, a1;
+        attn::unpack2(a, a0, a1);
+        p0 = attn::ex2(a0);
+        p1 = attn::ex2(a1);
+      }
+      if (!interior) {
+        if (k0 + 2 * e > kmax) p0 = 0.f;
+        if (k0 + 2 * e + 1 > kmax) p1 = 0.f;
+      }
+      l0 += p0;
+      l1 += p1;
+      pk[e] = attn::pack_bf16(p0, p1);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < N / 2; ++e) pk[e] = 0u;
+  }
+  if constexpr (N == 32) attn::tmem_st_32x32_x16(t_p, pk);
+  else attn::tmem_st_32x32_x8(t_p, pk);
+}
+
 template <bool CAUSAL>
 __global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
 attn_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, Params p) {
@@ -66,12 +126,13 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
   uint8_t* s_k = smem + OFF_K;
   uint8_t* s_v = smem + OFF_V;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* full = bars + 0;      // producer -> MMA: Q, K, V of the item have landed
-  uint64_t* s_full = bars + 1;    // MMA -> softmax: S complete
+  uint64_t* full_qk = bars + 0;   // producer -> MMA: Q and K of the item have landed
+  uint64_t* full_v = bars + 6;    // producer -> MMA: V of the item has landed
+  uint64_t* s_full = bars + 1;    // MMA -> softmax, producer: S complete (Q and K may be overwritten)
   uint64_t* p_full = bars + 2;    // softmax -> MMA: P written (and S read) by every active thread
-  uint64_t* o_full = bars + 3;    // MMA -> softmax, producer: PV retired (O complete; Q / K / V may be overwritten)
+  uint64_t* o_full = bars + 3;    // MMA -> softmax, producer: PV retired (O complete; V may be overwritten)
   uint64_t* o_empty = bars + 4;   // softmax -> MMA: O read out, the next S may overwrite the columns
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int active_warps = (p.T + 31) / 32;   // softmax warps that own at least one real query row (T = 77: three)
@@ -79,7 +140,8 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
   if (warp == WARP_TMA && lane == 0) {
     ptx::prefetch_tmap(&tm_qkv);
     ptx::prefetch_tmap(&tm_out);
-    ptx::mbar_init(full, 1);
+    ptx::mbar_init(full_qk, 1);
+    ptx::mbar_init(full_v, 1);
     ptx::mbar_init(s_full, 1);
     ptx::mbar_init(p_full, 32 * active_warps);
     ptx::mbar_init(o_full, 1);
@@ -97,11 +159,15 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
       uint32_t it = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
         const int h = item % p.H, b = item / p.H;
-        if (it > 0) ptx::mbar_wait(o_full, (it - 1) & 1);   // the previous item's MMAs have finished reading Q, K and V
-        ptx::mbar_arrive_expect_tx(full, TX_BYTES);
-        attn::tma_load_3d(&tm_qkv, full, s_q, h * HD, 0, b);
-        attn::tma_load_3d(&tm_qkv, full, s_k, (p.H + h) * HD, 0, b);
-        attn::tma_load_3d(&tm_qkv, full, s_v, (2 * p.H + h) * HD, 0, b);
+        // Q and K are free as soon as the previous item's QK^T has retired (its softmax, PV and epilogue still to come),
+        // V once its PV has: the next item's operands arrive under the current item's arithmetic
+        if (it > 0) ptx::mbar_wait(s_full, (it - 1) & 1);
+        ptx::mbar_arrive_expect_tx(full_qk, 2 * KV_BYTES);
+        attn::tma_load_3d(&tm_qkv, full_qk, s_q, h * HD, 0, b);
+        attn::tma_load_3d(&tm_qkv, full_qk, s_k, (p.H + h) * HD, 0, b);
+        if (it > 0) ptx::mbar_wait(o_full, (it - 1) & 1);
+        ptx::mbar_arrive_expect_tx(full_v, KV_BYTES);
+        attn::tma_load_3d(&tm_qkv, full_v, s_v, (2 * p.H + h) * HD, 0, b);
       }
     }
   } else if (warp == WARP_MMA) {
@@ -111,7 +177,7 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
     const uint32_t t_s = tmem_base + COL_S, t_p = tmem_base + COL_P, t_o = tmem_base + COL_O;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-      ptx::mbar_wait(full, it & 1);
+      ptx::mbar_wait(full_qk, it & 1);
       if (it > 0) ptx::mbar_wait(o_empty, (it - 1) & 1);   // S overlaps the previous item's O
       ptx::tc_fence_after();
       const uint64_t dq = ptx::make_kmajor_sw128_desc(q_addr), dk = ptx::make_kmajor_sw128_desc(k_addr);
@@ -119,6 +185,7 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
       for (int k = 0; k < HD / 16; ++k)
         ptx::umma_bf16_ss_w(t_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_qk, k != 0 ? 1u : 0u);
       ptx::umma_commit_w(s_full);
+      ptx::mbar_wait(full_v, it & 1);
       ptx::mbar_wait(p_full, it & 1);
       ptx::tc_fence_after();
 #pragma unroll
@@ -139,69 +206,25 @@ attn_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
     const int kmax = CAUSAL ? (row < p.T - 1 ? row : p.T - 1) : p.T - 1;
     const int warp_kmax = CAUSAL ? (quarter * 32 + 31 < p.T - 1 ? quarter * 32 + 31 : p.T - 1) : p.T - 1;
     const int warp_kmin = CAUSAL ? quarter * 32 : p.T - 1;   // smallest kmax among this warp's real rows
-    const int n_chunks = warp_kmax / 16 + 1;
     const uint64_t scale2 = attn::pack2(p.scale_log2e, p.scale_log2e);
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
       const int h = item % p.H, b = item / p.H;
       ptx::mbar_wait(s_full, it & 1);
       ptx::tc_fence_after();
-      // pass 1: row maximum of the raw scores over the visible keys
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
-        uint32_t r[16];
-        attn::tmem_ld_32x32_x16(t_s + static_cast<uint32_t>(c * 16), r);
-        ptx::tmem_ld_wait();
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        if (c * 16 + 15 <= warp_kmin) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(r[e]));
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], c * 16 + e <= kmax ? __uint_as_float(r[e]) : -INFINITY);
-        }
-        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
-      }
+      // pass 1: row maximum of the raw scores over the visible keys, in blocks of 32 / 32 / 16 columns
+      float mx = chunk_max<32>(t_s, 0, kmax, 31 <= warp_kmin);
+      if (warp_kmax >= 32) mx = fmaxf(mx, chunk_max<32>(t_s + 32, 32, kmax, 63 <= warp_kmin));
+      if (warp_kmax >= 64) mx = fmaxf(mx, chunk_max<16>(t_s + 64, 64, kmax, 79 <= warp_kmin));
       const float m = mx * p.scale_log2e;   // key 0 is visible to every row, so the maximum is finite for real rows
       const uint64_t negm2 = attn::pack2(-m, -m);
-      // pass 2: P = exp2(s * scale - m) -> bf16, written over S chunk by chunk (P chunk c lands in columns 8c .. 8c+7,
-      // i.e. inside S chunks <= c, which this thread has already consumed)
+      // pass 2: P = exp2(s * scale - m) -> bf16, written over S block by block (the P of keys [k0, k0 + n) lands in
+      // columns k0 / 2 .. , i.e. inside S columns this thread has already consumed); blocks that are masked for the
+      // whole warp are written as zeros (the PV product reads all 80 keys)
       float l0 = 0.f, l1 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 16; ++c) {
-        uint32_t pk[8];
-        if (c < n_chunks) {
-          uint32_t r[16];
-          attn::tmem_ld_32x32_x16(t_s + static_cast<uint32_t>(c * 16), r);
-          ptx::tmem_ld_wait();
-          const bool interior = c * 16 + 15 <= warp_kmin;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float p0, p1;
-            const uint64_t a = attn::fma2(attn::pack2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), scale2, negm2);
-            if ((e & 3) == 3) {   // a quarter of the exponentials on the FMA pipe (the MUFU is the shared resource of 16 warps)
-              attn::exp2_poly_pair(a, p0, p1);
-            } else {
-              float a0, a1;
-              attn::unpack2(a, a0, a1);
-              p0 = attn::ex2(a0);
-              p1 = attn::ex2(a1);
-            }
-            if (!interior) {
-              if (c * 16 + 2 * e > kmax) p0 = 0.f;
-              if (c * 16 + 2 * e + 1 > kmax) p1 = 0.f;
-            }
-            l0 += p0;
-            l1 += p1;
-            pk[e] = attn::pack_bf16(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) pk[e] = 0u;   // masked for the whole warp: P = 0 (the PV product reads all 80 keys)
-        }
-        attn::tmem_st_32x32_x8(t_p + static_cast<uint32_t>(c * 8), pk);
-      }
+      chunk_exp<32>(t_s, t_p, 0, kmax, 31 <= warp_kmin, true, scale2, negm2, l0, l1);
+      chunk_exp<32>(t_s + 32, t_p + 16, 32, kmax, 63 <= warp_kmin, warp_kmax >= 32, scale2, negm2, l0, l1);
+      chunk_exp<16>(t_s + 64, t_p + 32, 64, kmax, 79 <= warp_kmin, warp_kmax >= 64, scale2, negm2, l0, l1);
       attn::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(p_full);
