@@ -110,7 +110,7 @@ static int run_case(int B, int T, int H, int hd, bool causal, bool time_it, int 
     }
   }
   // fp32 reference on a few query rows
-  std::vector<int> qsel = {0, 1, T / 2, T - 1};
+  std::vector<int> qsel = {0, T > 1 ? 1 : 0, T / 2, T - 1};
   if (T > 130) { qsel.push_back(127); qsel.push_back(128); qsel.push_back(T - 64); }
   int* dq; float* dref;
   const int nsel = (int)qsel.size();
@@ -195,6 +195,12 @@ int main(int argc, char** argv) {
   run(256, 288, 16, 72, false, true);  // 16: 3 key blocks per item
   run(2048, 77, 16, 64, true, true);   // 17: DFN5B text micro-batch: one causal key block per item
   run(2048, 77, 8, 64, true, true);    // 18: ViT-B/32 text width
+  run(3, 1, 2, 64, true, false);       // 19..24: short-sequence kernel edges (one token; one / two / three active warps; T = 80)
+  run(2, 33, 4, 64, true, false);
+  run(2, 64, 2, 64, false, false);
+  run(5, 65, 3, 64, false, false);
+  run(2, 80, 2, 64, true, false);
+  run(300, 80, 1, 64, false, false);   // more items than resident CTAs: the persistent loop and its parities
 #ifdef CLIPB200_ATTN_TIMING
   {
     unsigned long long h[16];

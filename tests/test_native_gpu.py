@@ -46,6 +46,21 @@ def test_attention_protocol_switches(switch):
         assert out.returncode == 0 and "ATTN TEST PASSED" in out.stdout, (case, out.stdout[-2000:] + out.stderr[-2000:])
 
 
+def test_short_sequence_attention_kernel():
+    """`attn_short_sm100.cuh` (T <= 80, head dim 64: the CLIP text towers) against the mma.sync kernel and the fp32
+    reference: ViT-B/32 vision-like T = 50, causal T = 77, one token, 1 / 2 / 3 active softmax warps, T = 80, and more
+    items than resident CTAs.  `ATTN_NO_VT=1` selects the natural V layout, where the engine's `attn_auto` dispatch picks
+    the short kernel; `CLIPB200_ATTN_SHORT=0` must give the long kernel the same cases."""
+    path = os.path.join(NATIVE, "attn_test.bin")
+    if not os.path.exists(path):
+        pytest.fail(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    for extra in ({}, {"CLIPB200_ATTN_SHORT": "0"}):
+        env = dict(os.environ, ATTN_NO_VT="1", **extra)
+        for case in (6, 8, 19, 20, 21, 22, 23, 24):
+            out = subprocess.run([path, str(case)], capture_output=True, text=True, timeout=120, env=env)
+            assert out.returncode == 0 and "ATTN TEST PASSED" in out.stdout, (extra, case, out.stdout[-2000:] + out.stderr[-2000:])
+
+
 def test_loader_accepts_f16_bf16_and_identity_aliases(make_model, tmp_path):
     """The ONNX loader's claims beyond the synthetic exporter's defaults: fp16 / bf16 initializers, inline
     `float_data`, and exporter-style de-duplication (an `Identity` node aliasing one initializer under a second name)."""
