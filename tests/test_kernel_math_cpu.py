@@ -80,3 +80,35 @@ def test_fast_erf_gelu_matches_exact_gelu():
     want = 0.5 * xd * (1.0 + erf(xd / np.sqrt(2.0)))
     # 4.3e-7 is the formula's own bound; float32 evaluation and the approx MUFU ops add a few ulps
     assert np.abs(got - want).max() < 2.0e-6, np.abs(got - want).max()
+
+
+def test_fused_mlp_relu_form_gelu_matches_exact_gelu():
+    """fused_mlp_sm100.cuh gelu_erf_pair_bf16: gelu(x) = relu(x) - |x| * Phi(-|x|) in packed f32x2 arithmetic (no sign
+    select), same Abramowitz-Stegun constants as gelu_erf_fast.  Restated in float32 with the constants read from the
+    source; the result is rounded to bf16 by the kernel, so 2e-6 absolute is three orders below what H can resolve."""
+    from scipy.special import erf
+
+    src = open(os.path.join(CSRC, "fused_mlp_sm100.cuh")).read()
+    body = src[src.index("uint32_t gelu_erf_pair_bf16("):]
+    body = body[:body.index("\n}\n")]
+    body = body[body.index("#endif"):]   # skip the timing-only experiment branch
+    p = np.float32(re.search(r"f2_fma\(nax, f2_splat\((-[0-9.]+)f\), f2_splat\(1\.0f\)\)", body).group(1))
+    k = np.float32(re.search(r"f2_mul\(f2_mul\(nax, nax\), f2_splat\((-[0-9.]+)f\)\)", body).group(1))
+    a5, a4 = (np.float32(v) for v in re.search(r"q = f2_fma\(t, f2_splat\(([0-9.]+)f\), f2_splat\((-[0-9.]+)f\)\);", body).groups())
+    rest = [np.float32(v) for v in re.findall(r"q = f2_fma\(t, q, f2_splat\((-?[0-9.]+)f\)\);", body)]
+    assert len(rest) == 3 and p < 0
+    assert "f2_fma(nax, h, f2_pack(fmaxf(xa, 0.f), fmaxf(xb, 0.f)))" in body      # relu(x) + (-|x|) * h
+    a3, a2, a1 = rest
+
+    x = np.concatenate([np.linspace(-12, 12, 480001), np.random.default_rng(1).normal(0, 2, 200000)]).astype(np.float32)
+    nax = -np.abs(x)
+    t = (np.float32(1) / (nax * p + np.float32(1))).astype(np.float32)
+    e = np.exp2(((nax * nax).astype(np.float32) * k).astype(np.float32)).astype(np.float32)
+    q = (t * a5 + a4).astype(np.float32)
+    for a in (a3, a2, a1):
+        q = (t * q + a).astype(np.float32)
+    h = ((q * t).astype(np.float32) * e).astype(np.float32)
+    got = (nax * h + np.maximum(x, np.float32(0))).astype(np.float64)
+    xd = x.astype(np.float64)
+    want = 0.5 * xd * (1.0 + erf(xd / np.sqrt(2.0)))
+    assert np.abs(got - want).max() < 2.0e-6, np.abs(got - want).max()
