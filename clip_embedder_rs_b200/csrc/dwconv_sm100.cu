@@ -33,141 +33,95 @@ __device__ __forceinline__ void tma_load_4d(const void* tmap, uint64_t* bar, voi
       : "memory");
 }
 
-// CLIPB200_DWCONV_PACKED=1 at compile time selects the packed-f32x2 7x7 path below.  Measured on B200 (MobileCLIP2-S2,
-// 256 images, profiles/r02a_bench.json vs r02g_bench.json): depthwise class 8.62 ms scalar vs 8.76 ms packed — FFMA2 with
-// three 64-bit register operands does not issue faster than two FFMAs here, so the scalar path stays the default.
-#ifndef CLIPB200_DWCONV_PACKED
-#define CLIPB200_DWCONV_PACKED 0
-#endif
-constexpr bool kDwPacked = CLIPB200_DWCONV_PACKED != 0;
-[[maybe_unused]] __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-[[maybe_unused]] __device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-[[maybe_unused]] __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
+// (A packed-f32x2 variant of the 7x7 path — pairs of neighbouring output pixels per FFMA2 — was measured neutral in round 2:
+// depthwise class 8.62 ms scalar vs 8.76 ms packed, profiles/r02a_bench.json vs r02g_bench.json; an FFMA2 occupies the FMA
+// pipe for two cycles, so only issue slots are saved.  It lives in the git history)
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 
 template <int K, typename Tout>
 __global__ void __launch_bounds__(DW_THREADS, 2)
 dwconv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ w /*[K*K][C]*/,
-                  const float* __restrict__ bias, Tout* __restrict__ out, int H, int W, int C, int tiles_x) {
+                  const float* __restrict__ bias, Tout* __restrict__ out, int H, int W, int C, int tiles_x,
+                  int tiles_per_img, int total_tiles) {
   constexpr int IW = DW_TW + K - 1, IH = DW_TH + K - 1;
   extern __shared__ __align__(128) float tile[];  // [IH][IW][32]; declared aligned so the reads stay LDS (no generic LD)
   __shared__ __align__(8) uint64_t bar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c0 = blockIdx.y * DW_CI, b = blockIdx.z;
-  const int ty0 = (blockIdx.x / tiles_x) * DW_TH, tx0 = (blockIdx.x % tiles_x) * DW_TW;
+  const int c0 = blockIdx.y * DW_CI;
+  // Persistent over the (image, tile) pairs of one 32-channel block: the K*K taps are fetched ONCE per CTA instead of
+  // once per tile (the per-tile prologue — 49 predicated LDGs with 64-bit address arithmetic, barrier set-up, CTA launch —
+  // was 12 % of the instruction stream of a kernel that is bound by instruction issue), and the next tile's TMA load is
+  // requested as soon as the whole CTA has finished reading the current one, i.e. under the output stores; the second
+  // CTA resident on the SM computes meanwhile.
+  auto issue_load = [&](int t) {
+    const int b = t / tiles_per_img, r = t - b * tiles_per_img;
+    ptx::mbar_arrive_expect_tx(&bar, IH * IW * DW_CI * 4);
+    tma_load_4d(&tm_in, &bar, tile, c0, (r % tiles_x) * DW_TW - K / 2, (r / tiles_x) * DW_TH - K / 2, b);
+  };
   if (threadIdx.x == 0) {
     ptx::mbar_init(&bar, 1);
     ptx::fence_mbar_init();
-    ptx::mbar_arrive_expect_tx(&bar, IH * IW * DW_CI * 4);
-    tma_load_4d(&tm_in, &bar, tile, c0, tx0 - K / 2, ty0 - K / 2, b);
+    if (static_cast<int>(blockIdx.x) < total_tiles) issue_load(blockIdx.x);
   }
   const int c = c0 + lane;
   const bool c_ok = c < C;
   float wk[K * K];
+  {
+    const float* wp = w + c;
 #pragma unroll
-  for (int t = 0; t < K * K; ++t) wk[t] = c_ok ? __ldg(w + t * C + c) : 0.f;
+    for (int t = 0; t < K * K; ++t, wp += C) wk[t] = c_ok ? __ldg(wp) : 0.f;
+  }
   const float bv = c_ok ? __ldg(bias + c) : 0.f;
   __syncthreads();  // the barrier init is visible to everyone
-  ptx::mbar_wait(&bar, 0);
-
   const int r0 = warp * 2;  // this warp's two output rows inside the tile
-  if constexpr (K == 7 && kDwPacked) {
-    // 7x7: 49 FMAs per output made the kernel FFMA-issue bound (81 % of the 64 FMA/clk/SM three-register FFMA rate,
-    // profiles/r01f).  Packed f32x2 FMAs (FFMA2) do two outputs per issue slot: accumulators are pairs of neighbouring
-    // output pixels (x, x+1); the input pair (x+kx, x+kx+1) comes from one of two register copies of the staged row —
-    // `ev` holds the pairs that start at an even column, `od` those that start at an odd one — so every FFMA2 operand is
-    // an aligned register pair and no per-FMA shuffling is needed.  Costs twice the LDS (still under the FFMA2 time).
-    uint64_t acc0[DW_TW / 2], acc1[DW_TW / 2];
-#pragma unroll
-    for (int x = 0; x < DW_TW / 2; ++x) acc0[x] = acc1[x] = pack_f32x2(bv, bv);
-#pragma unroll
-    for (int iy = 0; iy < K + 1; ++iy) {
-      const float* src = tile + ((r0 + iy) * IW) * DW_CI + lane;
-      uint64_t ev[IW / 2], od[IW / 2];   // IW = 22: ev[i] = (row[2i], row[2i+1]), od[i] = (row[2i+1], row[2i+2])
-#pragma unroll
-      for (int i = 0; i < IW / 2; ++i) {
-        ev[i] = pack_f32x2(src[(2 * i) * DW_CI], src[(2 * i + 1) * DW_CI]);
-        od[i] = pack_f32x2(src[(2 * i + 1) * DW_CI], (2 * i + 2 < IW) ? src[(2 * i + 2) * DW_CI] : 0.f);
-      }
-      if (iy < K) {
-#pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          const uint64_t ww = pack_f32x2(wk[iy * K + kx], wk[iy * K + kx]);
-#pragma unroll
-          for (int x = 0; x < DW_TW / 2; ++x)   // outputs (2x, 2x+1) read columns (2x+kx, 2x+kx+1)
-            acc0[x] = fma_f32x2((kx & 1) ? od[x + kx / 2] : ev[x + kx / 2], ww, acc0[x]);
-        }
-      }
-      if (iy > 0) {
-#pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          const uint64_t ww = pack_f32x2(wk[(iy - 1) * K + kx], wk[(iy - 1) * K + kx]);
-#pragma unroll
-          for (int x = 0; x < DW_TW / 2; ++x)
-            acc1[x] = fma_f32x2((kx & 1) ? od[x + kx / 2] : ev[x + kx / 2], ww, acc1[x]);
-        }
-      }
-    }
-    if (!c_ok) return;
-    const int oy = ty0 + r0;
-    Tout* o0 = out + ((static_cast<long long>(b) * H + oy) * W + tx0) * C + c;
-#pragma unroll
-    for (int x = 0; x < DW_TW / 2; ++x) {
-      float a0, a1, b0, b1;
-      unpack_f32x2(acc0[x], a0, a1);
-      unpack_f32x2(acc1[x], b0, b1);
-      if (tx0 + 2 * x < W) {
-        if (oy < H) store_out(o0 + static_cast<long long>(2 * x) * C, a0);
-        if (oy + 1 < H) store_out(o0 + (static_cast<long long>(W) + 2 * x) * C, b0);
-      }
-      if (tx0 + 2 * x + 1 < W) {
-        if (oy < H) store_out(o0 + static_cast<long long>(2 * x + 1) * C, a1);
-        if (oy + 1 < H) store_out(o0 + (static_cast<long long>(W) + 2 * x + 1) * C, b1);
-      }
-    }
-    return;
-  } else {
+  uint32_t phase = 0;
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, phase ^= 1) {
+    const int b = t / tiles_per_img, r = t - b * tiles_per_img;
+    const int ty0 = (r / tiles_x) * DW_TH, tx0 = (r % tiles_x) * DW_TW;
+    ptx::mbar_wait(&bar, phase);
     float acc0[DW_TW], acc1[DW_TW];
-  #pragma unroll
+#pragma unroll
     for (int x = 0; x < DW_TW; ++x) acc0[x] = acc1[x] = bv;
-  #pragma unroll
+#pragma unroll
     for (int iy = 0; iy < K + 1; ++iy) {  // staged rows r0 .. r0+K feed output rows r0 (taps ky = iy) and r0+1 (ky = iy-1)
       float rv[IW];
       const float* src = tile + ((r0 + iy) * IW) * DW_CI + lane;
-  #pragma unroll
+#pragma unroll
       for (int i = 0; i < IW; ++i) rv[i] = src[i * DW_CI];
       if (iy < K) {
-  #pragma unroll
+#pragma unroll
         for (int x = 0; x < DW_TW; ++x)
-  #pragma unroll
+#pragma unroll
           for (int kx = 0; kx < K; ++kx) acc0[x] = fmaf(rv[x + kx], wk[iy * K + kx], acc0[x]);
       }
       if (iy > 0) {
-  #pragma unroll
+#pragma unroll
         for (int x = 0; x < DW_TW; ++x)
-  #pragma unroll
+#pragma unroll
           for (int kx = 0; kx < K; ++kx) acc1[x] = fmaf(rv[x + kx], wk[(iy - 1) * K + kx], acc1[x]);
       }
     }
-    if (!c_ok) return;
-    const int oy = ty0 + r0;
-    Tout* o0 = out + ((static_cast<long long>(b) * H + oy) * W + tx0) * C + c;
-  #pragma unroll
-    for (int x = 0; x < DW_TW; ++x) {
-      if (tx0 + x < W) {
-        if (oy < H) store_out(o0 + static_cast<long long>(x) * C, acc0[x]);
-        if (oy + 1 < H) store_out(o0 + (static_cast<long long>(W) + x) * C, acc1[x]);
+    __syncthreads();  // every warp has read its rows: the tile may be overwritten
+    if (threadIdx.x == 0 && t + static_cast<int>(gridDim.x) < total_tiles) issue_load(t + gridDim.x);
+    if (c_ok) {
+      const int oy = ty0 + r0;
+      Tout* o0 = out + ((static_cast<long long>(b) * H + oy) * W + tx0) * C + c;
+      Tout* o1 = o0 + static_cast<long long>(W) * C;
+      if (ty0 + DW_TH <= H && tx0 + DW_TW <= W) {   // interior tile (block-uniform): no per-pixel bounds checks
+#pragma unroll
+        for (int x = 0; x < DW_TW; ++x, o0 += C, o1 += C) {
+          store_out(o0, acc0[x]);
+          store_out(o1, acc1[x]);
+        }
+      } else {
+#pragma unroll
+        for (int x = 0; x < DW_TW; ++x, o0 += C, o1 += C) {
+          if (tx0 + x < W) {
+            if (oy < H) store_out(o0, acc0[x]);
+            if (oy + 1 < H) store_out(o1, acc1[x]);
+          }
+        }
       }
     }
   }
@@ -195,8 +149,18 @@ cudaError_t launch_t(const float* in, int n, int H, int W, int C, const float* w
   CUtensorMap tm;
   if (!make_tmap_nhwc_f32(&tm, in, n, H, W, C, IW, IH)) return cudaErrorInvalidValue;
   const int tiles_x = (W + DW_TW - 1) / DW_TW, tiles_y = (H + DW_TH - 1) / DW_TH;
-  dim3 grid(tiles_x * tiles_y, (C + DW_CI - 1) / DW_CI, n);
-  dwconv_tma_kernel<K, Tout><<<grid, DW_THREADS, smem, st>>>(tm, w, bias, out, H, W, C, tiles_x);
+  const int tiles_per_img = tiles_x * tiles_y, total = tiles_per_img * n, cblocks = (C + DW_CI - 1) / DW_CI;
+  // persistent CTAs: two per SM over all channel blocks together
+  static const int resident = [] {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return 2 * sms;
+  }();
+  int per_block = resident / cblocks;
+  if (per_block < 1) per_block = 1;
+  if (per_block > total) per_block = total;
+  dim3 grid(per_block, cblocks, 1);
+  dwconv_tma_kernel<K, Tout><<<grid, DW_THREADS, smem, st>>>(tm, w, bias, out, H, W, C, tiles_x, tiles_per_img, total);
   return cudaGetLastError();
 }
 
