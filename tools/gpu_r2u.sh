@@ -1,19 +1,15 @@
 #!/bin/bash
-# round 2, GPU call U: full GPU suite + smoke + default bench on the final build (short attention kernel, FastViT graph
+# round 2, GPU calls U / Y: full GPU suite + smoke + default bench on the final build (short attention kernel, FastViT graph
 # binding, fused ConvMlp), then ncu --set full of the short attention kernel
 mkdir -p gpurun_out
-timeout 1800 python -m pytest tests -m gpu -x -q -s > gpurun_out/r2u_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2u_pytest.log
-tail -4 gpurun_out/r2u_pytest.log
-timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2u_smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/r2u_smoke.log
-tail -4 gpurun_out/r2u_smoke.log
-timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/r2u_bench.json 2> gpurun_out/r2u_bench.err
+timeout 1800 python -m pytest tests -m gpu -x -q -s > gpurun_out/r2y_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2y_pytest.log
+tail -4 gpurun_out/r2y_pytest.log
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2y_smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/r2y_smoke.log
+tail -4 gpurun_out/r2y_smoke.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/r2y_bench.json 2> gpurun_out/r2y_bench.err
 python - <<'PY'
 import json
-d=json.loads(open("gpurun_out/r2u_bench.json").read().strip().splitlines()[0])
+d=json.loads(open("gpurun_out/r2y_bench.json").read().strip().splitlines()[0])
 r=d["roofline"]; print("bench", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), d["clocks"], {k:round(v,1) for k,v in r["kernel_ms_per_step"].items()}, "frac", round(r["frac"],3))
 print("text", d["text"]["value"]); m=d["mobileclip2"]; print("mobileclip2", m["vision"]["value"], m["text"]["value"])
 PY
-export ATTN_NO_VT=1
-timeout 60 tests/native/attn_test.bin 17 > gpurun_out/r2u_attn17_plain.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_short -s 3 -c 1 -o gpurun_out/r02u_attn_short tests/native/attn_test.bin 17 > gpurun_out/r2u_ncu.log 2>&1
-tail -2 gpurun_out/r2u_ncu.log
