@@ -54,6 +54,9 @@ WORKLOADS = {
     "small_vision": ("small_siglip", "vision", 256, 0.0, "images/s", "small SigLIP-shaped test tower"),
     "so400m_photos": ("so400m_siglip2_384", "vision", 56, 518.94, "images/s",
                       "ViT-SO400M-16-SigLIP2-384 embed_images on photo-sized inputs (GPU resize included)"),
+    # a crop-mode model (resize the shorter side, centre crop): only the rows / columns inside the crop cross PCIe
+    "mobileclip2_photos": ("mobileclip2_s2", "vision", 56, 0.0, "images/s",
+                           "MobileCLIP2-S2 embed_images on photo-sized inputs (GPU resize + centre crop included)"),
 }
 
 
@@ -313,9 +316,12 @@ def run_photos(args):
     from clip_embedder_rs_b200 import _native
 
     lib = _native.lib
-    mdir = model_dir_for("so400m_siglip2_384", ("vision",), 0, 1, lambda: None)
+    cfg_name, _, _, _, _, label = WORKLOADS[args.workload]
+    mdir = model_dir_for(cfg_name, ("vision",), 0, 1, lambda: None)
     emb = cb.VisionEmbedder.from_local_dir(mdir).micro_batch(args.micro_batch).profile(True).build()
     sess = emb.session
+    pc = emb.config.preprocess_cfg
+    size = emb.config.model_cfg.vision_cfg.image_size
     rng = np.random.default_rng(4)
     base = {}
     for (w, h) in set(PHOTO_SIZES):  # one random texture per size, shifted per image (generation is not what is timed)
@@ -359,19 +365,20 @@ def run_photos(args):
         t1 = time.perf_counter()
         k = 0
         for a in imgs[:2]:
-            RZ.resize_rgb8(a, 384, "bicubic", "squash")
+            RZ.resize_rgb8(a, size, pc.interpolation, pc.resize_mode)
             k += 1
         cpu_el = time.perf_counter() - t1
         cpu = {"value": k / cpu_el, "unit": "images/s (resize only)", "cores": 1, "kind": "port",
                "sample": f"{k} photos, oracle/resize.py (numpy) in {cpu_el:.1f} s; the reference README quotes 10-20 ms "
                          "per image for its preprocessing on the author's CPU"}
     ms = prof["ms"]
-    line = {"metric": "SigLIP2-SO400M-384 images/sec from photo-sized inputs (resize on the GPU)", "value": value,
+    line = {"metric": f"{label.split(' embed_images')[0]} images/sec from photo-sized inputs (resize on the GPU)", "value": value,
             "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"ViT-SO400M-16-SigLIP2-384 embed_images on {len(imgs)} photo-sized RGB8 images per step "
+            "config": {"workload": f"{label.split(' embed_images')[0]} embed_images on {len(imgs)} photo-sized RGB8 images per step "
                                    f"(sizes of the reference's assets/img: {sorted(set(PHOTO_SIZES))}), pageable host memory",
-                       "mean_photo_mb": src_bytes / len(imgs) / 1e6},
+                       "mean_photo_mb": src_bytes / len(imgs) / 1e6, "resize_mode": pc.resize_mode,
+                       "interpolation": pc.interpolation, "image_size": size},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": src_bytes, "d2h_bytes_per_step": len(imgs) * out.shape[1] * 4},
             "h2d_gb_per_s": src_bytes * args.steps / el / 1e9,
             "pcie_floor": {"measured_h2d_gb_per_s": pcie / 1e9, "images_per_s": pcie / (src_bytes / len(imgs))},
@@ -396,7 +403,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling and MobileCLIP2 extra keys")
     ap.add_argument("--pool", action="store_true",
                     help="ONE process feeding --gpus N devices through the in-process pool (clipb200_pool_*), no torchrun")
-    ap.add_argument("--photos", type=int, default=56, help="photos per step of --workload so400m_photos")
+    ap.add_argument("--photos", type=int, default=56, help="photos per step of --workload so400m_photos / mobileclip2_photos")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     wl = WORKLOADS[args.workload]
@@ -405,7 +412,7 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, wl, rank, world)
         return
-    if args.workload == "so400m_photos":
+    if args.workload in ("so400m_photos", "mobileclip2_photos"):
         run_photos(args)
         return
     if args.pool:

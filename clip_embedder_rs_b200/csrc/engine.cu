@@ -535,7 +535,18 @@ Status Engine::Init(const std::string& onnx_path, int dev, const clipb200_opts* 
   CUDA_RET(dwconv_tma_configure_device(), "configure depthwise-conv kernels");
   for (int k = 0; k < 2; ++k) CUDA_RET(cudaStreamCreateWithFlags(&lanes_[k].stream, cudaStreamNonBlocking), "stream");
   compute_ = lanes_[0].stream;
-  CUDA_RET(cudaStreamCreateWithFlags(&copy_in_, cudaStreamNonBlocking), "stream");
+  {
+    // copy-in stream (uploads) and resize stream (the photo path's resize kernels, so that the upload of staging group
+    // g + 1 does not queue behind the resize of group g).  CLIPB200_COPY_STREAM_PRIORITY=1 creates both at the highest
+    // priority; measured without effect on the photo workloads (profiles/r02z_photos.md), so the default is normal.
+    int lo = 0, hi = 0;
+    CUDA_RET(cudaDeviceGetStreamPriorityRange(&lo, &hi), "stream priority range");
+    const char* pr = getenv("CLIPB200_COPY_STREAM_PRIORITY");
+    const bool high = pr != nullptr && atoi(pr) != 0;
+    CUDA_RET(cudaStreamCreateWithPriority(&copy_in_, cudaStreamNonBlocking, high ? hi : lo), "stream");
+    CUDA_RET(cudaStreamCreateWithPriority(&resize_, cudaStreamNonBlocking, high ? hi : lo), "stream");
+    if (const char* v = getenv("CLIPB200_PHOTO_STAGES")) rs_stages_ = std::min(std::max(atoi(v), 2), kResizeStages);
+  }
   CUDA_RET(cudaStreamCreateWithFlags(&copy_out_, cudaStreamNonBlocking), "stream");
 
   bool is_text = false;
@@ -594,11 +605,13 @@ Engine::~Engine() {
     if (rs.d_arena) cudaFree(rs.d_arena);
     if (rs.d_jobs) cudaFree(rs.d_jobs);
     if (rs.free_ev) cudaEventDestroy(rs.free_ev);
+    if (rs.h2d_ev) cudaEventDestroy(rs.h2d_ev);
   }
   for (int k = 0; k < 2; ++k) if (lanes_[k].stream) cudaStreamDestroy(lanes_[k].stream);
   if (lane_fork_) cudaEventDestroy(lane_fork_);
   if (lane_join_) cudaEventDestroy(lane_join_);
   if (copy_in_) cudaStreamDestroy(copy_in_);
+  if (resize_) cudaStreamDestroy(resize_);
   if (copy_out_) cudaStreamDestroy(copy_out_);
 }
 
@@ -662,6 +675,7 @@ Status Engine::ElapsedMs(int a, int b, double* ms) {
 Status Engine::Synchronize() {
   CUDA_RET(cudaSetDevice(device), "cudaSetDevice");
   CUDA_RET(cudaStreamSynchronize(copy_in_), "sync");
+  CUDA_RET(cudaStreamSynchronize(resize_), "sync");
   for (int k = 0; k < n_lanes_; ++k) CUDA_RET(cudaStreamSynchronize(lanes_[k].stream), "sync");
   CUDA_RET(cudaStreamSynchronize(copy_out_), "sync");
   return Status::OK();
@@ -1088,6 +1102,7 @@ const Engine::AxisEntry& Engine::GetAxis(int in_size, double in0, double in1, in
 
 Status Engine::GrowStage(ResizeStage* st, size_t src, size_t tmp, size_t arena_words, size_t jobs) {
   if (st->free_ev == nullptr) CUDA_RET(cudaEventCreateWithFlags(&st->free_ev, cudaEventDisableTiming), "event");
+  if (st->h2d_ev == nullptr) CUDA_RET(cudaEventCreateWithFlags(&st->h2d_ev, cudaEventDisableTiming), "event");
   const bool grow = src > st->src_cap || tmp > st->tmp_cap || arena_words > st->arena_cap || jobs > st->jobs_cap;
   if (!grow) return Status::OK();
   CUDA_RET(cudaStreamSynchronize(copy_in_), "sync before growing the resize staging");
@@ -1132,23 +1147,35 @@ Status Engine::GrowStage(ResizeStage* st, size_t src, size_t tmp, size_t arena_w
 // Copies a list of (dst, src, bytes) with up to 16 host threads: one core moves ~10 GB/s from pageable memory, a photo
 // is tens of MB, and PCIe takes > 50 GB/s, so a single-threaded staging copy would be the bottleneck of the whole path.
 namespace {
-struct CopyPiece {
+struct CopyPiece {   // `rows` runs of `bytes` each, `src_pitch` apart in the source, packed in the destination
   uint8_t* dst;
   const uint8_t* src;
   size_t bytes;
+  size_t rows = 1, src_pitch = 0;
 };
 void parallel_copy(const std::vector<CopyPiece>& pieces) {
   constexpr size_t kChunk = size_t(4) << 20;
   std::vector<CopyPiece> chunks;
   size_t total = 0;
   for (const CopyPiece& p : pieces) {
-    total += p.bytes;
-    for (size_t o = 0; o < p.bytes; o += kChunk) chunks.push_back({p.dst + o, p.src + o, std::min(kChunk, p.bytes - o)});
+    total += p.bytes * p.rows;
+    if (p.rows <= 1 || p.src_pitch == p.bytes) {   // one contiguous run
+      const size_t n = p.bytes * p.rows;
+      for (size_t o = 0; o < n; o += kChunk) chunks.push_back({p.dst + o, p.src + o, std::min(kChunk, n - o)});
+    } else {                                       // strided rows: chunks of whole rows
+      const size_t per = std::max<size_t>(1, kChunk / p.bytes);
+      for (size_t r = 0; r < p.rows; r += per)
+        chunks.push_back({p.dst + r * p.bytes, p.src + r * p.src_pitch, p.bytes, std::min(per, p.rows - r), p.src_pitch});
+    }
   }
+  auto copy_chunk = [](const CopyPiece& c) {
+    if (c.rows <= 1) { memcpy(c.dst, c.src, c.bytes); return; }
+    for (size_t r = 0; r < c.rows; ++r) memcpy(c.dst + r * c.bytes, c.src + r * c.src_pitch, c.bytes);
+  };
   unsigned hw = std::thread::hardware_concurrency();
   const size_t threads = std::min<size_t>({size_t(16), hw > 2 ? hw - 1 : 1, chunks.size()});
   if (total < (size_t(8) << 20) || threads <= 1) {
-    for (const CopyPiece& c : chunks) memcpy(c.dst, c.src, c.bytes);
+    for (const CopyPiece& c : chunks) copy_chunk(c);
     return;
   }
   std::atomic<size_t> next(0);
@@ -1156,7 +1183,7 @@ void parallel_copy(const std::vector<CopyPiece>& pieces) {
     for (;;) {
       const size_t i = next.fetch_add(1);
       if (i >= chunks.size()) return;
-      memcpy(chunks[i].dst, chunks[i].src, chunks[i].bytes);
+      copy_chunk(chunks[i]);
     }
   };
   std::vector<std::thread> pool;
@@ -1221,6 +1248,8 @@ Status Engine::ResizeGroupToDevice(const uint8_t* const* imgs, const int32_t* wi
     j.dst_off = static_cast<long long>(static_cast<size_t>(n) * px);
     j.tmp_off = static_cast<long long>(tmp_bytes);
     size_t first_row = 0, n_rows = static_cast<size_t>(H);  // source rows that have to travel
+    size_t first_col = 0, n_cols = static_cast<size_t>(W);  // ... and the columns of each of them
+    j.pitch = W;
     if (W == S_ && H == S_) {
       j.mode = 2;  // the convolution is the identity at the model resolution (and the crop box is the whole image)
     } else {
@@ -1234,29 +1263,37 @@ Status Engine::ResizeGroupToDevice(const uint8_t* const* imgs, const int32_t* wi
         int xf, xl, yf, yl;
         place_axis(W, left, left + cw, &j.xstart, &j.xsize, &j.xw, &j.xwindow, &j.xprecision, &xf, &xl);
         place_axis(H, top, top + ch, &j.ystart, &j.ysize, &j.yw, &j.ywindow, &j.yprecision, &yf, &yl);
-        // only the rows the vertical pass reads cross PCIe (a centre crop of a portrait photo skips the rest)
+        // only the rows the vertical pass reads and the columns the horizontal pass reads cross PCIe (a centre crop
+        // of a portrait photo skips rows, of a landscape photo columns: 44 % of a 16:9 frame)
         first_row = static_cast<size_t>(yf);
         n_rows = static_cast<size_t>(std::max(yl - yf, 0));
         j.y_first = yf;  // staged row r is source row yf + r
         j.rows = static_cast<int>(n_rows);
+        static const bool full_rows = [] { const char* v = getenv("CLIPB200_STAGE_FULL_ROWS"); return v != nullptr && atoi(v) != 0; }();
+        if (!full_rows) {   // CLIPB200_STAGE_FULL_ROWS=1: A/B switch, stage whole rows as round 2's first version did
+          first_col = static_cast<size_t>(xf);
+          n_cols = static_cast<size_t>(std::max(xl - xf, 0));
+          j.x_first = xf;
+          j.pitch = static_cast<int>(n_cols);
+        }
         tmp_bytes += n_rows * S_ * 3;
         max_rows = std::max(max_rows, j.rows);
       }
     }
-    const size_t staged = n_rows * W * 3;
-    pieces.push_back({nullptr, imgs[n] + first_row * W * 3, staged});
+    const size_t staged = n_rows * n_cols * 3;
+    pieces.push_back({nullptr, imgs[n] + (first_row * W + first_col) * 3, n_cols * 3, n_rows, static_cast<size_t>(W) * 3});
     src_bytes += (staged + 15) & ~size_t(15);
     jobs.push_back(j);
   }
   *consumed = n;
-  ResizeStage* st = &rs_stage_[rs_groups_++ & 1];
+  ResizeStage* st = &rs_stage_[rs_groups_++ % static_cast<uint64_t>(rs_stages_)];
   if (st->in_flight) CUDA_RET(cudaEventSynchronize(st->free_ev), "wait resize staging");
   RET_IF_ERR(GrowStage(st, src_bytes, tmp_bytes, arena.size(), jobs.size()));
   {
     size_t off = 0;
     for (size_t i = 0; i < pieces.size(); ++i) {
       pieces[i].dst = st->h_src + off;
-      off += (pieces[i].bytes + 15) & ~size_t(15);
+      off += (pieces[i].bytes * pieces[i].rows + 15) & ~size_t(15);
     }
     parallel_copy(pieces);
   }
@@ -1270,12 +1307,15 @@ Status Engine::ResizeGroupToDevice(const uint8_t* const* imgs, const int32_t* wi
     e = cudaMemcpyAsync(st->d_arena, st->h_arena, arena.size() * 4, cudaMemcpyHostToDevice, copy_in_);
   ProfEnd(PC_H2D, copy_in_);
   CUDA_RET(e, "H2D copy");
-  ProfBegin(PC_PRE, copy_in_);
-  e = launch_resize_batched(st->d_src, st->d_jobs, st->d_arena, n, S_, max_rows, st->d_tmp, d_dst, copy_in_);
-  ProfEnd(PC_PRE, copy_in_);
+  // the resize kernels run on their own stream: the next group's upload does not wait for them
+  CUDA_RET(cudaEventRecord(st->h2d_ev, copy_in_), "record");
+  CUDA_RET(cudaStreamWaitEvent(resize_, st->h2d_ev, 0), "wait upload");
+  ProfBegin(PC_PRE, resize_);
+  e = launch_resize_batched(st->d_src, st->d_jobs, st->d_arena, n, S_, max_rows, st->d_tmp, d_dst, resize_);
+  ProfEnd(PC_PRE, resize_);
   if (max_rows > 0) ++launch_count;  // two launches per group (ProfBegin counted one)
   CUDA_RET(e, "resize");
-  CUDA_RET(cudaEventRecord(st->free_ev, copy_in_), "record");
+  CUDA_RET(cudaEventRecord(st->free_ev, resize_), "record");
   st->in_flight = true;
   return Status::OK();
 }
@@ -1288,8 +1328,8 @@ Status Engine::ResizeRgb8(const uint8_t* img, int width, int height, const clipb
   const int32_t w = width, h = height;
   int consumed = 0;
   RET_IF_ERR(ResizeGroupToDevice(&img, &w, &h, 1, pp, dst, &consumed));
-  CUDA_RET(cudaMemcpyAsync(out, dst, static_cast<size_t>(S_) * S_ * 3, cudaMemcpyDeviceToHost, copy_in_), "D2H copy");
-  CUDA_RET(cudaStreamSynchronize(copy_in_), "sync");
+  CUDA_RET(cudaMemcpyAsync(out, dst, static_cast<size_t>(S_) * S_ * 3, cudaMemcpyDeviceToHost, resize_), "D2H copy");
+  CUDA_RET(cudaStreamSynchronize(resize_), "sync");
   return Status::OK();
 }
 
@@ -1310,22 +1350,29 @@ Status Engine::VisionEmbedRgb8Var(const uint8_t* const* imgs, const int32_t* wid
   cudaGetLastError();
   // Photos are tens of MB each: staging + PCIe of a micro-batch takes as long as its tower, so the micro-batch is kept
   // small enough (<= 64 images) that even a call with a few dozen photos overlaps the two.
-  const int64_t mb = std::min<int64_t>(mb_, 64);
-  const int64_t steps = (batch + mb - 1) / mb;
+  static const int64_t photo_mb = [] { const char* v = getenv("CLIPB200_PHOTO_MB"); return v != nullptr && atoi(v) > 0 ? atoi(v) : 64; }();
+  const int64_t mb = std::min<int64_t>(mb_, photo_mb);
+  // Equal micro-batches.  (Measured and dropped: halving the tail of the call so that the last, exposed tower is a small
+  // one — 112 photos as 64 + 24 + 12 + 12 — is slower, 914 -> 804 img/s on SO400M: every micro-batch costs the staging
+  // host thread a tower's worth of kernel launches.  profiles/r02z_photos.md)
+  std::vector<std::pair<int64_t, int>> sched;   // (first image, count)
+  for (int64_t at = 0; at < batch; at += mb) sched.emplace_back(at, static_cast<int>(std::min<int64_t>(mb, batch - at)));
+  const int64_t steps = static_cast<int64_t>(sched.size());
   Status st = Status::OK();
   for (int64_t s = 0; s < steps && st.ok(); ++s) {
     const int slot = static_cast<int>(s & 1);
-    const int n = static_cast<int>(std::min<int64_t>(mb, batch - s * mb));
-    if (s >= 2) CUDA_RET(cudaStreamWaitEvent(copy_in_, in_consumed_[slot], 0), "wait consumed");
+    const int64_t at = sched[static_cast<size_t>(s)].first;
+    const int n = sched[static_cast<size_t>(s)].second;
+    if (s >= 2) CUDA_RET(cudaStreamWaitEvent(resize_, in_consumed_[slot], 0), "wait consumed");   // resize_ writes the slot
     uint8_t* d_slot = static_cast<uint8_t*>(d_in_[slot]);
     for (int i = 0; i < n && st.ok();) {
-      const int64_t g = s * mb + i;
+      const int64_t g = at + i;
       int consumed = 0;
       st = ResizeGroupToDevice(imgs + g, widths + g, heights + g, n - i, pp, d_slot + static_cast<size_t>(i) * px, &consumed);
       i += consumed;
     }
     if (!st.ok()) break;
-    CUDA_RET(cudaEventRecord(in_ready_[slot], copy_in_), "record");
+    CUDA_RET(cudaEventRecord(in_ready_[slot], resize_), "record");
     BindLane(slot);
     CUDA_RET(cudaStreamWaitEvent(compute_, in_ready_[slot], 0), "wait input");
     if (s >= 2) CUDA_RET(cudaStreamWaitEvent(compute_, out_copied_[slot], 0), "wait output slot");
@@ -1335,16 +1382,16 @@ Status Engine::VisionEmbedRgb8Var(const uint8_t* const* imgs, const int32_t* wid
     CUDA_RET(cudaEventRecord(out_ready_[slot], compute_), "record");
     CUDA_RET(cudaStreamWaitEvent(copy_out_, out_ready_[slot], 0), "wait output");
     ProfBegin(PC_D2H, copy_out_);
-    cudaError_t e = cudaMemcpyAsync(out_pinned ? out + static_cast<size_t>(s) * mb * E_ : h_out_[slot], d_out_[slot],
+    cudaError_t e = cudaMemcpyAsync(out_pinned ? out + static_cast<size_t>(at) * E_ : h_out_[slot], d_out_[slot],
                                     static_cast<size_t>(n) * E_ * 4, cudaMemcpyDeviceToHost, copy_out_);
     ProfEnd(PC_D2H, copy_out_);
     CUDA_RET(e, "D2H copy");
     CUDA_RET(cudaEventRecord(out_copied_[slot], copy_out_), "record");
     if (!out_pinned && s >= 1) {  // drain the previous step's output while this one runs
       const int ps = static_cast<int>((s - 1) & 1);
-      const int pn = static_cast<int>(std::min<int64_t>(mb, batch - (s - 1) * mb));
       CUDA_RET(cudaEventSynchronize(out_copied_[ps]), "wait D2H");
-      memcpy(out + static_cast<size_t>(s - 1) * mb * E_, h_out_[ps], static_cast<size_t>(pn) * E_ * 4);
+      memcpy(out + static_cast<size_t>(sched[static_cast<size_t>(s - 1)].first) * E_, h_out_[ps],
+             static_cast<size_t>(sched[static_cast<size_t>(s - 1)].second) * E_ * 4);
     }
   }
   BindLane(0);
@@ -1353,8 +1400,8 @@ Status Engine::VisionEmbedRgb8Var(const uint8_t* const* imgs, const int32_t* wid
   RET_IF_ERR(sync);
   if (!out_pinned) {
     const int64_t s = steps - 1;
-    const int n = static_cast<int>(std::min<int64_t>(mb, batch - s * mb));
-    memcpy(out + static_cast<size_t>(s) * mb * E_, h_out_[s & 1], static_cast<size_t>(n) * E_ * 4);
+    memcpy(out + static_cast<size_t>(sched[static_cast<size_t>(s)].first) * E_, h_out_[s & 1],
+           static_cast<size_t>(sched[static_cast<size_t>(s)].second) * E_ * 4);
   }
   return Status::OK();
 }

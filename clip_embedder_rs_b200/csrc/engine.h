@@ -161,10 +161,12 @@ class Engine {
     int32_t *h_arena = nullptr, *d_arena = nullptr;
     ResizeJob *h_jobs = nullptr, *d_jobs = nullptr;
     size_t src_cap = 0, tmp_cap = 0, arena_cap = 0, jobs_cap = 0;
-    cudaEvent_t free_ev = nullptr;
+    cudaEvent_t free_ev = nullptr, h2d_ev = nullptr;
     bool in_flight = false;
   };
-  ResizeStage rs_stage_[2];
+  static constexpr int kResizeStages = 4;   // pinned staging groups in flight (CLIPB200_PHOTO_STAGES=2..4; measured: no effect)
+  ResizeStage rs_stage_[kResizeStages];
+  int rs_stages_ = 2;
   uint64_t rs_groups_ = 0;
   size_t rs_group_bytes_ = size_t(192) << 20;
   Status ResizeGroupToDevice(const uint8_t* const* imgs, const int32_t* widths, const int32_t* heights, int count,
@@ -256,6 +258,7 @@ class Engine {
   void BindLane(int k);
   Status AllocActivations();
   cudaStream_t compute_ = nullptr, copy_in_ = nullptr, copy_out_ = nullptr;
+  cudaStream_t resize_ = nullptr;   // photo path: resize kernels of group g run while copy_in_ uploads group g + 1
   cudaEvent_t in_ready_[2] = {nullptr, nullptr}, in_consumed_[2] = {nullptr, nullptr},
               out_ready_[2] = {nullptr, nullptr}, out_copied_[2] = {nullptr, nullptr};
   cudaEvent_t user_events_[16] = {};

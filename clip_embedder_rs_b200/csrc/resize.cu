@@ -88,7 +88,8 @@ resize_h_batched_kernel(const uint8_t* __restrict__ src, const ResizeJob* __rest
   const int r = blockIdx.y;
   if (j.mode != 0 || ox >= S || r >= j.rows) return;
   const int x0 = arena[j.xstart + ox], n = arena[j.xsize + ox];
-  const uint8_t* row = src + j.src_off + (static_cast<long long>(r) * j.W + x0) * 3;  // staged row r = source row y_first + r
+  // staged row r = columns [x_first, x_first + pitch) of source row y_first + r
+  const uint8_t* row = src + j.src_off + (static_cast<long long>(r) * j.pitch + (x0 - j.x_first)) * 3;
   const int16_t* ww = reinterpret_cast<const int16_t*>(arena + j.xw) + static_cast<long long>(ox) * j.xwindow;
   const int half = j.xprecision > 0 ? (1 << (j.xprecision - 1)) : 0;
   int a0 = half, a1 = half, a2 = half;

@@ -19,6 +19,7 @@ struct ResizeJob {
   int W, H;
   int mode;                             // 0 two-pass convolution, 1 nearest, 2 copy (already S x S)
   int y_first, rows;                    // source rows [y_first, y_first + rows) are staged at src_off (mode 0)
+  int x_first, pitch;                   // ... and of each of them the columns [x_first, x_first + pitch) (mode 0; else 0, W)
   int xstart, xsize, xw, ystart, ysize, yw;  // word offsets into the arena
   int xwindow, ywindow, xprecision, yprecision;
   double left, top, sx, sy;             // nearest only
