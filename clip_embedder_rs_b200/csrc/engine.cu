@@ -6,6 +6,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 #include "attn_sm100.cuh"
@@ -1153,6 +1155,81 @@ struct CopyPiece {   // `rows` runs of `bytes` each, `src_pitch` apart in the so
   size_t bytes;
   size_t rows = 1, src_pitch = 0;
 };
+// Staging copies are issued group by group (a few dozen per call): spawning 15 threads for each cost the staging host
+// thread ~0.4 ms a time.  One process-wide set of workers (all engines, all pool replicas) sleeps on a condition variable
+// and pulls 4 MB chunks from whichever jobs are posted; the posting thread works on its own job too and returns when
+// that job's chunks are done.
+struct CopyJob {
+  const std::vector<CopyPiece>* chunks = nullptr;
+  void (*run)(const CopyPiece&) = nullptr;
+  std::atomic<size_t> next{0}, done{0};
+  int workers = 0;   // pool threads currently holding a pointer to this job (guarded by the pool mutex)
+};
+class CopyWorkers {
+ public:
+  static CopyWorkers& get() {
+    static CopyWorkers* w = new CopyWorkers();   // never destroyed: workers may outlive static destruction order
+    return *w;
+  }
+  size_t size() const { return threads_.size(); }
+  void run(CopyJob* job) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      jobs_.push_back(job);
+    }
+    cv_.notify_all();
+    work_on(job);
+    {   // every chunk has been claimed; wait until the workers that claimed the last ones have finished them
+      std::unique_lock<std::mutex> lk(mu_);
+      jobs_.erase(std::find(jobs_.begin(), jobs_.end(), job));
+      done_cv_.wait(lk, [&] { return job->done.load() == job->chunks->size() && job->workers == 0; });
+    }
+  }
+
+ private:
+  CopyWorkers() {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t n = std::min<size_t>(15, hw > 2 ? hw - 2 : 0);
+    for (size_t i = 0; i < n; ++i) threads_.emplace_back([this] { loop(); });
+    for (std::thread& t : threads_) t.detach();
+  }
+  void work_on(CopyJob* job) {
+    for (;;) {
+      const size_t i = job->next.fetch_add(1);
+      if (i >= job->chunks->size()) return;
+      job->run((*job->chunks)[i]);
+      if (job->done.fetch_add(1) + 1 == job->chunks->size()) {
+        std::lock_guard<std::mutex> lk(mu_);
+        done_cv_.notify_all();
+      }
+    }
+  }
+  void loop() {
+    for (;;) {
+      CopyJob* job = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] {
+          for (CopyJob* j : jobs_)
+            if (j->next.load() < j->chunks->size()) { job = j; return true; }
+          return false;
+        });
+        ++job->workers;   // the owner does not return (and destroy the job) while a worker still points at it
+      }
+      work_on(job);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        --job->workers;
+        done_cv_.notify_all();
+      }
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<CopyJob*> jobs_;
+  std::vector<std::thread> threads_;
+};
+
 void parallel_copy(const std::vector<CopyPiece>& pieces) {
   constexpr size_t kChunk = size_t(4) << 20;
   std::vector<CopyPiece> chunks;
@@ -1172,24 +1249,30 @@ void parallel_copy(const std::vector<CopyPiece>& pieces) {
     if (c.rows <= 1) { memcpy(c.dst, c.src, c.bytes); return; }
     for (size_t r = 0; r < c.rows; ++r) memcpy(c.dst + r * c.bytes, c.src + r * c.src_pitch, c.bytes);
   };
-  unsigned hw = std::thread::hardware_concurrency();
-  const size_t threads = std::min<size_t>({size_t(16), hw > 2 ? hw - 1 : 1, chunks.size()});
-  if (total < (size_t(8) << 20) || threads <= 1) {
+  if (total < (size_t(8) << 20) || chunks.size() <= 1 || CopyWorkers::get().size() == 0) {
     for (const CopyPiece& c : chunks) copy_chunk(c);
     return;
   }
-  std::atomic<size_t> next(0);
-  auto work = [&]() {
-    for (;;) {
-      const size_t i = next.fetch_add(1);
-      if (i >= chunks.size()) return;
-      copy_chunk(chunks[i]);
-    }
+  static const bool use_pool = [] { const char* v = getenv("CLIPB200_COPY_POOL"); return v == nullptr || atoi(v) != 0; }();
+  if (!use_pool) {   // A/B switch: round 2's first version, up to 15 freshly spawned threads per call
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+      for (size_t i; (i = next.fetch_add(1)) < chunks.size();) copy_chunk(chunks[i]);
+    };
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < std::min<size_t>(16, chunks.size()); ++t) pool.emplace_back(work);
+    work();
+    for (std::thread& t : pool) t.join();
+    return;
+  }
+  // a job = this call's chunk list; the process-wide workers and the calling thread pull chunks from it
+  CopyJob job;
+  job.chunks = &chunks;
+  job.run = +[](const CopyPiece& c) {
+    if (c.rows <= 1) { memcpy(c.dst, c.src, c.bytes); return; }
+    for (size_t r = 0; r < c.rows; ++r) memcpy(c.dst + r * c.bytes, c.src + r * c.src_pitch, c.bytes);
   };
-  std::vector<std::thread> pool;
-  for (size_t t = 1; t < threads; ++t) pool.emplace_back(work);
-  work();
-  for (std::thread& t : pool) t.join();
+  CopyWorkers::get().run(&job);
 }
 }  // namespace
 
