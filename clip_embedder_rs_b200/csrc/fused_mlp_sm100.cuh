@@ -49,6 +49,15 @@ namespace fmlp {
 #ifndef CLIPB200_FMLP_POLL
 #define CLIPB200_FMLP_POLL 0
 #endif
+//   CLIPB200_FMLP_CLUSTER     0: independent CTAs;  1: CTAs run as clusters of two on neighbouring tiles and share every W1 /
+//                                W2 tile (each CTA issues half of the TMA loads, multicast into both CTAs' rings; both MMA
+//                                warps release a slot), so the weights cross the L2 -> SM path once per PAIR of tiles.
+//                                Correct on every case, and no faster: C = 320 121.8 vs 119.1 us, C = 160 164.3 vs 164.0,
+//                                C = 80 273.1 vs 270.2 (profiles/r02ac_fmlp_cluster.log) — the MMA warp's waits for W1 are
+//                                latency and coupling, not L2 bandwidth
+#ifndef CLIPB200_FMLP_CLUSTER
+#define CLIPB200_FMLP_CLUSTER 0
+#endif
 
 constexpr int BM = 128;        // pixels per CTA
 constexpr int HC = 64;         // hidden columns per chunk (one 128B-swizzle atom of K for the second GEMM)
@@ -82,8 +91,8 @@ struct Cfg {
   static constexpr int OCW = DIRECT ? 16 : HC / SLOTS;     // output columns per final-epilogue chunk (staging: 128 B | 64 B rows)
   static constexpr int THREADS = 32 * (EPI_WARPS + 2);
   static constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
-  // ring depths: what the shared memory allows; at C = 320 the weight stream is the limiter whatever the split (a CTA
-  // re-reads 1.2 MB of W1 / W2 per tile: 6.5 TB/s of L2 -> SM traffic over the 148 SMs), and 4 + 4 measured best
+  // ring depths: what the shared memory allows; at C = 320 the MMA warp waits for W1 a quarter of the time whatever the split
+  // (4 + 4 measured best; halving the L2 -> SM weight traffic with cluster multicast changes nothing: CLIPB200_FMLP_CLUSTER)
   static constexpr int NS1 = C <= 80 ? KB + 1 : (C <= 96 ? KB : (C > 256 ? 4 : (3 * KB < 8 ? 3 * KB : 8)));   // W1 ring stages
   static constexpr int NS2 = C <= 96 ? 2 : (C > 256 ? 4 : (C > 192 ? 2 : 3));                                 // W2 ring stages
   static constexpr int STG_WARP = 32 * OCW * 4;            // per epilogue warp: [32 rows][OCW fp32]
@@ -213,6 +222,12 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n_chunks = (p.Hd + HC - 1) / HC;
   const int n_tiles = (p.M + BM - 1) / BM;
+  // Clusters of two: CTA rank r of cluster c walks tiles 2 * (c + k * n_clusters) + r, i.e. blockIdx.x + k * gridDim.x; both
+  // CTAs of a pair run the same number of tiles (an odd tile count gives the last pair a phantom tile beyond M: its A rows
+  // load as zeros and its output rows are clipped), because they consume the shared weight rings in lockstep.
+  constexpr bool CL = CLIPB200_FMLP_CLUSTER != 0;
+  const uint32_t rank = CL ? ptx::cluster_ctarank() : 0;
+  auto tile_valid = [&](int tile) { return CL ? ((tile & ~1) < n_tiles) : (tile < n_tiles); };
 
   if (warp == WARP_TMA && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
@@ -223,11 +238,11 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     ptx::mbar_init(a_empty, 1);
     for (int i = 0; i < K::NS1; ++i) {
       ptx::mbar_init(&w1_full[i], 1);
-      ptx::mbar_init(&w1_empty[i], 1);
+      ptx::mbar_init(&w1_empty[i], CL ? 2 : 1);   // clusters: the MMA warps of BOTH CTAs release a shared weight slot
     }
     for (int i = 0; i < K::NS2; ++i) {
       ptx::mbar_init(&w2_full[i], 1);
-      ptx::mbar_init(&w2_empty[i], 1);
+      ptx::mbar_init(&w2_empty[i], CL ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&s_full[i], 1);
@@ -242,6 +257,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == WARP_MMA) ptx::tmem_alloc<K::TMEM_COLS>(tmem_base_ptr);
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL) ptx::cluster_sync();   // the peer's barriers exist before anything is multicast at them
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);
 
@@ -251,7 +267,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == WARP_TMA) {
     if (lane == 0) {
       uint32_t t1 = 0, t2 = 0, it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile_valid(tile); tile += gridDim.x, ++it) {
         ptx::mbar_wait(a_empty, (it & 1) ^ 1);
         // A tile: KB boxes of 64 columns x 128 rows (columns >= C and rows >= M are zero-filled)
         ptx::mbar_arrive_expect_tx(a_full, K::KB * BM * 128);
@@ -261,13 +277,15 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int st = t1 % K::NS1;
             ptx::mbar_wait(&w1_empty[st], ((t1 / K::NS1) & 1) ^ 1);
             ptx::mbar_arrive_expect_tx(&w1_full[st], K::W1_TILE);
-            ptx::tma_load_2d(&tm_w1, &w1_full[st], s_w1 + st * K::W1_TILE, kb * 64, i * HC);
+            if (!CL) ptx::tma_load_2d(&tm_w1, &w1_full[st], s_w1 + st * K::W1_TILE, kb * 64, i * HC);
+            else if ((t1 & 1) == rank) ptx::tma_load_2d_multicast(&tm_w1, &w1_full[st], s_w1 + st * K::W1_TILE, kb * 64, i * HC, 3);
           }
           for (int part = 0; part < K::N2_PARTS; ++part, ++t2) {   // W2 rows = output channels, columns [i*64, +64) of the hidden dim
             const int st = t2 % K::NS2;
             ptx::mbar_wait(&w2_empty[st], ((t2 / K::NS2) & 1) ^ 1);
             ptx::mbar_arrive_expect_tx(&w2_full[st], K::N2 * 128);
-            ptx::tma_load_2d(&tm_w2, &w2_full[st], s_w2 + st * K::W2_TILE, i * HC, part * K::N2);
+            if (!CL) ptx::tma_load_2d(&tm_w2, &w2_full[st], s_w2 + st * K::W2_TILE, i * HC, part * K::N2);
+            else if ((t2 & 1) == rank) ptx::tma_load_2d_multicast(&tm_w2, &w2_full[st], s_w2 + st * K::W2_TILE, i * HC, part * K::N2, 3);
           }
         }
       }
@@ -302,7 +320,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             ptx::umma_bf16_ss_w(t_s, da, dw, idesc1, (kb | k) != 0 ? 1u : 0u);
           }
         }
-        ptx::umma_commit_w(&w1_empty[st]);
+        if (CL) ptx::umma_commit_multicast_w(&w1_empty[st], 3); else ptx::umma_commit_w(&w1_empty[st]);
       }
       ptx::umma_commit_w(&s_full[b]);
       if (last_of_tile) ptx::umma_commit_w(a_empty);   // every read of this tile's A has been issued
@@ -326,7 +344,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint64_t dw = ptx::make_kmajor_sw128_desc(w_addr) + static_cast<uint64_t>(2 * k);
           ptx::umma_bf16_ss_w(tmem_base + K::COL_O + static_cast<uint32_t>(part * K::N2), dh, dw, idesc2, (i | k) != 0 ? 1u : 0u);
         }
-        ptx::umma_commit_w(&w2_empty[st]);
+        if (CL) ptx::umma_commit_multicast_w(&w2_empty[st], 3); else ptx::umma_commit_w(&w2_empty[st]);
       }
       ptx::umma_commit_w(&h_empty[b]);
     };
@@ -340,6 +358,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // the producer's order (W1(c), W2(c), W1(c + 1), ...) cannot deadlock it while the W2 ring holds two chunks.
     // g1 - g2 <= 2 keeps that true with two warp groups as well (their S buffers free up early).
     static_assert(K::NS2 >= 2 * K::N2_PARTS, "W2 ring: two chunks' worth");
+    static_assert(!CL, "the polling issue order is not combined with clusters");
     const uint32_t my_tiles = (static_cast<uint32_t>(n_tiles) - blockIdx.x + gridDim.x - 1) / gridDim.x;
     const uint32_t total = my_tiles * static_cast<uint32_t>(n_chunks);
     uint32_t g1 = 0, g2 = 0, it1 = 0, it2 = 0;
@@ -379,7 +398,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
 #else
     uint32_t g1 = 0, g2 = 0, it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile_valid(tile); tile += gridDim.x, ++it) {
       ptx::mbar_wait(a_full, it & 1);
       // fixed order: the first GEMM runs one chunk ahead of the second, so chunk i's GELU overlaps S(i + 1)
       auto first = [&](bool last_of_tile) {
@@ -426,7 +445,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long e_begin = clock64();
 #endif
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile_valid(tile); tile += gridDim.x, ++it) {
       FMLP_T(eb0);
       if (!K::DIRECT && it > 0) {
         // the staging tiles of the previous tile's output alias the H buffers: every TMA read of them must be over, for
@@ -562,6 +581,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL) ptx::cluster_sync();   // the peer may still multicast into this CTA's rings / arrive on its barriers until here
   if (warp == WARP_MMA) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<K::TMEM_COLS>(tmem_base);
@@ -584,6 +604,23 @@ inline cudaError_t launch_t(const __nv_bfloat16* a, long long lda, const __nv_bf
   if (!make_tmap_2d(&tw2, w2, C, p.Hd, ldw2, K::N2, 2)) return cudaErrorUnknown;   // box = [N2 output channels][64 hidden]
   if (!make_tmap_2d(&tx, x, p.M, C, ldx, 32, 4, K::OCW * 4)) return cudaErrorUnknown;   // box = [32 rows][OCW fp32]
   const int tiles = (p.M + BM - 1) / BM, slots = num_sms * K::CTAS_PER_SM;
+  if (CLIPB200_FMLP_CLUSTER) {
+    const int pairs = (tiles + 1) / 2, max_clusters = slots / 2;
+    const int clusters = pairs < max_clusters ? pairs : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters, 1, 1);
+    cfg.blockDim = dim3(K::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = K::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fused_mlp_kernel<C>, ta, tw1, tw2, tx, p);
+  }
   const int grid = tiles < slots ? tiles : slots;   // persistent: every CTA walks tiles blockIdx.x, += gridDim.x
   fused_mlp_kernel<C><<<grid, K::THREADS, K::SMEM_BYTES, st>>>(ta, tw1, tw2, tx, p);
   return cudaGetLastError();

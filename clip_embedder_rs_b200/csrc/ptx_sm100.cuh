@@ -139,6 +139,27 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       "}\n" ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
+// TMA load multicast to the CTAs of the cluster selected by `cta_mask`: the tile lands at the same shared-memory offset
+// in each of them and each one's barrier at the same offset is credited with the bytes.
+__device__ __forceinline__ void tma_load_2d_multicast(const void* tmap, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1,
+                                                      uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit of THIS CTA's MMAs (cta_group::1) arriving on the barrier at the same offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_multicast_w(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+      "}\n" ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
 // 2-SM TMA load: data lands in THIS CTA's shared memory, the transaction bytes are credited to the barrier at the
 // same offset in the pair's leader CTA (peer bit of the shared::cluster address cleared)
 __device__ __forceinline__ void tma_load_2d_2sm(const void* tmap, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1) {
