@@ -58,6 +58,20 @@ namespace fmlp {
 #ifndef CLIPB200_FMLP_CLUSTER
 #define CLIPB200_FMLP_CLUSTER 0
 #endif
+//   CLIPB200_FMLP_W_ORDER     0: weight tiles requested as W1(i), W2(i), W1(i + 1), ...;  1: in the MMA warp's consumption
+//                                order (W1 one chunk ahead of W2), with CLIPB200_FMLP_NS1_WIDE / _NS2_WIDE = the ring depths of
+//                                the C > 256 instances.  Order x {4+4, 6+3, 8+2} stages all land on 117 / 163 / 272 us
+//                                (profiles/r02ad_fmlp_worder.log): the MMA warp does wait for W1 a quarter of a C = 320 tile,
+//                                but it is not on the critical path — the epilogue warps are
+#ifndef CLIPB200_FMLP_W_ORDER
+#define CLIPB200_FMLP_W_ORDER 0
+#endif
+#ifndef CLIPB200_FMLP_NS1_WIDE
+#define CLIPB200_FMLP_NS1_WIDE 4
+#endif
+#ifndef CLIPB200_FMLP_NS2_WIDE
+#define CLIPB200_FMLP_NS2_WIDE 4
+#endif
 
 constexpr int BM = 128;        // pixels per CTA
 constexpr int HC = 64;         // hidden columns per chunk (one 128B-swizzle atom of K for the second GEMM)
@@ -93,8 +107,8 @@ struct Cfg {
   static constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
   // ring depths: what the shared memory allows; at C = 320 the MMA warp waits for W1 a quarter of the time whatever the split
   // (4 + 4 measured best; halving the L2 -> SM weight traffic with cluster multicast changes nothing: CLIPB200_FMLP_CLUSTER)
-  static constexpr int NS1 = C <= 80 ? KB + 1 : (C <= 96 ? KB : (C > 256 ? 4 : (3 * KB < 8 ? 3 * KB : 8)));   // W1 ring stages
-  static constexpr int NS2 = C <= 96 ? 2 : (C > 256 ? 4 : (C > 192 ? 2 : 3));                                 // W2 ring stages
+  static constexpr int NS1 = C <= 80 ? KB + 1 : (C <= 96 ? KB : (C > 256 ? CLIPB200_FMLP_NS1_WIDE : (3 * KB < 8 ? 3 * KB : 8)));   // W1 ring stages
+  static constexpr int NS2 = C <= 96 ? 2 : (C > 256 ? CLIPB200_FMLP_NS2_WIDE : (C > 192 ? 2 : 3));                                 // W2 ring stages
   static constexpr int STG_WARP = 32 * OCW * 4;            // per epilogue warp: [32 rows][OCW fp32]
   static constexpr int STG_BYTES = EPI_WARPS * STG_WARP;   // aliases the H buffers
   static constexpr int OFF_A = 0;
@@ -272,7 +286,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // A tile: KB boxes of 64 columns x 128 rows (columns >= C and rows >= M are zero-filled)
         ptx::mbar_arrive_expect_tx(a_full, K::KB * BM * 128);
         for (int kb = 0; kb < K::KB; ++kb) ptx::tma_load_2d(&tm_a, a_full, s_a + kb * BM * 128, kb * 64, tile * BM);
-        for (int i = 0; i < n_chunks; ++i) {
+        auto load_w1 = [&](int i) {
           for (int kb = 0; kb < K::KB; ++kb, ++t1) {   // W1 rows [i*64, +64) (hidden units), columns kb*64.. (input channels)
             const int st = t1 % K::NS1;
             ptx::mbar_wait(&w1_empty[st], ((t1 / K::NS1) & 1) ^ 1);
@@ -280,12 +294,26 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (!CL) ptx::tma_load_2d(&tm_w1, &w1_full[st], s_w1 + st * K::W1_TILE, kb * 64, i * HC);
             else if ((t1 & 1) == rank) ptx::tma_load_2d_multicast(&tm_w1, &w1_full[st], s_w1 + st * K::W1_TILE, kb * 64, i * HC, 3);
           }
+        };
+        auto load_w2 = [&](int i) {
           for (int part = 0; part < K::N2_PARTS; ++part, ++t2) {   // W2 rows = output channels, columns [i*64, +64) of the hidden dim
             const int st = t2 % K::NS2;
             ptx::mbar_wait(&w2_empty[st], ((t2 / K::NS2) & 1) ^ 1);
             ptx::mbar_arrive_expect_tx(&w2_full[st], K::N2 * 128);
             if (!CL) ptx::tma_load_2d(&tm_w2, &w2_full[st], s_w2 + st * K::W2_TILE, i * HC, part * K::N2);
             else if ((t2 & 1) == rank) ptx::tma_load_2d_multicast(&tm_w2, &w2_full[st], s_w2 + st * K::W2_TILE, i * HC, part * K::N2, 3);
+          }
+        };
+        if (CLIPB200_FMLP_W_ORDER) {
+          load_w1(0);
+          for (int i = 0; i < n_chunks; ++i) {
+            if (i + 1 < n_chunks) load_w1(i + 1);
+            load_w2(i);
+          }
+        } else {
+          for (int i = 0; i < n_chunks; ++i) {
+            load_w1(i);
+            load_w2(i);
           }
         }
       }
