@@ -1855,7 +1855,7 @@ bool bind_fastvit_graph(OnnxModel* m, std::string* err) {
   };
   int bound = 0;
   for (const OnnxNode& bn : m->nodes) {
-    if (bn.op_type != "BatchNormalization" || bn.inputs.size() < 5) continue;
+    if (bn.op_type != "BatchNormalization" || bn.inputs.size() < 5 || bn.outputs.empty()) continue;
     const std::string& scale = bn.inputs[1];
     const std::string suffix = ".norm.weight";
     if (scale.size() <= suffix.size() || scale.compare(scale.size() - suffix.size(), suffix.size(), suffix) != 0) continue;
@@ -1872,7 +1872,7 @@ bool bind_fastvit_graph(OnnxModel* m, std::string* err) {
       for (const std::string& tname : frontier) {
         for (int ci : consumers[tname]) {
           const OnnxNode& n = m->nodes[static_cast<size_t>(ci)];
-          if (n.inputs[0] != tname) continue;   // only along the data input
+          if (n.inputs.empty() || n.outputs.empty() || n.inputs[0] != tname) continue;   // only along the data input
           if ((wq = const_b(n, C, 3 * C)) != nullptr) break;
           if (n.op_type == "Reshape" || n.op_type == "Flatten" || n.op_type == "Transpose" || n.op_type == "Identity" ||
               n.op_type == "Squeeze" || n.op_type == "Unsqueeze")

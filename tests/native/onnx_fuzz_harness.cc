@@ -4,7 +4,7 @@
 #include <stdio.h>
 #include "onnx_graph.h"
 int main(int argc, char** argv) {
-  int loaded = 0, recognised = 0;
+  int loaded = 0, recognised = 0, fastvit = 0;
   for (int i = 1; i < argc; ++i) {
     clipb200::OnnxModel m;
     std::string err;
@@ -16,8 +16,17 @@ int main(int argc, char** argv) {
       std::vector<float> v;  // touch every bound tensor the way the engine would
       for (const clipb200::GraphBinding& g : b)
         if (const clipb200::OnnxTensor* t = m.find(g.canonical)) clipb200::tensor_to_f32(*t, &v);
+    } else if (m.has("model.visual.trunk.stem.0.reparam_conv.weight")) {
+      // the FastViT route of Engine::Init: attention Linears located through the graph's edges
+      std::string fv_err;
+      if (clipb200::bind_fastvit_graph(&m, &fv_err)) {
+        ++fastvit;
+        std::vector<float> v;
+        for (const auto& kv : m.initializers)
+          if (kv.second.transposed) clipb200::tensor_to_f32(kv.second, &v);
+      }
     }
   }
-  printf("FUZZ HARNESS DONE files=%d loaded=%d recognised=%d\n", argc - 1, loaded, recognised);
+  printf("FUZZ HARNESS DONE files=%d loaded=%d recognised=%d fastvit=%d\n", argc - 1, loaded, recognised, fastvit);
   return 0;
 }

@@ -55,9 +55,13 @@ def _write_corpus(src_dir: str, fname: str, out_dir, n: int, seed: int):
     return paths
 
 
-@pytest.mark.parametrize("config,fname,seed", [("tiny_clip", "visual.onnx", 1), ("tiny_siglip", "text.onnx", 2)])
+@pytest.mark.parametrize("config,fname,seed", [("tiny_clip", "visual.onnx", 1), ("tiny_siglip", "text.onnx", 2),
+                                               ("tiny_mobileclip", "visual.onnx", 7)])
 def test_mutated_graphs_never_crash_the_library(make_real_model, tmp_path, config, fname, seed):
-    mdir = make_real_model(config, anonymize=(config == "tiny_siglip"))
+    if config == "tiny_mobileclip":   # FastViT conv graph: the name + graph-edge binder (bind_fastvit_graph)
+        mdir = make_real_model(config, towers=("vision",))
+    else:
+        mdir = make_real_model(config, anonymize=(config == "tiny_siglip"))
     paths = _write_corpus(mdir, fname, str(tmp_path / "corpus"), 160, seed)
     script = (
         "import sys, ctypes as C\n"
@@ -94,10 +98,14 @@ def test_mutated_graphs_under_address_and_ub_sanitizers(make_real_model, make_mo
         mdir = make_real_model(config, anonymize=(config == "tiny_siglip"))
         paths += _write_corpus(mdir, fname, str(tmp_path / f"corpus_{config}_{fname}"), 120, seed)
         paths.append(os.path.join(mdir, fname))  # and the unmodified file: must be recognised
+    # a FastViT conv graph: declined by the recogniser, its attention Linears bound through graph edges
+    fv = make_real_model("tiny_mobileclip", towers=("vision",))
+    paths += _write_corpus(fv, "visual.onnx", str(tmp_path / "corpus_fastvit"), 120, 8)
+    paths.append(os.path.join(fv, "visual.onnx"))
     # initializer-only files (tools/export_synthetic.py): the loader alone (typed data fields, external-data records)
     paths += _write_corpus(make_model("tiny_clip"), "visual.onnx", str(tmp_path / "corpus_synthetic"), 120, 6)
     for i in range(0, len(paths), 64):
         out = subprocess.run([exe] + paths[i:i + 64], capture_output=True, text=True, errors="replace", timeout=600)
         assert out.returncode == 0 and "FUZZ HARNESS DONE" in out.stdout, (paths[i:i + 64][:2], out.stderr[-3000:])
     out = subprocess.run([exe] + [p for p in paths if "/corpus_" not in p], capture_output=True, text=True, timeout=600)
-    assert "loaded=3 recognised=3" in out.stdout, out.stdout
+    assert "loaded=4 recognised=3 fastvit=1" in out.stdout, out.stdout
