@@ -127,6 +127,82 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __rest
   }
 }
 
+// Small feature maps (H, W <= TE, TE = 8 | 4: the last FastViT stages at 8x8 and 4x4): with 16x16 tiles three quarters
+// (fifteen sixteenths) of every tile's FMAs multiplied padding — the 8x8 stage of MobileCLIP2-S2 took twice as long per
+// launch as the 16x16 stage with twice the elements.  Here one CTA iteration takes 16 / TE whole images: the TMA box
+// spans {32 channels, TE+K-1, TE+K-1, 16/TE images}, every warp still owns two output rows (of TE pixels) and the
+// persistent / taps-once structure is the one above.
+template <int K, typename Tout, int TE>
+__global__ void __launch_bounds__(DW_THREADS, 2)
+dwconv_small_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ w /*[K*K][C]*/,
+                    const float* __restrict__ bias, Tout* __restrict__ out, int H, int W, int C, int n, int groups) {
+  constexpr int NI = 16 / TE, IE = TE + K - 1;   // images per iteration, staged tile edge
+  extern __shared__ __align__(128) float tile[];  // [NI][IE][IE][32]
+  __shared__ __align__(8) uint64_t bar;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.y * DW_CI;
+  auto issue_load = [&](int g) {
+    ptx::mbar_arrive_expect_tx(&bar, NI * IE * IE * DW_CI * 4);
+    tma_load_4d(&tm_in, &bar, tile, c0, -(K / 2), -(K / 2), g * NI);   // images beyond n arrive as zeros
+  };
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+    if (static_cast<int>(blockIdx.x) < groups) issue_load(blockIdx.x);
+  }
+  const int c = c0 + lane;
+  const bool c_ok = c < C;
+  float wk[K * K];
+  {
+    const float* wp = w + c;
+#pragma unroll
+    for (int t = 0; t < K * K; ++t, wp += C) wk[t] = c_ok ? __ldg(wp) : 0.f;
+  }
+  const float bv = c_ok ? __ldg(bias + c) : 0.f;
+  __syncthreads();
+  const int slot = (2 * warp) / TE, r0 = (2 * warp) % TE;   // which image of the group, first of this warp's two rows
+  uint32_t phase = 0;
+  for (int g = blockIdx.x; g < groups; g += gridDim.x, phase ^= 1) {
+    ptx::mbar_wait(&bar, phase);
+    float acc0[TE], acc1[TE];
+#pragma unroll
+    for (int x = 0; x < TE; ++x) acc0[x] = acc1[x] = bv;
+#pragma unroll
+    for (int iy = 0; iy < K + 1; ++iy) {
+      float rv[IE];
+      const float* src = tile + ((slot * IE + r0 + iy) * IE) * DW_CI + lane;
+#pragma unroll
+      for (int i = 0; i < IE; ++i) rv[i] = src[i * DW_CI];
+      if (iy < K) {
+#pragma unroll
+        for (int x = 0; x < TE; ++x)
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) acc0[x] = fmaf(rv[x + kx], wk[iy * K + kx], acc0[x]);
+      }
+      if (iy > 0) {
+#pragma unroll
+        for (int x = 0; x < TE; ++x)
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) acc1[x] = fmaf(rv[x + kx], wk[(iy - 1) * K + kx], acc1[x]);
+      }
+    }
+    __syncthreads();  // every warp has read its rows: the tile may be overwritten
+    if (threadIdx.x == 0 && g + static_cast<int>(gridDim.x) < groups) issue_load(g + gridDim.x);
+    const int b = g * NI + slot;
+    if (c_ok && b < n) {
+      Tout* o0 = out + ((static_cast<long long>(b) * H + r0) * W) * C + c;
+      Tout* o1 = o0 + static_cast<long long>(W) * C;
+#pragma unroll
+      for (int x = 0; x < TE; ++x, o0 += C, o1 += C) {
+        if (x < W) {
+          if (r0 < H) store_out(o0, acc0[x]);
+          if (r0 + 1 < H) store_out(o1, acc1[x]);
+        }
+      }
+    }
+  }
+}
+
 bool make_tmap_nhwc_f32(CUtensorMap* tm, const float* base, int n, int H, int W, int C, int box_w, int box_h) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (enc == nullptr) return false;
@@ -141,9 +217,50 @@ bool make_tmap_nhwc_f32(CUtensorMap* tm, const float* base, int n, int H, int W,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+bool make_tmap_nhwc_f32_small(CUtensorMap* tm, const float* base, int n, int H, int W, int C, int box_e, int box_n) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(n)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4,
+                           static_cast<cuuint64_t>(H) * W * C * 4};
+  cuuint32_t box[4] = {DW_CI, static_cast<cuuint32_t>(box_e), static_cast<cuuint32_t>(box_e), static_cast<cuuint32_t>(box_n)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline int resident_ctas() {
+  static const int resident = [] {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return 2 * sms;
+  }();
+  return resident;
+}
+
+template <int K, typename Tout, int TE>
+cudaError_t launch_small_t(const float* in, int n, int H, int W, int C, const float* w, const float* bias, Tout* out,
+                           cudaStream_t st) {
+  constexpr int NI = 16 / TE, IE = TE + K - 1;
+  constexpr int smem = NI * IE * IE * DW_CI * 4;
+  CUtensorMap tm;
+  if (!make_tmap_nhwc_f32_small(&tm, in, n, H, W, C, IE, NI)) return cudaErrorInvalidValue;
+  const int groups = (n + NI - 1) / NI, cblocks = (C + DW_CI - 1) / DW_CI;
+  int per_block = resident_ctas() / cblocks;
+  if (per_block < 1) per_block = 1;
+  if (per_block > groups) per_block = groups;
+  dwconv_small_kernel<K, Tout, TE><<<dim3(per_block, cblocks, 1), DW_THREADS, smem, st>>>(tm, w, bias, out, H, W, C, n, groups);
+  return cudaGetLastError();
+}
+
 template <int K, typename Tout>
 cudaError_t launch_t(const float* in, int n, int H, int W, int C, const float* w, const float* bias, Tout* out,
                      cudaStream_t st) {
+  static const bool small_on = [] { const char* v = getenv("CLIPB200_DWCONV_SMALL"); return v == nullptr || atoi(v) != 0; }();
+  if (small_on && H <= 4 && W <= 4) return launch_small_t<K, Tout, 4>(in, n, H, W, C, w, bias, out, st);
+  if (small_on && H <= 8 && W <= 8) return launch_small_t<K, Tout, 8>(in, n, H, W, C, w, bias, out, st);
   constexpr int IW = DW_TW + K - 1, IH = DW_TH + K - 1;
   constexpr int smem = IH * IW * DW_CI * 4;
   CUtensorMap tm;
@@ -151,12 +268,7 @@ cudaError_t launch_t(const float* in, int n, int H, int W, int C, const float* w
   const int tiles_x = (W + DW_TW - 1) / DW_TW, tiles_y = (H + DW_TH - 1) / DW_TH;
   const int tiles_per_img = tiles_x * tiles_y, total = tiles_per_img * n, cblocks = (C + DW_CI - 1) / DW_CI;
   // persistent CTAs: two per SM over all channel blocks together
-  static const int resident = [] {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return 2 * sms;
-  }();
-  int per_block = resident / cblocks;
+  int per_block = resident_ctas() / cblocks;
   if (per_block < 1) per_block = 1;
   if (per_block > total) per_block = total;
   dim3 grid(per_block, cblocks, 1);
@@ -276,7 +388,14 @@ cudaError_t configure_gen() {
 template <int K, typename Tout>
 cudaError_t configure_t() {
   constexpr int smem = (DW_TH + K - 1) * (DW_TW + K - 1) * DW_CI * 4;
-  return cudaFuncSetAttribute(dwconv_tma_kernel<K, Tout>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(dwconv_tma_kernel<K, Tout>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(dwconv_small_kernel<K, Tout, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             2 * (8 + K - 1) * (8 + K - 1) * DW_CI * 4);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(dwconv_small_kernel<K, Tout, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             4 * (4 + K - 1) * (4 + K - 1) * DW_CI * 4);
+  return e;
 }
 
 }  // namespace
