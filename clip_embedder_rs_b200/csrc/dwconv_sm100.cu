@@ -39,32 +39,45 @@ __device__ __forceinline__ void tma_load_4d(const void* tmap, uint64_t* bar, voi
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 
-template <int K, typename Tout>
+// CI = channels per CTA block: 32 (one lane per channel, one tile per iteration) or 16 — for widths like 80 = 5 x 16,
+// where blocks of 32 leave the lanes of the last block half idle (a sixth of the first S2 stage's work): the two
+// half-warps then work on TWO consecutive tiles of the same 16 channels (lane = 16 * tile-in-pair + channel), each staged
+// by its own TMA box (the two half-warps then share banks: two-way conflicts on the 22 shared-memory reads per staged
+// row, which the FFMA-bound loop hides).
+template <int K, typename Tout, int CI>
 __global__ void __launch_bounds__(DW_THREADS, 2)
 dwconv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ w /*[K*K][C]*/,
                   const float* __restrict__ bias, Tout* __restrict__ out, int H, int W, int C, int tiles_x,
                   int tiles_per_img, int total_tiles) {
   constexpr int IW = DW_TW + K - 1, IH = DW_TH + K - 1;
-  extern __shared__ __align__(128) float tile[];  // [IH][IW][32]; declared aligned so the reads stay LDS (no generic LD)
+  constexpr int NT = 32 / CI;                        // tiles per iteration
+  constexpr int SUB = IH * IW * CI;                  // floats between the staged tiles of a pair (a multiple of 128 B)
+  extern __shared__ __align__(128) float tile[];  // [NT][IH][IW][CI]; declared aligned so the reads stay LDS (no generic LD)
   __shared__ __align__(8) uint64_t bar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c0 = blockIdx.y * DW_CI;
-  // Persistent over the (image, tile) pairs of one 32-channel block: the K*K taps are fetched ONCE per CTA instead of
+  const int c0 = blockIdx.y * CI;
+  const int ch = lane % CI, sub = lane / CI;
+  const int iters = (total_tiles + NT - 1) / NT;
+  // Persistent over the (image, tile) pairs of one channel block: the K*K taps are fetched ONCE per CTA instead of
   // once per tile (the per-tile prologue — 49 predicated LDGs with 64-bit address arithmetic, barrier set-up, CTA launch —
   // was 12 % of the instruction stream of a kernel that is bound by instruction issue), and the next tile's TMA load is
   // requested as soon as the whole CTA has finished reading the current one, i.e. under the output stores; the second
   // CTA resident on the SM computes meanwhile.
-  auto issue_load = [&](int t) {
-    const int b = t / tiles_per_img, r = t - b * tiles_per_img;
-    ptx::mbar_arrive_expect_tx(&bar, IH * IW * DW_CI * 4);
-    tma_load_4d(&tm_in, &bar, tile, c0, (r % tiles_x) * DW_TW - K / 2, (r / tiles_x) * DW_TH - K / 2, b);
+  auto issue_load = [&](int it) {
+    ptx::mbar_arrive_expect_tx(&bar, NT * IH * IW * CI * 4);
+#pragma unroll
+    for (int s = 0; s < NT; ++s) {
+      const int t = it * NT + s;   // a tile index beyond the last one lands on an image beyond n: zeros, never stored
+      const int b = t / tiles_per_img, r = t - b * tiles_per_img;
+      tma_load_4d(&tm_in, &bar, tile + s * SUB, c0, (r % tiles_x) * DW_TW - K / 2, (r / tiles_x) * DW_TH - K / 2, b);
+    }
   };
   if (threadIdx.x == 0) {
     ptx::mbar_init(&bar, 1);
     ptx::fence_mbar_init();
-    if (static_cast<int>(blockIdx.x) < total_tiles) issue_load(blockIdx.x);
+    if (static_cast<int>(blockIdx.x) < iters) issue_load(blockIdx.x);
   }
-  const int c = c0 + lane;
+  const int c = c0 + ch;
   const bool c_ok = c < C;
   float wk[K * K];
   {
@@ -76,7 +89,8 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __rest
   __syncthreads();  // the barrier init is visible to everyone
   const int r0 = warp * 2;  // this warp's two output rows inside the tile
   uint32_t phase = 0;
-  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, phase ^= 1) {
+  for (int it = blockIdx.x; it < iters; it += gridDim.x, phase ^= 1) {
+    const int t = it * NT + sub;
     const int b = t / tiles_per_img, r = t - b * tiles_per_img;
     const int ty0 = (r / tiles_x) * DW_TH, tx0 = (r % tiles_x) * DW_TW;
     ptx::mbar_wait(&bar, phase);
@@ -86,9 +100,9 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __rest
 #pragma unroll
     for (int iy = 0; iy < K + 1; ++iy) {  // staged rows r0 .. r0+K feed output rows r0 (taps ky = iy) and r0+1 (ky = iy-1)
       float rv[IW];
-      const float* src = tile + ((r0 + iy) * IW) * DW_CI + lane;
+      const float* src = tile + sub * SUB + ((r0 + iy) * IW) * CI + ch;
 #pragma unroll
-      for (int i = 0; i < IW; ++i) rv[i] = src[i * DW_CI];
+      for (int i = 0; i < IW; ++i) rv[i] = src[i * CI];
       if (iy < K) {
 #pragma unroll
         for (int x = 0; x < DW_TW; ++x)
@@ -103,12 +117,12 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __rest
       }
     }
     __syncthreads();  // every warp has read its rows: the tile may be overwritten
-    if (threadIdx.x == 0 && t + static_cast<int>(gridDim.x) < total_tiles) issue_load(t + gridDim.x);
-    if (c_ok) {
+    if (threadIdx.x == 0 && it + static_cast<int>(gridDim.x) < iters) issue_load(it + gridDim.x);
+    if (c_ok && t < total_tiles) {
       const int oy = ty0 + r0;
       Tout* o0 = out + ((static_cast<long long>(b) * H + oy) * W + tx0) * C + c;
       Tout* o1 = o0 + static_cast<long long>(W) * C;
-      if (ty0 + DW_TH <= H && tx0 + DW_TW <= W) {   // interior tile (block-uniform): no per-pixel bounds checks
+      if (ty0 + DW_TH <= H && tx0 + DW_TW <= W) {   // interior tile: no per-pixel bounds checks
 #pragma unroll
         for (int x = 0; x < DW_TW; ++x, o0 += C, o1 += C) {
           store_out(o0, acc0[x]);
@@ -203,14 +217,14 @@ dwconv_small_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __re
   }
 }
 
-bool make_tmap_nhwc_f32(CUtensorMap* tm, const float* base, int n, int H, int W, int C, int box_w, int box_h) {
+bool make_tmap_nhwc_f32(CUtensorMap* tm, const float* base, int n, int H, int W, int C, int box_w, int box_h, int box_c = DW_CI) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (enc == nullptr) return false;
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
                         static_cast<cuuint64_t>(n)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4,
                            static_cast<cuuint64_t>(H) * W * C * 4};
-  cuuint32_t box[4] = {DW_CI, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -263,16 +277,21 @@ cudaError_t launch_t(const float* in, int n, int H, int W, int C, const float* w
   if (small_on && H <= 8 && W <= 8) return launch_small_t<K, Tout, 8>(in, n, H, W, C, w, bias, out, st);
   constexpr int IW = DW_TW + K - 1, IH = DW_TH + K - 1;
   constexpr int smem = IH * IW * DW_CI * 4;
+  static const bool half_on = [] { const char* v = getenv("CLIPB200_DWCONV_HALF_BLOCKS"); return v == nullptr || atoi(v) != 0; }();
+  const bool half = half_on && C % 32 == 16;   // e.g. 80 channels: five blocks of 16 (two tiles per iteration) instead of 32 + 32 + 16
+  const int ci = half ? 16 : DW_CI, nt = 32 / ci;
   CUtensorMap tm;
-  if (!make_tmap_nhwc_f32(&tm, in, n, H, W, C, IW, IH)) return cudaErrorInvalidValue;
+  if (!make_tmap_nhwc_f32(&tm, in, n, H, W, C, IW, IH, ci)) return cudaErrorInvalidValue;
   const int tiles_x = (W + DW_TW - 1) / DW_TW, tiles_y = (H + DW_TH - 1) / DW_TH;
-  const int tiles_per_img = tiles_x * tiles_y, total = tiles_per_img * n, cblocks = (C + DW_CI - 1) / DW_CI;
+  const int tiles_per_img = tiles_x * tiles_y, total = tiles_per_img * n, cblocks = (C + ci - 1) / ci;
+  const int iters = (total + nt - 1) / nt;
   // persistent CTAs: two per SM over all channel blocks together
   int per_block = resident_ctas() / cblocks;
   if (per_block < 1) per_block = 1;
-  if (per_block > total) per_block = total;
+  if (per_block > iters) per_block = iters;
   dim3 grid(per_block, cblocks, 1);
-  dwconv_tma_kernel<K, Tout><<<grid, DW_THREADS, smem, st>>>(tm, w, bias, out, H, W, C, tiles_x, tiles_per_img, total);
+  if (half) dwconv_tma_kernel<K, Tout, 16><<<grid, DW_THREADS, smem, st>>>(tm, w, bias, out, H, W, C, tiles_x, tiles_per_img, total);
+  else dwconv_tma_kernel<K, Tout, 32><<<grid, DW_THREADS, smem, st>>>(tm, w, bias, out, H, W, C, tiles_x, tiles_per_img, total);
   return cudaGetLastError();
 }
 
@@ -388,7 +407,8 @@ cudaError_t configure_gen() {
 template <int K, typename Tout>
 cudaError_t configure_t() {
   constexpr int smem = (DW_TH + K - 1) * (DW_TW + K - 1) * DW_CI * 4;
-  cudaError_t e = cudaFuncSetAttribute(dwconv_tma_kernel<K, Tout>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(dwconv_tma_kernel<K, Tout, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_tma_kernel<K, Tout, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(dwconv_small_kernel<K, Tout, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              2 * (8 + K - 1) * (8 + K - 1) * DW_CI * 4);
