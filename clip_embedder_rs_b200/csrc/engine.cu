@@ -1276,9 +1276,10 @@ void parallel_copy(const std::vector<CopyPiece>& pieces) {
 }
 }  // namespace
 
-// Takes as many of the `count` images as fit one staging group (at least one), stages them through pinned memory,
-// copies them and their coefficient tables to the device and resizes them into d_dst[i * S*S*3] with two launches,
-// everything on the copy-in stream: the caller's compute stream keeps running the previous micro-batch's tower.
+// Takes as many of the `count` images as fit one staging group (at least one), stages the rows and columns the resize
+// reads through pinned memory (process-wide copy workers), uploads them and their coefficient tables on the copy-in stream
+// and resizes them into d_dst[i * S*S*3] with two launches on the resize stream (so the next group's upload does not
+// queue behind them); the caller's compute stream keeps running the previous micro-batch's tower.
 Status Engine::ResizeGroupToDevice(const uint8_t* const* imgs, const int32_t* widths, const int32_t* heights, int count,
                                    const clipb200_preproc* pp, uint8_t* d_dst, int* consumed) {
   const size_t px = static_cast<size_t>(S_) * S_ * 3;
